@@ -1,0 +1,149 @@
+/*
+ * libtactile_gan_b200.so -- C-ABI of the B200 (sm_100a) kernels behind the tactile-gan G+D step.
+ *
+ * The reference (mmheydari97/tactile-gan) has no FFI: its hot path is a chain of ATen/cuDNN library
+ * calls issued by PyTorch eager.  Each entry point below replaces the library calls made at the
+ * cited reference lines; the Python host (tactile_gan_b200/*.py) binds them with ctypes.
+ *
+ * Conventions: plain pointers and sizes only; device pointers unless stated; activations are NHWC
+ * bf16 with the channel count padded to a multiple of 64; `stream` is a cudaStream_t passed as
+ * void*; every call returns 0 on success or a negative code (tg_last_error() gives the text),
+ * never throws, never allocates device memory and never synchronises.
+ */
+#ifndef TACTILE_GAN_B200_H
+#define TACTILE_GAN_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TG_MAX_SRC 6
+#define TG_MAX_TAPS 16
+
+enum { TG_ACT_NONE = 0, TG_ACT_LRELU = 1, TG_ACT_SIGMOID = 2, TG_ACT_RELU = 3, TG_ACT_TANH = 4 };
+enum { TG_GAN_LS = 0, TG_GAN_CE = 1, TG_GAN_W = 2, TG_GAN_HINGE = 3 };
+
+int tg_version(void);
+const char* tg_last_error(void);
+int tg_device_sm_count(void);
+
+/* NHWC bf16 tensor view: c contiguous, strides in elements. */
+typedef struct tg_view {
+  void* ptr;
+  int n, h, w, c;
+  long long sn, sh, sw;
+} tg_view;
+
+/* One operand of the (virtual-concat) K loop: activation view + its slice of the packed weights
+ * bf16 [wgt_taps][wgt_rows][wgt_k]; this source multiplies columns [k_off, k_off + act.c). */
+typedef struct tg_conv_src {
+  tg_view act;
+  const void* wgt;
+  int wgt_taps, wgt_rows, wgt_k, k_off, row_off;
+} tg_conv_src;
+
+/* Implicit-GEMM convolution (tcgen05 / TMEM / TMA).
+ *   out[n,y,x,co] = act( bias[co] + sum_src sum_tap sum_ci act_src[n, y*stride+dy[tap], x*stride+dx[tap], ci]
+ *                                                         * wgt_src[tap_w[tap]][row_off+co][k_off+ci] )
+ * Replaces nn.Conv2d / nn.ConvTranspose2d forward and their input-gradient (dgrad):
+ *   generators/UNet_plusplus.py:22,26  generators/UNet.py:21,25,40,44  generators/BCDUNet.py:122-137
+ *   discriminators/PatchDiscriminator.py:14,27 and torch.cat / nn.Upsample operands at
+ *   generators/UNet_plusplus.py:72-84 (the concat is the multi-source K loop, never materialised).
+ * stats_partial (optional): [n][tiles_per_img][c][2] fp32 (sum, sum of squares) per output tile for
+ * the InstanceNorm that follows (nn.InstanceNorm2d, UNet_plusplus.py:23,27). */
+typedef struct tg_conv_desc {
+  int num_src;
+  tg_conv_src src[TG_MAX_SRC];
+  tg_view out;
+  int taps, stride;
+  signed char tap_dy[TG_MAX_TAPS], tap_dx[TG_MAX_TAPS], tap_w[TG_MAX_TAPS];
+  const float* bias;
+  float* stats_partial;
+  int act;
+  float slope;
+} tg_conv_desc;
+
+/* Weight gradient (split-K implicit GEMM over pixels, fp32 accumulation into dw with red.add):
+ *   dw[tap_w[tap]][qc][pc] += sum_{n,y,x} P[n, y*stride+dy, x*stride+dx, pc] * Q[n,y,x,qc]
+ * Replaces the autograd wgrad of the convolutions above (loss.backward(), train.py:134,167). */
+typedef struct tg_wgrad_desc {
+  int num_src;
+  tg_view p[TG_MAX_SRC];
+  tg_view q;
+  int taps, stride;
+  signed char tap_dy[TG_MAX_TAPS], tap_dx[TG_MAX_TAPS], tap_w[TG_MAX_TAPS];
+  float* dw;
+  int dw_rows, dw_cols;
+} tg_wgrad_desc;
+
+typedef struct tg_plan tg_plan;
+int tg_conv_query_tiles(int n, int ho, int wo, int want_stats, int* out4 /* th, tw, tn, tiles_per_img */);
+int tg_conv_plan_create(const tg_conv_desc* desc, tg_plan** plan);
+int tg_wgrad_plan_create(const tg_wgrad_desc* desc, tg_plan** plan);
+int tg_plan_run(tg_plan* plan, void* stream);
+void tg_plan_destroy(tg_plan* plan);
+/* device int the kernels set (non-zero) when a pipeline wait times out; host-readable after sync */
+int* tg_error_flag_device_ptr(void);
+int tg_error_flag_read(void); /* synchronising D2H read of that flag (diagnostics / tests only) */
+
+/* ---- layout packs (train.py:101 `.to(device)` + torch.cat at PatchDiscriminator.py:36, and the
+ *      GP interpolation alpha*real + (1-alpha)*fake at util.py:79-83) */
+int tg_pack_nchw(const float* A, const float* B, const float* wa, const float* wb, void* out, int N,
+                 int HW, int cj, int C, int c_off, void* stream);
+int tg_unpack_nhwc(const void* in, float* out, int N, int HW, int C, int c_off, int cj, float scale,
+                   void* stream);
+
+/* ---- InstanceNorm2d(eps, biased var) (+affine) fused with ReLU / LeakyReLU, optional AvgPool2d(2) /
+ *      MaxPool2d(2) copy and nearest Upsample(x2) copy (UNet_plusplus.py:23-24,40-41; BCDUNet.py:110;
+ *      PatchDiscriminator.py:16-17) and their backward */
+int tg_in_finalize(const float* partial, float* mr, int N, int T, int C, int count, float eps, void* stream);
+int tg_in_stats_direct(const void* raw, float* mr, int N, int HW, int C, float eps, void* stream);
+int tg_in_act_fwd(const void* raw, const float* mr, const float* gamma, const float* beta, void* y,
+                  void* pool, int pool_mode, void* up, int N, int H, int W, int C, int act, float slope,
+                  void* stream);
+int tg_in_bwd_reduce(const void* raw, const void* y, const float* mr, const float* gamma,
+                     const float* beta, const void* g_same, const void* g_pool, int pool_mode,
+                     const void* g_up, void* dn, float* red, int N, int H, int W, int C, int act,
+                     float slope, void* stream);
+int tg_in_bwd_apply(const void* dn, const void* raw, const float* mr, const float* gamma,
+                    const float* red, void* dz, int N, int HW, int C, void* stream);
+int tg_affine_grad(const float* red, float* dgamma, float* dbeta, int N, int C, void* stream);
+int tg_bias_grad(const void* dz, float* db, long long rows, int C, int c_valid, void* stream);
+/* InstanceNorm double backward for the gradient penalty (util.py:88-93, create_graph=True) */
+int tg_in_bwd2(const void* u, const void* raw, const void* dn, const float* mr, const float* gamma,
+               const float* beta, const float* red1, float* red2, void* adj_da, void* adj_z, int N,
+               int HW, int C, int act, float slope, void* stream);
+int tg_gamma_grad2(const float* red2, float* dgamma, int N, int C, void* stream);
+int tg_add(const void* a, const void* b, void* out, long long numel, void* stream);
+int tg_act_bwd(const void* g, const void* y, void* out, long long numel, int act, float slope, void* stream);
+
+/* ---- FeatureMapBlock: 1x1 conv + bias (+Tanh) (UNet_plusplus.py:5-16) forward / backward */
+int tg_fmap_fwd(const void* x, const float* w, const float* b, float* out, int N, int HW, int C, int co,
+                int use_tanh, void* stream);
+int tg_fmap_bwd(const void* x, const float* w, const float* out, const float* g1, const float* g2,
+                void* dx, float* dw, float* db, int N, int HW, int C, int co, int use_tanh, void* stream);
+
+/* ---- losses: GANLoss (generators/generators.py:80-105), nn.L1Loss (train.py:145), pan_loss
+ *      (util.py:41-70), gradient_penalty norm (util.py:92-93) */
+int tg_gan_loss(const void* pred, const float* label, float label_const, int mode, int target_is_real,
+                int for_disc, int has_sigmoid, float scale, int n0, int n1, int HW, int C, float* loss,
+                void* dz, void* stream);
+int tg_gp_first_seed(const void* pred, int has_sigmoid, int n0, int n1, int HW, int C, void* dz, void* stream);
+int tg_gp_top(const void* w, const void* pred, int has_sigmoid, long long numel, int C, void* out, void* stream);
+int tg_l1_loss(const float* a, const float* b, long long numel, float scale, float* loss, float* grad_a,
+               void* stream);
+int tg_feat_loss(const void* a, const void* b, long long numel, float weight, int l2, float* loss, void* stream);
+int tg_gp_normsq(const void* g, int N, int HW, int C, int c_off, int cj, float* nsq, void* stream);
+int tg_gp_finish(const float* nsq, int N, float lambda, float constant, float* loss, float* coef, void* stream);
+int tg_gp_seed(const void* g, const float* coef, int N, int HW, int C, int c_off, int cj, void* seed, void* stream);
+
+/* ---- torch.optim.Adam.step (train.py:135,168) fused with the bf16 weight re-pack.
+ * table_dev: device array of `ntensors` rows, each row = 6 pointers, 1 int64, 6 int32
+ * (param, grad, exp_avg, exp_avg_sq, pack_fwd, pack_bwd, numel, kind, kh, kw, dim1, o_pad, i_pad). */
+int tg_adam_step(const void* table_dev, int ntensors, long long max_numel, float lr, float beta1,
+                 float beta2, float eps, int step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

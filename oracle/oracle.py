@@ -1,0 +1,271 @@
+"""ORACLE -- test infrastructure only (never imported by the product path).
+
+A CPU, fp32, plain-PyTorch *functional* restatement of the tactile-gan G+D training step. It works on
+flat ``state_dict``s (name -> tensor) whose keys are exactly the reference's parameter names, so the
+reference modules and this file can be driven with the same weights.
+
+What follows which reference lines (all under /root/reference):
+  unetpp_forward   generators/UNet_plusplus.py:18-34 (ConvBlock), :65-86 (forward), :5-16 (head)
+  unet_forward     generators/UNet.py:17-51 (ConvDown/DeconvUp), :80-99 (forward)
+  bcdunet_forward  generators/BCDUNet.py:120-143 (blocks), :154-181 (forward; ConvLSTM never called)
+  patchd_forward   discriminators/PatchDiscriminator.py:12-37 (+ the 4 LeakyReLU feature taps :39-43)
+  gan_loss         generators/generators.py:80-105
+  pan_loss         util.py:41-70 (mode='normal' only, as called from train.py:160)
+  gradient_penalty util.py:72-97
+  adam_update      torch.optim.Adam as configured at train.py:56-57 (betas=(beta1,0.99), eps=1e-8)
+  train_step       train.py:99-168
+
+Parity pin: the reference ships no tests or golden vectors, so this oracle is pinned
+against outputs of the reference's own modules executed here -- see oracle/make_golden.py, which
+imports /root/reference, and tests/test_oracle_golden.py which replays the committed fixtures.
+Arithmetic the reference delegates to third parties: PyTorch (torch 2.11.0 here; conv / instance_norm /
+autograd / Adam) and, for the version-1 perceptual term only, torchvision VGG16 weights (not
+obtainable offline: version 1 is compared with shared random-init weights).
+"""
+import math
+from collections import OrderedDict
+
+import torch
+import torch.nn.functional as F
+
+EPS_IN = 1e-5
+
+
+# --------------------------------------------------------------------------- generators
+def _in(x, sd, key):
+    """InstanceNorm2d, biased variance, eps 1e-5, optional affine (key.weight / key.bias)."""
+    return F.instance_norm(x, weight=sd.get(key + ".weight"), bias=sd.get(key + ".bias"), eps=EPS_IN)
+
+
+def _double_conv(x, sd, p, first=None):
+    """[conv -> IN -> ReLU] x 2 with parameter names p.0 / p.1 / p.3 / p.4.
+    `first` overrides the first op (strided conv / transposed conv for UNet)."""
+    if first is None:
+        x = F.conv2d(x, sd[p + ".0.weight"], sd.get(p + ".0.bias"), stride=1, padding=1)
+    else:
+        x = first(x)
+    x = F.relu(_in(x, sd, p + ".1"))
+    x = F.conv2d(x, sd[p + ".3.weight"], sd.get(p + ".3.bias"), stride=1, padding=1)
+    return F.relu(_in(x, sd, p + ".4"))
+
+
+def _head(x, sd, key, activation):
+    x = F.conv2d(x, sd[key + ".weight"], sd[key + ".bias"])
+    return torch.tanh(x) if activation else x
+
+
+def unetpp_forward(sd, x, activation=True):
+    up = lambda t: F.interpolate(t, scale_factor=2, mode="nearest")
+    down = lambda t: F.avg_pool2d(t, 2, 2)
+    X = {}
+    blk = lambda i, j, inp: _double_conv(inp, sd, f"conv{i}_{j}.layer")
+    X[0, 0] = blk(0, 0, x)
+    for i in range(1, 5):
+        X[i, 0] = blk(i, 0, down(X[i - 1, 0]))
+    for j in range(1, 5):
+        for i in range(0, 5 - j):
+            X[i, j] = blk(i, j, torch.cat([X[i, k] for k in range(j)] + [up(X[i + 1, j - 1])], 1))
+    return _head(X[0, 4], sd, "downfeature.conv", activation)
+
+
+def unet_forward(sd, x, activation=True):
+    c = [None]
+    t = x
+    for i in range(1, 8):
+        w = sd[f"conv{i}.layer.0.weight"]
+        t = _double_conv(t, sd, f"conv{i}.layer", first=lambda z, w=w: F.conv2d(z, w, None, stride=2, padding=1))
+        c.append(t)
+    d = c[7]
+    for i in range(2, 9):
+        w = sd[f"deconv{i}.layer.0.weight"]
+        inp = d if i == 2 else torch.cat([d, c[9 - i]], 1)  # d3 <- (d2, c6) ... d8 <- (d7, c1)
+        d = _double_conv(inp, sd, f"deconv{i}.layer",
+                         first=lambda z, w=w: F.conv_transpose2d(z, w, None, stride=2, padding=1))
+    return _head(d, sd, "downfeature.conv", activation)
+
+
+def bcdunet_forward(sd, x, activation=True):
+    blk = lambda name, inp: _double_conv(inp, sd, name)
+    pool = lambda t: F.max_pool2d(t, 2, 2)
+    c1 = blk("conv1", x)
+    c2 = blk("conv2", pool(c1))
+    c3 = blk("conv3", pool(c2))
+    c4 = blk("conv4", pool(c3))
+    u3 = F.conv_transpose2d(c4, sd["upconv3.weight"], sd["upconv3.bias"], stride=2)
+    m3 = blk("conv3m", torch.cat([c3, u3], 1))
+    u2 = F.conv_transpose2d(m3, sd["upconv2.weight"], sd["upconv2.bias"], stride=2)
+    m2 = blk("conv2m", torch.cat([c2, u2], 1))
+    u1 = F.conv_transpose2d(m2, sd["upconv1.weight"], sd["upconv1.bias"], stride=2)
+    m1 = blk("conv1m", torch.cat([c1, u1], 1))
+    return _head(m1, sd, "conv0", activation)
+
+
+GEN_FORWARD = {"unet++": unetpp_forward, "unet": unet_forward, "bcdunet": bcdunet_forward}
+
+
+def gen_forward(name, sd, x, activation=True):
+    return GEN_FORWARD[name.lower()](sd, x, activation)
+
+
+# --------------------------------------------------------------------------- discriminator
+def patchd_forward(sd, img_a, img_b, activation=True):
+    """Returns (prediction, [4 LeakyReLU feature maps])."""
+    feats = []
+    x = torch.cat([img_a, img_b], 1)
+    x = F.leaky_relu(F.conv2d(x, sd["model.0.weight"], sd["model.0.bias"], stride=2), 0.2)
+    feats.append(x)
+    for conv, norm, stride in ((2, 3, 2), (5, 6, 1), (8, 9, 1)):
+        x = F.conv2d(x, sd[f"model.{conv}.weight"], None, stride=stride)
+        x = F.leaky_relu(_in(x, sd, f"model.{norm}"), 0.2)
+        feats.append(x)
+    x = F.conv2d(x, sd["model.11.weight"], sd["model.11.bias"])
+    if activation:
+        x = torch.sigmoid(x)
+    return x, feats
+
+
+# --------------------------------------------------------------------------- losses
+def make_real_label(shape, smoothing=True, real_label=1.0, generator=None):
+    """GANLoss caches this on first use (generators.py:54-61): one CPU-RNG draw per run."""
+    if smoothing:
+        return torch.clamp(torch.normal(real_label, 0.02, size=shape, generator=generator), 0, 1)
+    return torch.full((1,), real_label)
+
+
+def gan_loss(pred, target_is_real, mode, real_label, for_discriminator=True, fake_label=0.0):
+    if mode in ("ls", "ce"):
+        tgt = real_label.to(pred).expand_as(pred) if target_is_real else torch.full_like(pred, fake_label)
+        if mode == "ls":
+            return F.mse_loss(pred, tgt)
+        return F.binary_cross_entropy_with_logits(pred, tgt)
+    if mode == "hinge":
+        if for_discriminator:
+            m = (pred - 1) if target_is_real else (-pred - 1)
+            return -torch.mean(torch.minimum(m, torch.zeros_like(m)))
+        return -torch.mean(pred)
+    if mode == "w":
+        return -pred.mean() if target_is_real else pred.mean()
+    raise ValueError(f"Unexpected gan mode {mode}")
+
+
+def pan_loss(real_feats, fake_feats, weights):
+    w = [float(v) / float(sum(weights)) for v in weights]
+    total = 0.0
+    for i in range(4):
+        total = total + F.l1_loss(real_feats[i], fake_feats[i]) * w[i]
+    return total
+
+
+def gradient_penalty(sd_d, real_a, real_b, fake_b, alpha, activation, lambda_gp, version=2, constant=1.0):
+    """alpha: (B,1) uniform draw (the reference draws it on the CUDA generator, util.py:79)."""
+    a = (alpha + 1) / 2 if version == 2 else alpha
+    a = a.view(-1, 1, 1, 1)
+    inter = (a * real_b + (1 - a) * fake_b).detach().requires_grad_(True)
+    pred, _ = patchd_forward(sd_d, real_a, inter, activation)
+    (g,) = torch.autograd.grad(pred, inter, torch.ones_like(pred), create_graph=True, retain_graph=True)
+    g = g.reshape(g.shape[0], -1)
+    return (((g + 1e-16).norm(2, dim=1) - constant) ** 2).mean() * lambda_gp
+
+
+# --------------------------------------------------------------------------- optimiser
+def adam_update(params, grads, state, lr, beta1, beta2=0.99, eps=1e-8):
+    """In-place Adam on dicts keyed by parameter name; state[name] = dict(step, exp_avg, exp_avg_sq)."""
+    for k, p in params.items():
+        g = grads.get(k)
+        if g is None:
+            continue
+        st = state.setdefault(k, dict(step=0, exp_avg=torch.zeros_like(p), exp_avg_sq=torch.zeros_like(p)))
+        st["step"] += 1
+        st["exp_avg"].mul_(beta1).add_(g, alpha=1 - beta1)
+        st["exp_avg_sq"].mul_(beta2).addcmul_(g, g, value=1 - beta2)
+        bc1 = 1 - beta1 ** st["step"]
+        bc2 = 1 - beta2 ** st["step"]
+        denom = (st["exp_avg_sq"].sqrt() / math.sqrt(bc2)).add_(eps)
+        p.data.addcdiv_(st["exp_avg"], denom, value=-lr / bc1)
+
+
+# --------------------------------------------------------------------------- the step
+class StepConfig:
+    def __init__(self, gen="UNet++", loss="ls", version=2, lambda_a=1.0, lambda_gp=0.01, lambda_per=1.0,
+                 w_per=(0, .1, .3, .6), lr=1e-3, beta1=0.9, regularize=True):
+        self.gen, self.loss, self.version = gen, loss, version
+        self.lambda_a, self.lambda_gp, self.lambda_per = lambda_a, lambda_gp, lambda_per
+        self.w_per, self.lr, self.beta1, self.regularize = tuple(w_per), lr, beta1, regularize
+        self.activation = loss == "ls"  # train.py:33
+
+
+def _leaf(sd):
+    return OrderedDict((k, v.detach().clone().requires_grad_(v.is_floating_point())) for k, v in sd.items())
+
+
+def train_step(sd_g, sd_d, opt_g, opt_d, real_a, real_b, real_label, alpha, cfg):
+    """One G+D iteration (train.py:99-168). Mutates sd_g / sd_d / opt_g / opt_d in place and returns
+    dict(loss_D (before GP), gp, G_GAN, L1, per, fake_B, grads_D, grads_G)."""
+    act = cfg.activation
+    pg = _leaf(sd_g)
+    pd = _leaf(sd_d)
+    fake_b = gen_forward(cfg.gen, pg, real_a, act)
+
+    # ---- D step (train.py:107-135)
+    pred_fake, _ = patchd_forward(pd, real_a, fake_b.detach(), act)
+    pred_real, _ = patchd_forward(pd, real_a, real_b, act)
+    loss_d = (gan_loss(pred_fake, False, cfg.loss, real_label) + gan_loss(pred_real, True, cfg.loss, real_label)) / 2
+    out = {"loss_D": float(loss_d)}
+    total_d = loss_d
+    if cfg.regularize and cfg.lambda_gp != 0:
+        gp = gradient_penalty(pd, real_a, real_b, fake_b.detach(), alpha, act, cfg.lambda_gp, cfg.version)
+        total_d = total_d + gp
+        out["gp"] = float(gp)
+    else:
+        out["gp"] = 0.0
+    names_d = [k for k, v in pd.items() if v.requires_grad]
+    gd = torch.autograd.grad(total_d, [pd[k] for k in names_d], allow_unused=True)
+    grads_d = {k: g for k, g in zip(names_d, gd) if g is not None}
+    adam_update(sd_d, grads_d, opt_d, cfg.lr, cfg.beta1)
+
+    # ---- G step (train.py:138-168), D already updated
+    pd2 = OrderedDict((k, v.detach()) for k, v in sd_d.items())
+    pred_fake, feats_fake = patchd_forward(pd2, real_a, fake_b, act)
+    g_gan = gan_loss(pred_fake, True, cfg.loss, real_label, for_discriminator=False)
+    l1 = F.l1_loss(real_b, fake_b)
+    total_g = g_gan + l1 * cfg.lambda_a
+    out["G_GAN"], out["L1"] = float(g_gan), float(l1)
+    if cfg.lambda_per != 0:
+        if cfg.version != 2:
+            raise NotImplementedError("version 1 (VGG16) is handled by oracle.vgg_perceptual")
+        _, feats_real = patchd_forward(pd2, real_a, real_b, act)
+        # the reference stores detached clones of both feature lists: the term carries no gradient
+        per = pan_loss([f.detach() for f in feats_real], [f.detach() for f in feats_fake], cfg.w_per) * cfg.lambda_per
+        total_g = total_g + per
+        out["per"] = float(per)
+    else:
+        out["per"] = 0.0
+    names_g = [k for k, v in pg.items() if v.requires_grad]
+    gg = torch.autograd.grad(total_g, [pg[k] for k in names_g], allow_unused=True)
+    grads_g = {k: g for k, g in zip(names_g, gg) if g is not None}
+    adam_update(sd_g, grads_g, opt_g, cfg.lr, cfg.beta1)
+    out.update(fake_B=fake_b.detach(), grads_D=grads_d, grads_G=grads_g)
+    return out
+
+
+def synthetic_batch(generator, batch, size, in_nc=3, out_nc=3):
+    """Synthetic pair in the ranges the dataset produces: source in [-1,1] (Normalize(.5,.5),
+    datasets/PairedDataset.py:52-58), target in [0,1] (ToTensor, :86)."""
+    real_a = torch.rand(batch, in_nc, size, size, generator=generator) * 2 - 1
+    real_b = torch.rand(batch, out_nc, size, size, generator=generator)
+    return real_a, real_b
+
+
+# --------------------------------------------------------------------------- init (util.py:23-34)
+def init_state_dict(shapes, generator, gain=0.02):
+    """N(0, gain) for conv weights, zeros for conv biases, (1, 0) for InstanceNorm affine.
+    `shapes`: OrderedDict name -> shape with the reference's parameter names."""
+    sd = OrderedDict()
+    for k, shp in shapes.items():
+        if len(shp) == 4:
+            sd[k] = torch.randn(shp, generator=generator) * gain
+        elif k.endswith(".weight"):
+            sd[k] = torch.ones(shp)
+        else:
+            sd[k] = torch.zeros(shp)
+    return sd

@@ -1,0 +1,316 @@
+// C-ABI front end: tensor-map construction, tile/split heuristics, plan objects, launches.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "../../include/tactile_gan_b200.h"
+#include "tg_api_internal.h"
+#include "tg_igemm.cuh"
+#include "tg_wgrad.cuh"
+
+static thread_local char g_err[512] = "";
+
+int tg_set_error(const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return -1;
+}
+int tg_check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) return 0;
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return -1;
+}
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int* g_err_flag = nullptr;
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+// 4-D NHWC map {C, W, H, N}; box {64, bw, bh, bn}; optional element strides on W/H.
+int make_act_map(CUtensorMap* m, const tg_view& v, int c_off, int c_len, int bw, int bh, int bn,
+                 int estride) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return tg_set_error("cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[4] = {cuuint64_t(c_len), cuuint64_t(v.w), cuuint64_t(v.h), cuuint64_t(v.n)};
+  cuuint64_t strides[3] = {cuuint64_t(v.sw) * 2, cuuint64_t(v.sh) * 2, cuuint64_t(v.sn) * 2};
+  cuuint32_t box[4] = {64, cuuint32_t(bw * estride), cuuint32_t(bh * estride), cuuint32_t(bn)};
+  cuuint32_t es[4] = {1, cuuint32_t(estride), cuuint32_t(estride), 1};
+  if (box[1] > 256 || box[2] > 256) return tg_set_error("TMA box too large");
+  void* base = static_cast<char*>(v.ptr) + size_t(c_off) * 2;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_err, sizeof(g_err),
+             "cuTensorMapEncodeTiled(act) failed: %d dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu) "
+             "box=(%u,%u,%u,%u) es=%d ptr=%p",
+             int(r), (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+             (unsigned long long)dims[3], (unsigned long long)strides[0], (unsigned long long)strides[1],
+             (unsigned long long)strides[2], box[0], box[1],
+             box[2], box[3], estride, base);
+    return -1;
+  }
+  return 0;
+}
+
+// 3-D weight map {K, rows, taps}; box {64, bn, 1}
+int make_wgt_map(CUtensorMap* m, const void* base, int k_len, int rows, int taps, int pitch_k,
+                 int pitch_rows, int bn) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return tg_set_error("cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[3] = {cuuint64_t(k_len), cuuint64_t(rows), cuuint64_t(taps)};
+  cuuint64_t strides[2] = {cuuint64_t(pitch_k) * 2, cuuint64_t(pitch_k) * pitch_rows * 2};
+  cuuint32_t box[3] = {64, cuuint32_t(bn), 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled(wgt) failed: %d k=%d rows=%d taps=%d pitch=%d",
+             int(r), k_len, rows, taps, pitch_k);
+    return -1;
+  }
+  return 0;
+}
+
+// choose (tn, th, tw) with tn*th*tw == pixels minimising padded work; stats need tn == 1
+void choose_tile(int n, int h, int w, int pixels, bool single_image, int* th, int* tw, int* tn) {
+  double best = 1e30;
+  *th = 1; *tw = pixels; *tn = 1;
+  for (int cw = 1; cw <= pixels; cw *= 2) {
+    for (int ch = 1; ch * cw <= pixels; ch *= 2) {
+      const int cn = pixels / (cw * ch);
+      if (single_image && cn != 1) continue;
+      if (cw > 128 || ch > 128 || cn > 256) continue;
+      const double tiles = double((w + cw - 1) / cw) * ((h + ch - 1) / ch) * ((n + cn - 1) / cn);
+      // tie-break: prefer 8..16 wide tiles (L2 locality of the shifted windows), then fewer images
+      const double cost = tiles * (1.0 + 1e-3 * (cw < 8 ? 8 - cw : 0) + 1e-4 * (cw > 16 ? 1 : 0) + 1e-5 * cn);
+      if (cost < best) { best = cost; *th = ch; *tw = cw; *tn = cn; }
+    }
+  }
+}
+
+}  // namespace
+
+struct tg_plan {
+  int kind;  // 0 conv, 1 wgrad
+  int bn;
+  int grid;
+  size_t smem;
+  tg::IgemmParams conv;
+  tg::WgradParams wg;
+};
+
+extern "C" {
+
+int tg_version(void) { return 100; }
+const char* tg_last_error(void) { return g_err; }
+int tg_device_sm_count(void) { return sm_count(); }
+
+int* tg_error_flag_device_ptr(void) {
+  if (!g_err_flag) {
+    if (cudaMalloc(&g_err_flag, sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(g_err_flag, 0, sizeof(int));
+  }
+  return g_err_flag;
+}
+
+int tg_error_flag_read(void) {
+  int v = 0;
+  if (!g_err_flag) return 0;
+  if (cudaMemcpy(&v, g_err_flag, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return v;
+}
+
+int tg_conv_query_tiles(int n, int ho, int wo, int want_stats, int* out4) {
+  int th, tw, tn;
+  choose_tile(n, ho, wo, tg::kTileM, want_stats != 0, &th, &tw, &tn);
+  out4[0] = th; out4[1] = tw; out4[2] = tn;
+  out4[3] = ((ho + th - 1) / th) * ((wo + tw - 1) / tw);
+  return 0;
+}
+
+int tg_conv_plan_create(const tg_conv_desc* d, tg_plan** out) {
+  if (!d || !out) return tg_set_error("tg_conv_plan_create: null argument");
+  if (d->num_src < 1 || d->num_src > TG_MAX_SRC) return tg_set_error("tg_conv_plan_create: bad num_src");
+  if (d->taps < 1 || d->taps > TG_MAX_TAPS) return tg_set_error("tg_conv_plan_create: bad taps");
+  if (d->out.c % 64) return tg_set_error("tg_conv_plan_create: Cout must be a multiple of 64");
+  tg_plan* pl = new (std::nothrow) tg_plan();
+  if (!pl) return tg_set_error("out of host memory");
+  pl->kind = 0;
+  tg::IgemmParams& p = pl->conv;
+  memset(&p, 0, sizeof(p));
+  const int cout = d->out.c;
+  const int bn = cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64);
+  pl->bn = bn;
+  int th, tw, tn;
+  choose_tile(d->out.n, d->out.h, d->out.w, tg::kTileM, d->stats_partial != nullptr, &th, &tw, &tn);
+  p.num_src = d->num_src;
+  p.taps = d->taps;
+  p.stride = d->stride;
+  memcpy(p.tap_dy, d->tap_dy, 16);
+  memcpy(p.tap_dx, d->tap_dx, 16);
+  memcpy(p.tap_w, d->tap_w, 16);
+  p.Ho = d->out.h; p.Wo = d->out.w; p.N = d->out.n;
+  p.th = th; p.tw = tw; p.tn = tn;
+  p.tiles_h = (p.Ho + th - 1) / th;
+  p.tiles_w = (p.Wo + tw - 1) / tw;
+  p.tiles_img = (p.N + tn - 1) / tn;
+  p.n_tiles = cout / bn;
+  p.act = d->act;
+  p.slope = d->slope;
+  p.bias = d->bias;
+  p.stats_partial = d->stats_partial;
+  p.cout = cout;
+  p.err_flag = tg_error_flag_device_ptr();
+  for (int s = 0; s < d->num_src; ++s) {
+    const tg_conv_src& cs = d->src[s];
+    if (cs.act.c % 64) { delete pl; return tg_set_error("tg_conv_plan_create: source C must be a multiple of 64"); }
+    if (cs.act.n != d->out.n) { delete pl; return tg_set_error("tg_conv_plan_create: batch mismatch"); }
+    if (make_act_map(&p.src[s].act, cs.act, 0, cs.act.c, tw, th, tn, d->stride)) { delete pl; return -1; }
+    const char* wbase = static_cast<const char*>(cs.wgt) + (size_t(cs.row_off) * cs.wgt_k + cs.k_off) * 2;
+    if (make_wgt_map(&p.src[s].wgt, wbase, cs.act.c, cout, cs.wgt_taps, cs.wgt_k, cs.wgt_rows, bn)) {
+      delete pl; return -1;
+    }
+    p.src[s].c_chunks = cs.act.c / 64;
+  }
+  if (make_act_map(&p.out, d->out, 0, cout, tw, th, tn, 1)) { delete pl; return -1; }
+  const int total = p.tiles_img * p.tiles_h * p.tiles_w * p.n_tiles;
+  pl->grid = total < sm_count() ? total : sm_count();
+  cudaError_t e;
+  if (bn == 256) {
+    pl->smem = tg::IgemmCfg<256>::kSmemTotal;
+    e = cudaFuncSetAttribute(tg::igemm_conv_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl->smem));
+  } else if (bn == 128) {
+    pl->smem = tg::IgemmCfg<128>::kSmemTotal;
+    e = cudaFuncSetAttribute(tg::igemm_conv_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl->smem));
+  } else {
+    pl->smem = tg::IgemmCfg<64>::kSmemTotal;
+    e = cudaFuncSetAttribute(tg::igemm_conv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl->smem));
+  }
+  if (e != cudaSuccess) {
+    delete pl;
+    snprintf(g_err, sizeof(g_err), "cudaFuncSetAttribute(conv): %s", cudaGetErrorString(e));
+    return -1;
+  }
+  *out = pl;
+  return 0;
+}
+
+int tg_wgrad_plan_create(const tg_wgrad_desc* d, tg_plan** out) {
+  if (!d || !out) return tg_set_error("tg_wgrad_plan_create: null argument");
+  if (d->num_src < 1 || d->num_src > TG_MAX_SRC) return tg_set_error("tg_wgrad_plan_create: bad num_src");
+  if (d->q.c % 64) return tg_set_error("tg_wgrad_plan_create: Q channels must be a multiple of 64");
+  tg_plan* pl = new (std::nothrow) tg_plan();
+  if (!pl) return tg_set_error("out of host memory");
+  pl->kind = 1;
+  tg::WgradParams& p = pl->wg;
+  memset(&p, 0, sizeof(p));
+  const int qc = d->q.c;
+  const int bn = qc % 256 == 0 ? 256 : (qc % 128 == 0 ? 128 : 64);
+  pl->bn = bn;
+  int th, tw, tn;
+  choose_tile(d->q.n, d->q.h, d->q.w, tg::kWgBoxPix, false, &th, &tw, &tn);
+  p.num_src = d->num_src;
+  p.taps = d->taps;
+  p.stride = d->stride;
+  memcpy(p.tap_dy, d->tap_dy, 16);
+  memcpy(p.tap_dx, d->tap_dx, 16);
+  memcpy(p.tap_w, d->tap_w, 16);
+  p.th = th; p.tw = tw; p.tn = tn;
+  p.tiles_h = (d->q.h + th - 1) / th;
+  p.tiles_w = (d->q.w + tw - 1) / tw;
+  p.tiles_img = (d->q.n + tn - 1) / tn;
+  int chunks = 0;
+  for (int s = 0; s < d->num_src; ++s) {
+    if (d->p[s].c % 64) { delete pl; return tg_set_error("tg_wgrad_plan_create: P channels must be a multiple of 64"); }
+    if (make_act_map(&p.src[s].act, d->p[s], 0, d->p[s].c, tw, th, tn, d->stride)) { delete pl; return -1; }
+    p.src[s].c_chunks = d->p[s].c / 64;
+    chunks += p.src[s].c_chunks;
+  }
+  if (make_act_map(&p.q, d->q, 0, qc, tw, th, tn, 1)) { delete pl; return -1; }
+  p.total_chunks = chunks;
+  p.m_tiles = (chunks + 1) / 2;
+  p.n_tiles = qc / bn;
+  p.dw = d->dw;
+  p.m_total = d->dw_cols;
+  p.n_total = d->dw_rows;
+  if (p.m_total != chunks * 64) { delete pl; return tg_set_error("tg_wgrad_plan_create: dw_cols != sum of P channels"); }
+  if (p.n_total < qc) { delete pl; return tg_set_error("tg_wgrad_plan_create: dw_rows < Q channels"); }
+  p.err_flag = tg_error_flag_device_ptr();
+  const int k_blocks = p.tiles_img * p.tiles_h * p.tiles_w;
+  const int items0 = p.taps * p.m_tiles * p.n_tiles;
+  int splits = (2 * sm_count() + items0 - 1) / items0;
+  const int max_splits = k_blocks / 8 > 1 ? k_blocks / 8 : 1;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  // no empty splits: splits <= k_blocks and ceil-division ranges must all be non-empty
+  while (splits > 1 && ((k_blocks + splits - 1) / splits) * (splits - 1) >= k_blocks) --splits;
+  p.splits = splits;
+  const int total = items0 * splits;
+  pl->grid = total < sm_count() ? total : sm_count();
+  cudaError_t e;
+  if (bn == 256) {
+    pl->smem = tg::WgradCfg<256>::kSmemTotal;
+    e = cudaFuncSetAttribute(tg::wgrad_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl->smem));
+  } else if (bn == 128) {
+    pl->smem = tg::WgradCfg<128>::kSmemTotal;
+    e = cudaFuncSetAttribute(tg::wgrad_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl->smem));
+  } else {
+    pl->smem = tg::WgradCfg<64>::kSmemTotal;
+    e = cudaFuncSetAttribute(tg::wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl->smem));
+  }
+  if (e != cudaSuccess) {
+    delete pl;
+    snprintf(g_err, sizeof(g_err), "cudaFuncSetAttribute(wgrad): %s", cudaGetErrorString(e));
+    return -1;
+  }
+  *out = pl;
+  return 0;
+}
+
+int tg_plan_run(tg_plan* pl, void* stream) {
+  if (!pl) return tg_set_error("tg_plan_run: null plan");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (pl->kind == 0) {
+    if (pl->bn == 256) tg::igemm_conv_kernel<256><<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->conv);
+    else if (pl->bn == 128) tg::igemm_conv_kernel<128><<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->conv);
+    else tg::igemm_conv_kernel<64><<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->conv);
+  } else {
+    if (pl->bn == 256) tg::wgrad_kernel<256><<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->wg);
+    else if (pl->bn == 128) tg::wgrad_kernel<128><<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->wg);
+    else tg::wgrad_kernel<64><<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->wg);
+  }
+  return tg_check_launch("tg_plan_run");
+}
+
+void tg_plan_destroy(tg_plan* pl) { delete pl; }
+
+}  // extern "C"

@@ -1,0 +1,27 @@
+// Internal glue shared by the translation units of libtactile_gan_b200.so (not part of the C-ABI).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_bf16.h>
+
+int tg_set_error(const char* msg);          // records msg, returns -1
+int tg_check_launch(const char* what);      // cudaGetLastError() -> 0 / -1
+
+namespace tg {
+
+// One row of the fused-Adam descriptor table (device resident).
+//   kind 0: plain vector (bias / affine / 1x1 head), grad has the same layout as param
+//   kind 1: Conv2d weight          torch [O][I][kh][kw]
+//   kind 2: ConvTranspose2d weight torch [I][O][kh][kw]
+struct AdamTensor {
+  float* param;
+  const float* grad;        // nullptr: re-pack only (no optimiser update)
+  float* m;
+  float* v;
+  __nv_bfloat16* pack_fwd;  // [taps][o_pad][i_pad]
+  __nv_bfloat16* pack_bwd;  // [taps][i_pad][o_pad]
+  long long numel;
+  int kind, kh, kw, dim1, o_pad, i_pad;
+};
+
+}  // namespace tg

@@ -1,0 +1,320 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+//   out[n, ho, wo, co] = sum_src sum_(r,s) sum_ci  act_src[n, ho*sy + r - pad, wo*sx + s - pad, ci]
+//                                                  * wgt_src[tap(r,s)][co][ci]
+//
+// One kernel serves forward convs (multi-source == virtual channel concat) and dgrad
+// (act = dY of every consumer, wgt = per-consumer transposed/flipped pack). Activations are
+// NHWC bf16 with channels padded to 64; a tile of 128 output pixels (tn x th x tw) is the UMMA M,
+// the Cout tile BN is the UMMA N, and the K loop walks (source, tap, 64-channel chunk). Each
+// k-iteration is one 4-D TMA box of the shifted input window (zero fill supplies the padding) and one
+// 3-D TMA box of weights, both landing in 128B-swizzled K-major shared memory.
+//
+// Warp roles: warp0 TMA producer, warp1 MMA issuer (+TMEM owner), warps2-5 epilogue
+// (TMEM -> regs -> bias/act -> bf16 -> swizzled smem -> TMA store, plus per-channel sum / sum-of-
+// squares partials for InstanceNorm). TMEM accumulators are double buffered so the epilogue of tile i
+// overlaps the MMAs of tile i+1. Persistent CTAs, static round-robin tile schedule.
+#pragma once
+#include "tg_ptx.cuh"
+
+namespace tg {
+
+constexpr int kMaxSrc = 6;
+constexpr int kTileM = 128;
+constexpr int kChunkK = 64;                       // bf16 elements per 128-byte swizzle row
+constexpr int kABytes = kTileM * kChunkK * 2;     // 16 KiB
+constexpr int kStoreBytes = kTileM * 64 * 2;      // one 64-channel output chunk
+constexpr int kNumThreads = 192;
+
+enum : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_SIGMOID = 2, ACT_RELU = 3, ACT_TANH = 4 };
+
+struct alignas(64) IgemmSrc {
+  CUtensorMap act;  // {C, W, H, N}
+  CUtensorMap wgt;  // {K, rows, taps}
+  int c_chunks;
+  int pad_[15];
+};
+
+struct alignas(64) IgemmParams {
+  IgemmSrc src[kMaxSrc];
+  CUtensorMap out;  // {Cout, Wo, Ho, N}
+  int num_src;
+  int taps, stride;                 // number of taps; input pixel = out pixel * stride + tap offset
+  int8_t tap_dy[16], tap_dx[16];    // per-tap input offset (padding / phase folded in)
+  int8_t tap_w[16];                 // per-tap index into the weight tensor's tap axis
+  int Ho, Wo, N;
+  int th, tw, tn;
+  int tiles_h, tiles_w, tiles_img;  // tiles_img = ceil(N / tn)
+  int n_tiles;                      // Cout / BN
+  int act;
+  float slope;
+  const float* bias;      // [Cout] or nullptr
+  float* stats_partial;   // [N][tiles_h*tiles_w][Cout][2] or nullptr (requires tn == 1)
+  int cout;               // padded Cout (row pitch of bias / stats)
+  int* err_flag;
+};
+
+template <int BN>
+struct IgemmCfg {
+  static constexpr int kBBytes = BN * kChunkK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = BN == 256 ? 3 : (BN == 128 ? 5 : 6);
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int kSmemStages = kStages * kStageBytes;
+  static constexpr int kSmemStore = 2 * kStoreBytes;
+  static constexpr int kSmemScratch = 4 * 64 * 2 * 4;  // [4 warps][64 ch][sum, sumsq]
+  static constexpr int kSmemBars = 256;
+  static constexpr int kSmemTotal = 1024 + kSmemStages + kSmemStore + kSmemScratch + kSmemBars;
+};
+
+// Bounded spin so a protocol bug reports an error instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait_guard(uint32_t bar, uint32_t parity, int* err, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s: a protocol bug, not a slow tile
+      if (err) atomicExch(err, code);
+      __trap();
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+igemm_conv_kernel(const __grid_constant__ IgemmParams p) {
+  using Cfg = IgemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_base = smem_base;
+  const uint32_t store_base = stage_base + Cfg::kSmemStages;
+  const uint32_t scratch_base = store_base + Cfg::kSmemStore;
+  const uint32_t bar_base = scratch_base + Cfg::kSmemScratch;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && elect_one()) {
+    for (int s = 0; s < p.num_src; ++s) {
+      tma_prefetch_desc(&p.src[s].act);
+      tma_prefetch_desc(&p.src[s].wgt);
+    }
+    tma_prefetch_desc(&p.out);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int s = 0; s < Cfg::kStages; ++s) {
+        mbar_init(full_bar(s), 1);
+        mbar_init(empty_bar(s), 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(tfull_bar(s), 1);
+        mbar_init(tempty_bar(s), 128);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int taps = p.taps;
+  int k_iters = 0;
+  for (int s = 0; s < p.num_src; ++s) k_iters += taps * p.src[s].c_chunks;
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
+  const int m_tiles = p.tiles_img * tiles_per_img;
+  const int total_tiles = m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        const int img = m_tile / tiles_per_img;
+        const int t_in = m_tile % tiles_per_img;
+        const int ho0 = (t_in / p.tiles_w) * p.th;
+        const int wo0 = (t_in % p.tiles_w) * p.tw;
+        const int n0 = img * p.tn;
+        for (int s = 0; s < p.num_src; ++s) {
+          const IgemmSrc& src = p.src[s];
+          for (int tap = 0; tap < taps; ++tap) {
+            const int hi0 = ho0 * p.stride + p.tap_dy[tap];
+            const int wi0 = wo0 * p.stride + p.tap_dx[tap];
+            const int wtap = p.tap_w[tap];
+            for (int cc = 0; cc < src.c_chunks; ++cc) {
+              mbar_wait_guard(empty_bar(stage), phase ^ 1, p.err_flag, 1);
+              const uint32_t a_dst = stage_base + stage * Cfg::kStageBytes;
+              const uint32_t b_dst = a_dst + kABytes;
+              mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+              tma_load_4d(a_dst, &src.act, full_bar(stage), cc * kChunkK, wi0, hi0, n0);
+              tma_load_3d(b_dst, &src.wgt, full_bar(stage), cc * kChunkK, n_tile * BN, wtap);
+              if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait_guard(tempty_bar(as), aphase ^ 1, p.err_flag, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(as * BN);
+        for (int ki = 0; ki < k_iters; ++ki) {
+          mbar_wait_guard(full_bar(stage), phase, p.err_flag, 3);
+          tc_fence_after();
+          const uint32_t a_addr = stage_base + stage * Cfg::kStageBytes;
+          const uint64_t a_desc = umma_smem_desc_sw128(a_addr, 16, 1024);
+          const uint64_t b_desc = umma_smem_desc_sw128(a_addr + kABytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kChunkK / 16; ++k) {
+            // +32 bytes along K inside the 128B swizzle row == +2 in the (addr >> 4) field
+            umma_f16(d_tmem, a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k), idesc,
+                     (ki | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(as));
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (128 threads)
+    const int et = threadIdx.x - 64;        // 0..127
+    const int q = warp & 3;                 // TMEM lane quarter this warp may touch
+    const int row = q * 32 + lane;          // tile row == TMEM lane
+    const int ew = et >> 5;                 // 0..3 (row group for the stats pass)
+    int as = 0;
+    uint32_t aphase = 0;
+    uint32_t chunk_ctr = 0;
+    float* scratch = reinterpret_cast<float*>(smem_gen + (scratch_base - smem_base));
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int img = m_tile / tiles_per_img;
+      const int t_in = m_tile % tiles_per_img;
+      const int ho0 = (t_in / p.tiles_w) * p.th;
+      const int wo0 = (t_in % p.tiles_w) * p.tw;
+      const int n0 = img * p.tn;
+      mbar_wait_guard(tfull_bar(as), aphase, p.err_flag, 4);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 64; ++chunk, ++chunk_ctr) {
+        const uint32_t sb = chunk_ctr & 1;
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN + chunk * 64);
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(taddr, v0);
+        tmem_ld_32x32(taddr + 32, v1);
+        tmem_ld_wait();
+        if (chunk == BN / 64 - 1) {
+          tc_fence_before();
+          mbar_arrive(tempty_bar(as));
+        }
+        const int c_base = n_tile * BN + chunk * 64;
+        uint32_t packed[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const uint32_t* v = j < 16 ? v0 : v1;
+          const int jj = (j & 15) * 2;
+          float x0 = __uint_as_float(v[jj]);
+          float x1 = __uint_as_float(v[jj + 1]);
+          if (p.bias) {
+            x0 += __ldg(p.bias + c_base + 2 * j);
+            x1 += __ldg(p.bias + c_base + 2 * j + 1);
+          }
+          if (p.act == ACT_LRELU) {
+            x0 = x0 > 0.f ? x0 : x0 * p.slope;
+            x1 = x1 > 0.f ? x1 : x1 * p.slope;
+          } else if (p.act == ACT_RELU) {
+            x0 = fmaxf(x0, 0.f);
+            x1 = fmaxf(x1, 0.f);
+          } else if (p.act == ACT_SIGMOID) {
+            x0 = 1.f / (1.f + __expf(-x0));
+            x1 = 1.f / (1.f + __expf(-x1));
+          } else if (p.act == ACT_TANH) {
+            x0 = tanhf(x0);
+            x1 = tanhf(x1);
+          }
+          packed[j] = pack_bf16x2(x0, x1);
+        }
+        // staging buffer `sb` must have been drained by the TMA store issued two chunks ago
+        if (et == 0) tma_store_wait_read<1>();
+        named_bar_sync(1, 128);
+        const uint32_t srow = store_base + sb * kStoreBytes + uint32_t(row) * 128u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t dst = srow + (uint32_t(j ^ (row & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(packed[4 * j]),
+                       "r"(packed[4 * j + 1]), "r"(packed[4 * j + 2]), "r"(packed[4 * j + 3])
+                       : "memory");
+        }
+        fence_proxy_async();
+        named_bar_sync(1, 128);
+        if (et == 0) {
+          tma_store_4d(&p.out, store_base + sb * kStoreBytes, c_base, wo0, ho0, n0);
+          tma_store_commit();
+        }
+        if (p.stats_partial) {
+          // column sums over the bf16 values actually stored (what the normalise pass will read)
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+          const uint32_t sbuf = store_base + sb * kStoreBytes;
+#pragma unroll 4
+          for (int r = ew * 32; r < ew * 32 + 32; ++r) {
+            const int hh = r / p.tw, ww = r % p.tw;
+            if (ho0 + hh < p.Ho && wo0 + ww < p.Wo) {
+              uint32_t w;
+              const uint32_t a = sbuf + uint32_t(r) * 128u + (uint32_t((lane >> 2) ^ (r & 7)) << 4) +
+                                 uint32_t(lane & 3) * 4u;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(a));
+              const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w);
+              const float f0 = __low2float(h), f1 = __high2float(h);
+              s0 += f0; s1 += f1; q0 += f0 * f0; q1 += f1 * f1;
+            }
+          }
+          float* sc = scratch + ew * 128;
+          sc[(2 * lane) * 2 + 0] = s0;
+          sc[(2 * lane) * 2 + 1] = q0;
+          sc[(2 * lane + 1) * 2 + 0] = s1;
+          sc[(2 * lane + 1) * 2 + 1] = q1;
+          named_bar_sync(1, 128);
+          // et -> (channel = et >> 1, stat = et & 1)
+          const float tot = scratch[et] + scratch[128 + et] + scratch[256 + et] + scratch[384 + et];
+          const size_t tile_lin = size_t(n0) * tiles_per_img + t_in;
+          p.stats_partial[(tile_lin * p.cout + c_base) * 2 + et] = tot;
+        }
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+    if (et == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+}  // namespace tg

@@ -1,0 +1,1147 @@
+// Bandwidth-bound tail of the G+D step: layout packs, InstanceNorm (+ReLU/LeakyReLU) forward /
+// backward / double-backward, pooling & nearest-upsample fused into the normalise pass, the 1x1
+// feature-map head, loss reductions, gradient-penalty pieces and the fused Adam + weight re-pack.
+// All activations are NHWC bf16 with C % 64 == 0; every access is a 128-bit vector of 8 channels.
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include "tg_api_internal.h"
+
+namespace tg {
+
+struct bf8 { uint4 v; };
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __low2float(h[i]);
+    f[2 * i + 1] = __high2float(h[i]);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void stg16(void* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// block-wide sum; result valid in thread 0
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (w == 0) {
+    r = l < (blockDim.x >> 5) ? sh[l] : 0.f;
+    r = warp_sum(r);
+  }
+  __syncthreads();
+  return r;
+}
+
+__device__ __forceinline__ float act_fwd(float x, int act, float slope) {
+  if (act == 3) return fmaxf(x, 0.f);
+  if (act == 1) return x > 0.f ? x : x * slope;
+  return x;
+}
+__device__ __forceinline__ float act_grad(float x, int act, float slope) {
+  if (act == 3) return x > 0.f ? 1.f : 0.f;
+  if (act == 1) return x > 0.f ? 1.f : slope;
+  return 1.f;
+}
+
+// ------------------------------------------------------------------ layout packs
+// out[n,h,w, c_off + j] = wa[n]*A[n,j,h,w] + wb[n]*B[n,j,h,w]   (fp32 NCHW -> bf16 NHWC), j < cj <= 8.
+// Only the 8-channel group containing c_off is written; the other groups of `out` keep their value.
+__global__ void pack_nchw_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                 const float* __restrict__ wa, const float* __restrict__ wb,
+                                 __nv_bfloat16* __restrict__ out, int N, int HW, int cj, int C,
+                                 int c_off) {
+  const size_t total = size_t(N) * HW;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total;
+       i += size_t(gridDim.x) * blockDim.x) {
+    const int n = int(i / HW);
+    const int pix = int(i % HW);
+    const float fa = wa ? wa[n] : 1.f;
+    const float fb = wb ? wb[n] : 0.f;
+    __nv_bfloat16* o = out + i * C + c_off;
+    for (int j = 0; j < cj; ++j) {
+      float v = fa * A[(size_t(n) * cj + j) * HW + pix];
+      if (B) v += fb * B[(size_t(n) * cj + j) * HW + pix];
+      o[j] = __float2bfloat16(v);
+    }
+  }
+}
+
+// bf16 NHWC (C channels, first cj used, starting at c_off) -> fp32 NCHW
+__global__ void unpack_nhwc_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out,
+                                   int N, int HW, int C, int c_off, int cj, float scale) {
+  const size_t total = size_t(N) * HW;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total;
+       i += size_t(gridDim.x) * blockDim.x) {
+    const int n = int(i / HW);
+    const int pix = int(i % HW);
+    const __nv_bfloat16* s = in + i * C + c_off;
+    for (int j = 0; j < cj; ++j) out[(size_t(n) * cj + j) * HW + pix] = scale * __bfloat162float(s[j]);
+  }
+}
+
+// ------------------------------------------------------------------ InstanceNorm forward
+// partial: [N][T][C][2] (sum, sumsq) from the conv epilogue -> mr: [N][C][2] (mean, rstd)
+__global__ void in_finalize_kernel(const float* __restrict__ partial, float* __restrict__ mr, int T,
+                                   int C, float inv_count, float eps) {
+  __shared__ float sh[16][64][2];
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int tl = threadIdx.x >> 6;  // 0..15
+  float s = 0.f, q = 0.f;
+  const float2* src = reinterpret_cast<const float2*>(partial) + (size_t(n) * T) * C + c;
+  for (int t = tl; t < T; t += 16) {
+    const float2 v = __ldg(src + size_t(t) * C);
+    s += v.x;
+    q += v.y;
+  }
+  sh[tl][threadIdx.x & 63][0] = s;
+  sh[tl][threadIdx.x & 63][1] = q;
+  __syncthreads();
+  if (tl == 0) {
+    for (int k = 1; k < 16; ++k) {
+      s += sh[k][threadIdx.x][0];
+      q += sh[k][threadIdx.x][1];
+    }
+    const float mean = s * inv_count;
+    const float var = fmaxf(q * inv_count - mean * mean, 0.f);
+    mr[(size_t(n) * C + c) * 2 + 0] = mean;
+    mr[(size_t(n) * C + c) * 2 + 1] = rsqrtf(var + eps);
+  }
+}
+
+// Direct statistics for a tensor the conv epilogue could not reduce (tiles spanning images).
+__global__ void in_stats_direct_kernel(const __nv_bfloat16* __restrict__ raw, float* __restrict__ mr,
+                                       int HW, int C, float eps) {
+  // grid (C/64, N), block 256: 8 channel groups x 32 pixel lanes
+  __shared__ float sh[32][64][2];
+  const int n = blockIdx.y;
+  const int g = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int c0 = blockIdx.x * 64 + g * 8;
+  float s[8] = {0}, q[8] = {0};
+  for (int pix = pl; pix < HW; pix += 32) {
+    float f[8];
+    unpack8(ldg16(raw + (size_t(n) * HW + pix) * C + c0), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] += f[j] * f[j]; }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sh[pl][g * 8 + j][0] = s[j]; sh[pl][g * 8 + j][1] = q[j]; }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float ss = 0.f, qq = 0.f;
+    for (int k = 0; k < 32; ++k) { ss += sh[k][threadIdx.x][0]; qq += sh[k][threadIdx.x][1]; }
+    const float mean = ss / HW;
+    const float var = fmaxf(qq / HW - mean * mean, 0.f);
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    mr[(size_t(n) * C + c) * 2 + 0] = mean;
+    mr[(size_t(n) * C + c) * 2 + 1] = rsqrtf(var + eps);
+  }
+}
+
+// y = act(gamma * (raw - mean) * rstd + beta); optional 2x2 pooled copy and 2x nearest-upsampled copy.
+template <int POOL, bool UP>
+__global__ void in_act_fwd_kernel(const __nv_bfloat16* __restrict__ raw, const float* __restrict__ mr,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ pool,
+                                  __nv_bfloat16* __restrict__ up, int N, int H, int W, int C, int act,
+                                  float slope) {
+  const int CG = C >> 3;
+  if (POOL == 0 && !UP) {
+    const size_t total = size_t(N) * H * W * CG;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total;
+         i += size_t(gridDim.x) * blockDim.x) {
+      const int cg = int(i % CG);
+      const size_t pix = i / CG;
+      const int n = int(pix / (size_t(H) * W));
+      const int c0 = cg * 8;
+      float f[8];
+      unpack8(ldg16(raw + pix * C + c0), f);
+      const float* m = mr + (size_t(n) * C + c0) * 2;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float g = gamma ? __ldg(gamma + c0 + j) : 1.f;
+        const float b = beta ? __ldg(beta + c0 + j) : 0.f;
+        f[j] = act_fwd(g * (f[j] - __ldg(m + 2 * j)) * __ldg(m + 2 * j + 1) + b, act, slope);
+      }
+      stg16(y + pix * C + c0, pack8(f));
+    }
+  } else {
+    const int H2 = H >> 1, W2 = W >> 1;
+    const size_t total = size_t(N) * H2 * W2 * CG;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total;
+         i += size_t(gridDim.x) * blockDim.x) {
+      const int cg = int(i % CG);
+      size_t r = i / CG;
+      const int qx = int(r % W2); r /= W2;
+      const int qy = int(r % H2);
+      const int n = int(r / H2);
+      const int c0 = cg * 8;
+      float sc[8], sh[8];
+      const float* m = mr + (size_t(n) * C + c0) * 2;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float g = gamma ? __ldg(gamma + c0 + j) : 1.f;
+        const float b = beta ? __ldg(beta + c0 + j) : 0.f;
+        sc[j] = g * __ldg(m + 2 * j + 1);
+        sh[j] = b - __ldg(m + 2 * j) * sc[j];
+      }
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = POOL == 2 ? -3.0e38f : 0.f;
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int yy = 2 * qy + a, xx = 2 * qx + b;
+          const size_t pix = (size_t(n) * H + yy) * W + xx;
+          float f[8];
+          unpack8(ldg16(raw + pix * C + c0), f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = act_fwd(f[j] * sc[j] + sh[j], act, slope);
+          const uint4 pv = pack8(f);
+          stg16(y + pix * C + c0, pv);
+          if (POOL) {
+            float fr[8];
+            unpack8(pv, fr);  // pool the bf16-rounded values the next layer would read
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = POOL == 2 ? fmaxf(acc[j], fr[j]) : acc[j] + fr[j];
+          }
+          if (UP) {
+            const int HU = 2 * H, WU = 2 * W;
+#pragma unroll
+            for (int ua = 0; ua < 2; ++ua)
+#pragma unroll
+              for (int ub = 0; ub < 2; ++ub) {
+                const size_t upix = (size_t(n) * HU + 2 * yy + ua) * WU + 2 * xx + ub;
+                stg16(up + upix * C + c0, pv);
+              }
+          }
+        }
+      if (POOL) {
+        if (POOL == 1) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] *= 0.25f;
+        }
+        const size_t ppix = (size_t(n) * H2 + qy) * W2 + qx;
+        stg16(pool + ppix * C + c0, pack8(acc));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ InstanceNorm backward
+// dn = (g_same + 0.25*g_pool[h/2,w/2] + sum_{2x2} g_up[2h+a,2w+b] (+ g_max routed)) * act'(n)
+// red[n][c] += (sum dn, sum dn*xhat). Block = strip of pixels of one image, all channels.
+// pool_mode: 1 avg (g_pool spread evenly), 2 max (g_pool routed to the arg-max element of y).
+struct InBwdArgs {
+  const __nv_bfloat16* raw;   // conv output (pre-norm); nullptr => no norm (y is act(raw+bias))
+  const __nv_bfloat16* y;     // post-activation output (needed for no-norm layers and max-pool routing)
+  const float* mr;
+  const float* gamma;
+  const float* beta;
+  const __nv_bfloat16* g_same;
+  const __nv_bfloat16* g_pool;
+  const __nv_bfloat16* g_up;
+  __nv_bfloat16* dn;
+  float* red;                 // [N][C][2]
+  int N, H, W, C, act, pool_mode;
+  float slope;
+};
+
+__global__ void in_bwd_reduce_kernel(const InBwdArgs a) {
+  extern __shared__ float shm[];  // [PL][C][2]
+  const int CG = a.C >> 3;
+  const int PL = blockDim.x / CG;   // pixel lanes
+  const int cg = threadIdx.x % CG, pl = threadIdx.x / CG;
+  const int n = blockIdx.y;
+  const int HW = a.H * a.W;
+  const int strip = (HW + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * strip, p1 = min(HW, p0 + strip);
+  const int c0 = cg * 8;
+  float sc[8], sh[8], mean[8], rstd[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float g = a.gamma ? a.gamma[c0 + j] : 1.f;
+    const float b = a.beta ? a.beta[c0 + j] : 0.f;
+    mean[j] = a.mr ? a.mr[(size_t(n) * a.C + c0 + j) * 2] : 0.f;
+    rstd[j] = a.mr ? a.mr[(size_t(n) * a.C + c0 + j) * 2 + 1] : 1.f;
+    sc[j] = g; sh[j] = b;
+  }
+  float s0[8] = {0}, s1[8] = {0};
+  if (pl < PL) {
+    for (int pix = p0 + pl; pix < p1; pix += PL) {
+      const int yy = pix / a.W, xx = pix % a.W;
+      const size_t lin = (size_t(n) * HW + pix) * a.C + c0;
+      float g[8] = {0};
+      if (a.g_same) unpack8(ldg16(a.g_same + lin), g);
+      if (a.g_pool) {
+        const int H2 = a.H >> 1, W2 = a.W >> 1;
+        float t[8];
+        unpack8(ldg16(a.g_pool + ((size_t(n) * H2 + (yy >> 1)) * W2 + (xx >> 1)) * a.C + c0), t);
+        if (a.pool_mode == 1) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] += 0.25f * t[j];
+        } else {
+          // max-pool routing: first element (row-major in the 2x2 window) equal to the window max
+          float me[8], best[8];
+          int first[8];
+          unpack8(ldg16(a.y + lin), me);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { best[j] = -3.0e38f; first[j] = 0; }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int y2 = (yy & ~1) + (k >> 1), x2 = (xx & ~1) + (k & 1);
+            float o[8];
+            unpack8(ldg16(a.y + ((size_t(n) * a.H + y2) * a.W + x2) * a.C + c0), o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (o[j] > best[j]) { best[j] = o[j]; first[j] = k; }
+          }
+          const int mine = ((yy & 1) << 1) | (xx & 1);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (first[j] == mine) g[j] += t[j];
+        }
+      }
+      if (a.g_up) {
+        const int HU = 2 * a.H, WU = 2 * a.W;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float t[8];
+          unpack8(ldg16(a.g_up + ((size_t(n) * HU + 2 * yy + (k >> 1)) * WU + 2 * xx + (k & 1)) * a.C + c0), t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] += t[j];
+        }
+      }
+      float xh[8], dn[8];
+      if (a.raw) {
+        float r[8];
+        unpack8(ldg16(a.raw + lin), r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[j] = (r[j] - mean[j]) * rstd[j];
+          dn[j] = g[j] * act_grad(sc[j] * xh[j] + sh[j], a.act, a.slope);
+        }
+      } else {
+        float o[8];
+        unpack8(ldg16(a.y + lin), o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { xh[j] = 0.f; dn[j] = g[j] * act_grad(o[j], a.act, a.slope); }
+      }
+      stg16(a.dn + lin, pack8(dn));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s0[j] += dn[j]; s1[j] += dn[j] * xh[j]; }
+    }
+  }
+  if (!a.red) return;
+  float* shp = shm + (size_t(pl) * a.C + c0) * 2;
+  if (pl < PL) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { shp[2 * j] = s0[j]; shp[2 * j + 1] = s1[j]; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.C * 2; i += blockDim.x) {
+    float t = 0.f;
+    for (int k = 0; k < PL; ++k) t += shm[size_t(k) * a.C * 2 + i];
+    atomicAdd(a.red + size_t(n) * a.C * 2 + i, t);
+  }
+}
+
+// dz = rstd * gamma * (dn - mean(dn) - xhat * mean(dn * xhat))
+__global__ void in_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dn,
+                                    const __nv_bfloat16* __restrict__ raw,
+                                    const float* __restrict__ mr, const float* __restrict__ gamma,
+                                    const float* __restrict__ red, __nv_bfloat16* __restrict__ dz,
+                                    int N, int HW, int C) {
+  const int CG = C >> 3;
+  const size_t total = size_t(N) * HW * CG;
+  const float inv = 1.f / float(HW);
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total;
+       i += size_t(gridDim.x) * blockDim.x) {
+    const int cg = int(i % CG);
+    const size_t pix = i / CG;
+    const int n = int(pix / HW);
+    const int c0 = cg * 8;
+    float d[8], r[8];
+    unpack8(ldg16(dn + pix * C + c0), d);
+    unpack8(ldg16(raw + pix * C + c0), r);
+    const float* m = mr + (size_t(n) * C + c0) * 2;
+    const float* rd = red + (size_t(n) * C + c0) * 2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float g = gamma ? __ldg(gamma + c0 + j) : 1.f;
+      const float rs = __ldg(m + 2 * j + 1);
+      const float xh = (r[j] - __ldg(m + 2 * j)) * rs;
+      d[j] = rs * g * (d[j] - __ldg(rd + 2 * j) * inv - xh * __ldg(rd + 2 * j + 1) * inv);
+    }
+    stg16(dz + pix * C + c0, pack8(d));
+  }
+}
+
+// dgamma[c] += sum_n red[n][c][1]; dbeta[c] += sum_n red[n][c][0]
+__global__ void affine_grad_kernel(const float* __restrict__ red, float* __restrict__ dgamma,
+                                   float* __restrict__ dbeta, int N, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float g = 0.f, b = 0.f;
+  for (int n = 0; n < N; ++n) {
+    b += red[(size_t(n) * C + c) * 2];
+    g += red[(size_t(n) * C + c) * 2 + 1];
+  }
+  if (dgamma) dgamma[c] += g;
+  if (dbeta) dbeta[c] += b;
+}
+
+// db[c] += sum over rows of dz[row][c], c < c_valid.  grid (C/64, strips)
+__global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ dz, float* __restrict__ db,
+                                 size_t rows, int C, int c_valid) {
+  __shared__ float sh[32][65];
+  const int g = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int c0 = blockIdx.x * 64 + g * 8;
+  const size_t strip = (rows + gridDim.y - 1) / gridDim.y;
+  const size_t r0 = blockIdx.y * strip, r1 = min(rows, r0 + strip);
+  float s[8] = {0};
+  for (size_t r = r0 + pl; r < r1; r += 32) {
+    float f[8];
+    unpack8(ldg16(dz + r * C + c0), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] += f[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[pl][g * 8 + j] = s[j];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+    for (int k = 0; k < 32; ++k) t += sh[k][threadIdx.x];
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    if (c < c_valid) atomicAdd(db + c, t);
+  }
+}
+
+// ------------------------------------------------------------------ InstanceNorm double backward
+// (gradient penalty). With xhat, r = rstd, dxh = gamma*dn (first backward), u = adj(dz):
+//   adj(dn) = gamma * r * (u - mean(u) - xhat*mean(u*xhat))              [continues the upward sweep]
+//   adj(z)  = r^2 * ( -b*(u - c1) - c2*(dxh - a) + xhat*(3*b*c2 + a*c1 - e) ) [injected downward]
+//   adj(gamma) += sum dn * r*(u - c1 - xhat*c2)
+// where a = mean(dxh), b = mean(dxh*xhat), c1 = mean(u), c2 = mean(u*xhat), e = mean(u*dxh).
+// Pass 1 reduces (sum u, sum u*xhat, sum u*dn) into red2[N][C][4].
+__global__ void in_bwd2_reduce_kernel(const __nv_bfloat16* __restrict__ u,
+                                      const __nv_bfloat16* __restrict__ raw,
+                                      const __nv_bfloat16* __restrict__ dn,
+                                      const float* __restrict__ mr, float* __restrict__ red2, int HW,
+                                      int C) {
+  extern __shared__ float shm[];  // [PL][C][3]
+  const int CG = C >> 3;
+  const int PL = blockDim.x / CG;
+  const int cg = threadIdx.x % CG, pl = threadIdx.x / CG;
+  const int n = blockIdx.y;
+  const int strip = (HW + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * strip, p1 = min(HW, p0 + strip);
+  const int c0 = cg * 8;
+  float s0[8] = {0}, s1[8] = {0}, s2[8] = {0};
+  if (pl < PL) {
+    float mean[8], rstd[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mean[j] = mr[(size_t(n) * C + c0 + j) * 2];
+      rstd[j] = mr[(size_t(n) * C + c0 + j) * 2 + 1];
+    }
+    for (int pix = p0 + pl; pix < p1; pix += PL) {
+      const size_t lin = (size_t(n) * HW + pix) * C + c0;
+      float fu[8], fr[8], fd[8];
+      unpack8(ldg16(u + lin), fu);
+      unpack8(ldg16(raw + lin), fr);
+      unpack8(ldg16(dn + lin), fd);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (fr[j] - mean[j]) * rstd[j];
+        s0[j] += fu[j];
+        s1[j] += fu[j] * xh;
+        s2[j] += fu[j] * fd[j];
+      }
+    }
+    float* shp = shm + (size_t(pl) * C + c0) * 3;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { shp[3 * j] = s0[j]; shp[3 * j + 1] = s1[j]; shp[3 * j + 2] = s2[j]; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 3; i += blockDim.x) {
+    float t = 0.f;
+    for (int k = 0; k < PL; ++k) t += shm[size_t(k) * C * 3 + i];
+    atomicAdd(red2 + (size_t(n) * C + i / 3) * 4 + (i % 3), t);
+  }
+}
+
+// Pass 2: writes adj_da = adj(dn) * act'(n) (upward) and adj_z (downward injection); accumulates
+// adj(gamma) partial sums into red2[..][3].
+__global__ void in_bwd2_apply_kernel(const __nv_bfloat16* __restrict__ u,
+                                     const __nv_bfloat16* __restrict__ raw,
+                                     const __nv_bfloat16* __restrict__ dn,
+                                     const float* __restrict__ mr, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, const float* __restrict__ red1,
+                                     float* __restrict__ red2, __nv_bfloat16* __restrict__ adj_da,
+                                     __nv_bfloat16* __restrict__ adj_z, int HW, int C, int act,
+                                     float slope) {
+  extern __shared__ float shm[];  // [PL][C]
+  const int CG = C >> 3;
+  const int PL = blockDim.x / CG;
+  const int cg = threadIdx.x % CG, pl = threadIdx.x / CG;
+  const int n = blockIdx.y;
+  const int strip = (HW + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * strip, p1 = min(HW, p0 + strip);
+  const int c0 = cg * 8;
+  const float inv = 1.f / float(HW);
+  float sg[8] = {0};
+  if (pl < PL) {
+    float mean[8], rstd[8], gm[8], bt[8], A[8], Bc[8], c1[8], c2[8], e[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const size_t k = size_t(n) * C + c0 + j;
+      mean[j] = mr[k * 2];
+      rstd[j] = mr[k * 2 + 1];
+      gm[j] = gamma ? gamma[c0 + j] : 1.f;
+      bt[j] = beta ? beta[c0 + j] : 0.f;
+      A[j] = gm[j] * red1[k * 2] * inv;       // mean(dxh)
+      Bc[j] = gm[j] * red1[k * 2 + 1] * inv;  // mean(dxh * xhat)
+      c1[j] = red2[k * 4] * inv;
+      c2[j] = red2[k * 4 + 1] * inv;
+      e[j] = gm[j] * red2[k * 4 + 2] * inv;   // mean(u * dxh)
+    }
+    for (int pix = p0 + pl; pix < p1; pix += PL) {
+      const size_t lin = (size_t(n) * HW + pix) * C + c0;
+      float fu[8], fr[8], fd[8], oa[8], oz[8];
+      unpack8(ldg16(u + lin), fu);
+      unpack8(ldg16(raw + lin), fr);
+      unpack8(ldg16(dn + lin), fd);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (fr[j] - mean[j]) * rstd[j];
+        const float adxh = rstd[j] * (fu[j] - c1[j] - xh * c2[j]);
+        sg[j] += fd[j] * adxh;
+        oa[j] = gm[j] * adxh * act_grad(gm[j] * xh + bt[j], act, slope);
+        const float dxh = gm[j] * fd[j];
+        oz[j] = rstd[j] * rstd[j] *
+                (-Bc[j] * (fu[j] - c1[j]) - c2[j] * (dxh - A[j]) +
+                 xh * (3.f * Bc[j] * c2[j] + A[j] * c1[j] - e[j]));
+      }
+      stg16(adj_da + lin, pack8(oa));
+      stg16(adj_z + lin, pack8(oz));
+    }
+    float* shp = shm + size_t(pl) * C + c0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) shp[j] = sg[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    float t = 0.f;
+    for (int k = 0; k < PL; ++k) t += shm[size_t(k) * C + i];
+    atomicAdd(red2 + (size_t(n) * C + i) * 4 + 3, t);
+  }
+}
+
+// dgamma[c] += sum_n red2[n][c][3]
+__global__ void gamma_grad2_kernel(const float* __restrict__ red2, float* __restrict__ dgamma, int N,
+                                   int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float g = 0.f;
+  for (int n = 0; n < N; ++n) g += red2[(size_t(n) * C + c) * 4 + 3];
+  dgamma[c] += g;
+}
+
+// ------------------------------------------------------------------ elementwise helpers
+// out = a + b (bf16, same shape); b optional
+__global__ void add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                           __nv_bfloat16* __restrict__ out, size_t n8) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n8;
+       i += size_t(gridDim.x) * blockDim.x) {
+    float x[8], y[8];
+    unpack8(ldg16(a + i * 8), x);
+    unpack8(ldg16(b + i * 8), y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] += y[j];
+    stg16(out + i * 8, pack8(x));
+  }
+}
+
+// out = g * act'(y)  where y is the post-activation value (sign-preserving activations only)
+__global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
+                               __nv_bfloat16* __restrict__ out, size_t n8, int act, float slope) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n8;
+       i += size_t(gridDim.x) * blockDim.x) {
+    float x[8], o[8];
+    unpack8(ldg16(g + i * 8), x);
+    unpack8(ldg16(y + i * 8), o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] *= act_grad(o[j], act, slope);
+    stg16(out + i * 8, pack8(x));
+  }
+}
+
+// ------------------------------------------------------------------ 1x1 feature-map head (64 -> co<=4)
+// out[n,o,h,w] = act(sum_c x[n,h,w,c] * w[o][c] + b[o]); fp32 NCHW out.
+__global__ void fmap_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                const float* __restrict__ b, float* __restrict__ out, int N, int HW,
+                                int C, int co, int use_tanh) {
+  __shared__ float sw[4 * 64 + 4];
+  for (int i = threadIdx.x; i < co * C; i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x < co) sw[4 * 64 + threadIdx.x] = b[threadIdx.x];
+  __syncthreads();
+  const size_t total = size_t(N) * HW;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total;
+       i += size_t(gridDim.x) * blockDim.x) {
+    const int n = int(i / HW), pix = int(i % HW);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c0 = 0; c0 < C; c0 += 8) {
+      float f[8];
+      unpack8(ldg16(x + i * C + c0), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+          if (o < co) acc[o] += f[j] * sw[o * C + c0 + j];
+    }
+    for (int o = 0; o < co; ++o) {
+      float v = acc[o] + sw[4 * 64 + o];
+      if (use_tanh) v = tanhf(v);
+      out[(size_t(n) * co + o) * HW + pix] = v;
+    }
+  }
+}
+
+// dz[o] = (g1 + g2)[n,o,pix] * (1 - out^2) ; dx[n,pix,c] = sum_o dz[o] w[o][c];
+// dw[o][c] += sum dz[o] x[c]; db[o] += sum dz[o]
+__global__ void fmap_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                const float* __restrict__ out, const float* __restrict__ g1,
+                                const float* __restrict__ g2, __nv_bfloat16* __restrict__ dx,
+                                float* __restrict__ dw, float* __restrict__ db, int N, int HW, int C,
+                                int co, int use_tanh) {
+  __shared__ float sw[4 * 64];
+  __shared__ float sacc[4 * 64 + 4];
+  for (int i = threadIdx.x; i < co * C; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < 4 * 64 + 4; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  float lw[4][8];  // this lane accumulates dw for channel group (lane & 7) only
+  float lb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int o = 0; o < 4; ++o)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) lw[o][j] = 0.f;
+  const int grp = threadIdx.x & 7;  // C == 64 -> 8 groups of 8 channels
+  const size_t total = size_t(N) * HW * 8;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total;
+       i += size_t(gridDim.x) * blockDim.x) {
+    const size_t p = i >> 3;
+    const int n = int(p / HW), pix = int(p % HW);
+    float dz[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      dz[o] = 0.f;
+      if (o < co) {
+        const size_t k = (size_t(n) * co + o) * HW + pix;
+        float g = g1 ? g1[k] : 0.f;
+        if (g2) g += g2[k];
+        if (use_tanh) {
+          const float t = out[k];
+          g *= 1.f - t * t;
+        }
+        dz[o] = g;
+      }
+    }
+    float f[8], d[8];
+    unpack8(ldg16(x + p * C + grp * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = 0.f;
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        if (o < co) {
+          a += dz[o] * sw[o * C + grp * 8 + j];
+          lw[o][j] += dz[o] * f[j];
+        }
+      }
+      d[j] = a;
+    }
+    if (grp == 0) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) lb[o] += dz[o];
+    }
+    if (dx) stg16(dx + p * C + grp * 8, pack8(d));
+  }
+  // lanes with equal grp are 8 apart: reduce over them with shuffles, then smem, then atomics
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = lw[o][j];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      lw[o][j] = v;
+    }
+    float v = lb[o];
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    lb[o] = v;
+  }
+  if ((threadIdx.x & 31) < 8) {
+    for (int o = 0; o < co; ++o) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&sacc[o * 64 + grp * 8 + j], lw[o][j]);
+      if (grp == 0) atomicAdd(&sacc[256 + o], lb[o]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < co * 64; i += blockDim.x) atomicAdd(dw + i, sacc[i]);
+  if (threadIdx.x < co) atomicAdd(db + threadIdx.x, sacc[256 + threadIdx.x]);
+}
+
+// ------------------------------------------------------------------ losses
+// GAN loss on channel 0 of pred (NHWC bf16, C channels). `pred` holds sigmoid(z) when has_sigmoid.
+// mode: 0 ls, 1 ce, 2 w, 3 hinge. Writes dz (grad wrt the pre-activation z, channel 0; other
+// channels of dz must already be zero) scaled by `scale`/numel and adds scale*mean-loss to *loss.
+// For samples >= n_loss_samples (GP interpolates riding in the same batch) dz = gp_seed (d sum(pred)/dz).
+__global__ void gan_loss_kernel(const __nv_bfloat16* __restrict__ pred, const float* __restrict__ label,
+                                float label_const, int mode, int target_is_real, int for_disc,
+                                int has_sigmoid, float scale, int n0, int n1, int HW, int C,
+                                float* __restrict__ loss, __nv_bfloat16* __restrict__ dz, int write_dz) {
+  __shared__ float sh[32];
+  const size_t numel = size_t(n1 - n0) * HW;
+  float acc = 0.f;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < numel;
+       i += size_t(gridDim.x) * blockDim.x) {
+    const size_t k = (size_t(n0) * HW + i) * C;
+    const float p = __bfloat162float(pred[k]);
+    const float t = label ? label[i] : label_const;
+    float l = 0.f, dp = 0.f;  // loss element, dloss/dp (p = network output incl. sigmoid if any)
+    if (mode == 0) { const float d = p - t; l = d * d; dp = 2.f * d; }
+    else if (mode == 1) {  // BCE with logits on p
+      l = fmaxf(p, 0.f) - p * t + log1pf(__expf(-fabsf(p)));
+      dp = 1.f / (1.f + __expf(-p)) - t;
+    } else if (mode == 2) { l = target_is_real ? -p : p; dp = target_is_real ? -1.f : 1.f; }
+    else {
+      if (for_disc) {
+        const float m = target_is_real ? p - 1.f : -p - 1.f;
+        l = -fminf(m, 0.f);
+        dp = m < 0.f ? (target_is_real ? -1.f : 1.f) : 0.f;
+      } else { l = -p; dp = -1.f; }
+    }
+    acc += l;
+    if (write_dz) {
+      float g = dp * scale / float(numel);
+      if (has_sigmoid) g *= p * (1.f - p);
+      dz[k] = __float2bfloat16(g);
+    }
+  }
+  const float tot = block_sum(acc, sh);
+  if (threadIdx.x == 0 && loss) atomicAdd(loss, tot * scale / float(numel));
+}
+
+// dz[k] = p(1-p) (or 1 without sigmoid) for samples [n0,n1): the seed of d sum(pred) / d input.
+__global__ void gp_first_seed_kernel(const __nv_bfloat16* __restrict__ pred, int has_sigmoid, int n0,
+                                     int n1, int HW, int C, __nv_bfloat16* __restrict__ dz) {
+  const size_t numel = size_t(n1 - n0) * HW;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < numel;
+       i += size_t(gridDim.x) * blockDim.x) {
+    const size_t k = (size_t(n0) * HW + i) * C;
+    const float p = __bfloat162float(pred[k]);
+    dz[k] = __float2bfloat16(has_sigmoid ? p * (1.f - p) : 1.f);
+  }
+}
+
+// Second-order seed at the top of D: adj(z5) = w * (1-2p) * p(1-p), w = adj(dz5) (channel 0).
+__global__ void gp_top_kernel(const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ pred,
+                              int has_sigmoid, size_t numel, int C, __nv_bfloat16* __restrict__ out) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < numel;
+       i += size_t(gridDim.x) * blockDim.x) {
+    const size_t k = i * C;
+    const float p = __bfloat162float(pred[k]);
+    const float v = has_sigmoid ? __bfloat162float(w[k]) * (1.f - 2.f * p) * p * (1.f - p) : 0.f;
+    out[k] = __float2bfloat16(v);
+  }
+}
+
+// L1 mean between fp32 NCHW tensors; grad (sign * scale / numel) optional.
+__global__ void l1_loss_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t numel,
+                               float scale, float* __restrict__ loss, float* __restrict__ grad_a) {
+  __shared__ float sh[32];
+  float acc = 0.f;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < numel;
+       i += size_t(gridDim.x) * blockDim.x) {
+    const float d = a[i] - b[i];
+    acc += fabsf(d);
+    if (grad_a) grad_a[i] = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * scale / float(numel);
+  }
+  const float tot = block_sum(acc, sh);
+  if (threadIdx.x == 0 && loss) atomicAdd(loss, tot * scale / float(numel));
+}
+
+// weighted L1 (or L2) mean between two bf16 tensors (feature maps), all channels valid.
+__global__ void feat_loss_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                 size_t n8, float weight, int l2, float* __restrict__ loss) {
+  __shared__ float sh[32];
+  float acc = 0.f;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n8;
+       i += size_t(gridDim.x) * blockDim.x) {
+    float x[8], y[8];
+    unpack8(ldg16(a + i * 8), x);
+    unpack8(ldg16(b + i * 8), y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = x[j] - y[j];
+      acc += l2 ? d * d : fabsf(d);
+    }
+  }
+  const float tot = block_sum(acc, sh);
+  if (threadIdx.x == 0) atomicAdd(loss, tot * weight / float(n8 * 8));
+}
+
+// Gradient penalty: nsq[n] = sum_{pix, j<cj} (g[n,pix,c_off+j] + 1e-16)^2
+__global__ void gp_normsq_kernel(const __nv_bfloat16* __restrict__ g, int HW, int C, int c_off, int cj,
+                                 float* __restrict__ nsq) {
+  __shared__ float sh[32];
+  const int n = blockIdx.y;
+  float acc = 0.f;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
+    const __nv_bfloat16* s = g + (size_t(n) * HW + pix) * C + c_off;
+    for (int j = 0; j < cj; ++j) {
+      const float v = __bfloat162float(s[j]) + 1e-16f;
+      acc += v * v;
+    }
+  }
+  const float tot = block_sum(acc, sh);
+  if (threadIdx.x == 0) atomicAdd(nsq + n, tot);
+}
+
+// penalty = lambda * mean_n (sqrt(nsq) - constant)^2 ; coef[n] = lambda * 2/N * (norm - constant)/norm
+__global__ void gp_finish_kernel(const float* __restrict__ nsq, int N, float lambda, float constant,
+                                 float* __restrict__ loss, float* __restrict__ coef) {
+  float acc = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const float nm = sqrtf(nsq[n]);
+    const float d = nm - constant;
+    acc += d * d;
+    coef[n] = nm > 0.f ? lambda * 2.f / float(N) * d / nm : 0.f;
+  }
+  __shared__ float sh[32];
+  const float tot = block_sum(acc, sh);
+  if (threadIdx.x == 0 && loss) atomicAdd(loss, lambda * tot / float(N));
+}
+
+// seed[n,pix,c_off+j] = coef[n] * (g[n,pix,c_off+j] + 1e-16); other channels of the 8-group zero.
+__global__ void gp_seed_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ coef,
+                               int N, int HW, int C, int c_off, int cj, __nv_bfloat16* __restrict__ seed) {
+  const size_t total = size_t(N) * HW;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total;
+       i += size_t(gridDim.x) * blockDim.x) {
+    const int n = int(i / HW);
+    const int g0 = (c_off / 8) * 8;
+    float f[8], o[8];
+    unpack8(ldg16(g + i * C + g0), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = g0 + j;
+      o[j] = (c >= c_off && c < c_off + cj) ? coef[n] * (f[j] + 1e-16f) : 0.f;
+    }
+    stg16(seed + i * C + g0, pack8(o));
+  }
+}
+
+// ------------------------------------------------------------------ fused Adam + weight re-pack
+__global__ void adam_kernel(const AdamTensor* __restrict__ tab, int ntensors, float lr, float beta1,
+                            float beta2, float eps, float bc1, float bc2, float grad_scale) {
+  const AdamTensor t = tab[blockIdx.y];
+  const size_t numel = t.numel;
+  const int taps = t.kh * t.kw;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < numel;
+       i += size_t(gridDim.x) * blockDim.x) {
+    // torch order: conv [O][I][kh][kw]; convT [I][O][kh][kw]; vectors: kind 0
+    size_t gi = i;
+    int o = 0, ic = 0, tap = 0;
+    if (t.kind != 0) {
+      tap = int(i % taps);
+      const size_t r = i / taps;
+      const int d1 = int(r % t.dim1), d0 = int(r / t.dim1);
+      if (t.kind == 1) { o = d0; ic = d1; } else { ic = d0; o = d1; }
+      // gradient lives in the packed forward layout [tap][rows_pad][cols_pad]
+      gi = t.kind == 1 ? (size_t(tap) * t.o_pad + o) * t.i_pad + ic
+                       : (size_t(tap) * t.i_pad + ic) * t.o_pad + o;
+    }
+    float p = t.param[i];
+    if (t.grad) {
+      const float g = t.grad[gi] * grad_scale;
+      float m = t.m[i], v = t.v[i];
+      m = beta1 * m + (1.f - beta1) * g;
+      v = beta2 * v + (1.f - beta2) * g * g;
+      t.m[i] = m;
+      t.v[i] = v;
+      const float denom = sqrtf(v) / sqrtf(bc2) + eps;
+      p -= (lr / bc1) * (m / denom);
+      t.param[i] = p;
+    }
+    if (t.kind != 0) {
+      const __nv_bfloat16 b = __float2bfloat16(p);
+      if (t.pack_fwd) {
+        // forward operand: [tap][rows][cols], cols contiguous = reduction channel of the forward op
+        const size_t k = t.kind == 1 ? (size_t(tap) * t.o_pad + o) * t.i_pad + ic
+                                     : (size_t(tap) * t.o_pad + o) * t.i_pad + ic;
+        t.pack_fwd[k] = b;
+      }
+      if (t.pack_bwd) {
+        // backward-data operand: transposed roles, taps mirrored for Conv2d (flip), same for convT
+        const int btap = t.kind == 1 ? (taps - 1 - tap) : tap;
+        t.pack_bwd[(size_t(btap) * t.i_pad + ic) * t.o_pad + o] = b;
+      }
+    }
+  }
+}
+
+}  // namespace tg
+
+// ====================================================================== C-ABI launchers
+using namespace tg;
+
+static inline int grid_for(size_t work, int block, int cap = 148 * 16) {
+  size_t g = (work + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > size_t(cap)) g = cap;
+  return int(g);
+}
+#define TG_STREAM(s) reinterpret_cast<cudaStream_t>(s)
+#define TG_RET() return tg_check_launch(__func__)
+
+extern "C" {
+
+int tg_pack_nchw(const float* A, const float* B, const float* wa, const float* wb, void* out, int N,
+                 int HW, int cj, int C, int c_off, void* stream) {
+  if (cj > 8 - (c_off & 7)) return tg_set_error("tg_pack_nchw: channels must stay inside one 8-group");
+  pack_nchw_kernel<<<grid_for(size_t(N) * HW, 256), 256, 0, TG_STREAM(stream)>>>(
+      A, B, wa, wb, (__nv_bfloat16*)out, N, HW, cj, C, c_off);
+  TG_RET();
+}
+
+int tg_unpack_nhwc(const void* in, float* out, int N, int HW, int C, int c_off, int cj, float scale,
+                   void* stream) {
+  unpack_nhwc_kernel<<<grid_for(size_t(N) * HW, 256), 256, 0, TG_STREAM(stream)>>>(
+      (const __nv_bfloat16*)in, out, N, HW, C, c_off, cj, scale);
+  TG_RET();
+}
+
+int tg_in_finalize(const float* partial, float* mr, int N, int T, int C, int count, float eps,
+                   void* stream) {
+  dim3 grid(C / 64, N);
+  in_finalize_kernel<<<grid, 1024, 0, TG_STREAM(stream)>>>(partial, mr, T, C, 1.f / float(count), eps);
+  TG_RET();
+}
+
+int tg_in_stats_direct(const void* raw, float* mr, int N, int HW, int C, float eps, void* stream) {
+  dim3 grid(C / 64, N);
+  in_stats_direct_kernel<<<grid, 256, 0, TG_STREAM(stream)>>>((const __nv_bfloat16*)raw, mr, HW, C, eps);
+  TG_RET();
+}
+
+int tg_in_act_fwd(const void* raw, const float* mr, const float* gamma, const float* beta, void* y,
+                  void* pool, int pool_mode, void* up, int N, int H, int W, int C, int act, float slope,
+                  void* stream) {
+  const __nv_bfloat16* r = (const __nv_bfloat16*)raw;
+  __nv_bfloat16 *yy = (__nv_bfloat16*)y, *pp = (__nv_bfloat16*)pool, *uu = (__nv_bfloat16*)up;
+  cudaStream_t s = TG_STREAM(stream);
+  const bool quad = pool || up;
+  if (quad && ((H | W) & 1)) return tg_set_error("tg_in_act_fwd: pool/upsample need even H, W");
+  const size_t work = size_t(N) * H * W * (C / 8) / (quad ? 4 : 1);
+  const int g = grid_for(work, 256, 148 * 32);
+  const int pm = pool ? pool_mode : 0;
+#define LAUNCH(P, U) in_act_fwd_kernel<P, U><<<g, 256, 0, s>>>(r, mr, gamma, beta, yy, pp, uu, N, H, W, C, act, slope)
+  if (pm == 0 && !up) LAUNCH(0, false);
+  else if (pm == 0 && up) LAUNCH(0, true);
+  else if (pm == 1 && !up) LAUNCH(1, false);
+  else if (pm == 1 && up) LAUNCH(1, true);
+  else if (pm == 2 && !up) LAUNCH(2, false);
+  else LAUNCH(2, true);
+#undef LAUNCH
+  TG_RET();
+}
+
+int tg_in_bwd_reduce(const void* raw, const void* y, const float* mr, const float* gamma,
+                     const float* beta, const void* g_same, const void* g_pool, int pool_mode,
+                     const void* g_up, void* dn, float* red, int N, int H, int W, int C, int act,
+                     float slope, void* stream) {
+  InBwdArgs a;
+  a.raw = (const __nv_bfloat16*)raw; a.y = (const __nv_bfloat16*)y; a.mr = mr; a.gamma = gamma;
+  a.beta = beta; a.g_same = (const __nv_bfloat16*)g_same; a.g_pool = (const __nv_bfloat16*)g_pool;
+  a.g_up = (const __nv_bfloat16*)g_up; a.dn = (__nv_bfloat16*)dn; a.red = red;
+  a.N = N; a.H = H; a.W = W; a.C = C; a.act = act; a.pool_mode = pool_mode; a.slope = slope;
+  const int CG = C / 8;
+  const int block = CG >= 256 ? CG : 256;
+  if (block > 1024) return tg_set_error("tg_in_bwd_reduce: C too large");
+  const int PL = block / CG;
+  const size_t smem = size_t(PL) * C * 2 * sizeof(float);
+  int strips = (H * W + PL * 8 - 1) / (PL * 8);
+  const int cap = (148 * 8 + N - 1) / N;
+  if (strips > cap) strips = cap;
+  if (strips < 1) strips = 1;
+  dim3 grid(strips, N);
+  in_bwd_reduce_kernel<<<grid, block, smem, TG_STREAM(stream)>>>(a);
+  TG_RET();
+}
+
+int tg_in_bwd_apply(const void* dn, const void* raw, const float* mr, const float* gamma,
+                    const float* red, void* dz, int N, int HW, int C, void* stream) {
+  in_bwd_apply_kernel<<<grid_for(size_t(N) * HW * (C / 8), 256, 148 * 32), 256, 0, TG_STREAM(stream)>>>(
+      (const __nv_bfloat16*)dn, (const __nv_bfloat16*)raw, mr, gamma, red, (__nv_bfloat16*)dz, N, HW, C);
+  TG_RET();
+}
+
+int tg_affine_grad(const float* red, float* dgamma, float* dbeta, int N, int C, void* stream) {
+  affine_grad_kernel<<<(C + 127) / 128, 128, 0, TG_STREAM(stream)>>>(red, dgamma, dbeta, N, C);
+  TG_RET();
+}
+
+int tg_bias_grad(const void* dz, float* db, long long rows, int C, int c_valid, void* stream) {
+  int strips = int((rows + 2047) / 2048);
+  if (strips > 148 * 4) strips = 148 * 4;
+  if (strips < 1) strips = 1;
+  dim3 grid(C / 64, strips);
+  bias_grad_kernel<<<grid, 256, 0, TG_STREAM(stream)>>>((const __nv_bfloat16*)dz, db, size_t(rows), C, c_valid);
+  TG_RET();
+}
+
+int tg_in_bwd2(const void* u, const void* raw, const void* dn, const float* mr, const float* gamma,
+               const float* beta, const float* red1, float* red2, void* adj_da, void* adj_z, int N,
+               int HW, int C, int act, float slope, void* stream) {
+  const int CG = C / 8;
+  const int block = CG >= 256 ? CG : 256;
+  if (block > 1024) return tg_set_error("tg_in_bwd2: C too large");
+  const int PL = block / CG;
+  int strips = (HW + PL * 8 - 1) / (PL * 8);
+  const int cap = (148 * 8 + N - 1) / N;
+  if (strips > cap) strips = cap;
+  if (strips < 1) strips = 1;
+  dim3 grid(strips, N);
+  cudaStream_t s = TG_STREAM(stream);
+  in_bwd2_reduce_kernel<<<grid, block, size_t(PL) * C * 3 * sizeof(float), s>>>(
+      (const __nv_bfloat16*)u, (const __nv_bfloat16*)raw, (const __nv_bfloat16*)dn, mr, red2, HW, C);
+  in_bwd2_apply_kernel<<<grid, block, size_t(PL) * C * sizeof(float), s>>>(
+      (const __nv_bfloat16*)u, (const __nv_bfloat16*)raw, (const __nv_bfloat16*)dn, mr, gamma, beta, red1,
+      red2, (__nv_bfloat16*)adj_da, (__nv_bfloat16*)adj_z, HW, C, act, slope);
+  TG_RET();
+}
+
+int tg_gamma_grad2(const float* red2, float* dgamma, int N, int C, void* stream) {
+  gamma_grad2_kernel<<<(C + 127) / 128, 128, 0, TG_STREAM(stream)>>>(red2, dgamma, N, C);
+  TG_RET();
+}
+
+int tg_add(const void* a, const void* b, void* out, long long numel, void* stream) {
+  add_kernel<<<grid_for(size_t(numel) / 8, 256, 148 * 32), 256, 0, TG_STREAM(stream)>>>(
+      (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)out, size_t(numel) / 8);
+  TG_RET();
+}
+
+int tg_act_bwd(const void* g, const void* y, void* out, long long numel, int act, float slope,
+               void* stream) {
+  act_bwd_kernel<<<grid_for(size_t(numel) / 8, 256, 148 * 32), 256, 0, TG_STREAM(stream)>>>(
+      (const __nv_bfloat16*)g, (const __nv_bfloat16*)y, (__nv_bfloat16*)out, size_t(numel) / 8, act, slope);
+  TG_RET();
+}
+
+int tg_fmap_fwd(const void* x, const float* w, const float* b, float* out, int N, int HW, int C, int co,
+                int use_tanh, void* stream) {
+  if (C != 64 || co > 4) return tg_set_error("tg_fmap_fwd: expects C == 64, co <= 4");
+  fmap_fwd_kernel<<<grid_for(size_t(N) * HW, 256, 148 * 16), 256, 0, TG_STREAM(stream)>>>(
+      (const __nv_bfloat16*)x, w, b, out, N, HW, C, co, use_tanh);
+  TG_RET();
+}
+
+int tg_fmap_bwd(const void* x, const float* w, const float* out, const float* g1, const float* g2,
+                void* dx, float* dw, float* db, int N, int HW, int C, int co, int use_tanh, void* stream) {
+  if (C != 64 || co > 4) return tg_set_error("tg_fmap_bwd: expects C == 64, co <= 4");
+  fmap_bwd_kernel<<<grid_for(size_t(N) * HW * 8, 256, 148 * 8), 256, 0, TG_STREAM(stream)>>>(
+      (const __nv_bfloat16*)x, w, out, g1, g2, (__nv_bfloat16*)dx, dw, db, N, HW, C, co, use_tanh);
+  TG_RET();
+}
+
+int tg_gan_loss(const void* pred, const float* label, float label_const, int mode, int target_is_real,
+                int for_disc, int has_sigmoid, float scale, int n0, int n1, int HW, int C, float* loss,
+                void* dz, void* stream) {
+  gan_loss_kernel<<<grid_for(size_t(n1 - n0) * HW, 256, 148 * 4), 256, 0, TG_STREAM(stream)>>>(
+      (const __nv_bfloat16*)pred, label, label_const, mode, target_is_real, for_disc, has_sigmoid, scale,
+      n0, n1, HW, C, loss, (__nv_bfloat16*)dz, dz != nullptr);
+  TG_RET();
+}
+
+int tg_gp_first_seed(const void* pred, int has_sigmoid, int n0, int n1, int HW, int C, void* dz,
+                     void* stream) {
+  gp_first_seed_kernel<<<grid_for(size_t(n1 - n0) * HW, 256, 148 * 4), 256, 0, TG_STREAM(stream)>>>(
+      (const __nv_bfloat16*)pred, has_sigmoid, n0, n1, HW, C, (__nv_bfloat16*)dz);
+  TG_RET();
+}
+
+int tg_gp_top(const void* w, const void* pred, int has_sigmoid, long long numel, int C, void* out,
+              void* stream) {
+  gp_top_kernel<<<grid_for(size_t(numel), 256, 148 * 4), 256, 0, TG_STREAM(stream)>>>(
+      (const __nv_bfloat16*)w, (const __nv_bfloat16*)pred, has_sigmoid, size_t(numel), C, (__nv_bfloat16*)out);
+  TG_RET();
+}
+
+int tg_l1_loss(const float* a, const float* b, long long numel, float scale, float* loss, float* grad_a,
+               void* stream) {
+  l1_loss_kernel<<<grid_for(size_t(numel), 256, 148 * 8), 256, 0, TG_STREAM(stream)>>>(
+      a, b, size_t(numel), scale, loss, grad_a);
+  TG_RET();
+}
+
+int tg_feat_loss(const void* a, const void* b, long long numel, float weight, int l2, float* loss,
+                 void* stream) {
+  feat_loss_kernel<<<grid_for(size_t(numel) / 8, 256, 148 * 8), 256, 0, TG_STREAM(stream)>>>(
+      (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, size_t(numel) / 8, weight, l2, loss);
+  TG_RET();
+}
+
+int tg_gp_normsq(const void* g, int N, int HW, int C, int c_off, int cj, float* nsq, void* stream) {
+  dim3 grid(grid_for(size_t(HW), 256, 64), N);
+  gp_normsq_kernel<<<grid, 256, 0, TG_STREAM(stream)>>>((const __nv_bfloat16*)g, HW, C, c_off, cj, nsq);
+  TG_RET();
+}
+
+int tg_gp_finish(const float* nsq, int N, float lambda, float constant, float* loss, float* coef,
+                 void* stream) {
+  gp_finish_kernel<<<1, 256, 0, TG_STREAM(stream)>>>(nsq, N, lambda, constant, loss, coef);
+  TG_RET();
+}
+
+int tg_gp_seed(const void* g, const float* coef, int N, int HW, int C, int c_off, int cj, void* seed,
+               void* stream) {
+  if (cj > 8 - (c_off & 7)) return tg_set_error("tg_gp_seed: channels must stay inside one 8-group");
+  gp_seed_kernel<<<grid_for(size_t(N) * HW, 256, 148 * 16), 256, 0, TG_STREAM(stream)>>>(
+      (const __nv_bfloat16*)g, coef, N, HW, C, c_off, cj, (__nv_bfloat16*)seed);
+  TG_RET();
+}
+
+int tg_adam_step(const void* table_dev, int ntensors, long long max_numel, float lr, float beta1,
+                 float beta2, float eps, int step, float grad_scale, void* stream) {
+  const float bc1 = 1.f - powf(beta1, float(step));
+  const float bc2 = 1.f - powf(beta2, float(step));
+  dim3 grid(grid_for(size_t(max_numel), 256, 256), ntensors);
+  adam_kernel<<<grid, 256, 0, TG_STREAM(stream)>>>((const AdamTensor*)table_dev, ntensors, lr, beta1,
+                                                    beta2, eps, bc1, bc2, grad_scale);
+  TG_RET();
+}
+
+}  // extern "C"

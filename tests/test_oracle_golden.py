@@ -1,0 +1,72 @@
+"""The oracle (oracle/oracle.py, a functional restatement) must reproduce what the UNMODIFIED reference
+modules produced when oracle/make_golden.py ran them (fixtures under tests/golden/)."""
+import os
+from collections import OrderedDict
+
+import pytest
+import torch
+
+import oracle as orc
+
+CASES = ["unetpp_ls", "unet_ls", "bcdunet_ls", "unetpp_hinge", "unetpp_ce", "unetpp_w"]
+TOL = dict(rtol=2e-4, atol=2e-6)  # same fp32 torch ops, different op order / fusion
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
+
+
+def _replay(fx):
+    m = fx["meta"]
+    cfg = orc.StepConfig(gen=m["gen"], loss=m["loss"], version=2, lambda_a=m["lambda_a"], lambda_gp=m["lambda_gp"],
+                         lambda_per=m["lambda_per"], w_per=m["w_per"], lr=m["lr"], beta1=m["beta1"])
+    sd_g = OrderedDict((k, v.clone()) for k, v in fx["init_G"].items())
+    sd_d = OrderedDict((k, v.clone()) for k, v in fx["init_D"].items())
+    opt_g, opt_d = {}, {}
+    g = torch.Generator().manual_seed(m["seed"] + 1000)
+    outs = []
+    label = None
+    for rec in fx["steps"]:
+        real_a, real_b = orc.synthetic_batch(g, m["batch"], m["size"])
+        alpha = torch.rand(m["batch"], 1, generator=g)  # same draw order as the fixture generator
+        assert torch.equal(alpha, rec["alpha"])
+        if label is None:
+            label = rec.get("real_label")
+            if label is None:
+                label = torch.ones(1)
+        outs.append(orc.train_step(sd_g, sd_d, opt_g, opt_d, real_a, real_b, label, alpha, cfg))
+    return outs, sd_g, sd_d
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_fixture(golden_dir, name):
+    torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+    fx = _load(golden_dir, name)
+    outs, sd_g, sd_d = _replay(fx)
+    for out, rec in zip(outs, fx["steps"]):
+        for k in ("loss_D", "gp", "G_GAN", "L1", "per"):
+            assert out[k] == pytest.approx(rec[k], rel=2e-4, abs=1e-6), k
+        torch.testing.assert_close(out["fake_B"][:, :, ::4, ::4], rec["fake_B_sub"], **TOL)
+    rec0, out0 = fx["steps"][0], outs[0]
+    for k, ref in rec0["grad_D"].items():
+        torch.testing.assert_close(out0["grads_D"][k], ref, rtol=1e-3, atol=1e-7, msg=lambda s: f"grad_D {k}: {s}")
+    for k, ref in rec0["grad_G"].items():
+        got = out0["grads_G"][k]
+        if isinstance(ref, dict):
+            assert float(got.norm()) == pytest.approx(ref["norm"], rel=1e-3, abs=1e-8), k
+            torch.testing.assert_close(got.flatten()[:8], ref["head"], rtol=2e-3, atol=1e-7)
+        else:
+            torch.testing.assert_close(got, ref, rtol=2e-3, atol=1e-7, msg=lambda s: f"grad_G {k}: {s}")
+    for k, ref in fx["final_D"].items():
+        torch.testing.assert_close(sd_d[k], ref, rtol=1e-3, atol=2e-5, msg=lambda s: f"final_D {k}: {s}")
+    for k, ref in fx["final_G"].items():
+        if isinstance(ref, dict):
+            assert float(sd_g[k].norm()) == pytest.approx(ref["norm"], rel=1e-3), k
+        else:
+            torch.testing.assert_close(sd_g[k], ref, rtol=1e-3, atol=2e-5, msg=lambda s: f"final_G {k}: {s}")
+
+
+def test_state_dict_key_inventory(golden_dir):
+    """Checkpoint-layout contract: 92 / 86 / 66 / 13 keys."""
+    inv = _load(golden_dir, "state_dict_keys")
+    assert len(inv["UNet++"]) == 92 and len(inv["UNet"]) == 86 and len(inv["BCDUNet"]) == 66 and len(inv["patch"]) == 13
