@@ -138,8 +138,9 @@ int tg_gp_finish(const float* nsq, int N, float lambda, float constant, float* l
 int tg_gp_seed(const void* g, const float* coef, int N, int HW, int C, int c_off, int cj, void* seed, void* stream);
 
 /* ---- torch.optim.Adam.step (train.py:135,168) fused with the bf16 weight re-pack.
- * table_dev: device array of `ntensors` rows, each row = 6 pointers, 1 int64, 6 int32
- * (param, grad, exp_avg, exp_avg_sq, pack_fwd, pack_bwd, numel, kind, kh, kw, dim1, o_pad, i_pad). */
+ * table_dev: device array of `ntensors` rows of 136 bytes: 6 pointers (param, grad, exp_avg,
+ * exp_avg_sq, pack_fwd, pack_bwd), int64 numel, int32 kind, kh, kw, dim1, o_pad, i_pad, nseg,
+ * seg_end[6], seg_shift[6], pad. */
 int tg_adam_step(const void* table_dev, int ntensors, long long max_numel, float lr, float beta1,
                  float beta2, float eps, int step, float grad_scale, void* stream);
 

@@ -21,7 +21,11 @@ struct AdamTensor {
   __nv_bfloat16* pack_fwd;  // [taps][o_pad][i_pad]
   __nv_bfloat16* pack_bwd;  // [taps][i_pad][o_pad]
   long long numel;
-  int kind, kh, kw, dim1, o_pad, i_pad;
+  int kind, kh, kw, dim1, o_pad, i_pad;  // i_pad = total padded reduction width (all concat sources)
+  // input channel -> padded position: the concat sources are padded to 64 separately, so channel ic of
+  // segment s (ic < seg_end[s]) sits at ic + seg_shift[s]
+  int nseg, seg_end[6], seg_shift[6];
+  int pad_;
 };
 
 }  // namespace tg

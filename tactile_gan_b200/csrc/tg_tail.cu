@@ -9,7 +9,7 @@
 
 namespace tg {
 
-struct bf8 { uint4 v; };
+static_assert(sizeof(AdamTensor) == 136, "AdamTensor layout is part of the C-ABI (tg_adam_step)");
 
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
@@ -879,6 +879,8 @@ __global__ void adam_kernel(const AdamTensor* __restrict__ tab, int ntensors, fl
       const size_t r = i / taps;
       const int d1 = int(r % t.dim1), d0 = int(r / t.dim1);
       if (t.kind == 1) { o = d0; ic = d1; } else { ic = d0; o = d1; }
+      for (int sgi = 0; sgi < t.nseg; ++sgi)
+        if (ic < t.seg_end[sgi]) { ic += t.seg_shift[sgi]; break; }
       // gradient lives in the packed forward layout [tap][rows_pad][cols_pad]
       gi = t.kind == 1 ? (size_t(tap) * t.o_pad + o) * t.i_pad + ic
                        : (size_t(tap) * t.i_pad + ic) * t.o_pad + o;

@@ -1,0 +1,276 @@
+"""Device-side parameter plumbing shared by the generator / discriminator engines.
+
+* ConvLayer   -- one nn.Conv2d / nn.ConvTranspose2d weight: fp32 master (the nn.Parameter, torch
+                 layout), bf16 packs in the two layouts the implicit-GEMM kernels read, an fp32
+                 gradient in the packed layout, and factories for the forward / dgrad / wgrad plans.
+* ParamStore  -- all parameters of one network: flat gradient arena (one NCCL allreduce), Adam
+                 moments in torch layout (so optimizer.state_dict() matches torch.optim.Adam), and the
+                 device table the fused Adam + re-pack kernel walks (tg_adam_step).
+"""
+import ctypes
+from ctypes import Structure, c_int, c_longlong, c_void_p
+
+import torch
+
+from . import _C
+from ._C import ACT_NONE
+
+
+def pad64(c):
+    return (c + 63) // 64 * 64
+
+
+class AdamRow(Structure):
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("m", c_void_p), ("v", c_void_p),
+                ("pack_fwd", c_void_p), ("pack_bwd", c_void_p), ("numel", c_longlong),
+                ("kind", c_int), ("kh", c_int), ("kw", c_int), ("dim1", c_int), ("o_pad", c_int),
+                ("i_pad", c_int), ("nseg", c_int), ("seg_end", c_int * 6), ("seg_shift", c_int * 6),
+                ("pad_", c_int)]
+
+
+assert ctypes.sizeof(AdamRow) == 136
+
+
+def conv_taps(kh, kw, pad):
+    """Forward taps of a stride-s Conv2d: input = out*s + (r - pad); weight tap index r*kw+s."""
+    return [(r - pad, s - pad, r * kw + s) for r in range(kh) for s in range(kw)]
+
+
+def dgrad_taps_s1(kh, kw, pad):
+    """dX[y] = sum_r' dY[y + r' - (k-1-pad)] * Wflip[r'] (pack_bwd stores taps mirrored)."""
+    return [(r - (kh - 1 - pad), s - (kw - 1 - pad), r * kw + s) for r in range(kh) for s in range(kw)]
+
+
+def phase_taps(kh, kw, pad, stride, py, px, flipped):
+    """Taps of output phase (py,px) of a transposed (fractionally strided) convolution:
+    out[stride*a + py] += in[a + (py + pad - r)/stride] * W[r] for r with (py+pad-r) % stride == 0.
+    `flipped`: weight tap axis stored mirrored (pack_bwd of a Conv2d) or not (pack_fwd of a ConvT)."""
+    taps = []
+    for r in range(kh):
+        if (py + pad - r) % stride:
+            continue
+        for s in range(kw):
+            if (px + pad - s) % stride:
+                continue
+            widx = ((kh - 1 - r) * kw + (kw - 1 - s)) if flipped else (r * kw + s)
+            taps.append(((py + pad - r) // stride, (px + pad - s) // stride, widx))
+    return taps
+
+
+class ConvLayer:
+    """kind 'conv': weight [O][I][kh][kw]; kind 'convT': weight [I][O][kh][kw] (torch layouts).
+    `in_split`: channel counts of the concatenated inputs (each padded to 64 separately)."""
+
+    def __init__(self, name, weight, bias, kind, stride, pad, in_split, device):
+        self.name, self.weight, self.bias, self.kind = name, weight, bias, kind
+        self.stride, self.pad = stride, pad
+        if kind == "conv":
+            self.O, self.I, self.kh, self.kw = weight.shape
+        else:
+            self.I, self.O, self.kh, self.kw = weight.shape
+        assert sum(in_split) == self.I, (name, in_split, self.I)
+        self.in_split = list(in_split)
+        self.seg_pad = [pad64(c) for c in in_split]
+        self.k_off = [sum(self.seg_pad[:i]) for i in range(len(in_split))]
+        self.i_pad = sum(self.seg_pad)
+        self.o_pad = pad64(self.O)
+        self.taps = self.kh * self.kw
+        bf = dict(dtype=torch.bfloat16, device=device)
+        self.pack_fwd = torch.zeros(self.taps, self.o_pad, self.i_pad, **bf)
+        self.pack_bwd = torch.zeros(self.taps, self.i_pad, self.o_pad, **bf)
+        self.bias_pad = None  # fp32 [o_pad] view into the store's gradient-free bias buffer
+        self.grad = None      # fp32 [taps][o_pad][i_pad] (conv) / [taps][i_pad][o_pad] (convT)
+        self.bias_grad = None
+
+    # ---- plan factories -------------------------------------------------------------------
+    def fwd_plan(self, srcs, out, stats_partial=None, act=ACT_NONE, slope=0.2, use_bias=True):
+        """srcs: NHWC bf16 tensors in concat order (conv) -- Conv2d forward."""
+        assert self.kind == "conv" and len(srcs) == len(self.in_split)
+        s = [dict(act=t, wgt=self.pack_fwd, k_off=o) for t, o in zip(srcs, self.k_off)]
+        return _C.conv_plan(s, out, conv_taps(self.kh, self.kw, self.pad), stride=self.stride,
+                            bias=self.bias_pad if use_bias else None, stats_partial=stats_partial,
+                            act=act, slope=slope)
+
+    def wgrad_plan(self, srcs, dy):
+        assert self.kind == "conv"
+        return _C.wgrad_plan(list(srcs), dy, conv_taps(self.kh, self.kw, self.pad), self.grad,
+                             stride=self.stride)
+
+    def dgrad_src(self, dy, seg):
+        """Operand descriptor for the input-gradient of concat segment `seg`."""
+        return dict(act=dy, wgt=self.pack_bwd, k_off=0, row_off=self.k_off[seg])
+
+    def dgrad_plans(self, dy, out, seg=0):
+        """Input gradient w.r.t. concat segment `seg` -> list of plans (one per output phase)."""
+        assert self.kind == "conv"
+        if self.stride == 1:
+            return [_C.conv_plan([self.dgrad_src(dy, seg)], out, dgrad_taps_s1(self.kh, self.kw, self.pad))]
+        plans = []
+        s = self.stride
+        for py in range(s):
+            for px in range(s):
+                taps = phase_taps(self.kh, self.kw, self.pad, s, py, px, flipped=True)
+                sub = out[:, py::s, px::s, :]
+                if sub.shape[1] == 0 or sub.shape[2] == 0:
+                    continue
+                if not taps:
+                    sub.zero_()
+                    continue
+                plans.append(_C.conv_plan([self.dgrad_src(dy, seg)], sub, taps))
+        return plans
+
+
+def multi_dgrad_plan(consumers, out):
+    """d(out) = sum over consumers (layer, dY, segment) of the stride-1 input gradients -- one
+    multi-source implicit GEMM (the K loop walks the consumers)."""
+    l0 = consumers[0][0]
+    for layer, _, _ in consumers:
+        assert layer.stride == 1 and (layer.kh, layer.kw, layer.pad) == (l0.kh, l0.kw, l0.pad)
+    srcs = [layer.dgrad_src(dy, seg) for layer, dy, seg in consumers]
+    return _C.conv_plan(srcs, out, dgrad_taps_s1(l0.kh, l0.kw, l0.pad))
+
+
+class ParamStore:
+    """Owns gradients / Adam state / packs for every parameter of one nn.Module, in
+    module.parameters() order (the order torch.optim.Adam indexes its state by)."""
+
+    def __init__(self, module, device):
+        self.module = module
+        self.device = device
+        self.params = list(module.parameters())
+        self.names = [n for n, _ in module.named_parameters()]
+        self.index = {id(p): i for i, p in enumerate(self.params)}
+        self.conv_of = {}      # param index -> ConvLayer
+        self.bias_of = {}      # param index -> ConvLayer whose bias this is
+        self.rows = None
+        self.table = None
+        self.step_count = 0
+
+    def register_conv(self, layer):
+        self.conv_of[self.index[id(layer.weight)]] = layer
+        if layer.bias is not None:
+            self.bias_of[self.index[id(layer.bias)]] = layer
+
+    def finalize(self):
+        """Allocate arenas once every conv is registered."""
+        dev = self.device
+        sizes = []
+        for i, p in enumerate(self.params):
+            if i in self.conv_of:
+                l = self.conv_of[i]
+                sizes.append(l.taps * l.o_pad * l.i_pad)
+            elif i in self.bias_of:
+                sizes.append(self.bias_of[i].o_pad)
+            else:
+                sizes.append(p.numel())
+        offs = [0]
+        for s in sizes:
+            offs.append(offs[-1] + (s + 3) // 4 * 4)
+        self.grad_arena = torch.zeros(offs[-1], dtype=torch.float32, device=dev)
+        self.grad_views = []
+        for i, p in enumerate(self.params):
+            g = self.grad_arena[offs[i]:offs[i] + sizes[i]]
+            if i in self.conv_of:
+                l = self.conv_of[i]
+                l.grad = g.view(l.taps, l.o_pad, l.i_pad) if l.kind == "conv" else g.view(l.taps, l.i_pad, l.o_pad)
+            elif i in self.bias_of:
+                self.bias_of[i].bias_grad = g
+            self.grad_views.append(g)
+        pn = [p.numel() for p in self.params]
+        po = [0]
+        for s in pn:
+            po.append(po[-1] + (s + 3) // 4 * 4)
+        self.exp_avg = torch.zeros(po[-1], dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(po[-1], dtype=torch.float32, device=dev)
+        self.m_views = [self.exp_avg[po[i]:po[i] + pn[i]].view_as(p) for i, p in enumerate(self.params)]
+        self.v_views = [self.exp_avg_sq[po[i]:po[i] + pn[i]].view_as(p) for i, p in enumerate(self.params)]
+        # conv biases are consumed padded to o_pad (epilogue reads bias[c] for padded c too)
+        nb = sum(l.o_pad for l in self.bias_of.values())
+        self.bias_arena = torch.zeros(max(nb, 1), dtype=torch.float32, device=dev)
+        o = 0
+        for i, l in self.bias_of.items():
+            l.bias_pad = self.bias_arena[o:o + l.o_pad]
+            o += l.o_pad
+        self._ptrs = None
+        self._versions = None
+        self.max_numel = max(pn)
+        self.refresh(force=True)
+
+    # ---- table -------------------------------------------------------------------------------
+    def _build_table(self, with_grad):
+        rows = (AdamRow * len(self.params))()
+        for i, p in enumerate(self.params):
+            r = rows[i]
+            r.param = p.data_ptr()
+            r.grad = self.grad_views[i].data_ptr() if with_grad else None
+            r.m = self.m_views[i].data_ptr()
+            r.v = self.v_views[i].data_ptr()
+            r.numel = p.numel()
+            if i in self.conv_of:
+                l = self.conv_of[i]
+                r.kind = 1 if l.kind == "conv" else 2
+                r.kh, r.kw = l.kh, l.kw
+                r.dim1 = p.shape[1]
+                r.o_pad, r.i_pad = l.o_pad, l.i_pad
+                r.pack_fwd = l.pack_fwd.data_ptr()
+                r.pack_bwd = l.pack_bwd.data_ptr()
+                r.nseg = len(l.in_split)
+                end = 0
+                for s, c in enumerate(l.in_split):
+                    end += c
+                    r.seg_end[s] = end
+                    r.seg_shift[s] = l.k_off[s] - (end - c)
+            else:
+                r.kind = 0
+        raw = bytes(rows)
+        return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
+
+    def refresh(self, force=False):
+        """Rebuild the device table / re-pack bf16 weights if parameters were touched from outside
+        (load_state_dict, init_weights, .to())."""
+        ptrs = [p.data_ptr() for p in self.params]
+        vers = [p._version for p in self.params]
+        if force or ptrs != self._ptrs:
+            for p in self.params:
+                assert p.is_cuda and p.dtype == torch.float32 and p.is_contiguous(), "parameters must be fp32 CUDA"
+            self.table = self._build_table(True)
+            self.table_nograd = self._build_table(False)
+            self._ptrs = ptrs
+            self._versions = None
+        if vers != self._versions:
+            self.repack()
+            self._versions = vers
+
+    def repack(self):
+        _C.call("adam_step", _C.ptr(self.table_nograd), len(self.params), _C.LL(self.max_numel),
+                _C.F(0.0), _C.F(0.0), _C.F(0.0), _C.F(1.0), 1, _C.F(1.0))
+        for i, l in self.bias_of.items():
+            l.bias_pad[:l.O].copy_(self.params[i].detach())
+
+    def zero_grad(self):
+        self.grad_arena.zero_()
+
+    def adam_step(self, lr, beta1, beta2=0.99, eps=1e-8, grad_scale=1.0):
+        self.step_count += 1
+        _C.call("adam_step", _C.ptr(self.table), len(self.params), _C.LL(self.max_numel), _C.F(lr),
+                _C.F(beta1), _C.F(beta2), _C.F(eps), self.step_count, _C.F(grad_scale))
+        for i, l in self.bias_of.items():
+            l.bias_pad[:l.O].copy_(self.params[i].detach())
+
+    # ---- gradients in torch layout (tests / autograd bridge) ---------------------------------
+    def grad_as_torch(self, i):
+        p = self.params[i]
+        g = self.grad_views[i]
+        if i in self.conv_of:
+            l = self.conv_of[i]
+            if l.kind == "conv":
+                parts = [l.grad[:, :l.O, o:o + c] for o, c in zip(l.k_off, l.in_split)]
+                return torch.cat(parts, 2).reshape(l.kh, l.kw, l.O, l.I).permute(2, 3, 0, 1).contiguous()
+            parts = [l.grad[:, o:o + c, :l.O] for o, c in zip(l.k_off, l.in_split)]
+            return torch.cat(parts, 1).reshape(l.kh, l.kw, l.I, l.O).permute(2, 3, 0, 1).contiguous()
+        if i in self.bias_of:
+            return g[:self.bias_of[i].O].clone()
+        return g.view_as(p).clone()
+
+    def grads_by_name(self):
+        return {n: self.grad_as_torch(i) for i, n in enumerate(self.names)}
