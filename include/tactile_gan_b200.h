@@ -49,7 +49,7 @@ typedef struct tg_conv_src {
  *   generators/UNet_plusplus.py:22,26  generators/UNet.py:21,25,40,44  generators/BCDUNet.py:122-137
  *   discriminators/PatchDiscriminator.py:14,27 and torch.cat / nn.Upsample operands at
  *   generators/UNet_plusplus.py:72-84 (the concat is the multi-source K loop, never materialised).
- * stats_partial (optional): [n][tiles_per_img][c][2] fp32 (sum, sum of squares) per output tile for
+ * stats_partial (optional): [n][stats_tiles_total][c][2] fp32 (sum, sum of squares) per output tile for
  * the InstanceNorm that follows (nn.InstanceNorm2d, UNet_plusplus.py:23,27). */
 typedef struct tg_conv_desc {
   int num_src;
@@ -57,8 +57,11 @@ typedef struct tg_conv_desc {
   tg_view out;
   int taps, stride;
   signed char tap_dy[TG_MAX_TAPS], tap_dx[TG_MAX_TAPS], tap_w[TG_MAX_TAPS];
-  const float* bias;
+  const float* bias;      /* fp32 [bias_len]; channels >= bias_len get no bias */
+  int bias_len;
   float* stats_partial;
+  int stats_tiles_total;  /* tiles per image in the partial buffer (0: this launch's tiles_per_img) */
+  int stats_tile_off;     /* first tile slot this launch writes (phase-decomposed outputs share a buffer) */
   int act;
   float slope;
 } tg_conv_desc;
@@ -99,21 +102,21 @@ int tg_unpack_nhwc(const void* in, float* out, int N, int HW, int C, int c_off, 
 int tg_in_finalize(const float* partial, float* mr, int N, int T, int C, int count, float eps, void* stream);
 int tg_in_stats_direct(const void* raw, float* mr, int N, int HW, int C, float eps, void* stream);
 int tg_in_act_fwd(const void* raw, const float* mr, const float* gamma, const float* beta, void* y,
-                  void* pool, int pool_mode, void* up, int N, int H, int W, int C, int act, float slope,
-                  void* stream);
+                  void* pool, int pool_mode, void* up, int N, int H, int W, int C, int c_valid, int act,
+                  float slope, void* stream);
 int tg_in_bwd_reduce(const void* raw, const void* y, const float* mr, const float* gamma,
                      const float* beta, const void* g_same, const void* g_pool, int pool_mode,
-                     const void* g_up, void* dn, float* red, int N, int H, int W, int C, int act,
-                     float slope, void* stream);
+                     const void* g_up, void* dn, float* red, int N, int H, int W, int C, int c_valid,
+                     int act, float slope, void* stream);
 int tg_in_bwd_apply(const void* dn, const void* raw, const float* mr, const float* gamma,
-                    const float* red, void* dz, int N, int HW, int C, void* stream);
-int tg_affine_grad(const float* red, float* dgamma, float* dbeta, int N, int C, void* stream);
+                    const float* red, void* dz, int N, int HW, int C, int c_valid, void* stream);
+int tg_affine_grad(const float* red, float* dgamma, float* dbeta, int N, int C, int c_valid, void* stream);
 int tg_bias_grad(const void* dz, float* db, long long rows, int C, int c_valid, void* stream);
 /* InstanceNorm double backward for the gradient penalty (util.py:88-93, create_graph=True) */
 int tg_in_bwd2(const void* u, const void* raw, const void* dn, const float* mr, const float* gamma,
                const float* beta, const float* red1, float* red2, void* adj_da, void* adj_z, int N,
-               int HW, int C, int act, float slope, void* stream);
-int tg_gamma_grad2(const float* red2, float* dgamma, int N, int C, void* stream);
+               int HW, int C, int c_valid, int act, float slope, void* stream);
+int tg_gamma_grad2(const float* red2, float* dgamma, int N, int C, int c_valid, void* stream);
 int tg_add(const void* a, const void* b, void* out, long long numel, void* stream);
 int tg_act_bwd(const void* g, const void* y, void* out, long long numel, int act, float slope, void* stream);
 

@@ -30,6 +30,30 @@ import torch.nn.functional as F
 
 EPS_IN = 1e-5
 
+# ---- optional bf16 storage emulation ---------------------------------------------------------------
+# The CUDA path stores activations / packed weights as bf16 (fp32 accumulate). With QUANT["on"] the oracle
+# rounds at exactly those storage points (straight-through in backward), which isolates logic errors
+# from the legitimate bf16-vs-fp32 drift (ReLU masks flip when activations move by ~1%).
+QUANT = {"on": False}
+
+
+class _RoundBF16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+ACT = {"relu": F.relu}   # tests may linearise the generators (ACT["relu"] = identity) to remove mask flips
+
+
+def _q(x):
+    return _RoundBF16.apply(x) if QUANT["on"] else x
+
+
 
 # --------------------------------------------------------------------------- generators
 def _in(x, sd, key):
@@ -41,12 +65,12 @@ def _double_conv(x, sd, p, first=None):
     """[conv -> IN -> ReLU] x 2 with parameter names p.0 / p.1 / p.3 / p.4.
     `first` overrides the first op (strided conv / transposed conv for UNet)."""
     if first is None:
-        x = F.conv2d(x, sd[p + ".0.weight"], sd.get(p + ".0.bias"), stride=1, padding=1)
+        x = F.conv2d(x, _q(sd[p + ".0.weight"]), sd.get(p + ".0.bias"), stride=1, padding=1)
     else:
         x = first(x)
-    x = F.relu(_in(x, sd, p + ".1"))
-    x = F.conv2d(x, sd[p + ".3.weight"], sd.get(p + ".3.bias"), stride=1, padding=1)
-    return F.relu(_in(x, sd, p + ".4"))
+    x = _q(ACT["relu"](_in(_q(x), sd, p + ".1")))
+    x = F.conv2d(x, _q(sd[p + ".3.weight"]), sd.get(p + ".3.bias"), stride=1, padding=1)
+    return _q(ACT["relu"](_in(_q(x), sd, p + ".4")))
 
 
 def _head(x, sd, key, activation):
@@ -56,7 +80,8 @@ def _head(x, sd, key, activation):
 
 def unetpp_forward(sd, x, activation=True):
     up = lambda t: F.interpolate(t, scale_factor=2, mode="nearest")
-    down = lambda t: F.avg_pool2d(t, 2, 2)
+    down = lambda t: _q(F.avg_pool2d(t, 2, 2))
+    x = _q(x)
     X = {}
     blk = lambda i, j, inp: _double_conv(inp, sd, f"conv{i}_{j}.layer")
     X[0, 0] = blk(0, 0, x)
@@ -70,32 +95,32 @@ def unetpp_forward(sd, x, activation=True):
 
 def unet_forward(sd, x, activation=True):
     c = [None]
-    t = x
+    t = _q(x)
     for i in range(1, 8):
         w = sd[f"conv{i}.layer.0.weight"]
-        t = _double_conv(t, sd, f"conv{i}.layer", first=lambda z, w=w: F.conv2d(z, w, None, stride=2, padding=1))
+        t = _double_conv(t, sd, f"conv{i}.layer", first=lambda z, w=w: F.conv2d(z, _q(w), None, stride=2, padding=1))
         c.append(t)
     d = c[7]
     for i in range(2, 9):
         w = sd[f"deconv{i}.layer.0.weight"]
         inp = d if i == 2 else torch.cat([d, c[9 - i]], 1)  # d3 <- (d2, c6) ... d8 <- (d7, c1)
         d = _double_conv(inp, sd, f"deconv{i}.layer",
-                         first=lambda z, w=w: F.conv_transpose2d(z, w, None, stride=2, padding=1))
+                         first=lambda z, w=w: F.conv_transpose2d(z, _q(w), None, stride=2, padding=1))
     return _head(d, sd, "downfeature.conv", activation)
 
 
 def bcdunet_forward(sd, x, activation=True):
     blk = lambda name, inp: _double_conv(inp, sd, name)
     pool = lambda t: F.max_pool2d(t, 2, 2)
-    c1 = blk("conv1", x)
+    c1 = blk("conv1", _q(x))
     c2 = blk("conv2", pool(c1))
     c3 = blk("conv3", pool(c2))
     c4 = blk("conv4", pool(c3))
-    u3 = F.conv_transpose2d(c4, sd["upconv3.weight"], sd["upconv3.bias"], stride=2)
+    u3 = _q(F.conv_transpose2d(c4, _q(sd["upconv3.weight"]), sd["upconv3.bias"], stride=2))
     m3 = blk("conv3m", torch.cat([c3, u3], 1))
-    u2 = F.conv_transpose2d(m3, sd["upconv2.weight"], sd["upconv2.bias"], stride=2)
+    u2 = _q(F.conv_transpose2d(m3, _q(sd["upconv2.weight"]), sd["upconv2.bias"], stride=2))
     m2 = blk("conv2m", torch.cat([c2, u2], 1))
-    u1 = F.conv_transpose2d(m2, sd["upconv1.weight"], sd["upconv1.bias"], stride=2)
+    u1 = _q(F.conv_transpose2d(m2, _q(sd["upconv1.weight"]), sd["upconv1.bias"], stride=2))
     m1 = blk("conv1m", torch.cat([c1, u1], 1))
     return _head(m1, sd, "conv0", activation)
 
@@ -111,17 +136,17 @@ def gen_forward(name, sd, x, activation=True):
 def patchd_forward(sd, img_a, img_b, activation=True):
     """Returns (prediction, [4 LeakyReLU feature maps])."""
     feats = []
-    x = torch.cat([img_a, img_b], 1)
-    x = F.leaky_relu(F.conv2d(x, sd["model.0.weight"], sd["model.0.bias"], stride=2), 0.2)
+    x = _q(torch.cat([img_a, img_b], 1))
+    x = _q(F.leaky_relu(F.conv2d(x, _q(sd["model.0.weight"]), sd["model.0.bias"], stride=2), 0.2))
     feats.append(x)
     for conv, norm, stride in ((2, 3, 2), (5, 6, 1), (8, 9, 1)):
-        x = F.conv2d(x, sd[f"model.{conv}.weight"], None, stride=stride)
-        x = F.leaky_relu(_in(x, sd, f"model.{norm}"), 0.2)
+        x = _q(F.conv2d(x, _q(sd[f"model.{conv}.weight"]), None, stride=stride))
+        x = _q(F.leaky_relu(_in(x, sd, f"model.{norm}"), 0.2))
         feats.append(x)
-    x = F.conv2d(x, sd["model.11.weight"], sd["model.11.bias"])
+    x = F.conv2d(x, _q(sd["model.11.weight"]), sd["model.11.bias"])
     if activation:
         x = torch.sigmoid(x)
-    return x, feats
+    return _q(x), feats
 
 
 # --------------------------------------------------------------------------- losses

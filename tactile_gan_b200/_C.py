@@ -36,7 +36,8 @@ class ConvSrc(Structure):
 class ConvDesc(Structure):
     _fields_ = [("num_src", c_int), ("src", ConvSrc * TG_MAX_SRC), ("out", View), ("taps", c_int),
                 ("stride", c_int), ("tap_dy", c_int8 * TG_MAX_TAPS), ("tap_dx", c_int8 * TG_MAX_TAPS),
-                ("tap_w", c_int8 * TG_MAX_TAPS), ("bias", c_void_p), ("stats_partial", c_void_p),
+                ("tap_w", c_int8 * TG_MAX_TAPS), ("bias", c_void_p), ("bias_len", c_int),
+                ("stats_partial", c_void_p), ("stats_tiles_total", c_int), ("stats_tile_off", c_int),
                 ("act", c_int), ("slope", c_float)]
 
 
@@ -115,7 +116,8 @@ def conv_query_tiles(n, ho, wo, want_stats):
     return tuple(out)  # th, tw, tn, tiles_per_img
 
 
-def conv_plan(srcs, out, taps, stride=1, bias=None, stats_partial=None, act=ACT_NONE, slope=0.2):
+def conv_plan(srcs, out, taps, stride=1, bias=None, stats_partial=None, act=ACT_NONE, slope=0.2,
+              stats_tiles_total=0, stats_tile_off=0):
     """srcs: list of dict(act=tensor NHWC, wgt=packed bf16 [taps][rows][k], k_off=0, row_off=0)
     taps: list of (dy, dx, w_index)."""
     d = ConvDesc()
@@ -137,7 +139,10 @@ def conv_plan(srcs, out, taps, stride=1, bias=None, stats_partial=None, act=ACT_
     _taps(d.tap_dx, [t[1] for t in taps])
     _taps(d.tap_w, [t[2] for t in taps])
     d.bias = bias.data_ptr() if bias is not None else None
+    d.bias_len = bias.numel() if bias is not None else 0
     d.stats_partial = stats_partial.data_ptr() if stats_partial is not None else None
+    d.stats_tiles_total = stats_tiles_total
+    d.stats_tile_off = stats_tile_off
     d.act = act
     d.slope = slope
     h = c_void_p()

@@ -187,7 +187,10 @@ int tg_conv_plan_create(const tg_conv_desc* d, tg_plan** out) {
   p.act = d->act;
   p.slope = d->slope;
   p.bias = d->bias;
+  p.bias_len = d->bias_len;
   p.stats_partial = d->stats_partial;
+  p.stats_tiles_total = d->stats_tiles_total > 0 ? d->stats_tiles_total : p.tiles_h * p.tiles_w;
+  p.stats_tile_off = d->stats_tile_off;
   p.cout = cout;
   p.err_flag = tg_error_flag_device_ptr();
   for (int s = 0; s < d->num_src; ++s) {

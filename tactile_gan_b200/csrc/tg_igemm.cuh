@@ -48,9 +48,11 @@ struct alignas(64) IgemmParams {
   int n_tiles;                      // Cout / BN
   int act;
   float slope;
-  const float* bias;      // [Cout] or nullptr
-  float* stats_partial;   // [N][tiles_h*tiles_w][Cout][2] or nullptr (requires tn == 1)
-  int cout;               // padded Cout (row pitch of bias / stats)
+  const float* bias;      // [bias_len] or nullptr
+  int bias_len;
+  float* stats_partial;   // [N][stats_tiles_total][Cout][2] or nullptr (requires tn == 1)
+  int stats_tiles_total, stats_tile_off;
+  int cout;               // padded Cout (row pitch of stats)
   int* err_flag;
 };
 
@@ -239,8 +241,8 @@ igemm_conv_kernel(const __grid_constant__ IgemmParams p) {
           float x0 = __uint_as_float(v[jj]);
           float x1 = __uint_as_float(v[jj + 1]);
           if (p.bias) {
-            x0 += __ldg(p.bias + c_base + 2 * j);
-            x1 += __ldg(p.bias + c_base + 2 * j + 1);
+            if (c_base + 2 * j < p.bias_len) x0 += __ldg(p.bias + c_base + 2 * j);
+            if (c_base + 2 * j + 1 < p.bias_len) x1 += __ldg(p.bias + c_base + 2 * j + 1);
           }
           if (p.act == ACT_LRELU) {
             x0 = x0 > 0.f ? x0 : x0 * p.slope;
@@ -299,7 +301,7 @@ igemm_conv_kernel(const __grid_constant__ IgemmParams p) {
           named_bar_sync(1, 128);
           // et -> (channel = et >> 1, stat = et & 1)
           const float tot = scratch[et] + scratch[128 + et] + scratch[256 + et] + scratch[384 + et];
-          const size_t tile_lin = size_t(n0) * tiles_per_img + t_in;
+          const size_t tile_lin = size_t(n0) * p.stats_tiles_total + p.stats_tile_off + t_in;
           p.stats_partial[(tile_lin * p.cout + c_base) * 2 + et] = tot;
         }
       }

@@ -49,6 +49,11 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
   return r;
 }
 
+// affine / bias vectors hold only the real channels; padded channels behave as (1, 0)
+__device__ __forceinline__ float ld_aff(const float* p, int c, int c_valid, float dflt) {
+  return (p && c < c_valid) ? __ldg(p + c) : dflt;
+}
+
 __device__ __forceinline__ float act_fwd(float x, int act, float slope) {
   if (act == 3) return fmaxf(x, 0.f);
   if (act == 1) return x > 0.f ? x : x * slope;
@@ -160,8 +165,8 @@ template <int POOL, bool UP>
 __global__ void in_act_fwd_kernel(const __nv_bfloat16* __restrict__ raw, const float* __restrict__ mr,
                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                   __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ pool,
-                                  __nv_bfloat16* __restrict__ up, int N, int H, int W, int C, int act,
-                                  float slope) {
+                                  __nv_bfloat16* __restrict__ up, int N, int H, int W, int C, int c_valid,
+                                  int act, float slope) {
   const int CG = C >> 3;
   if (POOL == 0 && !UP) {
     const size_t total = size_t(N) * H * W * CG;
@@ -176,8 +181,8 @@ __global__ void in_act_fwd_kernel(const __nv_bfloat16* __restrict__ raw, const f
       const float* m = mr + (size_t(n) * C + c0) * 2;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float g = gamma ? __ldg(gamma + c0 + j) : 1.f;
-        const float b = beta ? __ldg(beta + c0 + j) : 0.f;
+        const float g = ld_aff(gamma, c0 + j, c_valid, 1.f);
+        const float b = ld_aff(beta, c0 + j, c_valid, 0.f);
         f[j] = act_fwd(g * (f[j] - __ldg(m + 2 * j)) * __ldg(m + 2 * j + 1) + b, act, slope);
       }
       stg16(y + pix * C + c0, pack8(f));
@@ -197,8 +202,8 @@ __global__ void in_act_fwd_kernel(const __nv_bfloat16* __restrict__ raw, const f
       const float* m = mr + (size_t(n) * C + c0) * 2;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float g = gamma ? __ldg(gamma + c0 + j) : 1.f;
-        const float b = beta ? __ldg(beta + c0 + j) : 0.f;
+        const float g = ld_aff(gamma, c0 + j, c_valid, 1.f);
+        const float b = ld_aff(beta, c0 + j, c_valid, 0.f);
         sc[j] = g * __ldg(m + 2 * j + 1);
         sh[j] = b - __ldg(m + 2 * j) * sc[j];
       }
@@ -261,7 +266,7 @@ struct InBwdArgs {
   const __nv_bfloat16* g_up;
   __nv_bfloat16* dn;
   float* red;                 // [N][C][2]
-  int N, H, W, C, act, pool_mode;
+  int N, H, W, C, c_valid, act, pool_mode;
   float slope;
 };
 
@@ -278,8 +283,8 @@ __global__ void in_bwd_reduce_kernel(const InBwdArgs a) {
   float sc[8], sh[8], mean[8], rstd[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float g = a.gamma ? a.gamma[c0 + j] : 1.f;
-    const float b = a.beta ? a.beta[c0 + j] : 0.f;
+    const float g = ld_aff(a.gamma, c0 + j, a.c_valid, 1.f);
+    const float b = ld_aff(a.beta, c0 + j, a.c_valid, 0.f);
     mean[j] = a.mr ? a.mr[(size_t(n) * a.C + c0 + j) * 2] : 0.f;
     rstd[j] = a.mr ? a.mr[(size_t(n) * a.C + c0 + j) * 2 + 1] : 1.f;
     sc[j] = g; sh[j] = b;
@@ -369,7 +374,7 @@ __global__ void in_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dn,
                                     const __nv_bfloat16* __restrict__ raw,
                                     const float* __restrict__ mr, const float* __restrict__ gamma,
                                     const float* __restrict__ red, __nv_bfloat16* __restrict__ dz,
-                                    int N, int HW, int C) {
+                                    int N, int HW, int C, int c_valid) {
   const int CG = C >> 3;
   const size_t total = size_t(N) * HW * CG;
   const float inv = 1.f / float(HW);
@@ -386,7 +391,7 @@ __global__ void in_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dn,
     const float* rd = red + (size_t(n) * C + c0) * 2;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float g = gamma ? __ldg(gamma + c0 + j) : 1.f;
+      const float g = ld_aff(gamma, c0 + j, c_valid, 1.f);
       const float rs = __ldg(m + 2 * j + 1);
       const float xh = (r[j] - __ldg(m + 2 * j)) * rs;
       d[j] = rs * g * (d[j] - __ldg(rd + 2 * j) * inv - xh * __ldg(rd + 2 * j + 1) * inv);
@@ -397,9 +402,9 @@ __global__ void in_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dn,
 
 // dgamma[c] += sum_n red[n][c][1]; dbeta[c] += sum_n red[n][c][0]
 __global__ void affine_grad_kernel(const float* __restrict__ red, float* __restrict__ dgamma,
-                                   float* __restrict__ dbeta, int N, int C) {
+                                   float* __restrict__ dbeta, int N, int C, int c_valid) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  if (c >= c_valid) return;
   float g = 0.f, b = 0.f;
   for (int n = 0; n < N; ++n) {
     b += red[(size_t(n) * C + c) * 2];
@@ -497,8 +502,8 @@ __global__ void in_bwd2_apply_kernel(const __nv_bfloat16* __restrict__ u,
                                      const float* __restrict__ mr, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, const float* __restrict__ red1,
                                      float* __restrict__ red2, __nv_bfloat16* __restrict__ adj_da,
-                                     __nv_bfloat16* __restrict__ adj_z, int HW, int C, int act,
-                                     float slope) {
+                                     __nv_bfloat16* __restrict__ adj_z, int HW, int C, int c_valid,
+                                     int act, float slope) {
   extern __shared__ float shm[];  // [PL][C]
   const int CG = C >> 3;
   const int PL = blockDim.x / CG;
@@ -516,8 +521,8 @@ __global__ void in_bwd2_apply_kernel(const __nv_bfloat16* __restrict__ u,
       const size_t k = size_t(n) * C + c0 + j;
       mean[j] = mr[k * 2];
       rstd[j] = mr[k * 2 + 1];
-      gm[j] = gamma ? gamma[c0 + j] : 1.f;
-      bt[j] = beta ? beta[c0 + j] : 0.f;
+      gm[j] = ld_aff(gamma, c0 + j, c_valid, 1.f);
+      bt[j] = ld_aff(beta, c0 + j, c_valid, 0.f);
       A[j] = gm[j] * red1[k * 2] * inv;       // mean(dxh)
       Bc[j] = gm[j] * red1[k * 2 + 1] * inv;  // mean(dxh * xhat)
       c1[j] = red2[k * 4] * inv;
@@ -558,9 +563,9 @@ __global__ void in_bwd2_apply_kernel(const __nv_bfloat16* __restrict__ u,
 
 // dgamma[c] += sum_n red2[n][c][3]
 __global__ void gamma_grad2_kernel(const float* __restrict__ red2, float* __restrict__ dgamma, int N,
-                                   int C) {
+                                   int C, int c_valid) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  if (c >= c_valid) return;
   float g = 0.f;
   for (int n = 0; n < N; ++n) g += red2[(size_t(n) * C + c) * 4 + 3];
   dgamma[c] += g;
@@ -777,7 +782,8 @@ __global__ void gp_top_kernel(const __nv_bfloat16* __restrict__ w, const __nv_bf
   }
 }
 
-// L1 mean between fp32 NCHW tensors; grad (sign * scale / numel) optional.
+// L1 mean between fp32 NCHW tensors: *loss += mean|a-b| (unscaled, as the reference logs it,
+// train.py:145-146); grad_a = sign(a-b) * scale / numel (scale = lambda_a) optional.
 __global__ void l1_loss_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t numel,
                                float scale, float* __restrict__ loss, float* __restrict__ grad_a) {
   __shared__ float sh[32];
@@ -789,7 +795,7 @@ __global__ void l1_loss_kernel(const float* __restrict__ a, const float* __restr
     if (grad_a) grad_a[i] = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * scale / float(numel);
   }
   const float tot = block_sum(acc, sh);
-  if (threadIdx.x == 0 && loss) atomicAdd(loss, tot * scale / float(numel));
+  if (threadIdx.x == 0 && loss) atomicAdd(loss, tot / float(numel));
 }
 
 // weighted L1 (or L2) mean between two bf16 tensors (feature maps), all channels valid.
@@ -959,8 +965,8 @@ int tg_in_stats_direct(const void* raw, float* mr, int N, int HW, int C, float e
 }
 
 int tg_in_act_fwd(const void* raw, const float* mr, const float* gamma, const float* beta, void* y,
-                  void* pool, int pool_mode, void* up, int N, int H, int W, int C, int act, float slope,
-                  void* stream) {
+                  void* pool, int pool_mode, void* up, int N, int H, int W, int C, int c_valid, int act,
+                  float slope, void* stream) {
   const __nv_bfloat16* r = (const __nv_bfloat16*)raw;
   __nv_bfloat16 *yy = (__nv_bfloat16*)y, *pp = (__nv_bfloat16*)pool, *uu = (__nv_bfloat16*)up;
   cudaStream_t s = TG_STREAM(stream);
@@ -969,7 +975,7 @@ int tg_in_act_fwd(const void* raw, const float* mr, const float* gamma, const fl
   const size_t work = size_t(N) * H * W * (C / 8) / (quad ? 4 : 1);
   const int g = grid_for(work, 256, 148 * 32);
   const int pm = pool ? pool_mode : 0;
-#define LAUNCH(P, U) in_act_fwd_kernel<P, U><<<g, 256, 0, s>>>(r, mr, gamma, beta, yy, pp, uu, N, H, W, C, act, slope)
+#define LAUNCH(P, U) in_act_fwd_kernel<P, U><<<g, 256, 0, s>>>(r, mr, gamma, beta, yy, pp, uu, N, H, W, C, c_valid, act, slope)
   if (pm == 0 && !up) LAUNCH(0, false);
   else if (pm == 0 && up) LAUNCH(0, true);
   else if (pm == 1 && !up) LAUNCH(1, false);
@@ -982,13 +988,13 @@ int tg_in_act_fwd(const void* raw, const float* mr, const float* gamma, const fl
 
 int tg_in_bwd_reduce(const void* raw, const void* y, const float* mr, const float* gamma,
                      const float* beta, const void* g_same, const void* g_pool, int pool_mode,
-                     const void* g_up, void* dn, float* red, int N, int H, int W, int C, int act,
-                     float slope, void* stream) {
+                     const void* g_up, void* dn, float* red, int N, int H, int W, int C, int c_valid,
+                     int act, float slope, void* stream) {
   InBwdArgs a;
   a.raw = (const __nv_bfloat16*)raw; a.y = (const __nv_bfloat16*)y; a.mr = mr; a.gamma = gamma;
   a.beta = beta; a.g_same = (const __nv_bfloat16*)g_same; a.g_pool = (const __nv_bfloat16*)g_pool;
   a.g_up = (const __nv_bfloat16*)g_up; a.dn = (__nv_bfloat16*)dn; a.red = red;
-  a.N = N; a.H = H; a.W = W; a.C = C; a.act = act; a.pool_mode = pool_mode; a.slope = slope;
+  a.N = N; a.H = H; a.W = W; a.C = C; a.c_valid = c_valid; a.act = act; a.pool_mode = pool_mode; a.slope = slope;
   const int CG = C / 8;
   const int block = CG >= 256 ? CG : 256;
   if (block > 1024) return tg_set_error("tg_in_bwd_reduce: C too large");
@@ -1004,14 +1010,14 @@ int tg_in_bwd_reduce(const void* raw, const void* y, const float* mr, const floa
 }
 
 int tg_in_bwd_apply(const void* dn, const void* raw, const float* mr, const float* gamma,
-                    const float* red, void* dz, int N, int HW, int C, void* stream) {
+                    const float* red, void* dz, int N, int HW, int C, int c_valid, void* stream) {
   in_bwd_apply_kernel<<<grid_for(size_t(N) * HW * (C / 8), 256, 148 * 32), 256, 0, TG_STREAM(stream)>>>(
-      (const __nv_bfloat16*)dn, (const __nv_bfloat16*)raw, mr, gamma, red, (__nv_bfloat16*)dz, N, HW, C);
+      (const __nv_bfloat16*)dn, (const __nv_bfloat16*)raw, mr, gamma, red, (__nv_bfloat16*)dz, N, HW, C, c_valid);
   TG_RET();
 }
 
-int tg_affine_grad(const float* red, float* dgamma, float* dbeta, int N, int C, void* stream) {
-  affine_grad_kernel<<<(C + 127) / 128, 128, 0, TG_STREAM(stream)>>>(red, dgamma, dbeta, N, C);
+int tg_affine_grad(const float* red, float* dgamma, float* dbeta, int N, int C, int c_valid, void* stream) {
+  affine_grad_kernel<<<(C + 127) / 128, 128, 0, TG_STREAM(stream)>>>(red, dgamma, dbeta, N, C, c_valid);
   TG_RET();
 }
 
@@ -1026,7 +1032,7 @@ int tg_bias_grad(const void* dz, float* db, long long rows, int C, int c_valid, 
 
 int tg_in_bwd2(const void* u, const void* raw, const void* dn, const float* mr, const float* gamma,
                const float* beta, const float* red1, float* red2, void* adj_da, void* adj_z, int N,
-               int HW, int C, int act, float slope, void* stream) {
+               int HW, int C, int c_valid, int act, float slope, void* stream) {
   const int CG = C / 8;
   const int block = CG >= 256 ? CG : 256;
   if (block > 1024) return tg_set_error("tg_in_bwd2: C too large");
@@ -1041,12 +1047,12 @@ int tg_in_bwd2(const void* u, const void* raw, const void* dn, const float* mr, 
       (const __nv_bfloat16*)u, (const __nv_bfloat16*)raw, (const __nv_bfloat16*)dn, mr, red2, HW, C);
   in_bwd2_apply_kernel<<<grid, block, size_t(PL) * C * sizeof(float), s>>>(
       (const __nv_bfloat16*)u, (const __nv_bfloat16*)raw, (const __nv_bfloat16*)dn, mr, gamma, beta, red1,
-      red2, (__nv_bfloat16*)adj_da, (__nv_bfloat16*)adj_z, HW, C, act, slope);
+      red2, (__nv_bfloat16*)adj_da, (__nv_bfloat16*)adj_z, HW, C, c_valid, act, slope);
   TG_RET();
 }
 
-int tg_gamma_grad2(const float* red2, float* dgamma, int N, int C, void* stream) {
-  gamma_grad2_kernel<<<(C + 127) / 128, 128, 0, TG_STREAM(stream)>>>(red2, dgamma, N, C);
+int tg_gamma_grad2(const float* red2, float* dgamma, int N, int C, int c_valid, void* stream) {
+  gamma_grad2_kernel<<<(C + 127) / 128, 128, 0, TG_STREAM(stream)>>>(red2, dgamma, N, C, c_valid);
   TG_RET();
 }
 

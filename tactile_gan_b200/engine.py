@@ -1,0 +1,478 @@
+"""Static execution graphs for the generators: every buffer and kernel plan is created once for a
+fixed (N, H, W); forward / backward are then straight sequences of kernel launches on the current
+CUDA stream (capturable in a CUDA graph). No autograd, no torch math ops on the hot path.
+
+Graph vocabulary
+  Act        one NHWC bf16 activation tensor + who consumes it (for the fused multi-consumer dgrad)
+  ConvUnit   conv (implicit GEMM) -> [InstanceNorm(+affine)] -> activation, with optional pooled and
+             2x-upsampled copies of the output written by the same normalise pass
+  HeadUnit   FeatureMapBlock: 1x1 conv + bias (+tanh) -> fp32 NCHW
+"""
+import torch
+
+from . import _C
+from ._C import ACT_LRELU, ACT_NONE, ACT_RELU, F, LL, ptr
+from .layers import ConvLayer, ParamStore, multi_dgrad_plan, pad64
+
+EPS_IN = 1e-5
+
+
+def bf16(*shape, device):
+    return torch.zeros(*shape, dtype=torch.bfloat16, device=device)
+
+
+class Act:
+    def __init__(self, name, buf, c_real):
+        self.name, self.buf, self.c = name, buf, c_real
+        self.consumers = []   # (ConvUnit, segment index)
+        self.grad_plans = None
+        self.grad_buf = None
+
+    @property
+    def shape(self):
+        return self.buf.shape
+
+    def build_grad(self, scratch):
+        """Plan d(self) = sum of the input-gradients of all consuming convs (one launch when all
+        consumers are stride-1: the K loop of the implicit GEMM walks the consumers)."""
+        if not self.consumers:
+            return
+        n, h, w, c = self.buf.shape
+        self.grad_buf = scratch[: n * h * w * c].view(n, h, w, c)
+        units = [(u.layer, u.dz, seg) for u, seg in self.consumers]
+        if all(l.stride == 1 for l, _, _ in units):
+            self.grad_plans = [multi_dgrad_plan(units, self.grad_buf)]
+        else:
+            assert len(units) == 1, "strided consumers are single"
+            l, dz, seg = units[0]
+            self.grad_plans = l.dgrad_plans(dz, self.grad_buf, seg)
+
+    def run_grad(self):
+        for p in self.grad_plans:
+            p.run()
+        return self.grad_buf
+
+
+class ConvUnit:
+    def __init__(self, eng, name, layer, srcs, norm, gamma=None, beta=None, act=ACT_RELU, slope=0.2, pool=0,
+                 up=False):
+        dev = eng.device
+        self.eng, self.name, self.layer, self.srcs = eng, name, layer, srcs
+        self.norm, self.gamma, self.beta, self.act, self.slope = norm, gamma, beta, act, slope
+        n, h, w, _ = srcs[0].shape
+        k, s, p = layer.kh, layer.stride, layer.pad
+        self.ho, self.wo = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+        self.n, self.c, self.c_valid = n, layer.o_pad, layer.O
+        shp = (n, self.ho, self.wo, self.c)
+        self.y = Act(name + ".y", bf16(*shp, device=dev), layer.O)
+        self.dz = bf16(*shp, device=dev)
+        self.pool_mode, self.pool, self.up = pool, None, None
+        if pool:
+            self.pool = Act(name + ".pool", bf16(n, self.ho // 2, self.wo // 2, self.c, device=dev), layer.O)
+        if up:
+            self.up = Act(name + ".up", bf16(n, self.ho * 2, self.wo * 2, self.c, device=dev), layer.O)
+        for i, t in enumerate(srcs):
+            t.consumers.append((self, i))
+        self.raw = bf16(*shp, device=dev) if norm else None
+        if norm:
+            _, _, _, self.tpi = _C.conv_query_tiles(n, self.ho, self.wo, True)
+            self.partial = torch.zeros(n, self.tpi, self.c, 2, device=dev)
+            self.mr = torch.zeros(n, self.c, 2, device=dev)
+            self.red = torch.zeros(n, self.c, 2, device=dev)
+        eng.units.append(self)
+
+    def build(self, backward):
+        srcs = [t.buf for t in self.srcs]
+        if self.norm:
+            self.fwd_plan = self.layer.fwd_plan(srcs, self.raw, stats_partial=self.partial)
+        else:
+            self.fwd_plan = self.layer.fwd_plan(srcs, self.y.buf, act=self.act, slope=self.slope)
+        if backward:
+            eng = self.eng
+            self.wgrad_plan = self.layer.wgrad_plan(srcs, self.dz)
+            self.y.build_grad(eng.g_scratch)
+            if self.pool:
+                self.pool.build_grad(eng.gp_scratch)
+            if self.up:
+                self.up.build_grad(eng.gu_scratch)
+
+    def _aff(self):
+        g = self.gamma.detach() if self.gamma is not None else None
+        b = self.beta.detach() if self.beta is not None else None
+        return ptr(g), ptr(b)
+
+    # ---- forward
+    def forward(self):
+        self.fwd_plan.run()
+        if self.norm:
+            n, ho, wo, c = self.n, self.ho, self.wo, self.c
+            g, b = self._aff()
+            _C.call("in_finalize", ptr(self.partial), ptr(self.mr), n, self.tpi, c, ho * wo, F(EPS_IN))
+            _C.call("in_act_fwd", ptr(self.raw), ptr(self.mr), g, b, ptr(self.y.buf),
+                    ptr(self.pool.buf if self.pool else None), self.pool_mode,
+                    ptr(self.up.buf if self.up else None), n, ho, wo, c, self.c_valid, self.act, F(self.slope))
+
+    # ---- backward. The gradient of y = same-res consumers (+ explicit extra) + pooled copy + upsampled copy.
+    def backward(self, g_extra=None, wgrad=True, keep_dn=False):
+        eng = self.eng
+        dn = self.dn_keep if (keep_dn and self.norm) else eng.dn_scratch
+        n, ho, wo, c = self.n, self.ho, self.wo, self.c
+        g_same = self.y.run_grad() if self.y.consumers else None
+        if g_extra is not None:
+            assert g_same is None, "explicit output gradient only for units without conv consumers"
+            g_same = g_extra
+        g_pool = self.pool.run_grad() if (self.pool and self.pool.consumers) else None
+        g_up = self.up.run_grad() if (self.up and self.up.consumers) else None
+        g, b = self._aff()
+        if self.norm:
+            self.red.zero_()
+            _C.call("in_bwd_reduce", ptr(self.raw), ptr(self.y.buf), ptr(self.mr), g, b, ptr(g_same), ptr(g_pool),
+                    self.pool_mode, ptr(g_up), ptr(dn), ptr(self.red), n, ho, wo, c, self.c_valid,
+                    self.act, F(self.slope))
+            _C.call("in_bwd_apply", ptr(dn), ptr(self.raw), ptr(self.mr), g, ptr(self.red),
+                    ptr(self.dz), n, ho * wo, c, self.c_valid)
+            if wgrad and self.gamma is not None:
+                _C.call("affine_grad", ptr(self.red), ptr(eng.store.grad_of(self.gamma)),
+                        ptr(eng.store.grad_of(self.beta)), n, c, self.c_valid)
+        else:
+            _C.call("in_bwd_reduce", None, ptr(self.y.buf), None, None, None, ptr(g_same), ptr(g_pool),
+                    self.pool_mode, ptr(g_up), ptr(self.dz), None, n, ho, wo, c, self.c_valid, self.act,
+                    F(self.slope))
+        if wgrad:
+            if self.layer.bias is not None:
+                _C.call("bias_grad", ptr(self.dz), ptr(self.layer.bias_grad), LL(n * ho * wo), c, self.c_valid)
+            self.wgrad_plan.run()
+
+
+class HeadUnit:
+    """1x1 conv + bias (+tanh) on a 64-channel (padded) input -> fp32 NCHW output."""
+
+    def __init__(self, eng, name, weight, bias, src, use_tanh):
+        self.eng, self.src, self.weight, self.bias, self.use_tanh = eng, src, weight, bias, use_tanh
+        n, h, w, c = src.shape
+        self.co, self.ci = weight.shape[0], weight.shape[1]
+        assert c == 64 and self.co <= 4, "head kernel expects <= 64 input and <= 4 output channels"
+        self.n, self.hw = n, h * w
+        self.out = torch.zeros(n, self.co, h, w, device=eng.device)
+        self.dx = bf16(n, h, w, c, device=eng.device)
+        self.wpad = torch.zeros(self.co, 64, device=eng.device)     # fp32 [co][64]
+        self.dwpad = torch.zeros(self.co, 64, device=eng.device)
+
+    def forward(self):
+        self.wpad[:, :self.ci].copy_(self.weight.detach().view(self.co, self.ci))
+        _C.call("fmap_fwd", ptr(self.src.buf), ptr(self.wpad), ptr(self.bias.detach()), ptr(self.out), self.n,
+                self.hw, 64, self.co, int(self.use_tanh))
+        return self.out
+
+    def backward(self, g1, g2=None, wgrad=True):
+        st = self.eng.store
+        self.dwpad.zero_()
+        _C.call("fmap_bwd", ptr(self.src.buf), ptr(self.wpad), ptr(self.out), ptr(g1), ptr(g2), ptr(self.dx),
+                ptr(self.dwpad), ptr(st.grad_of(self.bias)), self.n, self.hw, 64, self.co, int(self.use_tanh))
+        if wgrad:
+            st.grad_of(self.weight).view(self.co, self.ci).add_(self.dwpad[:, :self.ci])
+        return self.dx
+
+
+class GraphEngine:
+    """Common machinery: parameter store, units in execution order, scratch buffers."""
+
+    def __init__(self, module, n, h, w, backward=True):
+        self.module = module
+        self.device = next(module.parameters()).device
+        if self.device.type != "cuda":
+            raise _C.TgError("the tactile-gan hot path only exists on CUDA (sm_100a); there is no CPU fallback")
+        self.n, self.h, self.w = n, h, w
+        self.with_backward = backward
+        self.store = getattr(module, "_tg_store", None)
+        self.own_store = self.store is None
+        if self.own_store:
+            self.store = ParamStore(module, self.device)
+        self.units = []
+        self.layers = {}
+
+    def conv_layer(self, name, conv, in_split, kind="conv"):
+        """One ConvLayer per nn.Conv2d, shared by every engine built on the same module."""
+        cache = self.store.layer_cache
+        if name not in cache:
+            l = ConvLayer(name, conv.weight, conv.bias, kind, conv.stride[0], conv.padding[0], in_split,
+                          self.device)
+            self.store.register_conv(l)
+            cache[name] = l
+        return cache[name]
+
+    def finish(self):
+        if self.own_store:
+            self.store.finalize()
+            self.module._tg_store = self.store
+        cu = [u for u in self.units if isinstance(u, ConvUnit)]
+        if self.with_backward:
+            mx = max(u.dz.numel() for u in cu)
+            mx_up = max([u.up.buf.numel() for u in cu if u.up] + [8])
+            dev = self.device
+            self.dn_scratch = bf16(mx, device=dev)
+            self.g_scratch = bf16(mx, device=dev)
+            self.gp_scratch = bf16(mx, device=dev)
+            self.gu_scratch = bf16(mx_up, device=dev)
+        for u in cu:
+            u.build(self.with_backward)
+
+
+def _block_params(block):
+    """(conv0, norm0, conv1, norm1) of a reference-style Sequential [conv, IN, act, conv, IN, act]."""
+    return block[0], block[1], block[3], block[4]
+
+
+def _affine(norm):
+    return (norm.weight, norm.bias) if getattr(norm, "weight", None) is not None else (None, None)
+
+
+class UNetPPEngine(GraphEngine):
+    """UNet++ (reference generators/UNet_plusplus.py:37-86): nested grid X(i,j) of ConvBlocks.
+    torch.cat and nn.Upsample never materialise a concat: each operand is a separate K-loop source;
+    the 2x nearest-upsampled and 2x2 average-pooled copies are written by the producer's normalise pass."""
+
+    def __init__(self, module, n, h, w, backward=True):
+        super().__init__(module, n, h, w, backward)
+        dev = self.device
+        nf = module.conv0_0.layer[0].out_channels
+        cin = module.conv0_0.layer[0].in_channels
+        if h % 16 or w % 16:
+            raise ValueError("UNet++ needs H, W divisible by 16")
+        self.x_in = Act("input", bf16(n, h, w, pad64(cin), device=dev), cin)
+        self.cin = cin
+        ch = [nf, nf * 2, nf * 4, nf * 8, nf * 16]
+        X = {}
+        order = [(i, 0) for i in range(5)] + [(i, j) for j in range(1, 5) for i in range(0, 5 - j)]
+        self.order = order
+        for (i, j) in order:
+            blk = getattr(module, f"conv{i}_{j}").layer
+            c0, n0, c1, n1 = _block_params(blk)
+            if j == 0:
+                srcs = [self.x_in] if i == 0 else [X[i - 1, 0][1].pool]
+            else:
+                srcs = [X[i, k][1].y for k in range(j)] + [X[i + 1, j - 1][1].up]
+            split = [t.c for t in srcs]
+            l0 = self.conv_layer(f"conv{i}_{j}.0", c0, split)
+            l1 = self.conv_layer(f"conv{i}_{j}.3", c1, [ch[i]])
+            g0, b0 = _affine(n0)
+            g1, b1 = _affine(n1)
+            relu = getattr(module, "_tg_debug_act", ACT_RELU)   # bring-up only: linearised network
+            u0 = ConvUnit(self, f"x{i}{j}a", l0, srcs, True, g0, b0, relu)
+            pool = 1 if (j == 0 and i < 4) else 0            # AvgPool2d feeds X(i+1,0)
+            up = i >= 1                                       # Upsample feeds X(i-1,j+1)
+            u1 = ConvUnit(self, f"x{i}{j}b", l1, [u0.y], True, g1, b1, relu, pool=pool, up=up)
+            X[i, j] = (u0, u1)
+        self.X = X
+        self.head = HeadUnit(self, "downfeature", module.downfeature.conv.weight, module.downfeature.conv.bias,
+                             X[0, 4][1].y, module.downfeature.activation)
+        self.finish()
+
+    def forward(self, x):
+        """x: fp32 NCHW on the engine's device -> fp32 NCHW (tensor owned by the engine)."""
+        assert x.shape == (self.n, self.cin, self.h, self.w) and x.dtype == torch.float32 and x.is_contiguous()
+        self.store.refresh()
+        _C.call("pack_nchw", ptr(x), None, None, None, ptr(self.x_in.buf), self.n, self.h * self.w, self.cin,
+                self.x_in.buf.shape[3], 0)
+        for (i, j) in self.order:
+            u0, u1 = self.X[i, j]
+            u0.forward()
+            u1.forward()
+        return self.head.forward()
+
+    def backward(self, g1, g2=None):
+        """g1 (+ g2): gradients w.r.t. the fp32 NCHW output. Accumulates into the store's grad arena."""
+        dx = self.head.backward(g1, g2)
+        for (i, j) in reversed(self.order):
+            u0, u1 = self.X[i, j]
+            u1.backward(g_extra=dx if (i, j) == (0, 4) else None)
+            u0.backward()
+
+
+def build_generator_engine(kind, module, n, h, w, backward=True):
+    kind = kind.lower()
+    if kind == "unet++":
+        return UNetPPEngine(module, n, h, w, backward)
+    raise NameError(f"{kind} has no engine")
+
+
+# ======================================================================================= discriminator
+class PatchDInstance(GraphEngine):
+    """PatchDiscriminator (reference discriminators/PatchDiscriminator.py:5-43) for a fixed batch:
+    cat(A,B) -> conv3x3 s2 +bias -> LReLU -> [conv3x3 -> IN(affine) -> LReLU] x3 (strides 2,1,1)
+    -> conv3x3 +bias -> (Sigmoid). `second_order` adds the buffers / plans of the gradient-penalty
+    double backward (reference util.py:72-97)."""
+
+    def __init__(self, module, n, h, w, backward=True, second_order=False):
+        super().__init__(module, n, h, w, backward)
+        dev = self.device
+        m = module.model
+        convs = [m[0], m[2], m[5], m[8], m[11]]
+        norms = [None, m[3], m[6], m[9], None]
+        self.c_in = convs[0].in_channels
+        self.has_sigmoid = len(m) > 12
+        self.x0 = Act("x0", bf16(n, h, w, pad64(self.c_in), device=dev), self.c_in)
+        self.u = []
+        src = self.x0
+        for k, (conv, norm) in enumerate(zip(convs, norms)):
+            layer = self.conv_layer(f"model.{[0, 2, 5, 8, 11][k]}", conv, [conv.in_channels])
+            if norm is not None:
+                g, b = _affine(norm)
+                unit = ConvUnit(self, f"d{k + 1}", layer, [src], True, g, b, ACT_LRELU, 0.2)
+            elif k == 0:
+                unit = ConvUnit(self, "d1", layer, [src], False, act=ACT_LRELU, slope=0.2)
+            else:
+                unit = ConvUnit(self, "d5", layer, [src], False, act=_C.ACT_SIGMOID if self.has_sigmoid else ACT_NONE)
+            self.u.append(unit)
+            src = unit.y
+        self.second_order = second_order
+        if second_order:
+            for unit in self.u[1:4]:
+                unit.dn_keep = bf16(*unit.dz.shape, device=dev)
+        self.finish()
+        self.pred = self.u[4].y.buf                      # [n, h5, w5, 64], channel 0 meaningful
+        self.hw5 = self.u[4].ho * self.u[4].wo
+        if backward:
+            self.dx0 = bf16(*self.x0.buf.shape, device=dev)
+            self.x0.build_grad(self.dx0.view(-1))
+        if second_order:
+            self._build_second_order()
+
+    # ---- forward / first-order backward
+    def pack_input(self, img_a, img_b, wa=None, b2=None, wb=None, n0=0, n=None):
+        """x0[n0:n0+n, ..., :ca] = A ; x0[n0:n0+n, ..., ca:ca+cb] = wa*B (+ wb*B2)  (fp32 NCHW sources;
+        wa / wb are per-sample weights, e.g. the gradient-penalty interpolation of util.py:79-83)."""
+        n = self.n if n is None else n
+        hw, c = self.h * self.w, self.x0.buf.shape[3]
+        dst = self.x0.buf[n0:n0 + n]
+        ca = img_a.shape[1]
+        _pack(img_a, None, None, None, dst, n, hw, c, 0)
+        _pack(img_b, b2, wa, wb, dst, n, hw, c, ca)
+
+    def forward(self):
+        self.store.refresh()
+        for unit in self.u:
+            unit.forward()
+        return self.pred
+
+    def backward(self, wgrad=True, input_grad=False):
+        """Expects d(loss)/d(z5) in self.u[4].dz (written by the loss kernels)."""
+        u5 = self.u[4]
+        if wgrad:
+            _C.call("bias_grad", ptr(u5.dz), ptr(u5.layer.bias_grad), LL(u5.n * u5.ho * u5.wo), u5.c, u5.c_valid)
+            u5.wgrad_plan.run()
+        for unit in reversed(self.u[:4]):
+            unit.backward(wgrad=wgrad)
+        if input_grad:
+            self.x0.run_grad()
+        return self.dx0
+
+    def features(self):
+        return [unit.y for unit in self.u[:4]]
+
+    # ---- gradient penalty: second-order sweep
+    def _build_second_order(self):
+        dev = self.device
+        u1, u2, u3, u4, u5 = self.u
+        L = [x.layer for x in self.u]
+        so = self.so = {}
+        so["seed"] = bf16(*self.x0.buf.shape, device=dev)
+        so["nsq"] = torch.zeros(self.n, device=dev)
+        so["coef"] = torch.zeros(self.n, device=dev)
+        so["U"] = [bf16(*x.dz.shape, device=dev) for x in self.u]      # adj(dz_k) (U[4] = adj(dz5))
+        so["V"] = [bf16(*x.dz.shape, device=dev) for x in self.u[:4]]  # adj(da_k)
+        so["INJ"] = [None] + [bf16(*x.dz.shape, device=dev) for x in self.u[1:4]]
+        so["red2"] = [None] + [torch.zeros(x.n, x.c, 4, device=dev) for x in self.u[1:4]]
+        so["T5"] = bf16(*u5.dz.shape, device=dev)
+        so["E"] = [bf16(*x.dz.shape, device=dev) for x in self.u[:4]]  # adj(a_k) in the downward sweep
+        so["Z"] = [bf16(*x.dz.shape, device=dev) for x in self.u[:4]]  # adj(z_k) total
+        so["red_dn"] = [None] + [torch.zeros(x.n, x.c, 2, device=dev) for x in self.u[1:4]]
+        # upward: U_k = conv_k(no bias)(V_{k-1}), V_0 = seed ; wgrad(P = V_{k-1}, Q = dz_k)
+        ins = [so["seed"]] + so["V"]
+        so["up_conv"] = [L[k].fwd_plan([ins[k]], so["U"][k], use_bias=False) for k in range(5)]
+        so["up_wgrad"] = [L[k].wgrad_plan([ins[k]], self.u[k].dz) for k in range(5)]
+        # downward: wgrad(P = a_{k-1}, Q = Z_k / T5), E_{k-1} = dgrad(Z_k)
+        acts_in = [self.x0.buf] + [x.y.buf for x in self.u[:4]]
+        outs = so["Z"] + [so["T5"]]
+        so["dn_wgrad"] = [L[k].wgrad_plan([acts_in[k]], outs[k]) for k in range(5)]
+        so["dn_dgrad"] = [None] + [L[k].dgrad_plans(outs[k], so["E"][k - 1]) for k in range(1, 5)]
+
+    def gp_first_backward(self):
+        """d(sum pred)/d(x0): seeds dz5 = sigmoid'(z5) and runs the activation-gradient chain only."""
+        u5 = self.u[4]
+        _C.call("gp_first_seed", ptr(self.pred), int(self.has_sigmoid), 0, self.n, self.hw5, u5.c, ptr(u5.dz))
+        for unit in reversed(self.u[:4]):
+            unit.backward(wgrad=False, keep_dn=True)
+        self.x0.run_grad()
+        return self.dx0
+
+    def gp_penalty(self, c_off, cj, lambda_gp, constant, loss_slot):
+        """penalty value -> *loss_slot; builds the second-order seed coef_n * (g_n + 1e-16)."""
+        so = self.so
+        n, hw, c = self.n, self.h * self.w, self.x0.buf.shape[3]
+        so["nsq"].zero_()
+        _C.call("gp_normsq", ptr(self.dx0), n, hw, c, c_off, cj, ptr(so["nsq"]))
+        _C.call("gp_finish", ptr(so["nsq"]), n, F(lambda_gp), F(constant), ptr(loss_slot), ptr(so["coef"]))
+        _C.call("gp_seed", ptr(self.dx0), ptr(so["coef"]), n, hw, c, c_off, cj, ptr(so["seed"]))
+
+    def gp_second_backward(self):
+        """Backward of the penalty through the first backward pass: accumulates weight gradients."""
+        so, st = self.so, self.store
+        u = self.u
+        # ---------------- upward sweep through the (linearised) backward graph
+        for k in range(5):
+            so["up_conv"][k].run()           # U_k = adj(dz_k)
+            so["up_wgrad"][k].run()          # from dX_{k-1} = W_k^T dz_k
+            if k == 0:
+                _C.call("act_bwd", ptr(so["U"][0]), ptr(u[0].y.buf), ptr(so["V"][0]), LL(so["U"][0].numel()),
+                        ACT_LRELU, F(0.2))
+            elif k < 4:
+                x = u[k]
+                g, b = x._aff()
+                so["red2"][k].zero_()
+                _C.call("in_bwd2", ptr(so["U"][k]), ptr(x.raw), ptr(x.dn_keep), ptr(x.mr), g, b, ptr(x.red),
+                        ptr(so["red2"][k]), ptr(so["V"][k]), ptr(so["INJ"][k]), x.n, x.ho * x.wo, x.c, x.c_valid,
+                        ACT_LRELU, F(0.2))
+                if x.gamma is not None:
+                    _C.call("gamma_grad2", ptr(so["red2"][k]), ptr(st.grad_of(x.gamma)), x.n, x.c, x.c_valid)
+        u5 = u[4]
+        _C.call("gp_top", ptr(so["U"][4]), ptr(self.pred), int(self.has_sigmoid), LL(u5.n * self.hw5), u5.c,
+                ptr(so["T5"]))
+        # ---------------- downward sweep: ordinary backward with the injected adj(z_k)
+        _C.call("bias_grad", ptr(so["T5"]), ptr(u5.layer.bias_grad), LL(u5.n * self.hw5), u5.c, u5.c_valid)
+        so["dn_wgrad"][4].run()
+        for k in range(4, 0, -1):
+            for p in so["dn_dgrad"][k]:
+                p.run()                       # E_{k-1} = adj(a_{k-1})
+            x = u[k - 1]
+            e, z = so["E"][k - 1], so["Z"][k - 1]
+            if k - 1 >= 1:
+                g, b = x._aff()
+                red = so["red_dn"][k - 1]
+                red.zero_()
+                _C.call("in_bwd_reduce", ptr(x.raw), ptr(x.y.buf), ptr(x.mr), g, b, ptr(e), None, 0, None,
+                        ptr(self.dn_scratch), ptr(red), x.n, x.ho, x.wo, x.c, x.c_valid, ACT_LRELU, F(0.2))
+                _C.call("in_bwd_apply", ptr(self.dn_scratch), ptr(x.raw), ptr(x.mr), g, ptr(red), ptr(z), x.n,
+                        x.ho * x.wo, x.c, x.c_valid)
+                _C.call("add", ptr(z), ptr(so["INJ"][k - 1]), ptr(z), LL(z.numel()))
+                if x.gamma is not None:
+                    _C.call("affine_grad", ptr(red), ptr(st.grad_of(x.gamma)), ptr(st.grad_of(x.beta)), x.n, x.c,
+                            x.c_valid)
+            else:
+                _C.call("act_bwd", ptr(e), ptr(x.y.buf), ptr(z), LL(z.numel()), ACT_LRELU, F(0.2))
+                _C.call("bias_grad", ptr(z), ptr(x.layer.bias_grad), LL(x.n * x.ho * x.wo), x.c, x.c_valid)
+            so["dn_wgrad"][k - 1].run()
+
+
+def _pack(a, b, wa, wb, out, n, hw, c, c_off):
+    """fp32 NCHW -> bf16 NHWC channel slice, split at 8-channel group boundaries."""
+    cj_total = a.shape[1]
+    j = 0
+    while j < cj_total:
+        room = 8 - ((c_off + j) & 7)
+        cj = min(room, cj_total - j)
+        if cj == cj_total and j == 0:
+            _C.call("pack_nchw", ptr(a), ptr(b), ptr(wa), ptr(wb), ptr(out), n, hw, cj, c, c_off)
+        else:
+            raise _C.TgError("channel slices that straddle an 8-channel group are not supported yet")
+        j += cj

@@ -78,7 +78,6 @@ class ConvLayer:
         bf = dict(dtype=torch.bfloat16, device=device)
         self.pack_fwd = torch.zeros(self.taps, self.o_pad, self.i_pad, **bf)
         self.pack_bwd = torch.zeros(self.taps, self.i_pad, self.o_pad, **bf)
-        self.bias_pad = None  # fp32 [o_pad] view into the store's gradient-free bias buffer
         self.grad = None      # fp32 [taps][o_pad][i_pad] (conv) / [taps][i_pad][o_pad] (convT)
         self.bias_grad = None
 
@@ -88,8 +87,8 @@ class ConvLayer:
         assert self.kind == "conv" and len(srcs) == len(self.in_split)
         s = [dict(act=t, wgt=self.pack_fwd, k_off=o) for t, o in zip(srcs, self.k_off)]
         return _C.conv_plan(s, out, conv_taps(self.kh, self.kw, self.pad), stride=self.stride,
-                            bias=self.bias_pad if use_bias else None, stats_partial=stats_partial,
-                            act=act, slope=slope)
+                            bias=self.bias.detach() if (use_bias and self.bias is not None) else None,
+                            stats_partial=stats_partial, act=act, slope=slope)
 
     def wgrad_plan(self, srcs, dy):
         assert self.kind == "conv"
@@ -142,7 +141,7 @@ class ParamStore:
         self.index = {id(p): i for i, p in enumerate(self.params)}
         self.conv_of = {}      # param index -> ConvLayer
         self.bias_of = {}      # param index -> ConvLayer whose bias this is
-        self.rows = None
+        self.layer_cache = {}  # name -> ConvLayer (shared by every engine built on this module)
         self.table = None
         self.step_count = 0
 
@@ -184,13 +183,6 @@ class ParamStore:
         self.exp_avg_sq = torch.zeros(po[-1], dtype=torch.float32, device=dev)
         self.m_views = [self.exp_avg[po[i]:po[i] + pn[i]].view_as(p) for i, p in enumerate(self.params)]
         self.v_views = [self.exp_avg_sq[po[i]:po[i] + pn[i]].view_as(p) for i, p in enumerate(self.params)]
-        # conv biases are consumed padded to o_pad (epilogue reads bias[c] for padded c too)
-        nb = sum(l.o_pad for l in self.bias_of.values())
-        self.bias_arena = torch.zeros(max(nb, 1), dtype=torch.float32, device=dev)
-        o = 0
-        for i, l in self.bias_of.items():
-            l.bias_pad = self.bias_arena[o:o + l.o_pad]
-            o += l.o_pad
         self._ptrs = None
         self._versions = None
         self.max_numel = max(pn)
@@ -244,8 +236,10 @@ class ParamStore:
     def repack(self):
         _C.call("adam_step", _C.ptr(self.table_nograd), len(self.params), _C.LL(self.max_numel),
                 _C.F(0.0), _C.F(0.0), _C.F(0.0), _C.F(1.0), 1, _C.F(1.0))
-        for i, l in self.bias_of.items():
-            l.bias_pad[:l.O].copy_(self.params[i].detach())
+
+    def grad_of(self, param):
+        """fp32 gradient buffer of a non-conv parameter (bias / affine / head), torch layout."""
+        return self.grad_views[self.index[id(param)]]
 
     def zero_grad(self):
         self.grad_arena.zero_()
@@ -254,8 +248,6 @@ class ParamStore:
         self.step_count += 1
         _C.call("adam_step", _C.ptr(self.table), len(self.params), _C.LL(self.max_numel), _C.F(lr),
                 _C.F(beta1), _C.F(beta2), _C.F(eps), self.step_count, _C.F(grad_scale))
-        for i, l in self.bias_of.items():
-            l.bias_pad[:l.O].copy_(self.params[i].detach())
 
     # ---- gradients in torch layout (tests / autograd bridge) ---------------------------------
     def grad_as_torch(self, i):

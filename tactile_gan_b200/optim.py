@@ -1,0 +1,58 @@
+"""torch.optim.Adam-compatible front end of the fused Adam + weight re-pack kernel (tg_adam_step).
+
+Replaces `torch.optim.Adam(net.parameters(), lr, betas=(beta1, 0.99))` (reference train.py:56-57): same
+param_groups / state_dict layout (state[i] = {step, exp_avg, exp_avg_sq}), so lr schedulers and
+checkpoints interchange with the reference in both directions. exp_avg / exp_avg_sq are views into the
+ParamStore's flat moment arenas, which is what the kernel updates."""
+import torch
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, module, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        params = list(module.parameters())
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False, maximize=False, foreach=None,
+                        capturable=False, differentiable=False, fused=None, decoupled_weight_decay=False)
+        super().__init__(params, defaults)
+        self.module = module
+
+    @property
+    def store(self):
+        st = getattr(self.module, "_tg_store", None)
+        if st is None:
+            raise RuntimeError("no engine has been built for this module yet (run a forward / TrainStep first)")
+        return st
+
+    def _bind_state(self):
+        """Expose the arenas through the standard Optimizer.state mapping."""
+        st = self.store
+        for i, p in enumerate(st.params):
+            s = self.state[p]
+            if "exp_avg" not in s or s["exp_avg"].data_ptr() != st.m_views[i].data_ptr():
+                if "exp_avg" in s:   # loaded from a checkpoint: move into the arenas
+                    st.m_views[i].copy_(s["exp_avg"])
+                    st.v_views[i].copy_(s["exp_avg_sq"])
+                    st.step_count = int(s["step"]) if "step" in s else st.step_count
+                s["exp_avg"], s["exp_avg_sq"] = st.m_views[i], st.v_views[i]
+            s["step"] = torch.tensor(float(st.step_count))
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale=1.0):
+        """Consumes the gradients the engines accumulated in the store's arena (not p.grad)."""
+        g = self.param_groups[0]
+        self.store.adam_step(g["lr"], g["betas"][0], g["betas"][1], g["eps"], grad_scale)
+
+    def zero_grad(self, set_to_none=True):
+        st = getattr(self.module, "_tg_store", None)
+        if st is not None:
+            st.zero_grad()
+        super().zero_grad(set_to_none)
+
+    def state_dict(self):
+        if getattr(self.module, "_tg_store", None) is not None and self.store.step_count > 0:
+            self._bind_state()
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        if getattr(self.module, "_tg_store", None) is not None:
+            self._bind_state()

@@ -1,0 +1,154 @@
+"""The fused G+D training iteration (reference train.py:99-168) as one static launch sequence.
+
+Everything between "inputs are in HBM" and "weights are updated" is a kernel of
+libtactile_gan_b200.so issued on the current CUDA stream: no autograd graph, no host syncs, five loss
+scalars accumulated in one device buffer. Differences from the reference that do not change results:
+  * the gradient-penalty interpolate is built from fake_B without a graph to G, so the reference's
+    wasted generator backward inside the D step (train.py:126,134 -> util.py:83) is not paid;
+  * fake/real discriminator passes of the D step run as one 2B batch (InstanceNorm is per sample);
+  * the version-2 perceptual term (pan_loss of detached D features, train.py:155-162) is evaluated
+    for logging only -- it has no gradient in the reference either.
+Data parallel: one process per GPU; the flat fp32 gradient arenas of D and G are all-reduced (sum) with
+NCCL and scaled by 1/world inside the fused Adam kernel.
+"""
+import torch
+
+from . import _C
+from ._C import F, LL, ptr
+from .engine import PatchDInstance, build_generator_engine
+
+SLOT = {"loss_D": 0, "gp": 1, "G_GAN": 2, "L1": 3, "per": 4}
+
+
+class TrainStep:
+    def __init__(self, netG, netD, batch, height, width, loss="ls", version=2, lambda_a=1.0, lambda_gp=0.01,
+                 lambda_per=1.0, w_per=(0, .1, .3, .6), lr=1e-3, beta1=0.9, label_smoothing=True, gen_kind=None,
+                 process_group=None):
+        self.netG, self.netD = netG, netD
+        self.B, self.H, self.W = batch, height, width
+        self.loss, self.version = loss, version
+        self.mode = _C.GAN_MODES[loss]
+        self.lambda_a, self.lambda_gp, self.lambda_per = float(lambda_a), float(lambda_gp), float(lambda_per)
+        self.w_per = [float(v) for v in w_per]
+        self.lr, self.beta1 = float(lr), float(beta1)
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if (
+            torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
+        dev = next(netG.parameters()).device
+        self.device = dev
+        kind = gen_kind or netG.engine_kind
+        self.G = netG._engine(batch, height, width, True) if hasattr(netG, "_engine") else \
+            build_generator_engine(kind, netG, batch, height, width, True)
+        self.DA = PatchDInstance(netD, 2 * batch, height, width, backward=True)
+        self.S1 = PatchDInstance(netD, batch, height, width, backward=True, second_order=True)
+        self.S2 = PatchDInstance(netD, batch, height, width, backward=False)
+        self.c_in = netD.model[0].in_channels
+        self.c_a = self.G.cin
+        self.c_b = self.c_in - self.c_a
+        u5 = self.S1.u[4]
+        self.h5, self.w5, self.c5 = u5.ho, u5.wo, u5.c
+        self.losses = torch.zeros(8, device=dev)
+        self.alpha = torch.zeros(batch, device=dev)
+        self.one_minus_alpha = torch.zeros(batch, device=dev)
+        self.gan_grad = torch.zeros(batch, self.c_b, height, width, device=dev)
+        self.l1_grad = torch.zeros(batch, self.c_b, height, width, device=dev)
+        self.real_label = None
+        self.label_smoothing = label_smoothing
+        self.fake_B = None
+
+    # ------------------------------------------------------------------ labels / alpha (host RNG parity)
+    def ensure_label(self, generator=None):
+        """GANLoss.get_target_tensor (generators/generators.py:52-63): one CPU-RNG draw, cached."""
+        if self.real_label is None and self.label_smoothing and self.loss in ("ls", "ce"):
+            shape = (self.B, 1, self.h5, self.w5)
+            lab = torch.clamp(torch.normal(1.0, 0.02, size=shape, generator=generator), 0, 1)
+            self.real_label = lab.to(self.device).contiguous()
+        return self.real_label
+
+    def set_label(self, label):
+        self.real_label = None if label is None else label.to(self.device).float().contiguous()
+
+    def draw_alpha(self, alpha=None):
+        """util.py:79-81: alpha ~ U[0,1) on the CUDA generator; version 2 maps it to [0.5, 1)."""
+        if alpha is None:
+            alpha = torch.rand(self.B, 1, device=self.device)
+        a = alpha.to(self.device).float().view(-1)
+        if self.version == 2:
+            a = (a + 1) / 2
+        self.alpha.copy_(a)
+        self.one_minus_alpha.copy_(1 - a)
+
+    def _gan_loss(self, inst, n0, n1, target_is_real, for_disc, scale, slot, write_dz=True):
+        u5 = inst.u[4]
+        lab = self.real_label if (target_is_real and self.loss in ("ls", "ce")) else None
+        const = 1.0 if target_is_real else 0.0
+        _C.call("gan_loss", ptr(inst.pred), ptr(lab), F(const), self.mode, int(target_is_real), int(for_disc),
+                int(inst.has_sigmoid), F(scale), n0, n1, self.h5 * self.w5, u5.c, ptr(self.losses[slot:slot + 1]),
+                ptr(u5.dz) if write_dz else None)
+
+    def _allreduce(self, store):
+        if self.world > 1:
+            torch.distributed.all_reduce(store.grad_arena, group=self.pg)
+
+    # ------------------------------------------------------------------ the iteration
+    def step(self, real_A, real_B, regularize=True, alpha=None):
+        """real_A (B,in,H,W) in [-1,1], real_B (B,out,H,W) in [0,1]: fp32, contiguous, on the device.
+        Returns the device tensor of loss slots (see SLOT); reading it is the caller's only sync."""
+        B, HW = self.B, self.H * self.W
+        G, DA, S1, S2 = self.G, self.DA, self.S1, self.S2
+        gs, ds = G.store, DA.store
+        self.ensure_label()
+        self.losses.zero_()
+        regularize = bool(regularize) and self.lambda_gp != 0
+        if regularize:
+            self.draw_alpha(alpha)
+        # ---- generator forward (train.py:104)
+        fake = G.forward(real_A)
+        self.fake_B = fake
+        # ---- D step (train.py:107-135)
+        ds.zero_grad()
+        DA.pack_input(real_A, fake, n0=0, n=B)
+        DA.pack_input(real_A, real_B, n0=B, n=B)
+        DA.forward()
+        DA.u[4].dz.zero_()
+        self._gan_loss(DA, 0, B, False, True, 0.5, SLOT["loss_D"])
+        self._gan_loss(DA, B, 2 * B, True, True, 0.5, SLOT["loss_D"])
+        DA.backward(wgrad=True)
+        if regularize:
+            S1.pack_input(real_A, real_B, wa=self.alpha, b2=fake, wb=self.one_minus_alpha)
+            S1.forward()
+            S1.gp_first_backward()
+            S1.gp_penalty(self.c_a, self.c_b, self.lambda_gp, 1.0, self.losses[1:2])
+            S1.gp_second_backward()
+        self._allreduce(ds)
+        ds.adam_step(self.lr, self.beta1, grad_scale=1.0 / self.world)
+        # ---- G step (train.py:138-168), discriminator already updated
+        gs.zero_grad()
+        S1.pack_input(real_A, fake)
+        S1.forward()
+        S1.u[4].dz.zero_()
+        self._gan_loss(S1, 0, B, True, False, 1.0, SLOT["G_GAN"])
+        dx0 = S1.backward(wgrad=False, input_grad=True)
+        _C.call("unpack_nhwc", ptr(dx0), ptr(self.gan_grad), B, HW, dx0.shape[3], self.c_a, self.c_b, F(1.0))
+        _C.call("l1_loss", ptr(fake), ptr(real_B), LL(fake.numel()), F(self.lambda_a),
+                ptr(self.losses[3:4]), ptr(self.l1_grad))
+        if self.lambda_per != 0 and self.version == 2:
+            S2.pack_input(real_A, real_B)
+            S2.forward()
+            wsum = sum(self.w_per)
+            for fr, ff, w in zip(S2.features(), S1.features(), self.w_per):
+                if w == 0:
+                    continue
+                cpad = fr.buf.shape[3]
+                _C.call("feat_loss", ptr(fr.buf), ptr(ff.buf), LL(fr.buf.numel()),
+                        F(self.lambda_per * w / wsum * cpad / fr.c), 0, ptr(self.losses[4:5]))
+        G.backward(self.gan_grad, self.l1_grad)
+        self._allreduce(gs)
+        gs.adam_step(self.lr, self.beta1, grad_scale=1.0 / self.world)
+        return self.losses
+
+    def loss_dict(self):
+        """Host copy of the loss slots with the reference's logging conventions (train.py:121-163):
+        loss_D excludes the penalty, L1 is logged unscaled."""
+        v = self.losses.tolist()
+        return {"loss_D": v[0], "gp": v[1], "G_GAN": v[2], "L1": v[3], "per": v[4]}

@@ -1,0 +1,200 @@
+"""Drop-in for the reference's train.py: same 27 flags, same Train_GAN surface, same files written
+(models/<folder_save>/{final_model.pth, params.txt, *loss.npy}, checkpoints/<folder_save>/model_<e>.pth).
+
+The loop body (reference train.py:99-168) is one call to step.TrainStep -- the fused sm_100a launch
+sequence -- instead of ~hundreds of eager ATen/cuDNN launches and five .item() syncs per step: the
+five loss scalars stay on the device and are read back once per epoch. Additive flags: --synthetic N
+(train on N synthetic pairs, no dataset needed) and --image_size."""
+import argparse
+import json
+import os
+import time
+
+import numpy as np
+import torch
+from torch.optim import lr_scheduler
+from torch.utils.data import DataLoader, Dataset
+
+from .discriminators.discriminators import create_disc
+from .generators.generators import create_gen
+from .optim import FusedAdam
+from .step import TrainStep
+from .util import init_weights, mkdir
+
+opt = None  # module-global read by Train_GAN.get_scheduler, like the reference (train.py:191-195)
+
+
+class SyntheticPairs(Dataset):
+    """Synthetic (source, target) pairs in the dataset's value ranges (PairedDataset.py:52-58,86)."""
+
+    def __init__(self, n, size, in_nc=3, out_nc=3, seed=21):
+        self.n, self.size, self.in_nc, self.out_nc, self.seed = n, size, in_nc, out_nc, seed
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        g = torch.Generator().manual_seed(self.seed + i)
+        return (torch.rand(self.in_nc, self.size, self.size, generator=g) * 2 - 1,
+                torch.rand(self.out_nc, self.size, self.size, generator=g))
+
+
+class Train_GAN:
+    """GAN model for the Pix2Pix-style training (reference train.py:22-227)."""
+
+    def __init__(self, opt_, traindataset):
+        global opt
+        if opt is None:
+            opt = opt_
+        o = opt_
+        self.opt = o
+        self.dataset = DataLoader(dataset=traindataset, batch_size=o.batch_size, shuffle=True,
+                                  num_workers=o.threads, drop_last=True, pin_memory=True)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.activation = o.loss == "ls"                       # reference train.py:33
+        self.return_filter = o.version == 2
+        self.netG = create_gen(o.gen, o.input_dim, o.output_dim, o.nf, self.activation).to(self.device)
+        init_weights(self.netG)
+        self.netD = create_disc("patch", o.input_dim, o.output_dim, o.nf, return_filter=self.return_filter,
+                                activation=self.activation).to(self.device)
+        init_weights(self.netD)
+        self.optimizer_G = FusedAdam(self.netG, lr=o.lr, betas=(o.beta1, 0.99))
+        self.optimizer_D = FusedAdam(self.netD, lr=o.lr, betas=(o.beta1, 0.99))
+        self.optimizers = [self.optimizer_G, self.optimizer_D]
+        self.schedulers = [self.get_scheduler(x) for x in self.optimizers]
+        self.gen_loss, self.disc_loss, self.l1_loss, self.per_loss, self.gp_loss = [], [], [], [], []
+        self.step = None
+        if o.continue_training:
+            ckpt = torch.load(os.path.join(f"{o.data.rsplit('/', 1)[0]}/models", o.folder_load, "final_model.pth"),
+                              map_location=self.device)
+            self.netG.load_state_dict(ckpt["gen"])
+            self.netD.load_state_dict(ckpt["disc"])
+            self._pending_opt_state = (ckpt["optimizerG_state_dict"], ckpt["optimizerD_state_dict"])
+        else:
+            self._pending_opt_state = None
+
+    def _build_step(self, h, w):
+        o = self.opt
+        if o.version != 2 and o.lambda_per != 0:
+            raise NotImplementedError("--version 1 (VGG16 perceptual term) is not built yet; use --version 2")
+        self.step = TrainStep(self.netG, self.netD, o.batch_size, h, w, loss=o.loss, version=o.version,
+                              lambda_a=o.lambda_a, lambda_gp=o.lambda_gp, lambda_per=o.lambda_per, w_per=o.w_per,
+                              lr=o.lr, beta1=o.beta1, label_smoothing=not o.no_label_smoothing)
+        if self._pending_opt_state is not None:
+            self.optimizer_G.load_state_dict(self._pending_opt_state[0])
+            self.optimizer_D.load_state_dict(self._pending_opt_state[1])
+            self._pending_opt_state = None
+
+    def train(self, o):
+        for i in range(o.total_epochs):
+            epoch = i + o.initial_epoch
+            t1 = time.time()
+            print("==training epoch ", epoch)
+            regularize = (o.reg_every != 0) and (epoch % o.reg_every == 0) and (o.lambda_gp != 0)
+            accum, steps = None, 0
+            for batch in self.dataset:
+                real_A = batch[0].to(self.device, non_blocking=True).float().contiguous()
+                real_B = batch[1].to(self.device, non_blocking=True).float().contiguous()
+                if self.step is None:
+                    self._build_step(real_A.shape[2], real_A.shape[3])
+                    accum = torch.zeros_like(self.step.losses)
+                if accum is None:
+                    accum = torch.zeros_like(self.step.losses)
+                self.step.lr = self.optimizer_G.param_groups[0]['lr']
+                losses = self.step.step(real_A, real_B, regularize=regularize)
+                accum += losses
+                steps += 1
+            for scheduler in self.schedulers:
+                scheduler.step()
+            lr = self.optimizers[0].param_groups[0]['lr']
+            m = (accum / max(steps, 1)).tolist() if accum is not None else [0.0] * 8   # the epoch's only sync
+            diff = time.time() - t1
+            print(f"\tloss functions => D:{m[0]:.5f}, G:{m[2]:.5f}, L1:{m[3]:.5f}, gp:{m[1]:.5f}, per:{m[4]:.5f}")
+            print(f'\tlearing rate: {lr:.5f}')
+            print(f"\ttook {diff:.2f} seconds")
+            print(f"\tapproximately {diff * (o.total_epochs - epoch):.2f} seconds left")
+            self.gen_loss.append(m[2])
+            self.disc_loss.append(m[0])
+            self.l1_loss.append(m[3])
+            self.per_loss.append(m[4])
+            self.gp_loss.append(m[1])
+            if o.checkpoint_interval != -1 and epoch % o.checkpoint_interval == 0:
+                self.save_model(f"{o.data.rsplit('/', 1)[0]}/checkpoints/{o.folder_save}/model_{epoch}.pth")
+
+    @staticmethod
+    def get_scheduler(optimizer):
+        milestone = np.int16(np.linspace(opt.epoch_constant, opt.total_epochs, 11)[:-1])
+        return lr_scheduler.MultiStepLR(optimizer, milestones=list(milestone), gamma=0.8)
+
+    def save_model(self, modelpath):
+        if not os.path.exists(modelpath.rsplit('/', 1)[0]):
+            mkdir(modelpath.rsplit('/', 1)[0])
+        torch.save({'gen': self.netG.state_dict(), 'disc': self.netD.state_dict(),
+                    'optimizerG_state_dict': self.optimizer_G.state_dict(),
+                    'optimizerD_state_dict': self.optimizer_D.state_dict()}, modelpath)
+
+    def save_arrays(self, path):
+        for name, arr in (("genloss", self.gen_loss), ("discloss", self.disc_loss), ("l1loss", self.l1_loss),
+                          ("perloss", self.per_loss), ("gploss", self.gp_loss)):
+            np.save(os.path.join(path, name), np.asarray(arr))
+
+    def save_hyper_params(self, folderpath, o):
+        with open(os.path.join(folderpath, 'params.txt'), 'w') as file:
+            file.write(json.dumps(o.__dict__))
+
+
+def build_parser():
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--data", default="./data", help="dataset directory")
+    parser.add_argument("--batch_size", type=int, default=4, help="training batch size")
+    parser.add_argument("--input_dim", type=int, default=3, help="input depth size")
+    parser.add_argument("--output_dim", type=int, default=3, help="output depth size")
+    parser.add_argument("--initial_epoch", type=int, default=1, help="starting epoch")
+    parser.add_argument("--total_epochs", type=int, default=135, help="total epochs we're training for")
+    parser.add_argument("--epoch_constant", type=int, default=25, help="epochs with constant learning rate")
+    parser.add_argument("--lr", type=float, default=0.001, help="learning rate")
+    parser.add_argument("--no_label_smoothing", default=False, action='store_true', help="no one sided label smoothing")
+    parser.add_argument("--beta1", type=float, default=0.9, help="beta1 for our Adam optimizer")
+    parser.add_argument("--threads", type=int, default=8, help="cpu threads for loading the dataset")
+    parser.add_argument("--lambda_a", type=float, default=1, help="L1 loss coefficient")
+    parser.add_argument('--lambda_gp', type=float, default=0.01, help="gradient penalty coefficient")
+    parser.add_argument("--lambda_per", type=float, default=1, help="perceptual loss coefficient")
+    parser.add_argument('--w_per', nargs=4, type=float, default=[0, .1, .3, .6], help='perceptual weights')
+    parser.add_argument("--gen", default="UNet++", choices=["UNet++", "UNet", "BCDUNet"], help="generator architecture")
+    parser.add_argument("--nf", type=int, default=64, help="base number of filters")
+    parser.add_argument("--loss", default="ls", choices=["ls", "ce", "w", "hinge"], help="loss function for ganloss")
+    parser.add_argument("--no_aug", default=False, action='store_true', help="do not augment the dataset")
+    parser.add_argument("--target", default="rgb", choices=["ch", "rgb"], help="target image format")
+    parser.add_argument("-v", "--version", type=int, default=1, choices=[1, 2], help="version of the tactile GAN")
+    parser.add_argument("--folder_save", default="pix2obj", help="where we want to save the model to")
+    parser.add_argument("--folder_load", default="pix2obj", help="where we want to load the model from")
+    parser.add_argument("--checkpoint_interval", type=int, default=-1, help="interval between model checkpoints")
+    parser.add_argument("--continue_training", default=False, action='store_true', help="load weights before training")
+    parser.add_argument('--reg_every', type=int, default=1, help='how frequently we regularize using gp')
+    # additive (not in the reference)
+    parser.add_argument("--synthetic", type=int, default=0, help="train on N synthetic pairs instead of --data")
+    parser.add_argument("--image_size", type=int, default=256, help="side of the synthetic pairs")
+    return parser
+
+
+def main(argv=None):
+    global opt
+    opt = build_parser().parse_args(argv)
+    if opt.synthetic > 0:
+        train_set = SyntheticPairs(opt.synthetic, opt.image_size, opt.input_dim, opt.output_dim)
+    else:
+        from .datasets.datasets import get_dataset
+        train_set = get_dataset(os.path.join(opt.data, "train", "source"), opt, mode='train')
+    experiment = Train_GAN(opt, train_set)
+    root = opt.data.rsplit('/', 1)[0]
+    mkdir(os.path.join(f"{root}/checkpoints", opt.folder_save))
+    save_path = os.path.join(f"{root}/models", opt.folder_save)
+    mkdir(save_path)
+    experiment.train(opt)
+    experiment.save_model(os.path.join(save_path, "final_model.pth"))
+    experiment.save_arrays(save_path)
+    experiment.save_hyper_params(save_path, opt)
+
+
+if __name__ == "__main__":
+    main()
