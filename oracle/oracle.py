@@ -235,12 +235,12 @@ def train_step(sd_g, sd_d, opt_g, opt_d, real_a, real_b, real_label, alpha, cfg)
     pred_fake, _ = patchd_forward(pd, real_a, fake_b.detach(), act)
     pred_real, _ = patchd_forward(pd, real_a, real_b, act)
     loss_d = (gan_loss(pred_fake, False, cfg.loss, real_label) + gan_loss(pred_real, True, cfg.loss, real_label)) / 2
-    out = {"loss_D": float(loss_d)}
+    out = {"loss_D": float(loss_d.detach())}
     total_d = loss_d
     if cfg.regularize and cfg.lambda_gp != 0:
         gp = gradient_penalty(pd, real_a, real_b, fake_b.detach(), alpha, act, cfg.lambda_gp, cfg.version)
         total_d = total_d + gp
-        out["gp"] = float(gp)
+        out["gp"] = float(gp.detach())
     else:
         out["gp"] = 0.0
     names_d = [k for k, v in pd.items() if v.requires_grad]
@@ -254,7 +254,7 @@ def train_step(sd_g, sd_d, opt_g, opt_d, real_a, real_b, real_label, alpha, cfg)
     g_gan = gan_loss(pred_fake, True, cfg.loss, real_label, for_discriminator=False)
     l1 = F.l1_loss(real_b, fake_b)
     total_g = g_gan + l1 * cfg.lambda_a
-    out["G_GAN"], out["L1"] = float(g_gan), float(l1)
+    out["G_GAN"], out["L1"] = float(g_gan.detach()), float(l1.detach())
     if cfg.lambda_per != 0:
         if cfg.version != 2:
             raise NotImplementedError("version 1 (VGG16) is handled by oracle.vgg_perceptual")
@@ -262,7 +262,7 @@ def train_step(sd_g, sd_d, opt_g, opt_d, real_a, real_b, real_label, alpha, cfg)
         # the reference stores detached clones of both feature lists: the term carries no gradient
         per = pan_loss([f.detach() for f in feats_real], [f.detach() for f in feats_fake], cfg.w_per) * cfg.lambda_per
         total_g = total_g + per
-        out["per"] = float(per)
+        out["per"] = float(per.detach())
     else:
         out["per"] = 0.0
     names_g = [k for k, v in pg.items() if v.requires_grad]

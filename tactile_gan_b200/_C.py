@@ -92,14 +92,31 @@ def _taps(arr, vals):
         arr[i] = int(v)
 
 
+# launch accounting (bench.py): number of kernels launched, and optional per-plan CUDA-event timing
+COUNTERS = {"launches": 0}
+TIMING = {"on": False, "records": []}   # records: (kind, flops, start_event, end_event)
+_KERNELS_PER_CALL = {"in_bwd2": 2}
+
+
 class Plan:
     """Owns a tg_plan*; keeps the tensors it points at alive."""
 
-    def __init__(self, handle, keep):
+    def __init__(self, handle, keep, kind="conv", flops=0.0):
         self.handle = handle
         self.keep = keep
+        self.kind = kind
+        self.flops = flops
 
     def run(self):
+        COUNTERS["launches"] += 1
+        if TIMING["on"]:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            check(lib().tg_plan_run(self.handle, stream_ptr()), "tg_plan_run")
+            e1.record()
+            TIMING["records"].append((self.kind, self.flops, e0, e1))
+            return
         check(lib().tg_plan_run(self.handle, stream_ptr()), "tg_plan_run")
 
     def __del__(self):
@@ -117,7 +134,7 @@ def conv_query_tiles(n, ho, wo, want_stats):
 
 
 def conv_plan(srcs, out, taps, stride=1, bias=None, stats_partial=None, act=ACT_NONE, slope=0.2,
-              stats_tiles_total=0, stats_tile_off=0):
+              stats_tiles_total=0, stats_tile_off=0, cout_real=None):
     """srcs: list of dict(act=tensor NHWC, wgt=packed bf16 [taps][rows][k], k_off=0, row_off=0)
     taps: list of (dy, dx, w_index)."""
     d = ConvDesc()
@@ -147,10 +164,15 @@ def conv_plan(srcs, out, taps, stride=1, bias=None, stats_partial=None, act=ACT_
     d.slope = slope
     h = c_void_p()
     check(lib().tg_conv_plan_create(byref(d), byref(h)), "tg_conv_plan_create")
-    return Plan(h, keep)
+    # algorithmic FLOPs of this launch: real (unpadded) channels, every output pixel, every tap
+    n, ho, wo, _ = out.shape
+    flops = 0.0
+    for s in srcs:
+        flops += 2.0 * n * ho * wo * len(taps) * s.get("c_real", s["act"].shape[3]) * (cout_real or out.shape[3])
+    return Plan(h, keep, "conv", flops)
 
 
-def wgrad_plan(p_srcs, q, taps, dw, stride=1):
+def wgrad_plan(p_srcs, q, taps, dw, stride=1, p_real=None, q_real=None):
     """dw: fp32 [taps_total][rows >= q.C][cols == sum p.C]."""
     d = WgradDesc()
     d.num_src = len(p_srcs)
@@ -167,7 +189,10 @@ def wgrad_plan(p_srcs, q, taps, dw, stride=1):
     d.dw_rows, d.dw_cols = dw.shape[1], dw.shape[2]
     h = c_void_p()
     check(lib().tg_wgrad_plan_create(byref(d), byref(h)), "tg_wgrad_plan_create")
-    return Plan(h, list(p_srcs) + [q, dw])
+    n, ho, wo, qc = q.shape
+    pc = p_real if p_real is not None else sum(t.shape[3] for t in p_srcs)
+    flops = 2.0 * n * ho * wo * len(taps) * pc * (q_real if q_real is not None else qc)
+    return Plan(h, list(p_srcs) + [q, dw], "wgrad", flops)
 
 
 def error_flag():
@@ -178,6 +203,7 @@ def error_flag():
 def call(name, *args):
     """Call a tail kernel launcher `tg_<name>(..., stream)`."""
     fn = getattr(lib(), "tg_" + name)
+    COUNTERS["launches"] += _KERNELS_PER_CALL.get(name, 1)
     check(fn(*args, stream_ptr()), "tg_" + name)
 
 

@@ -85,25 +85,26 @@ class ConvLayer:
     def fwd_plan(self, srcs, out, stats_partial=None, act=ACT_NONE, slope=0.2, use_bias=True):
         """srcs: NHWC bf16 tensors in concat order (conv) -- Conv2d forward."""
         assert self.kind == "conv" and len(srcs) == len(self.in_split)
-        s = [dict(act=t, wgt=self.pack_fwd, k_off=o) for t, o in zip(srcs, self.k_off)]
+        s = [dict(act=t, wgt=self.pack_fwd, k_off=o, c_real=c) for t, o, c in zip(srcs, self.k_off, self.in_split)]
         return _C.conv_plan(s, out, conv_taps(self.kh, self.kw, self.pad), stride=self.stride,
                             bias=self.bias.detach() if (use_bias and self.bias is not None) else None,
-                            stats_partial=stats_partial, act=act, slope=slope)
+                            stats_partial=stats_partial, act=act, slope=slope, cout_real=self.O)
 
     def wgrad_plan(self, srcs, dy):
         assert self.kind == "conv"
         return _C.wgrad_plan(list(srcs), dy, conv_taps(self.kh, self.kw, self.pad), self.grad,
-                             stride=self.stride)
+                             stride=self.stride, p_real=self.I, q_real=self.O)
 
     def dgrad_src(self, dy, seg):
         """Operand descriptor for the input-gradient of concat segment `seg`."""
-        return dict(act=dy, wgt=self.pack_bwd, k_off=0, row_off=self.k_off[seg])
+        return dict(act=dy, wgt=self.pack_bwd, k_off=0, row_off=self.k_off[seg], c_real=self.O)
 
     def dgrad_plans(self, dy, out, seg=0):
         """Input gradient w.r.t. concat segment `seg` -> list of plans (one per output phase)."""
         assert self.kind == "conv"
         if self.stride == 1:
-            return [_C.conv_plan([self.dgrad_src(dy, seg)], out, dgrad_taps_s1(self.kh, self.kw, self.pad))]
+            return [_C.conv_plan([self.dgrad_src(dy, seg)], out, dgrad_taps_s1(self.kh, self.kw, self.pad),
+                                 cout_real=self.in_split[seg])]
         plans = []
         s = self.stride
         for py in range(s):
@@ -115,7 +116,7 @@ class ConvLayer:
                 if not taps:
                     sub.zero_()
                     continue
-                plans.append(_C.conv_plan([self.dgrad_src(dy, seg)], sub, taps))
+                plans.append(_C.conv_plan([self.dgrad_src(dy, seg)], sub, taps, cout_real=self.in_split[seg]))
         return plans
 
 
@@ -126,7 +127,7 @@ def multi_dgrad_plan(consumers, out):
     for layer, _, _ in consumers:
         assert layer.stride == 1 and (layer.kh, layer.kw, layer.pad) == (l0.kh, l0.kw, l0.pad)
     srcs = [layer.dgrad_src(dy, seg) for layer, dy, seg in consumers]
-    return _C.conv_plan(srcs, out, dgrad_taps_s1(l0.kh, l0.kw, l0.pad))
+    return _C.conv_plan(srcs, out, dgrad_taps_s1(l0.kh, l0.kw, l0.pad), cout_real=l0.in_split[consumers[0][2]])
 
 
 class ParamStore:

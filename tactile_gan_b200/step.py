@@ -147,6 +147,17 @@ class TrainStep:
         gs.adam_step(self.lr, self.beta1, grad_scale=1.0 / self.world)
         return self.losses
 
+    def step_from_host(self, host_A, host_B, regularize=True):
+        """End-to-end iteration as a training loop issues it (reference train.py:101-168): pinned host
+        batch -> H2D copy -> fused step -> D2H read of the five loss scalars (the only sync)."""
+        if not hasattr(self, "_dev_A"):
+            self._dev_A = torch.empty(host_A.shape, device=self.device)
+            self._dev_B = torch.empty(host_B.shape, device=self.device)
+        self._dev_A.copy_(host_A, non_blocking=True)
+        self._dev_B.copy_(host_B, non_blocking=True)
+        self.step(self._dev_A, self._dev_B, regularize=regularize)
+        return self.loss_dict()
+
     def loss_dict(self):
         """Host copy of the loss slots with the reference's logging conventions (train.py:121-163):
         loss_D excludes the penalty, L1 is logged unscaled."""

@@ -1,0 +1,122 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/*.h declares; host-side
+index math (tap tables, tile choice, module key layout) -- no kernel is launched here."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    return ctypes.CDLL(ge.LIB)
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "tactile_gan_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(lib):
+    syms = declared_symbols()
+    assert len(syms) >= 30
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    assert lib.tg_version() >= 100
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from tactile_gan_b200 import _C
+    monkeypatch.setattr(_C, "_lib", None)
+    monkeypatch.setattr(_C, "LIB_PATH", "/nonexistent/libtactile_gan_b200.so")
+    with pytest.raises(_C.TgError):
+        _C.lib()
+
+
+def test_cpu_tensor_is_rejected():
+    from tactile_gan_b200 import _C
+    from tactile_gan_b200.generators.generators import create_gen
+    net = create_gen("UNet++", 3, 3, 4, True)
+    with pytest.raises(_C.TgError):
+        net(torch.zeros(1, 3, 32, 32))
+
+
+def test_tile_choice(lib):
+    out = (ctypes.c_int * 4)()
+    for n, h, w, stats in [(32, 256, 256, 1), (32, 127, 127, 0), (2, 59, 59, 1), (4, 16, 16, 1), (8, 4, 4, 0),
+                           (64, 2, 2, 0)]:
+        assert lib.tg_conv_query_tiles(n, h, w, stats, out) == 0
+        th, tw, tn, tpi = out
+        assert th * tw * tn == 128
+        if stats:
+            assert tn == 1
+        assert tpi == -(-h // th) * -(-w // tw)
+
+
+def test_phase_taps_cover_transposed_conv():
+    """Every (output pixel, tap) pair of a stride-2 transposed conv appears in exactly one phase."""
+    from tactile_gan_b200.layers import phase_taps
+    for k, pad in [(3, 0), (4, 1), (2, 0)]:
+        s = 2
+        hin = 5
+        hout = (hin - 1) * s - 2 * pad + k
+        ref = {}
+        for i in range(hin):
+            for r in range(k):
+                o = i * s - pad + r
+                if 0 <= o < hout:
+                    ref.setdefault(o, set()).add((i, r))
+        got = {}
+        for py in range(s):
+            taps = phase_taps(k, 1, pad, s, py, 0, flipped=False) if False else phase_taps(k, k, pad, s, py, py, False)
+            for a in range((hout - py + s - 1) // s):
+                o = s * a + py
+                for dy, dx, widx in taps:
+                    r = widx // k
+                    if widx % k != r:       # look at the diagonal taps only (1-D check on the y axis)
+                        continue
+                    i = a + dy
+                    if 0 <= i < hin:
+                        got.setdefault(o, set()).add((i, r))
+        assert got == ref, (k, pad)
+
+
+def test_state_dict_layout_matches_reference(golden_dir):
+    from tactile_gan_b200.discriminators.discriminators import create_disc
+    from tactile_gan_b200.generators.generators import create_gen
+    inv = torch.load(os.path.join(golden_dir, "state_dict_keys.pt"))
+    for name in ["UNet++"] + [n for n in ("UNet", "BCDUNet") if _has_gen(n)]:
+        sd = create_gen(name, 3, 3, 64, True).state_dict()
+        assert list(sd.keys()) == list(inv[name].keys()), name
+        assert all(tuple(sd[k].shape) == inv[name][k] for k in sd), name
+    sd = create_disc("patch", 3, 3, 64, True, True).state_dict()
+    assert list(sd.keys()) == list(inv["patch"].keys())
+    assert all(tuple(sd[k].shape) == inv["patch"][k] for k in sd)
+    with pytest.raises(NameError):
+        create_gen("resnet", 3, 3, 64)
+    with pytest.raises(NameError):
+        create_disc("pixel", 3, 3, 64, True)
+
+
+def _has_gen(name):
+    mod = {"UNet": "UNet", "BCDUNet": "BCDUNet"}[name]
+    return os.path.exists(os.path.join(ROOT, "tactile_gan_b200", "generators", mod + ".py"))
+
+
+def test_train_cli_surface():
+    """The 27 reference flags with the reference's (code) defaults (train.py:231-257)."""
+    from tactile_gan_b200.train import build_parser
+    o = build_parser().parse_args([])
+    exp = dict(data="./data", batch_size=4, input_dim=3, output_dim=3, initial_epoch=1, total_epochs=135,
+               epoch_constant=25, lr=0.001, no_label_smoothing=False, beta1=0.9, threads=8, lambda_a=1,
+               lambda_gp=0.01, lambda_per=1, w_per=[0, .1, .3, .6], gen="UNet++", nf=64, loss="ls", no_aug=False,
+               target="rgb", version=1, folder_save="pix2obj", folder_load="pix2obj", checkpoint_interval=-1,
+               continue_training=False, reg_every=1)
+    for k, v in exp.items():
+        assert getattr(o, k) == v, k
