@@ -160,92 +160,111 @@ __global__ void in_stats_direct_kernel(const __nv_bfloat16* __restrict__ raw, fl
   }
 }
 
-// y = act(gamma * (raw - mean) * rstd + beta); optional 2x2 pooled copy and 2x nearest-upsampled copy.
-template <int POOL, bool UP>
-__global__ void in_act_fwd_kernel(const __nv_bfloat16* __restrict__ raw, const float* __restrict__ mr,
-                                  const float* __restrict__ gamma, const float* __restrict__ beta,
-                                  __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ pool,
-                                  __nv_bfloat16* __restrict__ up, int N, int H, int W, int C, int c_valid,
-                                  int act, float slope) {
+// Thread layout shared by the normalise / backward passes: a block works on one image (blockIdx.y) and a
+// strip of its pixels (blockIdx.x); a thread owns one 8-channel group (so per-channel constants live in
+// registers for the whole strip) and walks pixels with stride PL = blockDim.x / (C/8). Consecutive threads
+// touch consecutive 16-byte vectors, i.e. whole 128-byte lines.
+struct StripIdx {
+  int cg, pl, PL, c0, p0, p1;
+};
+__device__ __forceinline__ StripIdx strip_index(int C, int units) {
+  StripIdx s;
   const int CG = C >> 3;
-  if (POOL == 0 && !UP) {
-    const size_t total = size_t(N) * H * W * CG;
-    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total;
-         i += size_t(gridDim.x) * blockDim.x) {
-      const int cg = int(i % CG);
-      const size_t pix = i / CG;
-      const int n = int(pix / (size_t(H) * W));
-      const int c0 = cg * 8;
-      float f[8];
-      unpack8(ldg16(raw + pix * C + c0), f);
-      const float* m = mr + (size_t(n) * C + c0) * 2;
+  s.PL = blockDim.x / CG;
+  s.cg = threadIdx.x % CG;
+  s.pl = threadIdx.x / CG;
+  s.c0 = s.cg * 8;
+  const int strip = (units + gridDim.x - 1) / gridDim.x;
+  s.p0 = blockIdx.x * strip;
+  s.p1 = min(units, s.p0 + strip);
+  return s;
+}
+
+// y = act(gamma * (raw - mean) * rstd + beta) = act(S*raw + T); optional 2x2 pooled copy and 2x
+// nearest-upsampled copy written by the same pass (units = pixels, or 2x2 quads when POOL/UP).
+template <int POOL, bool UP>
+__global__ void __launch_bounds__(256)
+in_act_fwd_kernel(const __nv_bfloat16* __restrict__ raw, const float* __restrict__ mr,
+                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                  __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ pool,
+                  __nv_bfloat16* __restrict__ up, int H, int W, int C, int c_valid, int act, float slope) {
+  const int n = blockIdx.y;
+  constexpr bool QUAD = POOL != 0 || UP;
+  const int H2 = H >> 1, W2 = W >> 1;
+  const StripIdx t = strip_index(C, QUAD ? H2 * W2 : H * W);
+  if (t.pl >= t.PL) return;
+  float S[8], T[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float g = ld_aff(gamma, c0 + j, c_valid, 1.f);
-        const float b = ld_aff(beta, c0 + j, c_valid, 0.f);
-        f[j] = act_fwd(g * (f[j] - __ldg(m + 2 * j)) * __ldg(m + 2 * j + 1) + b, act, slope);
+  for (int j = 0; j < 8; ++j) {
+    const float g = ld_aff(gamma, t.c0 + j, c_valid, 1.f);
+    const float b = ld_aff(beta, t.c0 + j, c_valid, 0.f);
+    const float mean = mr[(size_t(n) * C + t.c0 + j) * 2];
+    const float rstd = mr[(size_t(n) * C + t.c0 + j) * 2 + 1];
+    S[j] = g * rstd;
+    T[j] = b - mean * S[j];
+  }
+  const size_t img = size_t(n) * H * W;
+  if (!QUAD) {
+    int pix = t.p0 + t.pl;
+    for (; pix + 3 * t.PL < t.p1; pix += 4 * t.PL) {
+      uint4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = ldg16(raw + (img + pix + k * t.PL) * C + t.c0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float f[8];
+        unpack8(v[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = act_fwd(fmaf(f[j], S[j], T[j]), act, slope);
+        stg16(y + (img + pix + k * t.PL) * C + t.c0, pack8(f));
       }
-      stg16(y + pix * C + c0, pack8(f));
+    }
+    for (; pix < t.p1; pix += t.PL) {
+      float f[8];
+      unpack8(ldg16(raw + (img + pix) * C + t.c0), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = act_fwd(fmaf(f[j], S[j], T[j]), act, slope);
+      stg16(y + (img + pix) * C + t.c0, pack8(f));
     }
   } else {
-    const int H2 = H >> 1, W2 = W >> 1;
-    const size_t total = size_t(N) * H2 * W2 * CG;
-    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total;
-         i += size_t(gridDim.x) * blockDim.x) {
-      const int cg = int(i % CG);
-      size_t r = i / CG;
-      const int qx = int(r % W2); r /= W2;
-      const int qy = int(r % H2);
-      const int n = int(r / H2);
-      const int c0 = cg * 8;
-      float sc[8], sh[8];
-      const float* m = mr + (size_t(n) * C + c0) * 2;
+    for (int q = t.p0 + t.pl; q < t.p1; q += t.PL) {
+      const int qy = q / W2, qx = q % W2;
+      uint4 v[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float g = ld_aff(gamma, c0 + j, c_valid, 1.f);
-        const float b = ld_aff(beta, c0 + j, c_valid, 0.f);
-        sc[j] = g * __ldg(m + 2 * j + 1);
-        sh[j] = b - __ldg(m + 2 * j) * sc[j];
-      }
+      for (int k = 0; k < 4; ++k)
+        v[k] = ldg16(raw + (img + size_t(2 * qy + (k >> 1)) * W + 2 * qx + (k & 1)) * C + t.c0);
       float acc[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = POOL == 2 ? -3.0e38f : 0.f;
 #pragma unroll
-      for (int a = 0; a < 2; ++a)
+      for (int k = 0; k < 4; ++k) {
+        const int yy = 2 * qy + (k >> 1), xx = 2 * qx + (k & 1);
+        float f[8];
+        unpack8(v[k], f);
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          const int yy = 2 * qy + a, xx = 2 * qx + b;
-          const size_t pix = (size_t(n) * H + yy) * W + xx;
-          float f[8];
-          unpack8(ldg16(raw + pix * C + c0), f);
+        for (int j = 0; j < 8; ++j) f[j] = act_fwd(fmaf(f[j], S[j], T[j]), act, slope);
+        const uint4 pv = pack8(f);
+        stg16(y + (img + size_t(yy) * W + xx) * C + t.c0, pv);
+        if (POOL) {
+          float fr[8];
+          unpack8(pv, fr);  // pool the bf16-rounded values the next layer would read
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = act_fwd(f[j] * sc[j] + sh[j], act, slope);
-          const uint4 pv = pack8(f);
-          stg16(y + pix * C + c0, pv);
-          if (POOL) {
-            float fr[8];
-            unpack8(pv, fr);  // pool the bf16-rounded values the next layer would read
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = POOL == 2 ? fmaxf(acc[j], fr[j]) : acc[j] + fr[j];
-          }
-          if (UP) {
-            const int HU = 2 * H, WU = 2 * W;
-#pragma unroll
-            for (int ua = 0; ua < 2; ++ua)
-#pragma unroll
-              for (int ub = 0; ub < 2; ++ub) {
-                const size_t upix = (size_t(n) * HU + 2 * yy + ua) * WU + 2 * xx + ub;
-                stg16(up + upix * C + c0, pv);
-              }
-          }
+          for (int j = 0; j < 8; ++j) acc[j] = POOL == 2 ? fmaxf(acc[j], fr[j]) : acc[j] + fr[j];
         }
+        if (UP) {
+          const size_t ubase = (size_t(n) * 2 * H + 2 * yy) * (2 * W) + 2 * xx;
+          stg16(up + ubase * C + t.c0, pv);
+          stg16(up + (ubase + 1) * C + t.c0, pv);
+          stg16(up + (ubase + 2 * W) * C + t.c0, pv);
+          stg16(up + (ubase + 2 * W + 1) * C + t.c0, pv);
+        }
+      }
       if (POOL) {
         if (POOL == 1) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] *= 0.25f;
         }
-        const size_t ppix = (size_t(n) * H2 + qy) * W2 + qx;
-        stg16(pool + ppix * C + c0, pack8(acc));
+        stg16(pool + ((size_t(n) * H2 + qy) * W2 + qx) * C + t.c0, pack8(acc));
       }
     }
   }
@@ -270,44 +289,62 @@ struct InBwdArgs {
   float slope;
 };
 
-__global__ void in_bwd_reduce_kernel(const InBwdArgs a) {
+__global__ void __launch_bounds__(256, 3) in_bwd_reduce_kernel(const InBwdArgs a) {
   extern __shared__ float shm[];  // [PL][C][2]
-  const int CG = a.C >> 3;
-  const int PL = blockDim.x / CG;   // pixel lanes
-  const int cg = threadIdx.x % CG, pl = threadIdx.x / CG;
   const int n = blockIdx.y;
   const int HW = a.H * a.W;
-  const int strip = (HW + gridDim.x - 1) / gridDim.x;
-  const int p0 = blockIdx.x * strip, p1 = min(HW, p0 + strip);
-  const int c0 = cg * 8;
-  float sc[8], sh[8], mean[8], rstd[8];
+  const StripIdx t = strip_index(a.C, HW);
+  const int c0 = t.c0;
+  // n = A*raw + B (pre-activation); xhat = (raw - mean)*rstd is folded into the finalisation:
+  // sum dn*xhat = rstd * (sum dn*raw - mean * sum dn)
+  float A[8], B[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float g = ld_aff(a.gamma, c0 + j, a.c_valid, 1.f);
     const float b = ld_aff(a.beta, c0 + j, a.c_valid, 0.f);
-    mean[j] = a.mr ? a.mr[(size_t(n) * a.C + c0 + j) * 2] : 0.f;
-    rstd[j] = a.mr ? a.mr[(size_t(n) * a.C + c0 + j) * 2 + 1] : 1.f;
-    sc[j] = g; sh[j] = b;
+    const float mean = a.mr ? a.mr[(size_t(n) * a.C + c0 + j) * 2] : 0.f;
+    const float rstd = a.mr ? a.mr[(size_t(n) * a.C + c0 + j) * 2 + 1] : 1.f;
+    A[j] = g * rstd;
+    B[j] = b - mean * A[j];
   }
   float s0[8] = {0}, s1[8] = {0};
-  if (pl < PL) {
-    for (int pix = p0 + pl; pix < p1; pix += PL) {
+  if (t.pl < t.PL) {
+    for (int pix = t.p0 + t.pl; pix < t.p1; pix += t.PL) {
       const int yy = pix / a.W, xx = pix % a.W;
       const size_t lin = (size_t(n) * HW + pix) * a.C + c0;
       float g[8] = {0};
+      const uint4 vr = ldg16((a.raw ? a.raw : a.y) + lin);
       if (a.g_same) unpack8(ldg16(a.g_same + lin), g);
+      if (a.g_up) {
+        const int WU = 2 * a.W;
+        const size_t ub = (size_t(n) * 2 * a.H + 2 * yy) * WU + 2 * xx;
+        const uint4 u0 = ldg16(a.g_up + ub * a.C + c0), u1 = ldg16(a.g_up + (ub + 1) * a.C + c0);
+        const uint4 u2 = ldg16(a.g_up + (ub + WU) * a.C + c0), u3 = ldg16(a.g_up + (ub + WU + 1) * a.C + c0);
+        float f[8];
+        unpack8(u0, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] += f[j];
+        unpack8(u1, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] += f[j];
+        unpack8(u2, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] += f[j];
+        unpack8(u3, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] += f[j];
+      }
       if (a.g_pool) {
         const int H2 = a.H >> 1, W2 = a.W >> 1;
-        float t[8];
-        unpack8(ldg16(a.g_pool + ((size_t(n) * H2 + (yy >> 1)) * W2 + (xx >> 1)) * a.C + c0), t);
+        float f[8];
+        unpack8(ldg16(a.g_pool + ((size_t(n) * H2 + (yy >> 1)) * W2 + (xx >> 1)) * a.C + c0), f);
         if (a.pool_mode == 1) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) g[j] += 0.25f * t[j];
+          for (int j = 0; j < 8; ++j) g[j] += 0.25f * f[j];
         } else {
           // max-pool routing: first element (row-major in the 2x2 window) equal to the window max
-          float me[8], best[8];
+          float best[8];
           int first[8];
-          unpack8(ldg16(a.y + lin), me);
 #pragma unroll
           for (int j = 0; j < 8; ++j) { best[j] = -3.0e38f; first[j] = 0; }
 #pragma unroll
@@ -322,81 +359,91 @@ __global__ void in_bwd_reduce_kernel(const InBwdArgs a) {
           const int mine = ((yy & 1) << 1) | (xx & 1);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            if (first[j] == mine) g[j] += t[j];
+            if (first[j] == mine) g[j] += f[j];
         }
       }
-      if (a.g_up) {
-        const int HU = 2 * a.H, WU = 2 * a.W;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float t[8];
-          unpack8(ldg16(a.g_up + ((size_t(n) * HU + 2 * yy + (k >> 1)) * WU + 2 * xx + (k & 1)) * a.C + c0), t);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) g[j] += t[j];
-        }
-      }
-      float xh[8], dn[8];
+      float r[8];
+      unpack8(vr, r);
       if (a.raw) {
-        float r[8];
-        unpack8(ldg16(a.raw + lin), r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          xh[j] = (r[j] - mean[j]) * rstd[j];
-          dn[j] = g[j] * act_grad(sc[j] * xh[j] + sh[j], a.act, a.slope);
+          g[j] *= act_grad(fmaf(r[j], A[j], B[j]), a.act, a.slope);
+          s0[j] += g[j];
+          s1[j] = fmaf(g[j], r[j], s1[j]);
         }
       } else {
-        float o[8];
-        unpack8(ldg16(a.y + lin), o);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { xh[j] = 0.f; dn[j] = g[j] * act_grad(o[j], a.act, a.slope); }
+        for (int j = 0; j < 8; ++j) g[j] *= act_grad(r[j], a.act, a.slope);
       }
-      stg16(a.dn + lin, pack8(dn));
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { s0[j] += dn[j]; s1[j] += dn[j] * xh[j]; }
+      stg16(a.dn + lin, pack8(g));
     }
   }
   if (!a.red) return;
-  float* shp = shm + (size_t(pl) * a.C + c0) * 2;
-  if (pl < PL) {
+  float* shp = shm + (size_t(t.pl) * a.C + c0) * 2;
+  if (t.pl < t.PL) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) { shp[2 * j] = s0[j]; shp[2 * j + 1] = s1[j]; }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < a.C * 2; i += blockDim.x) {
-    float t = 0.f;
-    for (int k = 0; k < PL; ++k) t += shm[size_t(k) * a.C * 2 + i];
-    atomicAdd(a.red + size_t(n) * a.C * 2 + i, t);
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    float d0 = 0.f, d1 = 0.f;
+    for (int k = 0; k < t.PL; ++k) {
+      d0 += shm[(size_t(k) * a.C + c) * 2];
+      d1 += shm[(size_t(k) * a.C + c) * 2 + 1];
+    }
+    const float mean = a.mr[(size_t(n) * a.C + c) * 2], rstd = a.mr[(size_t(n) * a.C + c) * 2 + 1];
+    atomicAdd(a.red + (size_t(n) * a.C + c) * 2, d0);
+    atomicAdd(a.red + (size_t(n) * a.C + c) * 2 + 1, rstd * (d1 - mean * d0));
   }
 }
 
-// dz = rstd * gamma * (dn - mean(dn) - xhat * mean(dn * xhat))
-__global__ void in_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dn,
-                                    const __nv_bfloat16* __restrict__ raw,
-                                    const float* __restrict__ mr, const float* __restrict__ gamma,
-                                    const float* __restrict__ red, __nv_bfloat16* __restrict__ dz,
-                                    int N, int HW, int C, int c_valid) {
-  const int CG = C >> 3;
-  const size_t total = size_t(N) * HW * CG;
+// dz = rstd * gamma * (dn - mean(dn) - xhat * mean(dn * xhat)) = P*dn + Q*raw + R
+__global__ void __launch_bounds__(256)
+in_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dn, const __nv_bfloat16* __restrict__ raw,
+                    const float* __restrict__ mr, const float* __restrict__ gamma,
+                    const float* __restrict__ red, __nv_bfloat16* __restrict__ dz, int HW, int C,
+                    int c_valid) {
+  const int n = blockIdx.y;
+  const StripIdx t = strip_index(C, HW);
+  if (t.pl >= t.PL) return;
   const float inv = 1.f / float(HW);
-  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total;
-       i += size_t(gridDim.x) * blockDim.x) {
-    const int cg = int(i % CG);
-    const size_t pix = i / CG;
-    const int n = int(pix / HW);
-    const int c0 = cg * 8;
-    float d[8], r[8];
-    unpack8(ldg16(dn + pix * C + c0), d);
-    unpack8(ldg16(raw + pix * C + c0), r);
-    const float* m = mr + (size_t(n) * C + c0) * 2;
-    const float* rd = red + (size_t(n) * C + c0) * 2;
+  float P[8], Q[8], R[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float g = ld_aff(gamma, c0 + j, c_valid, 1.f);
-      const float rs = __ldg(m + 2 * j + 1);
-      const float xh = (r[j] - __ldg(m + 2 * j)) * rs;
-      d[j] = rs * g * (d[j] - __ldg(rd + 2 * j) * inv - xh * __ldg(rd + 2 * j + 1) * inv);
+  for (int j = 0; j < 8; ++j) {
+    const size_t k = size_t(n) * C + t.c0 + j;
+    const float g = ld_aff(gamma, t.c0 + j, c_valid, 1.f);
+    const float mean = mr[k * 2], rstd = mr[k * 2 + 1];
+    const float am = red[k * 2] * inv, bm = red[k * 2 + 1] * inv;
+    P[j] = g * rstd;
+    Q[j] = -g * rstd * rstd * bm;
+    R[j] = -P[j] * am - Q[j] * mean;
+  }
+  const size_t img = size_t(n) * HW;
+  int pix = t.p0 + t.pl;
+  for (; pix + 3 * t.PL < t.p1; pix += 4 * t.PL) {
+    uint4 vd[4], vr[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      vd[k] = ldg16(dn + (img + pix + k * t.PL) * C + t.c0);
+      vr[k] = ldg16(raw + (img + pix + k * t.PL) * C + t.c0);
     }
-    stg16(dz + pix * C + c0, pack8(d));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float d[8], r[8];
+      unpack8(vd[k], d);
+      unpack8(vr[k], r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = fmaf(P[j], d[j], fmaf(Q[j], r[j], R[j]));
+      stg16(dz + (img + pix + k * t.PL) * C + t.c0, pack8(d));
+    }
+  }
+  for (; pix < t.p1; pix += t.PL) {
+    float d[8], r[8];
+    unpack8(ldg16(dn + (img + pix) * C + t.c0), d);
+    unpack8(ldg16(raw + (img + pix) * C + t.c0), r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] = fmaf(P[j], d[j], fmaf(Q[j], r[j], R[j]));
+    stg16(dz + (img + pix) * C + t.c0, pack8(d));
   }
 }
 
@@ -964,6 +1011,15 @@ int tg_in_stats_direct(const void* raw, float* mr, int N, int HW, int C, float e
   TG_RET();
 }
 
+static inline int strip_block(int C) { return (C >> 3) >= 256 ? (C >> 3) : 256; }
+static inline int strip_count(int units, int C, int N, int per_thread) {
+  const int PL = strip_block(C) / (C >> 3);
+  int strips = (units + PL * per_thread - 1) / (PL * per_thread);
+  const int cap = (148 * 8 + N - 1) / N;
+  if (strips > cap) strips = cap;
+  return strips < 1 ? 1 : strips;
+}
+
 int tg_in_act_fwd(const void* raw, const float* mr, const float* gamma, const float* beta, void* y,
                   void* pool, int pool_mode, void* up, int N, int H, int W, int C, int c_valid, int act,
                   float slope, void* stream) {
@@ -972,10 +1028,12 @@ int tg_in_act_fwd(const void* raw, const float* mr, const float* gamma, const fl
   cudaStream_t s = TG_STREAM(stream);
   const bool quad = pool || up;
   if (quad && ((H | W) & 1)) return tg_set_error("tg_in_act_fwd: pool/upsample need even H, W");
-  const size_t work = size_t(N) * H * W * (C / 8) / (quad ? 4 : 1);
-  const int g = grid_for(work, 256, 148 * 32);
+  if (C > 8192) return tg_set_error("tg_in_act_fwd: C too large");
+  const int units = quad ? (H / 2) * (W / 2) : H * W;
+  dim3 grid(strip_count(units, C, N, quad ? 4 : 16), N);
+  const int block = strip_block(C);
   const int pm = pool ? pool_mode : 0;
-#define LAUNCH(P, U) in_act_fwd_kernel<P, U><<<g, 256, 0, s>>>(r, mr, gamma, beta, yy, pp, uu, N, H, W, C, c_valid, act, slope)
+#define LAUNCH(P, U) in_act_fwd_kernel<P, U><<<grid, block, 0, s>>>(r, mr, gamma, beta, yy, pp, uu, H, W, C, c_valid, act, slope)
   if (pm == 0 && !up) LAUNCH(0, false);
   else if (pm == 0 && up) LAUNCH(0, true);
   else if (pm == 1 && !up) LAUNCH(1, false);
@@ -995,24 +1053,21 @@ int tg_in_bwd_reduce(const void* raw, const void* y, const float* mr, const floa
   a.beta = beta; a.g_same = (const __nv_bfloat16*)g_same; a.g_pool = (const __nv_bfloat16*)g_pool;
   a.g_up = (const __nv_bfloat16*)g_up; a.dn = (__nv_bfloat16*)dn; a.red = red;
   a.N = N; a.H = H; a.W = W; a.C = C; a.c_valid = c_valid; a.act = act; a.pool_mode = pool_mode; a.slope = slope;
-  const int CG = C / 8;
-  const int block = CG >= 256 ? CG : 256;
+  if (red && !mr) return tg_set_error("tg_in_bwd_reduce: reductions need the (mean, rstd) table");
+  const int block = strip_block(C);
   if (block > 1024) return tg_set_error("tg_in_bwd_reduce: C too large");
-  const int PL = block / CG;
-  const size_t smem = size_t(PL) * C * 2 * sizeof(float);
-  int strips = (H * W + PL * 8 - 1) / (PL * 8);
-  const int cap = (148 * 8 + N - 1) / N;
-  if (strips > cap) strips = cap;
-  if (strips < 1) strips = 1;
-  dim3 grid(strips, N);
+  const int PL = block / (C / 8);
+  const size_t smem = red ? size_t(PL) * C * 2 * sizeof(float) : 0;
+  dim3 grid(strip_count(H * W, C, N, 16), N);
   in_bwd_reduce_kernel<<<grid, block, smem, TG_STREAM(stream)>>>(a);
   TG_RET();
 }
 
 int tg_in_bwd_apply(const void* dn, const void* raw, const float* mr, const float* gamma,
                     const float* red, void* dz, int N, int HW, int C, int c_valid, void* stream) {
-  in_bwd_apply_kernel<<<grid_for(size_t(N) * HW * (C / 8), 256, 148 * 32), 256, 0, TG_STREAM(stream)>>>(
-      (const __nv_bfloat16*)dn, (const __nv_bfloat16*)raw, mr, gamma, red, (__nv_bfloat16*)dz, N, HW, C, c_valid);
+  dim3 grid(strip_count(HW, C, N, 16), N);
+  in_bwd_apply_kernel<<<grid, strip_block(C), 0, TG_STREAM(stream)>>>(
+      (const __nv_bfloat16*)dn, (const __nv_bfloat16*)raw, mr, gamma, red, (__nv_bfloat16*)dz, HW, C, c_valid);
   TG_RET();
 }
 

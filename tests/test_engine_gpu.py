@@ -1,0 +1,223 @@
+"""-m gpu: the generator / discriminator engines and the fused G+D step against the CPU oracle.
+
+Tolerances (bf16 storage, fp32 accumulate): a bf16 round-off is 2^-9 ~ 0.2-0.4 %; through the ~30
+conv+InstanceNorm layers of UNet++ that accumulates to a few % on activations. ReLU masks of near-zero
+pre-activations then flip, which makes per-element gradients of the ReLU network ill-conditioned -- so
+gradient *logic* is checked tightly on the linearised network (identity activations, <= 4 %) and on the
+discriminator (LeakyReLU, <= 5 %), and the ReLU generator by direction (cosine >= 0.9)."""
+import os
+from collections import OrderedDict
+
+import pytest
+import torch
+
+from gpu_util import cos, randomize, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup():
+    import oracle as orc
+    from tactile_gan_b200 import _C
+    return orc, _C
+
+
+@pytest.mark.parametrize("linear", [True, False])
+def test_unetpp_forward_backward(linear):
+    orc, _C = _setup()
+    from tactile_gan_b200.generators.generators import create_gen
+    nf, size, n = 64, 64, 2
+    net = create_gen("UNet++", 3, 3, nf, True)
+    sd = randomize(net)
+    if linear:
+        orc.ACT["relu"] = lambda t: t
+        net._tg_debug_act = 0
+    try:
+        g = torch.Generator().manual_seed(1)
+        x, _ = orc.synthetic_batch(g, n, size)
+        gout = torch.randn(n, 3, size, size, generator=g) * 0.01
+        orc.QUANT["on"] = True
+        psd = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in sd.items())
+        ref = orc.gen_forward("UNet++", psd, x, True)
+        names = list(psd)
+        rg = dict(zip(names, torch.autograd.grad(ref, [psd[k] for k in names], gout)))
+    finally:
+        orc.QUANT["on"] = False
+        orc.ACT["relu"] = torch.nn.functional.relu
+    net = net.cuda()
+    out = net(x.cuda())
+    assert rel(out, ref) < (0.02 if linear else 0.06)
+    out.backward(gout.cuda())
+    torch.cuda.synchronize()
+    assert _C.error_flag() == 0
+    for k, p in net.named_parameters():
+        if linear:
+            assert rel(p.grad, rg[k]) < 0.04, k
+        else:
+            assert cos(p.grad, rg[k]) > 0.9, k
+
+
+@pytest.mark.parametrize("nf,size,loss", [(64, 96, "ls"), (8, 64, "hinge"), (16, 64, "ce"), (16, 64, "w")])
+def test_discriminator_losses_gradient_penalty(nf, size, loss):
+    """D forward, D-loss gradients, the gradient penalty value + its double-backward gradients, and the
+    input gradient of the generator-side GAN loss."""
+    orc, _C = _setup()
+    from tactile_gan_b200._C import F, ptr
+    from tactile_gan_b200.discriminators.discriminators import create_disc
+    from tactile_gan_b200.engine import PatchDInstance
+    n, act = 2, loss == "ls"
+    net = create_disc("patch", 3, 3, nf, True, act)
+    sd = randomize(net)
+    g = torch.Generator().manual_seed(1)
+    a, b = orc.synthetic_batch(g, n, size)
+    fake = torch.rand(n, 3, size, size, generator=g)
+    alpha = torch.rand(n, 1, generator=g)
+    orc.QUANT["on"] = True
+    try:
+        psd = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in sd.items())
+        names = list(psd)
+        pred_r, feats_r = orc.patchd_forward(psd, a, b, act)
+        label = orc.make_real_label(pred_r.shape, True, generator=g) if loss in ("ls", "ce") else torch.ones(1)
+        pred_f, _ = orc.patchd_forward(psd, a, fake, act)
+        loss_d = (orc.gan_loss(pred_f, False, loss, label) + orc.gan_loss(pred_r, True, loss, label)) / 2
+        gd = dict(zip(names, torch.autograd.grad(loss_d, [psd[k] for k in names], retain_graph=True, allow_unused=True)))
+        gp = orc.gradient_penalty(psd, a, b, fake, alpha, act, 0.01)
+        ggp = dict(zip(names, torch.autograd.grad(gp, [psd[k] for k in names], allow_unused=True)))
+        fake_g = fake.clone().requires_grad_(True)
+        pred_g, _ = orc.patchd_forward(OrderedDict((k, v.detach()) for k, v in psd.items()), a, fake_g, act)
+        lg = orc.gan_loss(pred_g, True, loss, label, for_discriminator=False)
+        (gin,) = torch.autograd.grad(lg, fake_g)
+    finally:
+        orc.QUANT["on"] = False
+    net = net.cuda()
+    A = PatchDInstance(net, 2 * n, size, size, backward=True)
+    S = PatchDInstance(net, n, size, size, backward=True, second_order=True)
+    A.pack_input(torch.cat([a, a]).cuda(), torch.cat([fake, b]).cuda())
+    pred = A.forward()
+    u5 = A.u[4]
+    hw5 = u5.ho * u5.wo
+    assert rel(pred[:n, :, :, 0], pred_f[:, 0]) < 5e-3 and rel(pred[n:, :, :, 0], pred_r[:, 0]) < 5e-3
+    for f, fr in zip(A.features(), feats_r):
+        assert rel(f.buf[n:, :, :, :f.c].permute(0, 3, 1, 2), fr) < 5e-3
+    losses = torch.zeros(8, device="cuda")
+    lab = label.cuda().contiguous() if loss in ("ls", "ce") else None
+    mode = _C.GAN_MODES[loss]
+    A.store.zero_grad()
+    u5.dz.zero_()
+    _C.call("gan_loss", ptr(pred), None, F(0.0), mode, 0, 1, int(A.has_sigmoid), F(0.5), 0, n, hw5, u5.c,
+            ptr(losses[0:1]), ptr(u5.dz))
+    _C.call("gan_loss", ptr(pred), ptr(lab), F(1.0), mode, 1, 1, int(A.has_sigmoid), F(0.5), n, 2 * n, hw5, u5.c,
+            ptr(losses[0:1]), ptr(u5.dz))
+    A.backward(wgrad=True)
+    got = A.store.grads_by_name()
+    # 'w' is a difference of two means of O(1) logits: scale the absolute tolerance by the logit magnitude
+    mag = float(pred_r.abs().mean() + pred_f.abs().mean())
+    assert losses[0].item() == pytest.approx(loss_d.item(), rel=2e-3, abs=2e-3 * mag)
+    for k in names:
+        if gd[k] is not None and gd[k].norm() > 0:
+            assert rel(got[k], gd[k]) < 0.05, k
+    al = ((alpha + 1) / 2).view(-1).cuda().contiguous()
+    S.store.zero_grad()
+    S.pack_input(a.cuda(), b.cuda(), wa=al, b2=fake.cuda(), wb=(1 - al).contiguous())
+    S.forward()
+    S.gp_first_backward()
+    S.gp_penalty(3, 3, 0.01, 1.0, losses[1:2])
+    S.gp_second_backward()
+    got = S.store.grads_by_name()
+    assert losses[1].item() == pytest.approx(gp.item(), rel=5e-3)
+    for k in names:
+        if ggp[k] is None or ggp[k].norm() == 0:
+            assert got[k].abs().max().item() < 1e-6, k
+        else:
+            assert rel(got[k], ggp[k]) < 0.05, k
+    S.pack_input(a.cuda(), fake.cuda())
+    p2 = S.forward()
+    S.u[4].dz.zero_()
+    _C.call("gan_loss", ptr(p2), ptr(lab), F(1.0), mode, 1, 0, int(S.has_sigmoid), F(1.0), 0, n, hw5, u5.c,
+            ptr(losses[2:3]), ptr(S.u[4].dz))
+    dx0 = S.backward(wgrad=False, input_grad=True)
+    assert losses[2].item() == pytest.approx(lg.item(), rel=2e-3, abs=2e-3 * mag)
+    assert rel(dx0[..., 3:6].permute(0, 3, 1, 2), gin) < 0.05
+    assert _C.error_flag() == 0
+
+
+def _replay_fixture(name, steps=None):
+    """Run the fused TrainStep from a committed reference fixture's initial weights."""
+    orc, _C = _setup()
+    from tactile_gan_b200.discriminators.discriminators import create_disc
+    from tactile_gan_b200.generators.generators import create_gen
+    from tactile_gan_b200.step import TrainStep
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", name + ".pt"), weights_only=False)
+    m = fx["meta"]
+    act = m["loss"] == "ls"
+    netG = create_gen(m["gen"], 3, 3, m["nf"], act)
+    netD = create_disc("patch", 3, 3, m["nf"], True, act)
+    netG.load_state_dict(fx["init_G"], strict=False)
+    netD.load_state_dict(fx["init_D"])
+    netG, netD = netG.cuda(), netD.cuda()
+    ts = TrainStep(netG, netD, m["batch"], m["size"], m["size"], loss=m["loss"], version=2, lambda_a=m["lambda_a"],
+                   lambda_gp=m["lambda_gp"], lambda_per=m["lambda_per"], w_per=m["w_per"], lr=m["lr"], beta1=m["beta1"])
+    g = torch.Generator().manual_seed(m["seed"] + 1000)
+    outs = []
+    for rec in fx["steps"][:steps]:
+        a, b = orc.synthetic_batch(g, m["batch"], m["size"])
+        alpha = torch.rand(m["batch"], 1, generator=g)
+        if rec.get("real_label") is not None:
+            ts.set_label(rec["real_label"])
+        ts.step(a.cuda(), b.cuda(), regularize=True, alpha=alpha)
+        outs.append((ts.loss_dict(), ts.fake_B.cpu().clone()))
+    assert _C.error_flag() == 0
+    return fx, outs, netG, netD
+
+
+@pytest.mark.parametrize("name", ["unetpp_ls", "unetpp_hinge", "unetpp_ce", "unetpp_w"])
+def test_train_step_against_reference_fixture(name):
+    """Losses and generated images of the first step(s) vs what the UNMODIFIED reference produced
+    (tests/golden, generated by oracle/make_golden.py). Step 1 starts from identical weights; the
+    tolerance covers bf16 activations (losses 3 % + 2e-3 abs; fake_B 8 % rel-l2)."""
+    fx, outs, netG, netD = _replay_fixture(name, steps=1)
+    rec = fx["steps"][0]
+    got, fake = outs[0]
+    # G_GAN is evaluated after the first Adam step of D, which moves EVERY weight by lr*sign(grad): weights
+    # with near-zero gradients flip under bf16 noise. For the unsquashed modes (w, hinge) G_GAN is a raw mean
+    # logit, so it gets an absolute band of 0.02; everything else 3 % (+2e-3).
+    raw_logit = fx["meta"]["loss"] in ("w", "hinge")
+    for k in ("loss_D", "gp", "G_GAN", "L1", "per"):
+        tol = 0.02 if (raw_logit and k == "G_GAN") else 2e-3
+        assert got[k] == pytest.approx(rec[k], rel=0.03, abs=tol), (k, got[k], rec[k])
+    assert rel(fake[:, :, ::4, ::4], rec["fake_B_sub"]) < 0.08
+
+
+def test_two_step_trajectory_and_checkpoint_roundtrip(tmp_path):
+    """Second step (after both Adam updates) still tracks the reference; the checkpoint written in the
+    reference's final_model.pth layout reloads into fresh modules and into torch.optim.Adam."""
+    from tactile_gan_b200.optim import FusedAdam
+    fx, outs, netG, netD = _replay_fixture("unetpp_ls", steps=2)
+    rec = fx["steps"][1]
+    got, _ = outs[1]
+    for k in ("loss_D", "G_GAN", "L1", "per"):
+        assert got[k] == pytest.approx(rec[k], rel=0.10, abs=5e-3), (k, got[k], rec[k])
+    # each early Adam step moves a weight by ~lr*sign(grad): a sign flip of a near-zero gradient costs 2*lr, so
+    # after two steps the worst case is 4*lr = 4e-3; the bulk of the weights must agree far better.
+    for k, ref in fx["final_D"].items():
+        d = (netD.state_dict()[k].cpu() - ref).abs()
+        assert d.max().item() < 4.2e-3, k
+        assert d.mean().item() < 3e-4, (k, d.mean().item())
+    optD = FusedAdam(netD, lr=1e-3, betas=(0.9, 0.99))
+    optG = FusedAdam(netG, lr=1e-3, betas=(0.9, 0.99))
+    path = tmp_path / "final_model.pth"
+    torch.save({"gen": netG.state_dict(), "disc": netD.state_dict(), "optimizerG_state_dict": optG.state_dict(),
+                "optimizerD_state_dict": optD.state_dict()}, path)
+    ck = torch.load(path, weights_only=False)
+    assert set(ck) == {"gen", "disc", "optimizerG_state_dict", "optimizerD_state_dict"}
+    assert list(ck["disc"].keys()) == list(fx["final_D"].keys())
+    ref_opt = fx["optD_state"]
+    assert ck["optimizerD_state_dict"]["param_groups"][0]["betas"] == ref_opt["param_groups"][0]["betas"]
+    assert sorted(ck["optimizerD_state_dict"]["state"].keys()) == sorted(ref_opt["state"].keys())
+    for i, st in ck["optimizerD_state_dict"]["state"].items():
+        assert set(st) == {"step", "exp_avg", "exp_avg_sq"} and st["exp_avg"].shape == ref_opt["state"][i]["exp_avg"].shape
+        assert float(st["step"]) == float(ref_opt["state"][i]["step"])
+    plain = torch.optim.Adam([torch.nn.Parameter(p.detach().clone()) for p in netD.parameters()], lr=1e-3, betas=(0.9, 0.99))
+    plain.load_state_dict(ck["optimizerD_state_dict"])     # loads into the stock optimizer unchanged
+    optD.load_state_dict(ref_opt)                          # and the reference's state loads into ours
+    assert netD._tg_store.step_count == int(ref_opt["state"][0]["step"])

@@ -1,0 +1,214 @@
+"""-m gpu: the tcgen05 implicit-GEMM kernels and the bandwidth tail against plain fp32 torch math on the
+same bf16-rounded operands (tolerances: bf16 output rounding 2^-9 -> rel_l2 <= 5e-3 for convs that store
+bf16; fp32 wgrad accumulation -> 1e-4), plus size-independent properties at BASELINE.json's full sizes."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gpu_util import conv_taps, nhwc_pad, pad64, rel
+
+pytestmark = pytest.mark.gpu
+dev = "cuda"
+
+
+def _C():
+    from tactile_gan_b200 import _C as c
+    return c
+
+
+def run_conv(n, cins, cout, h, w, k, stride, pad, bias=False, act=0, stats=False, seed=0):
+    C = _C()
+    g = torch.Generator().manual_seed(seed)
+    xs = [torch.randn(n, c, h, w, generator=g).to(dev) for c in cins]
+    wt = (torch.randn(cout, sum(cins), k, k, generator=g) * 0.05).to(dev)
+    b = torch.randn(cout, generator=g).to(dev) if bias else None
+    ref = F.conv2d(torch.cat([x.bfloat16().float() for x in xs], 1), wt.bfloat16().float(), b, stride=stride, padding=pad)
+    ref = {0: ref, 1: F.leaky_relu(ref, 0.2), 2: torch.sigmoid(ref), 3: F.relu(ref)}[act]
+    ho, wo = ref.shape[2:]
+    cop, ipads = pad64(cout), [pad64(c) for c in cins]
+    wp = torch.zeros(k * k, cop, sum(ipads), dtype=torch.bfloat16, device=dev)
+    ko = ci = 0
+    srcs = []
+    for x, c, ip in zip(xs, cins, ipads):
+        wp[:, :cout, ko:ko + c] = wt[:, ci:ci + c].permute(2, 3, 0, 1).reshape(k * k, cout, c).bfloat16()
+        srcs.append(dict(act=nhwc_pad(x), wgt=wp, k_off=ko))
+        ko, ci = ko + ip, ci + c
+    out = torch.full((n, ho, wo, cop), 7.0, dtype=torch.bfloat16, device=dev)
+    sp = None
+    if stats:
+        tpi = C.conv_query_tiles(n, ho, wo, True)[3]
+        sp = torch.zeros(n, tpi, cop, 2, device=dev)
+    C.conv_plan(srcs, out, conv_taps(k, k, pad), stride=stride, bias=b, stats_partial=sp, act=act).run()
+    torch.cuda.synchronize()
+    assert C.error_flag() == 0
+    assert rel(out[..., :cout].permute(0, 3, 1, 2), ref) < 5e-3
+    if cop > cout and not bias and act != 2:
+        assert out[..., cout:].float().abs().max().item() == 0
+    if stats:
+        got = out[..., :cout].float()
+        s = sp.sum(1)
+        assert rel(s[:, :cout, 0], got.sum((1, 2))) < 1e-5
+        assert rel(s[:, :cout, 1], (got * got).sum((1, 2))) < 1e-5
+
+
+CONV_CASES = [
+    dict(n=2, cins=[64], cout=64, h=16, w=16, k=1, stride=1, pad=0),
+    dict(n=2, cins=[128], cout=128, h=32, w=32, k=3, stride=1, pad=1, stats=True),
+    dict(n=3, cins=[256], cout=256, h=16, w=16, k=3, stride=1, pad=1),
+    dict(n=2, cins=[512], cout=512, h=16, w=16, k=3, stride=1, pad=1),
+    dict(n=2, cins=[64, 64, 128], cout=64, h=64, w=64, k=3, stride=1, pad=1, stats=True),   # virtual concat
+    dict(n=2, cins=[3], cout=64, h=64, w=64, k=3, stride=1, pad=1),                           # padded Cin
+    dict(n=2, cins=[24, 8], cout=24, h=32, w=32, k=3, stride=1, pad=1, stats=True),           # ragged channels
+    dict(n=2, cins=[128], cout=256, h=61, w=61, k=3, stride=1, pad=0, stats=True),            # odd sizes (D)
+    dict(n=2, cins=[6], cout=64, h=64, w=64, k=3, stride=2, pad=0, bias=True, act=1),         # D layer 1
+    dict(n=2, cins=[64], cout=128, h=127, w=127, k=3, stride=2, pad=0, stats=True),           # D layer 2
+    dict(n=2, cins=[512], cout=1, h=59, w=59, k=3, stride=1, pad=0, bias=True, act=2),        # D head
+    dict(n=2, cins=[64], cout=128, h=64, w=64, k=4, stride=2, pad=1),                         # UNet down conv
+    dict(n=1, cins=[64], cout=64, h=16, w=16, k=3, stride=1, pad=1, stats=True),              # single image
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: f"{c['cins']}to{c['cout']}_{c['h']}_k{c['k']}s{c['stride']}")
+def test_conv_forward(case):
+    run_conv(**case)
+
+
+WGRAD_CASES = [
+    (2, [64], 64, 16, 16, 1, 1, 0), (2, [128], 256, 32, 32, 3, 1, 1), (2, [64, 64, 128], 64, 64, 64, 3, 1, 1),
+    (2, [3], 64, 64, 64, 3, 1, 1), (2, [128], 256, 61, 61, 3, 1, 0), (2, [64], 128, 127, 127, 3, 2, 0),
+    (2, [64], 128, 64, 64, 4, 2, 1), (2, [24, 8], 24, 32, 32, 3, 1, 1), (1, [512], 1, 59, 59, 3, 1, 0),
+]
+
+
+@pytest.mark.parametrize("n,cins,cout,h,w,k,stride,pad", WGRAD_CASES)
+def test_wgrad(n, cins, cout, h, w, k, stride, pad):
+    C = _C()
+    g = torch.Generator().manual_seed(1)
+    xs = [torch.randn(n, c, h, w, generator=g).to(dev) for c in cins]
+    xcat = torch.cat([x.bfloat16().float() for x in xs], 1)
+    wt = torch.zeros(cout, sum(cins), k, k, device=dev, requires_grad=True)
+    y = F.conv2d(xcat, wt, None, stride=stride, padding=pad)
+    dy = (torch.randn(y.shape, generator=g) * 0.1).to(dev)
+    (ref,) = torch.autograd.grad(y, wt, dy.bfloat16().float())
+    ipads, cop = [pad64(c) for c in cins], pad64(cout)
+    dw = torch.zeros(k * k, cop, sum(ipads), device=dev)
+    C.wgrad_plan([nhwc_pad(x) for x in xs], nhwc_pad(dy), conv_taps(k, k, pad), dw, stride=stride).run()
+    torch.cuda.synchronize()
+    assert C.error_flag() == 0
+    parts, ko = [], 0
+    for c, ip in zip(cins, ipads):
+        parts.append(dw[:, :cout, ko:ko + c])
+        ko += ip
+    got = torch.cat(parts, 2).reshape(k, k, cout, sum(cins)).permute(2, 3, 0, 1)
+    assert rel(got, ref) < 1e-4
+    # wgrad accumulates (+=): a second launch doubles the result
+    C.wgrad_plan([nhwc_pad(x) for x in xs], nhwc_pad(dy), conv_taps(k, k, pad), dw, stride=stride).run()
+    torch.cuda.synchronize()
+    assert rel(torch.cat([dw[:, :cout, :cins[0]]], 2), 2 * ref[:, :cins[0]].permute(2, 3, 0, 1).reshape(k * k, cout, cins[0])) < 1e-4
+
+
+def test_instance_norm_forward_backward_pool_upsample():
+    """IN(affine)+ReLU with fused AvgPool/Upsample copies and the backward with the three gradient routes,
+    against torch autograd on the same bf16 inputs."""
+    C = _C()
+    from tactile_gan_b200._C import F as f32, ptr
+    g = torch.Generator().manual_seed(3)
+    n, c, h, w = 2, 72, 16, 24
+    cp = pad64(c)
+    x = torch.randn(n, c, h, w, generator=g).to(dev) * 2 + 0.5
+    gamma = (1 + 0.1 * torch.randn(c, generator=g)).to(dev)
+    beta = (0.1 * torch.randn(c, generator=g)).to(dev)
+    raw = nhwc_pad(x)
+    xb = raw[..., :c].permute(0, 3, 1, 2).float().requires_grad_(True)
+    ga, be = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y_ref = F.relu(F.instance_norm(xb, weight=ga, bias=be, eps=1e-5))
+    pool_ref = F.avg_pool2d(y_ref, 2)
+    up_ref = F.interpolate(y_ref, scale_factor=2, mode="nearest")
+    mr = torch.zeros(n, cp, 2, device=dev)
+    C.call("in_stats_direct", ptr(raw), ptr(mr), n, h * w, cp, f32(1e-5))
+    y = torch.zeros_like(raw)
+    pool = torch.zeros(n, h // 2, w // 2, cp, dtype=torch.bfloat16, device=dev)
+    up = torch.zeros(n, 2 * h, 2 * w, cp, dtype=torch.bfloat16, device=dev)
+    C.call("in_act_fwd", ptr(raw), ptr(mr), ptr(gamma), ptr(beta), ptr(y), ptr(pool), 1, ptr(up), n, h, w, cp, c, 3,
+           f32(0.0))
+    assert rel(y[..., :c].permute(0, 3, 1, 2), y_ref) < 4e-3
+    assert rel(pool[..., :c].permute(0, 3, 1, 2), pool_ref) < 5e-3
+    assert rel(up[..., :c].permute(0, 3, 1, 2), up_ref) < 4e-3
+    assert y[..., c:].float().abs().max().item() == 0
+    gs = torch.randn(n, c, h, w, generator=g).to(dev)
+    gp = torch.randn(n, c, h // 2, w // 2, generator=g).to(dev)
+    gu = torch.randn(n, c, 2 * h, 2 * w, generator=g).to(dev)
+    q = lambda t: t.bfloat16().float()
+    loss = (y_ref * q(gs)).sum() + (pool_ref * q(gp)).sum() + (up_ref * q(gu)).sum()
+    dx_ref, dg_ref, db_ref = torch.autograd.grad(loss, [xb, ga, be])
+    dn = torch.zeros_like(raw)
+    dz = torch.zeros_like(raw)
+    red = torch.zeros(n, cp, 2, device=dev)
+    gs_p, gp_p, gu_p = nhwc_pad(gs), nhwc_pad(gp), nhwc_pad(gu)   # keep alive: the launch is asynchronous
+    C.call("in_bwd_reduce", ptr(raw), ptr(y), ptr(mr), ptr(gamma), ptr(beta), ptr(gs_p), ptr(gp_p), 1,
+           ptr(gu_p), ptr(dn), ptr(red), n, h, w, cp, c, 3, f32(0.0))
+    C.call("in_bwd_apply", ptr(dn), ptr(raw), ptr(mr), ptr(gamma), ptr(red), ptr(dz), n, h * w, cp, c)
+    dgam, dbet = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
+    C.call("affine_grad", ptr(red), ptr(dgam), ptr(dbet), n, cp, c)
+    torch.cuda.synchronize()
+    assert rel(dz[..., :c].permute(0, 3, 1, 2), dx_ref) < 1e-2   # dn is stored as bf16
+    assert rel(dgam, dg_ref) < 5e-3 and rel(dbet, db_ref) < 5e-3
+
+
+def test_adam_kernel_matches_torch_adam():
+    """tg_adam_step against torch.optim.Adam(betas=(0.9,0.99)) over 3 steps, incl. the bf16 re-pack."""
+    from tactile_gan_b200.layers import ConvLayer, ParamStore
+    conv = torch.nn.Conv2d(40, 24, 3, bias=True).to(dev)
+    ref = torch.nn.Conv2d(40, 24, 3, bias=True).to(dev)
+    ref.load_state_dict(conv.state_dict())
+    store = ParamStore(conv, dev)
+    layer = ConvLayer("c", conv.weight, conv.bias, "conv", 1, 0, [30, 10], dev)
+    store.register_conv(layer)
+    store.finalize()
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-3, betas=(0.9, 0.99))
+    g = torch.Generator().manual_seed(0)
+    for _ in range(3):
+        gw = torch.randn(24, 40, 3, 3, generator=g).to(dev)
+        gb = torch.randn(24, generator=g).to(dev)
+        ref.weight.grad, ref.bias.grad = gw.clone(), gb.clone()
+        opt.step()
+        store.zero_grad()
+        packed = gw.permute(2, 3, 0, 1).reshape(9, 24, 40)
+        layer.grad[:, :24, 0:30] = packed[:, :, :30]
+        layer.grad[:, :24, 64:74] = packed[:, :, 30:]
+        layer.bias_grad[:24] = gb
+        store.adam_step(1e-3, 0.9, 0.99, 1e-8)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(conv.weight, ref.weight, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(conv.bias, ref.bias, rtol=1e-5, atol=1e-7)
+    w = conv.weight.detach()
+    exp = w.permute(2, 3, 0, 1).reshape(9, 24, 40).bfloat16()
+    assert torch.equal(layer.pack_fwd[:, :24, 0:30], exp[:, :, :30])
+    assert torch.equal(layer.pack_fwd[:, :24, 64:74], exp[:, :, 30:])
+    assert torch.equal(layer.pack_bwd[:, 64:74, :24], exp.flip(0)[:, :, 30:].transpose(1, 2))
+    assert layer.pack_fwd[:, 24:].float().abs().max().item() == 0
+
+
+def test_full_size_properties():
+    """BASELINE.json sizes (batch 32, 256x256, 64 channels): exact scaling linearity of the conv
+    (x -> 2x is exact in bf16) and epilogue statistics == direct reduction of the stored output."""
+    C = _C()
+    n, c, h, w = 32, 64, 256, 256
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(n, h, w, c, generator=g).to(dev).bfloat16()
+    wt = (torch.randn(9, c, c, generator=g) * 0.05).to(dev).bfloat16()
+    out1 = torch.zeros(n, h, w, c, dtype=torch.bfloat16, device=dev)
+    out2 = torch.zeros_like(out1)
+    tpi = C.conv_query_tiles(n, h, w, True)[3]
+    sp = torch.zeros(n, tpi, c, 2, device=dev)
+    C.conv_plan([dict(act=x, wgt=wt)], out1, conv_taps(3, 3, 1), stats_partial=sp).run()
+    C.conv_plan([dict(act=x * 2, wgt=wt)], out2, conv_taps(3, 3, 1)).run()
+    torch.cuda.synchronize()
+    assert C.error_flag() == 0
+    assert torch.equal(out2, out1 * 2)
+    o = out1.float()
+    assert rel(sp.sum(1)[..., 0], o.sum((1, 2))) < 1e-5
+    assert rel(sp.sum(1)[..., 1], (o * o).sum((1, 2))) < 1e-5
+    # spot check 2 images against torch
+    ref = F.conv2d(x[:2].permute(0, 3, 1, 2).float(), wt.float().reshape(3, 3, c, c).permute(2, 3, 0, 1), padding=1)
+    assert rel(out1[:2].permute(0, 3, 1, 2), ref) < 5e-3
