@@ -158,6 +158,8 @@ def conv_plan(srcs, out, taps, stride=1, bias=None, stats_partial=None, act=ACT_
     d.bias = bias.data_ptr() if bias is not None else None
     d.bias_len = bias.numel() if bias is not None else 0
     d.stats_partial = stats_partial.data_ptr() if stats_partial is not None else None
+    if stats_partial is not None and not stats_tiles_total:
+        stats_tiles_total = stats_partial.shape[1]   # [n][tile slots][c][2]
     d.stats_tiles_total = stats_tiles_total
     d.stats_tile_off = stats_tile_off
     d.act = act

@@ -8,6 +8,8 @@
 #include "tg_api_internal.h"
 #include "tg_igemm.cuh"
 #include "tg_wgrad.cuh"
+#include "tg_igemm_halo.cuh"
+#include <cstdlib>
 
 static thread_local char g_err[512] = "";
 
@@ -55,6 +57,13 @@ int sm_count() {
 
 // 4-D NHWC map {C, W, H, N}; box {64, bw, bh, bn}; optional element strides on W/H.
 int make_act_map(CUtensorMap* m, const tg_view& v, int c_off, int c_len, int bw, int bh, int bn,
+                 int estride);
+
+// 3-D weight map with a box covering `box_taps` taps: {64, rows_box, box_taps}
+int make_wgt_map_taps(CUtensorMap* m, const void* base, int k_len, int rows, int taps, int pitch_k,
+                      int pitch_rows, int rows_box, int box_taps);
+
+int make_act_map(CUtensorMap* m, const tg_view& v, int c_off, int c_len, int bw, int bh, int bn,
                  int estride) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return tg_set_error("cuTensorMapEncodeTiled entry point unavailable");
@@ -83,11 +92,16 @@ int make_act_map(CUtensorMap* m, const tg_view& v, int c_off, int c_len, int bw,
 // 3-D weight map {K, rows, taps}; box {64, bn, 1}
 int make_wgt_map(CUtensorMap* m, const void* base, int k_len, int rows, int taps, int pitch_k,
                  int pitch_rows, int bn) {
+  return make_wgt_map_taps(m, base, k_len, rows, taps, pitch_k, pitch_rows, bn, 1);
+}
+
+int make_wgt_map_taps(CUtensorMap* m, const void* base, int k_len, int rows, int taps, int pitch_k,
+                      int pitch_rows, int bn, int box_taps) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return tg_set_error("cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[3] = {cuuint64_t(k_len), cuuint64_t(rows), cuuint64_t(taps)};
   cuuint64_t strides[2] = {cuuint64_t(pitch_k) * 2, cuuint64_t(pitch_k) * pitch_rows * 2};
-  cuuint32_t box[3] = {64, cuuint32_t(bn), 1};
+  cuuint32_t box[3] = {64, cuuint32_t(bn), cuuint32_t(box_taps)};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -120,13 +134,87 @@ void choose_tile(int n, int h, int w, int pixels, bool single_image, int* th, in
 }  // namespace
 
 struct tg_plan {
-  int kind;  // 0 conv, 1 wgrad
+  int kind;  // 0 conv, 1 wgrad, 2 halo-resident conv
   int bn;
   int grid;
   size_t smem;
   tg::IgemmParams conv;
   tg::WgradParams wg;
+  tg::HaloParams halo;
 };
+
+namespace {
+// 3x3-window stride-1 convolutions with a 64/128-wide output run the halo-resident kernel.
+bool halo_eligible(const tg_conv_desc* d, int* dy0, int* dx0, int* eh, int* ew) {
+  static const bool disabled = getenv("TG_DISABLE_HALO") != nullptr;
+  if (disabled || d->stride != 1 || d->taps > 9 || d->taps < 2) return false;
+  if (d->out.c != 64 && d->out.c != 128) return false;
+  int ymin = 127, ymax = -127, xmin = 127, xmax = -127;
+  for (int t = 0; t < d->taps; ++t) {
+    ymin = d->tap_dy[t] < ymin ? d->tap_dy[t] : ymin; ymax = d->tap_dy[t] > ymax ? d->tap_dy[t] : ymax;
+    xmin = d->tap_dx[t] < xmin ? d->tap_dx[t] : xmin; xmax = d->tap_dx[t] > xmax ? d->tap_dx[t] : xmax;
+  }
+  if (ymax - ymin > 2 || xmax - xmin > 2) return false;
+  for (int s = 0; s < d->num_src; ++s)
+    if (d->src[s].wgt_taps > 9 || d->src[s].wgt_taps != d->src[0].wgt_taps) return false;
+  for (int t = 0; t < d->taps; ++t)
+    if (d->tap_w[t] < 0 || d->tap_w[t] >= d->src[0].wgt_taps) return false;
+  *dy0 = ymin; *dx0 = xmin; *eh = ymax - ymin; *ew = xmax - xmin;
+  return true;
+}
+
+int create_halo_plan(const tg_conv_desc* d, tg_plan* pl, int dy0, int dx0, int eh, int ew) {
+  pl->kind = 2;
+  tg::HaloParams& p = pl->halo;
+  memset(&p, 0, sizeof(p));
+  const int cout = d->out.c;
+  p.num_src = d->num_src;
+  p.taps = d->taps;
+  for (int t = 0; t < d->taps; ++t) {
+    p.tap_dy[t] = int8_t(d->tap_dy[t] - dy0);
+    p.tap_dx[t] = int8_t(d->tap_dx[t] - dx0);
+    p.tap_w[t] = d->tap_w[t];
+  }
+  p.org_dy = dy0; p.org_dx = dx0;
+  p.halo_w = tg::kHaloTW + ew;
+  p.a_bytes = (tg::kHaloTW + ew) * (tg::kHaloTH + eh) * 128;
+  p.b_bytes = d->src[0].wgt_taps * tg::kHaloBN * 128;
+  p.Ho = d->out.h; p.Wo = d->out.w; p.N = d->out.n;
+  p.tiles_h = (p.Ho + tg::kHaloTH - 1) / tg::kHaloTH;
+  p.tiles_w = (p.Wo + tg::kHaloTW - 1) / tg::kHaloTW;
+  p.n_tiles = cout / tg::kHaloBN;
+  p.act = d->act; p.slope = d->slope;
+  p.bias = d->bias; p.bias_len = d->bias_len;
+  p.stats_partial = d->stats_partial;
+  p.stats_tiles_total = d->stats_tiles_total > 0 ? d->stats_tiles_total : p.tiles_h * p.tiles_w;
+  p.stats_tile_off = d->stats_tile_off;
+  if (p.stats_partial && p.stats_tiles_total < p.stats_tile_off + p.tiles_h * p.tiles_w)
+    return tg_set_error("tg_conv_plan_create: stats buffer has too few tile slots");
+  p.cout = cout;
+  p.err_flag = tg_error_flag_device_ptr();
+  for (int s = 0; s < d->num_src; ++s) {
+    const tg_conv_src& cs = d->src[s];
+    if (cs.act.c % 64) return tg_set_error("tg_conv_plan_create: source C must be a multiple of 64");
+    if (make_act_map(&p.src[s].act, cs.act, 0, cs.act.c, tg::kHaloTW + ew, tg::kHaloTH + eh, 1, 1)) return -1;
+    const char* wbase = static_cast<const char*>(cs.wgt) + (size_t(cs.row_off) * cs.wgt_k + cs.k_off) * 2;
+    if (make_wgt_map_taps(&p.src[s].wgt, wbase, cs.act.c, cout, cs.wgt_taps, cs.wgt_k, cs.wgt_rows, tg::kHaloBN,
+                          cs.wgt_taps))
+      return -1;
+    p.src[s].c_chunks = cs.act.c / 64;
+  }
+  if (make_act_map(&p.out, d->out, 0, cout, tg::kHaloTW, tg::kHaloTH, 1, 1)) return -1;
+  const int m_tiles = p.N * p.tiles_h * p.tiles_w;
+  const int total = ((m_tiles + tg::kHaloR - 1) / tg::kHaloR) * p.n_tiles;
+  pl->grid = total < sm_count() ? total : sm_count();
+  pl->smem = tg::kHaloSmem;
+  cudaError_t e = cudaFuncSetAttribute(tg::igemm_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl->smem));
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "cudaFuncSetAttribute(halo): %s", cudaGetErrorString(e));
+    return -1;
+  }
+  return 0;
+}
+}  // namespace
 
 extern "C" {
 
@@ -154,6 +242,9 @@ int tg_conv_query_tiles(int n, int ho, int wo, int want_stats, int* out4) {
   choose_tile(n, ho, wo, tg::kTileM, want_stats != 0, &th, &tw, &tn);
   out4[0] = th; out4[1] = tw; out4[2] = tn;
   out4[3] = ((ho + th - 1) / th) * ((wo + tw - 1) / tw);
+  // the halo-resident kernel tiles 16x8: report enough tile slots for either kernel
+  const int halo_tiles = ((ho + tg::kHaloTH - 1) / tg::kHaloTH) * ((wo + tg::kHaloTW - 1) / tg::kHaloTW);
+  if (want_stats && halo_tiles > out4[3]) out4[3] = halo_tiles;
   return 0;
 }
 
@@ -164,6 +255,16 @@ int tg_conv_plan_create(const tg_conv_desc* d, tg_plan** out) {
   if (d->out.c % 64) return tg_set_error("tg_conv_plan_create: Cout must be a multiple of 64");
   tg_plan* pl = new (std::nothrow) tg_plan();
   if (!pl) return tg_set_error("out of host memory");
+  {
+    int dy0, dx0, eh, ew;
+    if (halo_eligible(d, &dy0, &dx0, &eh, &ew)) {
+      for (int s = 0; s < d->num_src; ++s)
+        if (d->src[s].act.n != d->out.n) { delete pl; return tg_set_error("tg_conv_plan_create: batch mismatch"); }
+      if (create_halo_plan(d, pl, dy0, dx0, eh, ew)) { delete pl; return -1; }
+      *out = pl;
+      return 0;
+    }
+  }
   pl->kind = 0;
   tg::IgemmParams& p = pl->conv;
   memset(&p, 0, sizeof(p));
@@ -302,7 +403,9 @@ int tg_wgrad_plan_create(const tg_wgrad_desc* d, tg_plan** out) {
 int tg_plan_run(tg_plan* pl, void* stream) {
   if (!pl) return tg_set_error("tg_plan_run: null plan");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (pl->kind == 0) {
+  if (pl->kind == 2) {
+    tg::igemm_halo_kernel<<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->halo);
+  } else if (pl->kind == 0) {
     if (pl->bn == 256) tg::igemm_conv_kernel<256><<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->conv);
     else if (pl->bn == 128) tg::igemm_conv_kernel<128><<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->conv);
     else tg::igemm_conv_kernel<64><<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->conv);

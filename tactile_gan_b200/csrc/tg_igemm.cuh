@@ -81,6 +81,81 @@ __device__ __forceinline__ void mbar_wait_guard(uint32_t bar, uint32_t parity, i
   }
 }
 
+// ---- epilogue helpers (one warp per scheduler runs these: keep the instruction count low) ----------
+// 64 fp32 accumulator columns -> 32 packed bf16x2 words, with the optional bias / activation hoisted
+// out of the common (InstanceNorm follows: no bias, no activation) path.
+__device__ __forceinline__ void epi_pack(const uint32_t (&v0)[32], const uint32_t (&v1)[32],
+                                         uint32_t (&packed)[32], int act, float slope,
+                                         const float* __restrict__ bias, int bias_len, int c_base) {
+  if (act == ACT_NONE && bias == nullptr) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      packed[j] = pack_bf16x2(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1]));
+      packed[16 + j] = pack_bf16x2(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]));
+    }
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float x0 = __uint_as_float(j < 16 ? v0[2 * j] : v1[2 * (j - 16)]);
+    float x1 = __uint_as_float(j < 16 ? v0[2 * j + 1] : v1[2 * (j - 16) + 1]);
+    if (bias) {
+      if (c_base + 2 * j < bias_len) x0 += __ldg(bias + c_base + 2 * j);
+      if (c_base + 2 * j + 1 < bias_len) x1 += __ldg(bias + c_base + 2 * j + 1);
+    }
+    if (act == ACT_LRELU) {
+      x0 = x0 > 0.f ? x0 : x0 * slope;
+      x1 = x1 > 0.f ? x1 : x1 * slope;
+    } else if (act == ACT_RELU) {
+      x0 = fmaxf(x0, 0.f);
+      x1 = fmaxf(x1, 0.f);
+    } else if (act == ACT_SIGMOID) {
+      x0 = 1.f / (1.f + __expf(-x0));
+      x1 = 1.f / (1.f + __expf(-x1));
+    } else if (act == ACT_TANH) {
+      x0 = tanhf(x0);
+      x1 = tanhf(x1);
+    }
+    packed[j] = pack_bf16x2(x0, x1);
+  }
+}
+
+// this thread's row (128 B = 64 bf16) of the staging tile, 128B-swizzled like the TMA store expects
+__device__ __forceinline__ void epi_store_row(uint32_t stage, int row, const uint32_t (&packed)[32]) {
+  const uint32_t srow = stage + uint32_t(row) * 128u;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t dst = srow + (uint32_t(j ^ (row & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(packed[4 * j]),
+                 "r"(packed[4 * j + 1]), "r"(packed[4 * j + 2]), "r"(packed[4 * j + 3])
+                 : "memory");
+  }
+}
+
+// per-channel (sum, sum of squares) over rows [r0, r0+32) of the staged bf16 tile for channel pair `lane`.
+// `valid_mask` bit i == row r0+i lies inside the image.
+__device__ __forceinline__ void epi_stats_rows(uint32_t sbuf, int r0, int lane, uint32_t valid_mask,
+                                               float& s0, float& s1, float& q0, float& q1) {
+  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f, c0 = 0.f, c1 = 0.f, d0 = 0.f, d1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    uint32_t w0, w1;
+    const int ra = r0 + i, rb = r0 + i + 1;
+    const uint32_t aa = sbuf + uint32_t(ra) * 128u + (uint32_t((lane >> 2) ^ (ra & 7)) << 4) + uint32_t(lane & 3) * 4u;
+    const uint32_t ab = sbuf + uint32_t(rb) * 128u + (uint32_t((lane >> 2) ^ (rb & 7)) << 4) + uint32_t(lane & 3) * 4u;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(aa));
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w1) : "r"(ab));
+    if (!((valid_mask >> i) & 1u)) w0 = 0u;
+    if (!((valid_mask >> (i + 1)) & 1u)) w1 = 0u;
+    const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&w0);
+    const __nv_bfloat162 h1 = *reinterpret_cast<const __nv_bfloat162*>(&w1);
+    const float f0 = __low2float(h0), f1 = __high2float(h0), g0 = __low2float(h1), g1 = __high2float(h1);
+    a0 += f0; a1 += f1; b0 = fmaf(f0, f0, b0); b1 = fmaf(f1, f1, b1);
+    c0 += g0; c1 += g1; d0 = fmaf(g0, g0, d0); d1 = fmaf(g1, g1, d1);
+  }
+  s0 = a0 + c0; s1 = a1 + c1; q0 = b0 + d0; q1 = b1 + d1;
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kNumThreads, 1)
 igemm_conv_kernel(const __grid_constant__ IgemmParams p) {
@@ -210,6 +285,10 @@ igemm_conv_kernel(const __grid_constant__ IgemmParams p) {
     uint32_t aphase = 0;
     uint32_t chunk_ctr = 0;
     float* scratch = reinterpret_cast<float*>(smem_gen + (scratch_base - smem_base));
+    const int e_act = p.act, e_bias_len = p.bias_len;
+    const float e_slope = p.slope;
+    const float* e_bias = p.bias;
+    float* e_stats = p.stats_partial;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
@@ -218,6 +297,15 @@ igemm_conv_kernel(const __grid_constant__ IgemmParams p) {
       const int ho0 = (t_in / p.tiles_w) * p.th;
       const int wo0 = (t_in % p.tiles_w) * p.tw;
       const int n0 = img * p.tn;
+      // which of this warp-group's 32 statistic rows lie inside the image (tiles may overhang)
+      uint32_t valid_mask = 0xffffffffu;
+      if (e_stats && (ho0 + p.th > p.Ho || wo0 + p.tw > p.Wo)) {
+        valid_mask = 0u;
+        for (int i = 0; i < 32; ++i) {
+          const int r = ew * 32 + i;
+          if (ho0 + r / p.tw < p.Ho && wo0 + r % p.tw < p.Wo) valid_mask |= 1u << i;
+        }
+      }
       mbar_wait_guard(tfull_bar(as), aphase, p.err_flag, 4);
       tc_fence_after();
 #pragma unroll 1
@@ -234,65 +322,21 @@ igemm_conv_kernel(const __grid_constant__ IgemmParams p) {
         }
         const int c_base = n_tile * BN + chunk * 64;
         uint32_t packed[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const uint32_t* v = j < 16 ? v0 : v1;
-          const int jj = (j & 15) * 2;
-          float x0 = __uint_as_float(v[jj]);
-          float x1 = __uint_as_float(v[jj + 1]);
-          if (p.bias) {
-            if (c_base + 2 * j < p.bias_len) x0 += __ldg(p.bias + c_base + 2 * j);
-            if (c_base + 2 * j + 1 < p.bias_len) x1 += __ldg(p.bias + c_base + 2 * j + 1);
-          }
-          if (p.act == ACT_LRELU) {
-            x0 = x0 > 0.f ? x0 : x0 * p.slope;
-            x1 = x1 > 0.f ? x1 : x1 * p.slope;
-          } else if (p.act == ACT_RELU) {
-            x0 = fmaxf(x0, 0.f);
-            x1 = fmaxf(x1, 0.f);
-          } else if (p.act == ACT_SIGMOID) {
-            x0 = 1.f / (1.f + __expf(-x0));
-            x1 = 1.f / (1.f + __expf(-x1));
-          } else if (p.act == ACT_TANH) {
-            x0 = tanhf(x0);
-            x1 = tanhf(x1);
-          }
-          packed[j] = pack_bf16x2(x0, x1);
-        }
+        epi_pack(v0, v1, packed, e_act, e_slope, e_bias, e_bias_len, c_base);
         // staging buffer `sb` must have been drained by the TMA store issued two chunks ago
         if (et == 0) tma_store_wait_read<1>();
         named_bar_sync(1, 128);
-        const uint32_t srow = store_base + sb * kStoreBytes + uint32_t(row) * 128u;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t dst = srow + (uint32_t(j ^ (row & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(packed[4 * j]),
-                       "r"(packed[4 * j + 1]), "r"(packed[4 * j + 2]), "r"(packed[4 * j + 3])
-                       : "memory");
-        }
+        epi_store_row(store_base + sb * kStoreBytes, row, packed);
         fence_proxy_async();
         named_bar_sync(1, 128);
         if (et == 0) {
           tma_store_4d(&p.out, store_base + sb * kStoreBytes, c_base, wo0, ho0, n0);
           tma_store_commit();
         }
-        if (p.stats_partial) {
+        if (e_stats) {
           // column sums over the bf16 values actually stored (what the normalise pass will read)
-          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-          const uint32_t sbuf = store_base + sb * kStoreBytes;
-#pragma unroll 4
-          for (int r = ew * 32; r < ew * 32 + 32; ++r) {
-            const int hh = r / p.tw, ww = r % p.tw;
-            if (ho0 + hh < p.Ho && wo0 + ww < p.Wo) {
-              uint32_t w;
-              const uint32_t a = sbuf + uint32_t(r) * 128u + (uint32_t((lane >> 2) ^ (r & 7)) << 4) +
-                                 uint32_t(lane & 3) * 4u;
-              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(a));
-              const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w);
-              const float f0 = __low2float(h), f1 = __high2float(h);
-              s0 += f0; s1 += f1; q0 += f0 * f0; q1 += f1 * f1;
-            }
-          }
+          float s0, s1, q0, q1;
+          epi_stats_rows(store_base + sb * kStoreBytes, ew * 32, lane, valid_mask, s0, s1, q0, q1);
           float* sc = scratch + ew * 128;
           sc[(2 * lane) * 2 + 0] = s0;
           sc[(2 * lane) * 2 + 1] = q0;
@@ -302,7 +346,7 @@ igemm_conv_kernel(const __grid_constant__ IgemmParams p) {
           // et -> (channel = et >> 1, stat = et & 1)
           const float tot = scratch[et] + scratch[128 + et] + scratch[256 + et] + scratch[384 + et];
           const size_t tile_lin = size_t(n0) * p.stats_tiles_total + p.stats_tile_off + t_in;
-          p.stats_partial[(tile_lin * p.cout + c_base) * 2 + et] = tot;
+          e_stats[(tile_lin * p.cout + c_base) * 2 + et] = tot;
         }
       }
       as ^= 1;

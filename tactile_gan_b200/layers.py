@@ -83,12 +83,14 @@ class ConvLayer:
 
     # ---- plan factories -------------------------------------------------------------------
     def fwd_plan(self, srcs, out, stats_partial=None, act=ACT_NONE, slope=0.2, use_bias=True):
+        tiles_total = stats_partial.shape[1] if stats_partial is not None else 0
         """srcs: NHWC bf16 tensors in concat order (conv) -- Conv2d forward."""
         assert self.kind == "conv" and len(srcs) == len(self.in_split)
         s = [dict(act=t, wgt=self.pack_fwd, k_off=o, c_real=c) for t, o, c in zip(srcs, self.k_off, self.in_split)]
         return _C.conv_plan(s, out, conv_taps(self.kh, self.kw, self.pad), stride=self.stride,
                             bias=self.bias.detach() if (use_bias and self.bias is not None) else None,
-                            stats_partial=stats_partial, act=act, slope=slope, cout_real=self.O)
+                            stats_partial=stats_partial, act=act, slope=slope, cout_real=self.O,
+                            stats_tiles_total=tiles_total)
 
     def wgrad_plan(self, srcs, dy):
         assert self.kind == "conv"
