@@ -9,6 +9,7 @@
 #include "tg_igemm.cuh"
 #include "tg_wgrad.cuh"
 #include "tg_igemm_halo.cuh"
+#include "tg_wgrad_halo.cuh"
 #include <cstdlib>
 
 static thread_local char g_err[512] = "";
@@ -141,6 +142,7 @@ struct tg_plan {
   tg::IgemmParams conv;
   tg::WgradParams wg;
   tg::HaloParams halo;
+  tg::WgradHaloParams wgh;
 };
 
 namespace {
@@ -328,12 +330,86 @@ int tg_conv_plan_create(const tg_conv_desc* d, tg_plan** out) {
   return 0;
 }
 
+static int create_wgrad_halo_plan(const tg_wgrad_desc* d, tg_plan* pl, int ymin, int ymax, int xmin, int xmax) {
+  pl->kind = 3;
+  tg::WgradHaloParams& p = pl->wgh;
+  memset(&p, 0, sizeof(p));
+  const int eh = ymax - ymin, ew = xmax - xmin;
+  p.num_src = d->num_src;
+  p.taps = d->taps;
+  for (int t = 0; t < d->taps; ++t) {
+    p.tap_dy[t] = int8_t(ymax - d->tap_dy[t]);   // dY pixel = X pixel - tap offset
+    p.tap_dx[t] = int8_t(xmax - d->tap_dx[t]);
+    p.tap_w[t] = d->tap_w[t];
+  }
+  p.org_dy = -ymax; p.org_dx = -xmax;
+  p.halo_w = tg::kHaloTW + ew;
+  p.y_bytes = (tg::kHaloTW + ew) * (tg::kHaloTH + eh) * 128;
+  // pixel domain = the X (input) grid, which for stride-1 convs covers every pixel any tap touches
+  const int H = d->p[0].h, W = d->p[0].w;
+  p.N = d->q.n;
+  p.tiles_h = (H + tg::kHaloTH - 1) / tg::kHaloTH;
+  p.tiles_w = (W + tg::kHaloTW - 1) / tg::kHaloTW;
+  int chunks = 0;
+  for (int s = 0; s < d->num_src; ++s) {
+    if (d->p[s].c % 64) return tg_set_error("tg_wgrad_plan_create: P channels must be a multiple of 64");
+    if (d->p[s].h != H || d->p[s].w != W) return tg_set_error("tg_wgrad_plan_create: source size mismatch");
+    if (make_act_map(&p.src[s].act, d->p[s], 0, d->p[s].c, tg::kHaloTW, tg::kHaloTH, 1, 1)) return -1;
+    p.src[s].c_chunks = d->p[s].c / 64;
+    chunks += p.src[s].c_chunks;
+  }
+  if (make_act_map(&p.q, d->q, 0, d->q.c, tg::kHaloTW + ew, tg::kHaloTH + eh, 1, 1)) return -1;
+  p.total_chunks = chunks;
+  p.m_tiles = (chunks + 1) / 2;
+  p.n_tiles = d->q.c / 64;
+  p.tap_groups = (d->taps + tg::kWhTaps - 1) / tg::kWhTaps;
+  p.dw = d->dw;
+  p.m_total = d->dw_cols;
+  p.n_total = d->dw_rows;
+  if (p.m_total != chunks * 64) return tg_set_error("tg_wgrad_plan_create: dw_cols != sum of P channels");
+  if (p.n_total < d->q.c) return tg_set_error("tg_wgrad_plan_create: dw_rows < Q channels");
+  p.err_flag = tg_error_flag_device_ptr();
+  const int k_tiles = p.N * p.tiles_h * p.tiles_w;
+  const int items0 = p.tap_groups * p.m_tiles * p.n_tiles;
+  int splits = (2 * sm_count() + items0 - 1) / items0;
+  const int max_splits = k_tiles / 4 > 1 ? k_tiles / 4 : 1;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  while (splits > 1 && ((k_tiles + splits - 1) / splits) * (splits - 1) >= k_tiles) --splits;
+  p.splits = splits;
+  const int total = items0 * splits;
+  pl->grid = total < sm_count() ? total : sm_count();
+  pl->smem = tg::kWhSmem;
+  cudaError_t e = cudaFuncSetAttribute(tg::wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl->smem));
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "cudaFuncSetAttribute(wgrad halo): %s", cudaGetErrorString(e));
+    return -1;
+  }
+  return 0;
+}
+
 int tg_wgrad_plan_create(const tg_wgrad_desc* d, tg_plan** out) {
   if (!d || !out) return tg_set_error("tg_wgrad_plan_create: null argument");
   if (d->num_src < 1 || d->num_src > TG_MAX_SRC) return tg_set_error("tg_wgrad_plan_create: bad num_src");
   if (d->q.c % 64) return tg_set_error("tg_wgrad_plan_create: Q channels must be a multiple of 64");
   tg_plan* pl = new (std::nothrow) tg_plan();
   if (!pl) return tg_set_error("out of host memory");
+  {
+    static const bool disabled = getenv("TG_DISABLE_HALO") != nullptr;
+    int ymin = 127, ymax = -127, xmin = 127, xmax = -127;
+    for (int t = 0; t < d->taps; ++t) {
+      ymin = d->tap_dy[t] < ymin ? d->tap_dy[t] : ymin; ymax = d->tap_dy[t] > ymax ? d->tap_dy[t] : ymax;
+      xmin = d->tap_dx[t] < xmin ? d->tap_dx[t] : xmin; xmax = d->tap_dx[t] > xmax ? d->tap_dx[t] : xmax;
+    }
+    // same-size (pad = (k-1)/2) stride-1 windows only: the X grid then equals the dY grid
+    const bool same = d->p[0].h == d->q.h && d->p[0].w == d->q.w;
+    if (!disabled && d->stride == 1 && d->taps >= 2 && d->taps <= 9 && ymax - ymin <= 2 && xmax - xmin <= 2 && same &&
+        (d->q.c == 64 || d->q.c == 128)) {
+      if (create_wgrad_halo_plan(d, pl, ymin, ymax, xmin, xmax)) { delete pl; return -1; }
+      *out = pl;
+      return 0;
+    }
+  }
   pl->kind = 1;
   tg::WgradParams& p = pl->wg;
   memset(&p, 0, sizeof(p));
@@ -405,6 +481,8 @@ int tg_plan_run(tg_plan* pl, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (pl->kind == 2) {
     tg::igemm_halo_kernel<<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->halo);
+  } else if (pl->kind == 3) {
+    tg::wgrad_halo_kernel<<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->wgh);
   } else if (pl->kind == 0) {
     if (pl->bn == 256) tg::igemm_conv_kernel<256><<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->conv);
     else if (pl->bn == 128) tg::igemm_conv_kernel<128><<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->conv);
