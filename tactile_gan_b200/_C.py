@@ -174,7 +174,7 @@ def conv_plan(srcs, out, taps, stride=1, bias=None, stats_partial=None, act=ACT_
     return Plan(h, keep, "conv", flops)
 
 
-def wgrad_plan(p_srcs, q, taps, dw, stride=1, p_real=None, q_real=None):
+def wgrad_plan(p_srcs, q, taps, dw, stride=1, p_real=None, q_real=None, dw_row_off=0):
     """dw: fp32 [taps_total][rows >= q.C][cols == sum p.C]."""
     d = WgradDesc()
     d.num_src = len(p_srcs)
@@ -187,7 +187,7 @@ def wgrad_plan(p_srcs, q, taps, dw, stride=1, p_real=None, q_real=None):
     _taps(d.tap_dx, [t[1] for t in taps])
     _taps(d.tap_w, [t[2] for t in taps])
     assert dw.dtype == torch.float32 and dw.dim() == 3 and dw.is_contiguous()
-    d.dw = dw.data_ptr()
+    d.dw = dw.data_ptr() + dw_row_off * dw.shape[2] * 4   # row slice of every tap plane
     d.dw_rows, d.dw_cols = dw.shape[1], dw.shape[2]
     h = c_void_p()
     check(lib().tg_wgrad_plan_create(byref(d), byref(h)), "tg_wgrad_plan_create")

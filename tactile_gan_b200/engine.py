@@ -32,24 +32,35 @@ class Act:
     def shape(self):
         return self.buf.shape
 
-    def build_grad(self, scratch):
-        """Plan d(self) = sum of the input-gradients of all consuming convs (one launch when all
-        consumers are stride-1: the K loop of the implicit GEMM walks the consumers)."""
+    def build_grad(self, scratch, scratch2=None):
+        """Plan d(self) = sum of the input-gradients of all consuming convs. All stride-1 Conv2d consumers
+        share ONE launch (the K loop of the implicit GEMM walks the consumers); a strided Conv2d or a
+        ConvTranspose2d consumer gets its own launch(es) into a second buffer that is then added."""
         if not self.consumers:
             return
         n, h, w, c = self.buf.shape
         self.grad_buf = scratch[: n * h * w * c].view(n, h, w, c)
         units = [(u.layer, u.dz, seg) for u, seg in self.consumers]
-        if all(l.stride == 1 for l, _, _ in units):
-            self.grad_plans = [multi_dgrad_plan(units, self.grad_buf)]
-        else:
-            assert len(units) == 1, "strided consumers are single"
-            l, dz, seg = units[0]
-            self.grad_plans = l.dgrad_plans(dz, self.grad_buf, seg)
+        same = [x for x in units if x[0].kind == "conv" and x[0].stride == 1]
+        other = [x for x in units if not (x[0].kind == "conv" and x[0].stride == 1)]
+        self.grad_plans, self.grad_adds = [], []
+        if same:
+            self.grad_plans.append(multi_dgrad_plan(same, self.grad_buf))
+        for i, (l, dz, seg) in enumerate(other):
+            if not same and i == 0:
+                self.grad_plans += l.dgrad_plans(dz, self.grad_buf, seg)
+            else:
+                assert scratch2 is not None and len(other) - (0 if same else 1) <= 1, "one extra gradient route"
+                buf2 = scratch2[: n * h * w * c].view(n, h, w, c)
+                self.grad_adds.append((l.dgrad_plans(dz, buf2, seg), buf2))
 
     def run_grad(self):
         for p in self.grad_plans:
             p.run()
+        for plans, buf2 in self.grad_adds:
+            for p in plans:
+                p.run()
+            _C.call("add", ptr(self.grad_buf), ptr(buf2), ptr(self.grad_buf), LL(buf2.numel()))
         return self.grad_buf
 
 
@@ -60,8 +71,7 @@ class ConvUnit:
         self.eng, self.name, self.layer, self.srcs = eng, name, layer, srcs
         self.norm, self.gamma, self.beta, self.act, self.slope = norm, gamma, beta, act, slope
         n, h, w, _ = srcs[0].shape
-        k, s, p = layer.kh, layer.stride, layer.pad
-        self.ho, self.wo = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+        self.ho, self.wo = layer.out_hw(h, w)
         self.n, self.c, self.c_valid = n, layer.o_pad, layer.O
         shp = (n, self.ho, self.wo, self.c)
         self.y = Act(name + ".y", bf16(*shp, device=dev), layer.O)
@@ -75,8 +85,13 @@ class ConvUnit:
             t.consumers.append((self, i))
         self.raw = bf16(*shp, device=dev) if norm else None
         if norm:
-            _, _, _, self.tpi = _C.conv_query_tiles(n, self.ho, self.wo, True)
-            self.partial = torch.zeros(n, self.tpi, self.c, 2, device=dev)
+            # statistics come from the conv epilogue when a 128-pixel tile stays inside one image; tiny maps
+            # (UNet's 2x2 .. 8x8 levels) use a direct reduction instead
+            ph = layer.stride if layer.kind == "convT" else 1
+            gh, gw = self.ho // ph, self.wo // ph
+            self.epi_stats = gh * gw >= 128
+            self.tpi = _C.conv_query_tiles(n, gh, gw, True)[3] * ph * ph if self.epi_stats else 1
+            self.partial = torch.zeros(n, self.tpi, self.c, 2, device=dev) if self.epi_stats else None
             self.mr = torch.zeros(n, self.c, 2, device=dev)
             self.red = torch.zeros(n, self.c, 2, device=dev)
         eng.units.append(self)
@@ -84,13 +99,13 @@ class ConvUnit:
     def build(self, backward):
         srcs = [t.buf for t in self.srcs]
         if self.norm:
-            self.fwd_plan = self.layer.fwd_plan(srcs, self.raw, stats_partial=self.partial)
+            self.fwd_plans = self.layer.fwd_plans(srcs, self.raw, stats_partial=self.partial)
         else:
-            self.fwd_plan = self.layer.fwd_plan(srcs, self.y.buf, act=self.act, slope=self.slope)
+            self.fwd_plans = self.layer.fwd_plans(srcs, self.y.buf, act=self.act, slope=self.slope)
         if backward:
             eng = self.eng
-            self.wgrad_plan = self.layer.wgrad_plan(srcs, self.dz)
-            self.y.build_grad(eng.g_scratch)
+            self.wgrad_plans = self.layer.wgrad_plans(srcs, self.dz)
+            self.y.build_grad(eng.g_scratch, eng.g2_scratch)
             if self.pool:
                 self.pool.build_grad(eng.gp_scratch)
             if self.up:
@@ -103,11 +118,15 @@ class ConvUnit:
 
     # ---- forward
     def forward(self):
-        self.fwd_plan.run()
+        for p in self.fwd_plans:
+            p.run()
         if self.norm:
             n, ho, wo, c = self.n, self.ho, self.wo, self.c
             g, b = self._aff()
-            _C.call("in_finalize", ptr(self.partial), ptr(self.mr), n, self.tpi, c, ho * wo, F(EPS_IN))
+            if self.epi_stats:
+                _C.call("in_finalize", ptr(self.partial), ptr(self.mr), n, self.tpi, c, ho * wo, F(EPS_IN))
+            else:
+                _C.call("in_stats_direct", ptr(self.raw), ptr(self.mr), n, ho * wo, c, F(EPS_IN))
             _C.call("in_act_fwd", ptr(self.raw), ptr(self.mr), g, b, ptr(self.y.buf),
                     ptr(self.pool.buf if self.pool else None), self.pool_mode,
                     ptr(self.up.buf if self.up else None), n, ho, wo, c, self.c_valid, self.act, F(self.slope))
@@ -141,7 +160,8 @@ class ConvUnit:
         if wgrad:
             if self.layer.bias is not None:
                 _C.call("bias_grad", ptr(self.dz), ptr(self.layer.bias_grad), LL(n * ho * wo), c, self.c_valid)
-            self.wgrad_plan.run()
+            for p in self.wgrad_plans:
+                p.run()
 
 
 class HeadUnit:
@@ -194,6 +214,8 @@ class GraphEngine:
     def conv_layer(self, name, conv, in_split, kind="conv"):
         """One ConvLayer per nn.Conv2d, shared by every engine built on the same module."""
         cache = self.store.layer_cache
+        if isinstance(conv, torch.nn.ConvTranspose2d):
+            kind = "convT"
         if name not in cache:
             l = ConvLayer(name, conv.weight, conv.bias, kind, conv.stride[0], conv.padding[0], in_split,
                           self.device)
@@ -212,6 +234,7 @@ class GraphEngine:
             dev = self.device
             self.dn_scratch = bf16(mx, device=dev)
             self.g_scratch = bf16(mx, device=dev)
+            self.g2_scratch = bf16(mx, device=dev)
             self.gp_scratch = bf16(mx, device=dev)
             self.gu_scratch = bf16(mx_up, device=dev)
         for u in cu:
@@ -289,10 +312,97 @@ class UNetPPEngine(GraphEngine):
             u0.backward()
 
 
+class SequentialGenEngine(GraphEngine):
+    """Generators whose units run in construction order (UNet, BCDUNet)."""
+
+    def forward(self, x):
+        assert x.shape == (self.n, self.cin, self.h, self.w) and x.dtype == torch.float32 and x.is_contiguous()
+        self.store.refresh()
+        _C.call("pack_nchw", ptr(x), None, None, None, ptr(self.x_in.buf), self.n, self.h * self.w, self.cin,
+                self.x_in.buf.shape[3], 0)
+        for u in self.units:
+            u.forward()
+        return self.head.forward()
+
+    def backward(self, g1, g2=None):
+        dx = self.head.backward(g1, g2)
+        for u in reversed(self.units):
+            u.backward(g_extra=dx if u is self.last else None)
+
+    def _double(self, name, block, srcs, pool=0):
+        """[conv | convT] -> IN -> ReLU -> conv3x3 -> IN -> ReLU (reference ConvDown / DeconvUp / conv_block)."""
+        c0, n0, c1, n1 = _block_params(block)
+        relu = getattr(self.module, "_tg_debug_act", ACT_RELU)   # bring-up only: linearised network
+        l0 = self.conv_layer(name + ".0", c0, [t.c for t in srcs])
+        g0, b0 = _affine(n0)
+        u0 = ConvUnit(self, name + "a", l0, srcs, True, g0, b0, relu)
+        l1 = self.conv_layer(name + ".3", c1, [l0.O])
+        g1, b1 = _affine(n1)
+        return ConvUnit(self, name + "b", l1, [u0.y], True, g1, b1, relu, pool=pool)
+
+
+class UNetEngine(SequentialGenEngine):
+    """UNet (reference generators/UNet.py:55-99): 7 x ConvDown (conv k4 s2 p1 first), 7 x DeconvUp
+    (ConvTranspose k4 s2 p1 first, run as 4 sub-pixel phase convs), skip concats as K-loop sources."""
+
+    def __init__(self, module, n, h, w, backward=True):
+        super().__init__(module, n, h, w, backward)
+        if h % 128 or w % 128 or h < 256 or w < 256:
+            raise ValueError("UNet needs H, W >= 256 and divisible by 128 (7 halvings, InstanceNorm on >1 pixel)")
+        cin = module.conv1.layer[0].in_channels
+        self.cin = cin
+        self.x_in = Act("input", bf16(n, h, w, pad64(cin), device=self.device), cin)
+        c = [None]
+        t = self.x_in
+        for i in range(1, 8):
+            u = self._double(f"conv{i}", getattr(module, f"conv{i}").layer, [t])
+            c.append(u.y)
+            t = u.y
+        d = c[7]
+        for i in range(2, 9):
+            srcs = [d] if i == 2 else [d, c[9 - i]]
+            d = self._double(f"deconv{i}", getattr(module, f"deconv{i}").layer, srcs).y
+        self.last = self.units[-1]
+        self.head = HeadUnit(self, "downfeature", module.downfeature.conv.weight, module.downfeature.conv.bias, d,
+                             module.downfeature.activation)
+        self.finish()
+
+
+class BCDUNetEngine(SequentialGenEngine):
+    """BCDUNet (reference generators/BCDUNet.py:106-181): 4 levels of [conv3x3+bias -> IN (no affine) ->
+    ReLU] x 2 with MaxPool2d between them, ConvTranspose k2 s2 (+bias) up, skip concats. The ConvLSTM modules
+    are parameters only (never called by the reference forward)."""
+
+    def __init__(self, module, n, h, w, backward=True):
+        super().__init__(module, n, h, w, backward)
+        if h % 8 or w % 8:
+            raise ValueError("BCDUNet needs H, W divisible by 8")
+        cin = module.conv1[0].in_channels
+        self.cin = cin
+        self.x_in = Act("input", bf16(n, h, w, pad64(cin), device=self.device), cin)
+        u1 = self._double("conv1", module.conv1, [self.x_in], pool=2)
+        u2 = self._double("conv2", module.conv2, [u1.pool], pool=2)
+        u3 = self._double("conv3", module.conv3, [u2.pool], pool=2)
+        u4 = self._double("conv4", module.conv4, [u3.pool])
+        t = u4.y
+        for k, skip in ((3, u3), (2, u2), (1, u1)):
+            up = getattr(module, f"upconv{k}")
+            lu = self.conv_layer(f"upconv{k}", up, [t.c])
+            uu = ConvUnit(self, f"upconv{k}", lu, [t], False, act=ACT_NONE)
+            t = self._double(f"conv{k}m", getattr(module, f"conv{k}m"), [skip.y, uu.y]).y
+        self.last = self.units[-1]
+        self.head = HeadUnit(self, "conv0", module.conv0.weight, module.conv0.bias, t, module.activation)
+        self.finish()
+
+
 def build_generator_engine(kind, module, n, h, w, backward=True):
     kind = kind.lower()
     if kind == "unet++":
         return UNetPPEngine(module, n, h, w, backward)
+    if kind == "unet":
+        return UNetEngine(module, n, h, w, backward)
+    if kind == "bcdunet":
+        return BCDUNetEngine(module, n, h, w, backward)
     raise NameError(f"{kind} has no engine")
 
 
@@ -360,7 +470,8 @@ class PatchDInstance(GraphEngine):
         u5 = self.u[4]
         if wgrad:
             _C.call("bias_grad", ptr(u5.dz), ptr(u5.layer.bias_grad), LL(u5.n * u5.ho * u5.wo), u5.c, u5.c_valid)
-            u5.wgrad_plan.run()
+            for p in u5.wgrad_plans:
+                p.run()
         for unit in reversed(self.u[:4]):
             unit.backward(wgrad=wgrad)
         if input_grad:

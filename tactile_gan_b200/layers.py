@@ -82,9 +82,39 @@ class ConvLayer:
         self.bias_grad = None
 
     # ---- plan factories -------------------------------------------------------------------
-    def fwd_plan(self, srcs, out, stats_partial=None, act=ACT_NONE, slope=0.2, use_bias=True):
+    def out_hw(self, h, w):
+        k, s, p = self.kh, self.stride, self.pad
+        if self.kind == "conv":
+            return (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+        return (h - 1) * s - 2 * p + k, (w - 1) * s - 2 * p + k
+
+    def fwd_plans(self, srcs, out, stats_partial=None, act=ACT_NONE, slope=0.2, use_bias=True):
+        """List of launches computing the layer's forward: one for Conv2d, stride^2 phase launches for
+        ConvTranspose2d (each output phase is a small stride-1 conv written to a strided view)."""
+        if self.kind == "conv":
+            return [self.fwd_plan(srcs, out, stats_partial, act, slope, use_bias)]
+        assert len(srcs) == len(self.in_split)
+        s = self.stride
+        srcd = [dict(act=t, wgt=self.pack_fwd, k_off=o, c_real=c) for t, o, c in zip(srcs, self.k_off, self.in_split)]
+        plans = []
+        bias = self.bias.detach() if (use_bias and self.bias is not None) else None
         tiles_total = stats_partial.shape[1] if stats_partial is not None else 0
+        slot = tiles_total // (s * s) if stats_partial is not None else 0
+        ph = 0
+        for py in range(s):
+            for px in range(s):
+                taps = phase_taps(self.kh, self.kw, self.pad, s, py, px, flipped=False)
+                sub = out[:, py::s, px::s, :]
+                assert taps, "every phase of the supported transposed convs has taps"
+                plans.append(_C.conv_plan(srcd, sub, taps, bias=bias, stats_partial=stats_partial, act=act,
+                                          slope=slope, cout_real=self.O, stats_tiles_total=tiles_total,
+                                          stats_tile_off=ph * slot))
+                ph += 1
+        return plans
+
+    def fwd_plan(self, srcs, out, stats_partial=None, act=ACT_NONE, slope=0.2, use_bias=True):
         """srcs: NHWC bf16 tensors in concat order (conv) -- Conv2d forward."""
+        tiles_total = stats_partial.shape[1] if stats_partial is not None else 0
         assert self.kind == "conv" and len(srcs) == len(self.in_split)
         s = [dict(act=t, wgt=self.pack_fwd, k_off=o, c_real=c) for t, o, c in zip(srcs, self.k_off, self.in_split)]
         return _C.conv_plan(s, out, conv_taps(self.kh, self.kw, self.pad), stride=self.stride,
@@ -92,10 +122,20 @@ class ConvLayer:
                             stats_partial=stats_partial, act=act, slope=slope, cout_real=self.O,
                             stats_tiles_total=tiles_total)
 
+    def wgrad_plans(self, srcs, dy):
+        """Conv2d: one launch (P = concat inputs, Q = dY). ConvTranspose2d: the strided operand is dY
+        (P) and the fixed one the input (Q), one launch per concat segment into its row slice of
+        grad[taps][i_pad][o_pad]."""
+        if self.kind == "conv":
+            return [_C.wgrad_plan(list(srcs), dy, conv_taps(self.kh, self.kw, self.pad), self.grad,
+                                  stride=self.stride, p_real=self.I, q_real=self.O)]
+        taps = conv_taps(self.kh, self.kw, self.pad)
+        return [_C.wgrad_plan([dy], x, taps, self.grad, stride=self.stride, p_real=self.O, q_real=c, dw_row_off=o)
+                for x, o, c in zip(srcs, self.k_off, self.in_split)]
+
     def wgrad_plan(self, srcs, dy):
         assert self.kind == "conv"
-        return _C.wgrad_plan(list(srcs), dy, conv_taps(self.kh, self.kw, self.pad), self.grad,
-                             stride=self.stride, p_real=self.I, q_real=self.O)
+        return self.wgrad_plans(srcs, dy)[0]
 
     def dgrad_src(self, dy, seg):
         """Operand descriptor for the input-gradient of concat segment `seg`."""
@@ -103,7 +143,10 @@ class ConvLayer:
 
     def dgrad_plans(self, dy, out, seg=0):
         """Input gradient w.r.t. concat segment `seg` -> list of plans (one per output phase)."""
-        assert self.kind == "conv"
+        if self.kind == "convT":
+            # d(input) of a transposed conv is an ordinary strided conv over dY with the [tap][ci][co] pack
+            return [_C.conv_plan([self.dgrad_src(dy, seg)], out, conv_taps(self.kh, self.kw, self.pad),
+                                 stride=self.stride, cout_real=self.in_split[seg])]
         if self.stride == 1:
             return [_C.conv_plan([self.dgrad_src(dy, seg)], out, dgrad_taps_s1(self.kh, self.kw, self.pad),
                                  cout_real=self.in_split[seg])]

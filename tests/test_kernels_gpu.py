@@ -212,3 +212,97 @@ def test_full_size_properties():
     # spot check 2 images against torch
     ref = F.conv2d(x[:2].permute(0, 3, 1, 2).float(), wt.float().reshape(3, 3, c, c).permute(2, 3, 0, 1), padding=1)
     assert rel(out1[:2].permute(0, 3, 1, 2), ref) < 5e-3
+
+
+LAYER_CASES = [
+    # kind, in_split, cout, k, stride, pad, h, w, bias
+    ("conv", [128], 128, 4, 2, 1, 32, 32, False),          # UNet down conv, multi-chunk + stride 2
+    ("conv", [64], 128, 3, 1, 1, 8, 8, True),              # image smaller than the 16x8 tile, Cout 128
+    ("convT", [128], 64, 2, 2, 0, 8, 8, True),             # BCDUNet upconv
+    ("convT", [128, 128], 128, 4, 2, 1, 8, 8, False),      # UNet deconv on a skip concat
+    ("convT", [40], 24, 4, 2, 1, 16, 16, False),           # ragged channels, 4 sub-pixel phases
+    ("convT", [64, 64], 64, 4, 2, 1, 64, 64, False),       # large enough for epilogue statistics
+]
+
+
+@pytest.mark.parametrize("kind,in_split,cout,k,stride,pad,h,w,bias", LAYER_CASES)
+def test_conv_layer_forward_dgrad_wgrad(kind, in_split, cout, k, stride, pad, h, w, bias):
+    """ConvLayer plans (forward incl. transposed-conv phases, input gradient per concat segment, weight
+    gradient) against torch autograd, with the weights packed by the fused Adam/re-pack kernel."""
+    C = _C()
+    from tactile_gan_b200.layers import ConvLayer, ParamStore
+    n, cin = 2, sum(in_split)
+    mod = (torch.nn.Conv2d(cin, cout, k, stride, pad, bias=bias) if kind == "conv"
+           else torch.nn.ConvTranspose2d(cin, cout, k, stride, pad, bias=bias)).to(dev)
+    g = torch.Generator().manual_seed(4)
+    with torch.no_grad():
+        mod.weight.copy_((torch.randn(mod.weight.shape, generator=g) * 0.05).to(dev))
+    store = ParamStore(mod, dev)
+    layer = ConvLayer("l", mod.weight, mod.bias, kind, stride, pad, in_split, dev)
+    store.register_conv(layer)
+    store.finalize()
+    xs = [torch.randn(n, c, h, w, generator=g).to(dev) for c in in_split]
+    xq = [x.bfloat16().float().requires_grad_(True) for x in xs]
+    wq = mod.weight.detach().bfloat16().float().requires_grad_(True)
+    fn = torch.nn.functional.conv2d if kind == "conv" else torch.nn.functional.conv_transpose2d
+    ref = fn(torch.cat(xq, 1), wq, mod.bias, stride=stride, padding=pad)
+    ho, wo = ref.shape[2:]
+    assert (ho, wo) == layer.out_hw(h, w)
+    srcs = [nhwc_pad(x) for x in xs]
+    out = torch.zeros(n, ho, wo, pad64(cout), dtype=torch.bfloat16, device=dev)
+    for p in layer.fwd_plans(srcs, out):
+        p.run()
+    torch.cuda.synchronize()
+    assert C.error_flag() == 0
+    assert rel(out[..., :cout].permute(0, 3, 1, 2), ref) < 5e-3
+    dy = (torch.randn(ref.shape, generator=g) * 0.1).to(dev)
+    dyq = dy.bfloat16().float()
+    grads = torch.autograd.grad(ref, xq + [wq], dyq)
+    dyp = nhwc_pad(dy)
+    for seg, (x, gx) in enumerate(zip(xs, grads[:-1])):
+        dx = torch.zeros(n, h, w, pad64(x.shape[1]), dtype=torch.bfloat16, device=dev)
+        for p in layer.dgrad_plans(dyp, dx, seg):
+            p.run()
+        assert rel(dx[..., :x.shape[1]].permute(0, 3, 1, 2), gx) < 6e-3, seg
+    store.zero_grad()
+    for p in layer.wgrad_plans(srcs, dyp):
+        p.run()
+    torch.cuda.synchronize()
+    assert C.error_flag() == 0
+    assert rel(store.grad_as_torch(0), grads[-1]) < 1e-4
+
+
+def test_maxpool_forward_backward():
+    """IN(no affine)+ReLU with the fused MaxPool2d(2) copy, and gradient routing to the arg-max."""
+    C = _C()
+    from tactile_gan_b200._C import F as f32, ptr
+    g = torch.Generator().manual_seed(6)
+    n, c, h, w = 2, 64, 16, 16
+    x = torch.randn(n, c, h, w, generator=g).to(dev)
+    raw = nhwc_pad(x)
+    xb = raw.permute(0, 3, 1, 2).float().requires_grad_(True)
+    y_ref = F.relu(F.instance_norm(xb, eps=1e-5))
+    mr = torch.zeros(n, c, 2, device=dev)
+    C.call("in_stats_direct", ptr(raw), ptr(mr), n, h * w, c, f32(1e-5))
+    y = torch.zeros_like(raw)
+    pool = torch.zeros(n, h // 2, w // 2, c, dtype=torch.bfloat16, device=dev)
+    C.call("in_act_fwd", ptr(raw), ptr(mr), None, None, ptr(y), ptr(pool), 2, None, n, h, w, c, c, 3, f32(0.0))
+    yq = y.permute(0, 3, 1, 2).float()
+    assert rel(yq, y_ref) < 4e-3
+    assert torch.equal(pool.permute(0, 3, 1, 2).float(), F.max_pool2d(yq, 2))
+    # backward through pool only: gradient lands on the window maximum (computed on the stored y)
+    yq2 = yq.clone().requires_grad_(True)
+    gp = torch.randn(n, c, h // 2, w // 2, generator=g).to(dev).bfloat16().float()
+    (g_y,) = torch.autograd.grad(F.max_pool2d(yq2, 2), yq2, gp)
+    mask = (F.instance_norm(xb, eps=1e-5) > 0).float()
+    gpp = nhwc_pad(gp)
+    dn = torch.zeros_like(raw)
+    red = torch.zeros(n, c, 2, device=dev)
+    C.call("in_bwd_reduce", ptr(raw), ptr(y), ptr(mr), None, None, None, ptr(gpp), 2, None, ptr(dn), ptr(red), n, h, w,
+           c, c, 3, f32(0.0))
+    torch.cuda.synchronize()
+    # ties (several zeros in a window) are routed to the first element by both implementations only when
+    # the maximum is positive; compare where the pooled value is > 0
+    pos = (F.max_pool2d(yq, 2) > 0).float()
+    pos_full = F.interpolate(pos, scale_factor=2, mode="nearest")
+    assert rel(dn.permute(0, 3, 1, 2).float() * pos_full, g_y * mask.detach() * pos_full) < 1e-2
