@@ -56,7 +56,9 @@ def test_tile_choice(lib):
         assert th * tw * tn == 128
         if stats:
             assert tn == 1
-        assert tpi == -(-h // th) * -(-w // tw)
+        generic = -(-h // th) * -(-w // tw)
+        halo = -(-h // 16) * -(-w // 8)           # the halo-resident kernels tile 16x8
+        assert tpi == (max(generic, halo) if stats else generic)
 
 
 def test_phase_taps_cover_transposed_conv():
@@ -120,3 +122,24 @@ def test_train_cli_surface():
                continue_training=False, reg_every=1)
     for k, v in exp.items():
         assert getattr(o, k) == v, k
+
+
+@pytest.mark.parametrize("mode", ["ls", "ce", "w", "hinge"])
+def test_ganloss_class_matches_oracle(mode):
+    """GANLoss (compat surface) against the oracle's restatement on CPU tensors, incl. error behaviour."""
+    import oracle as orc
+    from tactile_gan_b200.generators.generators import GANLoss
+    g = torch.Generator().manual_seed(0)
+    pred = torch.randn(2, 1, 7, 7, generator=g)
+    gl = GANLoss(gan_mode=mode, label_smoothing=False)
+    one = torch.ones(1)
+    for real, disc in ((True, True), (False, True), (True, False)):
+        assert float(gl(pred, real, for_discriminator=disc)) == pytest.approx(
+            float(orc.gan_loss(pred, real, mode, one, for_discriminator=disc)), rel=1e-6, abs=1e-7)
+    with pytest.raises(ValueError):
+        GANLoss(gan_mode="nope")
+    torch.manual_seed(3)
+    sm = GANLoss(gan_mode="ls", label_smoothing=True)
+    a = sm.get_target_tensor(pred, True)
+    assert a.shape == pred.shape and float(a.max()) <= 1.0 and sm.get_target_tensor(pred, True) is not None
+    assert torch.equal(sm.real_label_tensor, a)     # cached: drawn once
