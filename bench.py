@@ -114,6 +114,38 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def layer_table(ts, batch, path):
+    """Diagnostic (not a bench number): two more steps with a CUDA-event pair around every launch;
+    per-shape implicit-GEMM TFLOP/s and per-kernel tail time go to `path` as JSON."""
+    from tactile_gan_b200 import _C
+    _C.TIMING["records"].clear()
+    _C.TIMING["tail_records"].clear()
+    _C.TIMING["on"] = _C.TIMING["tail"] = True
+    reps = 2
+    for _ in range(reps):
+        ts.step(*batch)
+    torch.cuda.synchronize()
+    _C.TIMING["on"] = _C.TIMING["tail"] = False
+    gemm, tail = {}, {}
+    for kind, flops, a, b, tag in _C.TIMING["records"]:
+        t, f, c = gemm.get(tag, (0.0, 0.0, 0))
+        gemm[tag] = (t + a.elapsed_time(b), f + flops, c + 1)
+    for name, a, b in _C.TIMING["tail_records"]:
+        t, c = tail.get(name, (0.0, 0))
+        tail[name] = (t + a.elapsed_time(b), c + 1)
+    _C.TIMING["records"].clear()
+    _C.TIMING["tail_records"].clear()
+    out = {"gemm": [{"tag": k, "ms_per_step": t / reps, "launches_per_step": c / reps,
+                     "tflops": (f / (t / 1e3) / 1e12) if t > 0 else 0.0, "gflop_per_step": f / reps / 1e9}
+                    for k, (t, f, c) in sorted(gemm.items(), key=lambda kv: -kv[1][0])],
+           "tail": [{"kernel": k, "ms_per_step": t / reps, "launches_per_step": c / reps}
+                    for k, (t, c) in sorted(tail.items(), key=lambda kv: -kv[1][0])]}
+    out["gemm_ms_per_step"] = sum(r["ms_per_step"] for r in out["gemm"])
+    out["tail_ms_per_step"] = sum(r["ms_per_step"] for r in out["tail"])
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    json.dump(out, open(path, "w"), indent=1)
+
+
 def run_ours(args):
     from tactile_gan_b200 import _C
     from tactile_gan_b200.discriminators.discriminators import create_disc
@@ -175,10 +207,12 @@ def run_ours(args):
     losses = ts.loss_dict()
     # per-kernel-kind roofline from the CUDA events recorded around every implicit-GEMM launch
     agg = {}
-    for kind, flops, a, b in _C.TIMING["records"]:
+    for kind, flops, a, b, _tag in _C.TIMING["records"]:
         t, f, c = agg.get(kind, (0.0, 0.0, 0))
         agg[kind] = (t + a.elapsed_time(b), f + flops, c + 1)
     _C.TIMING["records"].clear()
+    if args.layers and rank == 0:
+        layer_table(ts, devb[0], args.layers)
     # end-to-end through the public call with host buffers
     for i in range(min(2, args.warmup)):
         ts.step_from_host(*host[i % pool])
@@ -229,6 +263,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch (configs[1]: 32)")
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--layers", default="", help="diagnostic: write a per-shape / per-kernel timing table (JSON)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -94,18 +94,20 @@ def _taps(arr, vals):
 
 # launch accounting (bench.py): number of kernels launched, and optional per-plan CUDA-event timing
 COUNTERS = {"launches": 0}
-TIMING = {"on": False, "records": []}   # records: (kind, flops, start_event, end_event)
+TIMING = {"on": False, "records": [], "tail": False, "tail_records": []}
+# records: (kind, flops, start_event, end_event, tag); tail_records: (name, start_event, end_event)
 _KERNELS_PER_CALL = {"in_bwd2": 2}
 
 
 class Plan:
     """Owns a tg_plan*; keeps the tensors it points at alive."""
 
-    def __init__(self, handle, keep, kind="conv", flops=0.0):
+    def __init__(self, handle, keep, kind="conv", flops=0.0, tag=""):
         self.handle = handle
         self.keep = keep
         self.kind = kind
         self.flops = flops
+        self.tag = tag
 
     def run(self):
         COUNTERS["launches"] += 1
@@ -115,7 +117,7 @@ class Plan:
             e0.record()
             check(lib().tg_plan_run(self.handle, stream_ptr()), "tg_plan_run")
             e1.record()
-            TIMING["records"].append((self.kind, self.flops, e0, e1))
+            TIMING["records"].append((self.kind, self.flops, e0, e1, self.tag))
             return
         check(lib().tg_plan_run(self.handle, stream_ptr()), "tg_plan_run")
 
@@ -171,7 +173,10 @@ def conv_plan(srcs, out, taps, stride=1, bias=None, stats_partial=None, act=ACT_
     flops = 0.0
     for s in srcs:
         flops += 2.0 * n * ho * wo * len(taps) * s.get("c_real", s["act"].shape[3]) * (cout_real or out.shape[3])
-    return Plan(h, keep, "conv", flops)
+    tag = "conv n%d %dx%d cin[%s] cout%d taps%d s%d%s" % (
+        n, ho, wo, ",".join(str(s["act"].shape[3]) for s in srcs), out.shape[3], len(taps), stride,
+        " stats" if stats_partial is not None else "")
+    return Plan(h, keep, "conv", flops, tag)
 
 
 def wgrad_plan(p_srcs, q, taps, dw, stride=1, p_real=None, q_real=None, dw_row_off=0):
@@ -194,7 +199,9 @@ def wgrad_plan(p_srcs, q, taps, dw, stride=1, p_real=None, q_real=None, dw_row_o
     n, ho, wo, qc = q.shape
     pc = p_real if p_real is not None else sum(t.shape[3] for t in p_srcs)
     flops = 2.0 * n * ho * wo * len(taps) * pc * (q_real if q_real is not None else qc)
-    return Plan(h, list(p_srcs) + [q, dw], "wgrad", flops)
+    tag = "wgrad n%d %dx%d p[%s] q%d taps%d s%d" % (
+        n, ho, wo, ",".join(str(t.shape[3]) for t in p_srcs), qc, len(taps), stride)
+    return Plan(h, list(p_srcs) + [q, dw], "wgrad", flops, tag)
 
 
 def error_flag():
@@ -206,6 +213,15 @@ def call(name, *args):
     """Call a tail kernel launcher `tg_<name>(..., stream)`."""
     fn = getattr(lib(), "tg_" + name)
     COUNTERS["launches"] += _KERNELS_PER_CALL.get(name, 1)
+    if TIMING["tail"]:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(fn(*args, stream_ptr()), "tg_" + name)
+        e1.record()
+        shape = ",".join(str(a) for a in args if isinstance(a, int))
+        TIMING["tail_records"].append((name + "(" + shape + ")", e0, e1))
+        return
     check(fn(*args, stream_ptr()), "tg_" + name)
 
 
