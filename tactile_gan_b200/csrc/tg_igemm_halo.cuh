@@ -139,7 +139,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_halo_kernel(const __grid
     // ------------------------------------------------------------ MMA issuer
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(kTileM, kHaloBN, 0, 0);
-      const uint32_t sbo = uint32_t(p.halo_w) * 128u;
+      // descriptor halves that never change, and the per-tap start-address steps (in 16-byte units), are
+      // computed once: the issue loop below is then two adds + one MMA per instruction, which a single
+      // thread must sustain at one MMA every 32 cycles (N = 64)
+      const uint32_t a_hi = umma_desc_hi_sw128(uint32_t(p.halo_w) * 128u);
+      const uint32_t b_hi = umma_desc_hi_sw128(1024u);
+      uint32_t a_step[9], b_step[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        a_step[t] = t < p.taps ? uint32_t(p.tap_dy[t] * p.halo_w + p.tap_dx[t]) * 8u : 0u;
+        b_step[t] = t < p.taps ? uint32_t(p.tap_w[t]) * (kHaloBN * 8u) : 0u;
+      }
+      const int ntaps = p.taps;
       int bs = 0, as = 0, set = 0;
       uint32_t bphase = 0, aphase = 0, tphase = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -149,19 +160,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_halo_kernel(const __grid
         tc_fence_after();
         for (int c = 0; c < chunks; ++c) {
           mbar_wait_guard(bfull(bs), bphase, p.err_flag, 24);
-          const uint32_t b_addr = b_base + bs * kHaloBStage;
+          const uint32_t b_lo0 = umma_desc_lo(b_base + bs * kHaloBStage, 16);
           for (int r = 0; r < cnt; ++r) {
             mbar_wait_guard(afull(as), aphase, p.err_flag, 25);
             tc_fence_after();
-            const uint32_t a_addr = a_base + as * kHaloAStage;
+            const uint32_t a_lo0 = umma_desc_lo(a_base + as * kHaloAStage, 16);
             const uint32_t d_tmem = tmem_base + uint32_t((set * kHaloR + r) * kHaloBN);
-            for (int tap = 0; tap < p.taps; ++tap) {
-              const uint32_t a_tap = a_addr + uint32_t(p.tap_dy[tap] * p.halo_w + p.tap_dx[tap]) * 128u;
-              const uint32_t b_tap = b_addr + uint32_t(p.tap_w[tap]) * (kHaloBN * 128u);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_f16(d_tmem, umma_smem_desc_sw128(a_tap + k * 32, 16, sbo),
-                         umma_smem_desc_sw128(b_tap + k * 32, 16, 1024), idesc, (c | tap | k) != 0 ? 1u : 0u);
+            for (int tap = 0; tap < 9; ++tap) {
+              if (tap < ntaps) {
+                const uint32_t a_lo = a_lo0 + a_step[tap], b_lo = b_lo0 + b_step[tap];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_f16_split(d_tmem, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc,
+                                 (tap | k) != 0 ? 1u : uint32_t(c != 0));
               }
             }
             umma_commit(aempty(as));

@@ -289,7 +289,62 @@ struct InBwdArgs {
   float slope;
 };
 
-__global__ void __launch_bounds__(256, 3) in_bwd_reduce_kernel(const InBwdArgs a) {
+// Per-pixel work of the backward reduce for the general case (pooled / upsampled gradient routes).
+__device__ __forceinline__ void in_bwd_gather(const InBwdArgs& a, int n, int pix, int c0, float (&g)[8]) {
+  const int yy = pix / a.W, xx = pix % a.W;
+  if (a.g_up) {
+    const int WU = 2 * a.W;
+    const size_t ub = (size_t(n) * 2 * a.H + 2 * yy) * WU + 2 * xx;
+    const uint4 u0 = ldg16(a.g_up + ub * a.C + c0), u1 = ldg16(a.g_up + (ub + 1) * a.C + c0);
+    const uint4 u2 = ldg16(a.g_up + (ub + WU) * a.C + c0), u3 = ldg16(a.g_up + (ub + WU + 1) * a.C + c0);
+    float f[8];
+    unpack8(u0, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] += f[j];
+    unpack8(u1, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] += f[j];
+    unpack8(u2, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] += f[j];
+    unpack8(u3, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] += f[j];
+  }
+  if (a.g_pool) {
+    const int H2 = a.H >> 1, W2 = a.W >> 1;
+    float f[8];
+    unpack8(ldg16(a.g_pool + ((size_t(n) * H2 + (yy >> 1)) * W2 + (xx >> 1)) * a.C + c0), f);
+    if (a.pool_mode == 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += 0.25f * f[j];
+    } else {
+      // max-pool routing: first element (row-major in the 2x2 window) equal to the window max
+      float best[8];
+      int first[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { best[j] = -3.0e38f; first[j] = 0; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int y2 = (yy & ~1) + (k >> 1), x2 = (xx & ~1) + (k & 1);
+        float o[8];
+        unpack8(ldg16(a.y + ((size_t(n) * a.H + y2) * a.W + x2) * a.C + c0), o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (o[j] > best[j]) { best[j] = o[j]; first[j] = k; }
+      }
+      const int mine = ((yy & 1) << 1) | (xx & 1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (first[j] == mine) g[j] += f[j];
+    }
+  }
+}
+
+// PLAIN: the only gradient route is g_same (no pooled / upsampled copies) -> four pixels per iteration with
+// all eight 16-byte loads in flight before the first use.
+template <bool PLAIN>
+__global__ void __launch_bounds__(256, 2) in_bwd_reduce_kernel(const InBwdArgs a) {
   extern __shared__ float shm[];  // [PL][C][2]
   const int n = blockIdx.y;
   const int HW = a.H * a.W;
@@ -308,74 +363,75 @@ __global__ void __launch_bounds__(256, 3) in_bwd_reduce_kernel(const InBwdArgs a
     B[j] = b - mean * A[j];
   }
   float s0[8] = {0}, s1[8] = {0};
+  const __nv_bfloat16* src = a.raw ? a.raw : a.y;
+  const bool has_raw = a.raw != nullptr;
+  const int act = a.act;
+  const float slope = a.slope;
+  auto finish = [&](const uint4& vr, float (&g)[8], size_t lin) {
+    float r[8];
+    unpack8(vr, r);
+    if (has_raw) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        g[j] *= act_grad(fmaf(r[j], A[j], B[j]), act, slope);
+        s0[j] += g[j];
+        s1[j] = fmaf(g[j], r[j], s1[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] *= act_grad(r[j], act, slope);
+    }
+    stg16(a.dn + lin, pack8(g));
+  };
   if (t.pl < t.PL) {
-    for (int pix = t.p0 + t.pl; pix < t.p1; pix += t.PL) {
-      const int yy = pix / a.W, xx = pix % a.W;
-      const size_t lin = (size_t(n) * HW + pix) * a.C + c0;
-      float g[8] = {0};
-      const uint4 vr = ldg16((a.raw ? a.raw : a.y) + lin);
-      if (a.g_same) unpack8(ldg16(a.g_same + lin), g);
-      if (a.g_up) {
-        const int WU = 2 * a.W;
-        const size_t ub = (size_t(n) * 2 * a.H + 2 * yy) * WU + 2 * xx;
-        const uint4 u0 = ldg16(a.g_up + ub * a.C + c0), u1 = ldg16(a.g_up + (ub + 1) * a.C + c0);
-        const uint4 u2 = ldg16(a.g_up + (ub + WU) * a.C + c0), u3 = ldg16(a.g_up + (ub + WU + 1) * a.C + c0);
-        float f[8];
-        unpack8(u0, f);
+    const size_t img = size_t(n) * HW;
+    int pix = t.p0 + t.pl;
+    if (PLAIN) {
+      for (; pix + 3 * t.PL < t.p1; pix += 4 * t.PL) {
+        uint4 vr[4], vg[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] += f[j];
-        unpack8(u1, f);
+        for (int k = 0; k < 4; ++k) {
+          const size_t lin = (img + pix + k * t.PL) * a.C + c0;
+          vr[k] = ldg16(src + lin);
+          vg[k] = ldg16(a.g_same + lin);
+        }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] += f[j];
-        unpack8(u2, f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] += f[j];
-        unpack8(u3, f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] += f[j];
-      }
-      if (a.g_pool) {
-        const int H2 = a.H >> 1, W2 = a.W >> 1;
-        float f[8];
-        unpack8(ldg16(a.g_pool + ((size_t(n) * H2 + (yy >> 1)) * W2 + (xx >> 1)) * a.C + c0), f);
-        if (a.pool_mode == 1) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) g[j] += 0.25f * f[j];
-        } else {
-          // max-pool routing: first element (row-major in the 2x2 window) equal to the window max
-          float best[8];
-          int first[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { best[j] = -3.0e38f; first[j] = 0; }
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int y2 = (yy & ~1) + (k >> 1), x2 = (xx & ~1) + (k & 1);
-            float o[8];
-            unpack8(ldg16(a.y + ((size_t(n) * a.H + y2) * a.W + x2) * a.C + c0), o);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (o[j] > best[j]) { best[j] = o[j]; first[j] = k; }
-          }
-          const int mine = ((yy & 1) << 1) | (xx & 1);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (first[j] == mine) g[j] += f[j];
+        for (int k = 0; k < 4; ++k) {
+          float g[8];
+          unpack8(vg[k], g);
+          finish(vr[k], g, (img + pix + k * t.PL) * a.C + c0);
         }
       }
-      float r[8];
-      unpack8(vr, r);
-      if (a.raw) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          g[j] *= act_grad(fmaf(r[j], A[j], B[j]), a.act, a.slope);
-          s0[j] += g[j];
-          s1[j] = fmaf(g[j], r[j], s1[j]);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] *= act_grad(r[j], a.act, a.slope);
+      for (; pix < t.p1; pix += t.PL) {
+        const size_t lin = (img + pix) * a.C + c0;
+        float g[8];
+        const uint4 vr = ldg16(src + lin);
+        unpack8(ldg16(a.g_same + lin), g);
+        finish(vr, g, lin);
       }
-      stg16(a.dn + lin, pack8(g));
+    } else {
+      for (; pix + t.PL < t.p1; pix += 2 * t.PL) {
+        const size_t l0 = (img + pix) * a.C + c0, l1 = (img + pix + t.PL) * a.C + c0;
+        const uint4 r0 = ldg16(src + l0), r1 = ldg16(src + l1);
+        float g0[8] = {0}, g1[8] = {0};
+        if (a.g_same) {
+          const uint4 v0 = ldg16(a.g_same + l0), v1 = ldg16(a.g_same + l1);
+          unpack8(v0, g0);
+          unpack8(v1, g1);
+        }
+        in_bwd_gather(a, n, pix, c0, g0);
+        in_bwd_gather(a, n, pix + t.PL, c0, g1);
+        finish(r0, g0, l0);
+        finish(r1, g1, l1);
+      }
+      for (; pix < t.p1; pix += t.PL) {
+        const size_t lin = (img + pix) * a.C + c0;
+        const uint4 vr = ldg16(src + lin);
+        float g[8] = {0};
+        if (a.g_same) unpack8(ldg16(a.g_same + lin), g);
+        in_bwd_gather(a, n, pix, c0, g);
+        finish(vr, g, lin);
+      }
     }
   }
   if (!a.red) return;
@@ -1059,7 +1115,8 @@ int tg_in_bwd_reduce(const void* raw, const void* y, const float* mr, const floa
   const int PL = block / (C / 8);
   const size_t smem = red ? size_t(PL) * C * 2 * sizeof(float) : 0;
   dim3 grid(strip_count(H * W, C, N, 16), N);
-  in_bwd_reduce_kernel<<<grid, block, smem, TG_STREAM(stream)>>>(a);
+  if (g_same && !g_pool && !g_up) in_bwd_reduce_kernel<true><<<grid, block, smem, TG_STREAM(stream)>>>(a);
+  else in_bwd_reduce_kernel<false><<<grid, block, smem, TG_STREAM(stream)>>>(a);
   TG_RET();
 }
 

@@ -97,13 +97,15 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
   const int kb_per_split = (k_blocks + p.splits - 1) / p.splits;
   const int total_items = p.taps * p.m_tiles * p.n_tiles * p.splits;
 
-  // item -> (split fastest, then n_tile, m_tile, tap) so concurrently running CTAs share operands
+  // item -> (tap fastest, then n_tile, m_tile; pixel split slowest): CTAs running at the same time work on
+  // the same pixel range, so the (shifted) P windows and Q blocks they stream are shared through L2 and the
+  // operands cross HBM once even when they are larger than L2
   auto decode = [&](int item, int& tap, int& m_tile, int& n_tile, int& kb0, int& kb1) {
-    const int split = item % p.splits;
-    int r = item / p.splits;
+    int r = item;
+    tap = r % p.taps; r /= p.taps;
     n_tile = r % p.n_tiles; r /= p.n_tiles;
     m_tile = r % p.m_tiles; r /= p.m_tiles;
-    tap = r;
+    const int split = r;
     kb0 = split * kb_per_split;
     kb1 = min(k_blocks, kb0 + kb_per_split);
   };

@@ -75,11 +75,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) wgrad_halo_kernel(const __grid
   const int per_split = (k_tiles + p.splits - 1) / p.splits;
   const int total_items = p.tap_groups * p.m_tiles * p.n_tiles * p.splits;
   auto decode = [&](int item, int& tg0, int& ntap, int& m_tile, int& n_tile, int& k0, int& k1) {
-    const int split = item % p.splits;
-    int r = item / p.splits;
+    // tap group fastest, pixel split slowest: concurrent CTAs share the X / dY tiles through L2
+    int r = item;
+    tg0 = (r % p.tap_groups) * kWhTaps; r /= p.tap_groups;
     n_tile = r % p.n_tiles; r /= p.n_tiles;
     m_tile = r % p.m_tiles; r /= p.m_tiles;
-    tg0 = r * kWhTaps;
+    const int split = r;
     ntap = min(kWhTaps, p.taps - tg0);
     k0 = split * per_split;
     k1 = min(k_tiles, k0 + per_split);
@@ -122,29 +123,42 @@ __global__ void __launch_bounds__(kNumThreads, 1) wgrad_halo_kernel(const __grid
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(kTileM, 64, 1, 1);
       const uint32_t sbo_y = uint32_t(p.halo_w) * 128u;
+      // constant descriptor halves and per-tap start steps (16-byte units) hoisted out of the issue loop
+      const uint32_t a_hi = umma_desc_hi_sw128(1024u);
+      const uint32_t b_hi = umma_desc_hi_sw128(sbo_y);
+      const uint32_t b_kstep = 2u * (sbo_y >> 4);          // 16 pixels (K) = two halo rows
+      uint32_t y_step[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+        y_step[t] = t < p.taps ? uint32_t(p.tap_dy[t] * p.halo_w + p.tap_dx[t]) * 8u : 0u;
       int stage = 0;
       uint32_t phase = 0, tphase = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         int tg0, ntap, m_tile, n_tile, k0, k1;
         decode(item, tg0, ntap, m_tile, n_tile, k0, k1);
+        // this item's taps -> registers (tg0 is 0 or kWhTaps)
+        uint32_t ys[kWhTaps];
+#pragma unroll
+        for (int t = 0; t < kWhTaps; ++t) ys[t] = tg0 == 0 ? y_step[t] : (t + kWhTaps < 9 ? y_step[t + kWhTaps] : 0u);
         mbar_wait_guard(tempty, tphase ^ 1, p.err_flag, 32);
         tc_fence_after();
         for (int kt = k0; kt < k1; ++kt) {
           mbar_wait_guard(full_bar(stage), phase, p.err_flag, 33);
           tc_fence_after();
           const uint32_t xs = smem_base + stage * kWhStageBytes;
-          const uint32_t ys = xs + kWhXBytes;
-          for (int t = 0; t < ntap; ++t) {
-            const int tap = tg0 + t;
-            const uint32_t y_tap = ys + uint32_t(p.tap_dy[tap] * p.halo_w + p.tap_dx[tap]) * 128u;
-            const uint32_t d_tmem = tmem_base + uint32_t(t * 64);
+          // K step = 16 pixels = two image rows of the tile: X rows are dense (8 px = 1 KiB, +2 KiB per step),
+          // dY rows sit in the halo tile with a pitch of halo_w pixels
+          const uint32_t a_lo0 = umma_desc_lo(xs, kTileM * 128);
+          const uint32_t b_lo0 = umma_desc_lo(xs + kWhXBytes, 16);
+          const uint32_t first = kt > k0 ? 1u : 0u;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              // K step = 16 pixels = two image rows of the tile: X rows are dense (8 px = 1 KiB),
-              // dY rows sit in the halo tile with a pitch of halo_w pixels
-              const uint64_t a_desc = umma_smem_desc_sw128(xs + k * 2048, kTileM * 128, 1024);
-              const uint64_t b_desc = umma_smem_desc_sw128(y_tap + uint32_t(2 * k) * sbo_y, 16, sbo_y);
-              umma_f16(d_tmem, a_desc, b_desc, idesc, (kt > k0 || k > 0) ? 1u : 0u);
+          for (int t = 0; t < kWhTaps; ++t) {
+            if (t < ntap) {
+              const uint32_t d_tmem = tmem_base + uint32_t(t * 64);
+              const uint32_t b_lo = b_lo0 + ys[t];
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                umma_f16_split(d_tmem, a_lo0 + k * 128, a_hi, b_lo + k * b_kstep, b_hi, idesc, k > 0 ? 1u : first);
             }
           }
           umma_commit(empty_bar(stage));
