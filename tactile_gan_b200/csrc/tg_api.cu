@@ -10,6 +10,7 @@
 #include "tg_wgrad.cuh"
 #include "tg_igemm_halo.cuh"
 #include "tg_wgrad_halo.cuh"
+#include "tg_wgrad_taps.cuh"
 #include <cstdlib>
 
 static thread_local char g_err[512] = "";
@@ -143,6 +144,7 @@ struct tg_plan {
   tg::WgradParams wg;
   tg::HaloParams halo;
   tg::WgradHaloParams wgh;
+  tg::WgradTapsParams wgt;
 };
 
 namespace {
@@ -388,6 +390,55 @@ static int create_wgrad_halo_plan(const tg_wgrad_desc* d, tg_plan* pl, int ymin,
   return 0;
 }
 
+// 3x3-window stride-1 same-size convolutions: tap-tiled kernel (tg_wgrad_taps.cuh)
+static int create_wgrad_taps_plan(const tg_wgrad_desc* d, tg_plan* pl) {
+  pl->kind = 4;
+  tg::WgradTapsParams& p = pl->wgt;
+  memset(&p, 0, sizeof(p));
+  p.num_src = d->num_src;
+  memset(p.tap_w, -1, sizeof(p.tap_w));
+  for (int t = 0; t < d->taps; ++t) p.tap_w[d->tap_dy[t] + 1][d->tap_dx[t] + 1] = d->tap_w[t];
+  const int H = d->q.h, W = d->q.w;
+  p.N = d->q.n;
+  p.tiles_h = (H + tg::kWtTH - 1) / tg::kWtTH;
+  p.tiles_w = (W + tg::kWtTW - 1) / tg::kWtTW;
+  int chunks = 0;
+  for (int s = 0; s < d->num_src; ++s) {
+    if (d->p[s].c % 64) return tg_set_error("tg_wgrad_plan_create: P channels must be a multiple of 64");
+    if (d->p[s].h != H || d->p[s].w != W || d->p[s].n != d->q.n)
+      return tg_set_error("tg_wgrad_plan_create: source size mismatch");
+    if (make_act_map(&p.src[s].act, d->p[s], 0, d->p[s].c, tg::kWtTW, tg::kWtTH + 2, 1, 1)) return -1;
+    p.src[s].c_chunks = d->p[s].c / 64;
+    chunks += p.src[s].c_chunks;
+  }
+  if (make_act_map(&p.q, d->q, 0, d->q.c, tg::kWtTW + 2, tg::kWtTH, 1, 1)) return -1;
+  p.total_chunks = chunks;
+  p.n_tiles = d->q.c / 64;
+  p.dw = d->dw;
+  p.m_total = d->dw_cols;
+  p.n_total = d->dw_rows;
+  if (p.m_total != chunks * 64) return tg_set_error("tg_wgrad_plan_create: dw_cols != sum of P channels");
+  if (p.n_total < d->q.c) return tg_set_error("tg_wgrad_plan_create: dw_rows < Q channels");
+  p.err_flag = tg_error_flag_device_ptr();
+  const int k_tiles = p.N * p.tiles_h * p.tiles_w;
+  const int items0 = chunks * p.n_tiles;
+  int splits = (2 * sm_count() + items0 - 1) / items0;
+  const int max_splits = k_tiles / 4 > 1 ? k_tiles / 4 : 1;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  while (splits > 1 && ((k_tiles + splits - 1) / splits) * (splits - 1) >= k_tiles) --splits;
+  p.splits = splits;
+  const int total = items0 * splits;
+  pl->grid = total < sm_count() ? total : sm_count();
+  pl->smem = tg::kWtSmem;
+  cudaError_t e = cudaFuncSetAttribute(tg::wgrad_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl->smem));
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "cudaFuncSetAttribute(wgrad taps): %s", cudaGetErrorString(e));
+    return -1;
+  }
+  return 0;
+}
+
 int tg_wgrad_plan_create(const tg_wgrad_desc* d, tg_plan** out) {
   if (!d || !out) return tg_set_error("tg_wgrad_plan_create: null argument");
   if (d->num_src < 1 || d->num_src > TG_MAX_SRC) return tg_set_error("tg_wgrad_plan_create: bad num_src");
@@ -403,6 +454,18 @@ int tg_wgrad_plan_create(const tg_wgrad_desc* d, tg_plan** out) {
     }
     // same-size (pad = (k-1)/2) stride-1 windows only: the X grid then equals the dY grid
     const bool same = d->p[0].h == d->q.h && d->p[0].w == d->q.w;
+    {
+      static const bool use_old = getenv("TG_WGRAD_HALO") != nullptr;
+      static const int max_qc = getenv("TG_WGRAD_TAPS_MAXC") ? atoi(getenv("TG_WGRAD_TAPS_MAXC")) : 128;
+      bool centred = d->taps <= 9;
+      for (int t = 0; t < d->taps && centred; ++t)
+        centred = d->tap_dy[t] >= -1 && d->tap_dy[t] <= 1 && d->tap_dx[t] >= -1 && d->tap_dx[t] <= 1;
+      if (!disabled && !use_old && d->stride == 1 && d->taps >= 2 && centred && same && d->q.c <= max_qc) {
+        if (create_wgrad_taps_plan(d, pl)) { delete pl; return -1; }
+        *out = pl;
+        return 0;
+      }
+    }
     if (!disabled && d->stride == 1 && d->taps >= 2 && d->taps <= 9 && ymax - ymin <= 2 && xmax - xmin <= 2 && same &&
         (d->q.c == 64 || d->q.c == 128)) {
       if (create_wgrad_halo_plan(d, pl, ymin, ymax, xmin, xmax)) { delete pl; return -1; }
@@ -448,6 +511,15 @@ int tg_wgrad_plan_create(const tg_wgrad_desc* d, tg_plan** out) {
   const int k_blocks = p.tiles_img * p.tiles_h * p.tiles_w;
   const int items0 = p.taps * p.m_tiles * p.n_tiles;
   int splits = (2 * sm_count() + items0 - 1) / items0;
+  {
+    // the pixel ranges being streamed at any one time (one per concurrently active split) should stay
+    // L2-resident, because every (tap, m, n) item of a split re-reads them
+    double bytes = double(d->q.n) * d->q.h * d->q.w * d->q.c * 2.0;
+    for (int s = 0; s < d->num_src; ++s) bytes += double(d->p[s].n) * d->p[s].h * d->p[s].w * d->p[s].c * 2.0;
+    const double concurrent = items0 >= sm_count() ? 1.0 : double(sm_count()) / items0;
+    const int need = int(bytes * concurrent / (48.0 * 1024 * 1024)) + 1;
+    if (need > splits) splits = need;
+  }
   const int max_splits = k_blocks / 8 > 1 ? k_blocks / 8 : 1;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
@@ -483,6 +555,8 @@ int tg_plan_run(tg_plan* pl, void* stream) {
     tg::igemm_halo_kernel<<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->halo);
   } else if (pl->kind == 3) {
     tg::wgrad_halo_kernel<<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->wgh);
+  } else if (pl->kind == 4) {
+    tg::wgrad_taps_kernel<<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->wgt);
   } else if (pl->kind == 0) {
     if (pl->bn == 256) tg::igemm_conv_kernel<256><<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->conv);
     else if (pl->bn == 128) tg::igemm_conv_kernel<128><<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->conv);
