@@ -96,6 +96,20 @@ int tg_pack_nchw(const float* A, const float* B, const float* wa, const float* w
 int tg_unpack_nhwc(const void* in, float* out, int N, int HW, int C, int c_off, int cj, float scale,
                    void* stream);
 
+/* ---- thin-channel discriminator layers restated as dense 1x1 GEMMs (PatchDiscriminator.py:14,27,36):
+ *      tg_im2col_pack writes cat(A, wa*B + wb*B2) as im2col rows (k*k*(ca+cb) <= 64 channels, no padding) so the
+ *      first conv is a 1-tap GEMM; tg_col2im_grad folds its input gradient back to an fp32 NCHW image;
+ *      tg_head_gather sums the 9 tap channels of the head's 1x1 GEMM (+bias, sigmoid); tg_head_scatter is
+ *      its transpose; tg_gp_normsq_img is the penalty norm (util.py:92) on the image-space gradient */
+int tg_im2col_pack(const float* A, const float* B, const float* B2, const float* wa, const float* wb, void* cols,
+                   int N, int ca, int cb, int H, int W, int k, int stride, void* stream);
+int tg_col2im_grad(const void* dcols, float* g, int N, int ct, int c_off, int cj, int H, int W, int k, int stride,
+                   float scale, void* stream);
+int tg_head_gather(const void* hc, const float* bias, void* out, int N, int Hi, int Wi, int k, int C, int act,
+                   float slope, void* stream);
+int tg_head_scatter(const void* dz, void* dzc, int N, int Hi, int Wi, int k, int C, void* stream);
+int tg_gp_normsq_img(const float* g, int N, long long per_img, float* nsq, void* stream);
+
 /* ---- InstanceNorm2d(eps, biased var) (+affine) fused with ReLU / LeakyReLU, optional AvgPool2d(2) /
  *      MaxPool2d(2) copy and nearest Upsample(x2) copy (UNet_plusplus.py:23-24,40-41; BCDUNet.py:110;
  *      PatchDiscriminator.py:16-17) and their backward */

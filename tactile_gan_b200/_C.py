@@ -136,7 +136,7 @@ def conv_query_tiles(n, ho, wo, want_stats):
 
 
 def conv_plan(srcs, out, taps, stride=1, bias=None, stats_partial=None, act=ACT_NONE, slope=0.2,
-              stats_tiles_total=0, stats_tile_off=0, cout_real=None):
+              stats_tiles_total=0, stats_tile_off=0, cout_real=None, flops=None):
     """srcs: list of dict(act=tensor NHWC, wgt=packed bf16 [taps][rows][k], k_off=0, row_off=0)
     taps: list of (dy, dx, w_index)."""
     d = ConvDesc()
@@ -170,16 +170,17 @@ def conv_plan(srcs, out, taps, stride=1, bias=None, stats_partial=None, act=ACT_
     check(lib().tg_conv_plan_create(byref(d), byref(h)), "tg_conv_plan_create")
     # algorithmic FLOPs of this launch: real (unpadded) channels, every output pixel, every tap
     n, ho, wo, _ = out.shape
-    flops = 0.0
-    for s in srcs:
-        flops += 2.0 * n * ho * wo * len(taps) * s.get("c_real", s["act"].shape[3]) * (cout_real or out.shape[3])
+    if flops is None:
+        flops = 0.0
+        for s in srcs:
+            flops += 2.0 * n * ho * wo * len(taps) * s.get("c_real", s["act"].shape[3]) * (cout_real or out.shape[3])
     tag = "conv n%d %dx%d cin[%s] cout%d taps%d s%d%s" % (
         n, ho, wo, ",".join(str(s["act"].shape[3]) for s in srcs), out.shape[3], len(taps), stride,
         " stats" if stats_partial is not None else "")
     return Plan(h, keep, "conv", flops, tag)
 
 
-def wgrad_plan(p_srcs, q, taps, dw, stride=1, p_real=None, q_real=None, dw_row_off=0):
+def wgrad_plan(p_srcs, q, taps, dw, stride=1, p_real=None, q_real=None, dw_row_off=0, flops=None):
     """dw: fp32 [taps_total][rows >= q.C][cols == sum p.C]."""
     d = WgradDesc()
     d.num_src = len(p_srcs)
@@ -198,7 +199,8 @@ def wgrad_plan(p_srcs, q, taps, dw, stride=1, p_real=None, q_real=None, dw_row_o
     check(lib().tg_wgrad_plan_create(byref(d), byref(h)), "tg_wgrad_plan_create")
     n, ho, wo, qc = q.shape
     pc = p_real if p_real is not None else sum(t.shape[3] for t in p_srcs)
-    flops = 2.0 * n * ho * wo * len(taps) * pc * (q_real if q_real is not None else qc)
+    if flops is None:
+        flops = 2.0 * n * ho * wo * len(taps) * pc * (q_real if q_real is not None else qc)
     tag = "wgrad n%d %dx%d p[%s] q%d taps%d s%d" % (
         n, ho, wo, ",".join(str(t.shape[3]) for t in p_srcs), qc, len(taps), stride)
     return Plan(h, list(p_srcs) + [q, dw], "wgrad", flops, tag)

@@ -89,8 +89,7 @@ class _DiscFn(torch.autograd.Function):
         gb = None
         if ctx.need_b:
             gb = torch.empty(inst.n, ctx.cb, inst.h, inst.w, device=g.device)
-            _C.call("unpack_nhwc", _C.ptr(inst.dx0), _C.ptr(gb), inst.n, inst.h * inst.w, inst.dx0.shape[3],
-                    ctx.ca, ctx.cb, _C.F(1.0))
+            inst.input_grad_image(ctx.ca, ctx.cb, gb)
         grads = [inst.store.grad_as_torch(i) if want_w else None for i in range(ctx.nparams)]
         return (None, gb, None, *grads)
 

@@ -101,6 +101,120 @@ __global__ void unpack_nhwc_kernel(const __nv_bfloat16* __restrict__ in, float* 
   }
 }
 
+// ------------------------------------------------------------------ thin-channel layers as 1x1 GEMMs
+// The discriminator's first conv (6 -> 64, 3x3, stride 2) and its head (512 -> 1, 3x3) would waste >= 90 % of
+// a 64-channel-padded implicit GEMM. Both are restated so the tensor-core kernel sees a dense 1-tap problem:
+//   first layer: the pack writes the im2col rows directly, cols[n,oy,ox, tap*Ct + c] = x[n, c, oy*s+dy, ox*s+dx]
+//                (Ct = ca + cb <= 7 -> 9*Ct <= 64 channels), so the conv is a 1x1 GEMM with K = 64;
+//   head:        hc[n,y,x,tap] = sum_ci X[n,y,x,ci] * W[tap,ci] is a 1x1 GEMM with 9 output channels and
+//                z[n,oy,ox] = sum_tap hc[n,oy+dy,ox+dx,tap]; the backward scatters dz to dzc[n,y,x,tap] = dz[n,y-dy,x-dx].
+
+// cols <- im2col of cat(A, wa*B + wb*B2) (fp32 NCHW sources), k x k taps, stride s, no padding. One thread per
+// output pixel writes its 128-byte row.
+__global__ void im2col_pack_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                   const float* __restrict__ B2, const float* __restrict__ wa,
+                                   const float* __restrict__ wb, __nv_bfloat16* __restrict__ cols, int N, int ca,
+                                   int cb, int H, int W, int Ho, int Wo, int k, int stride) {
+  const size_t total = size_t(N) * Ho * Wo;
+  const int ct = ca + cb;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int ox = int(i % Wo), oy = int((i / Wo) % Ho), n = int(i / (size_t(Wo) * Ho));
+    const float fa = wa ? wa[n] : 1.f, fb = wb ? wb[n] : 0.f;
+    __align__(16) __nv_bfloat16 row[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) row[j] = __float2bfloat16(0.f);
+    for (int t = 0; t < k * k; ++t) {
+      const int y = oy * stride + t / k, x = ox * stride + t % k;
+      const size_t pix = size_t(y) * W + x;
+      for (int c = 0; c < ca; ++c)
+        if (A) row[t * ct + c] = __float2bfloat16(__ldg(A + (size_t(n) * ca + c) * H * W + pix));
+      for (int c = 0; c < cb; ++c) {
+        float v = fa * __ldg(B + (size_t(n) * cb + c) * H * W + pix);
+        if (B2) v += fb * __ldg(B2 + (size_t(n) * cb + c) * H * W + pix);
+        row[t * ct + ca + c] = __float2bfloat16(v);
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(cols + i * 64);
+    const uint4* src = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j] = src[j];
+  }
+}
+
+// g[n, c, y, x] = sum over taps whose window covers (y, x) of dcols[n, oy, ox, tap*ct + c_off + c]  (fp32 NCHW)
+__global__ void col2im_grad_kernel(const __nv_bfloat16* __restrict__ dcols, float* __restrict__ g, int N, int ct,
+                                   int c_off, int cj, int H, int W, int Ho, int Wo, int k, int stride, float scale) {
+  const size_t total = size_t(N) * H * W;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int x = int(i % W), y = int((i / W) % H), n = int(i / (size_t(W) * H));
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int t = 0; t < k * k; ++t) {
+      const int yy = y - t / k, xx = x - t % k;
+      if (yy < 0 || xx < 0 || yy % stride || xx % stride) continue;
+      const int oy = yy / stride, ox = xx / stride;
+      if (oy >= Ho || ox >= Wo) continue;
+      const __nv_bfloat16* r = dcols + ((size_t(n) * Ho + oy) * Wo + ox) * 64 + t * ct + c_off;
+      for (int c = 0; c < cj; ++c) acc[c] += __bfloat162float(r[c]);
+    }
+    for (int c = 0; c < cj; ++c) g[(size_t(n) * cj + c) * H * W + size_t(y) * W + x] = scale * acc[c];
+  }
+}
+
+// out[n,oy,ox,0] = act(sum_tap hc[n, oy + t/k, ox + t%k, tap] + bias); channels 1..7 of the pixel are zeroed
+__global__ void head_gather_kernel(const __nv_bfloat16* __restrict__ hc, const float* __restrict__ bias,
+                                   __nv_bfloat16* __restrict__ out, int N, int Hi, int Wi, int Ho, int Wo, int k,
+                                   int C, int act, float slope) {
+  const size_t total = size_t(N) * Ho * Wo;
+  const float b = bias ? __ldg(bias) : 0.f;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int ox = int(i % Wo), oy = int((i / Wo) % Ho), n = int(i / (size_t(Wo) * Ho));
+    float v = b;
+    for (int t = 0; t < k * k; ++t)
+      v += __bfloat162float(hc[((size_t(n) * Hi + oy + t / k) * Wi + ox + t % k) * 64 + t]);
+    if (act == 2) v = 1.f / (1.f + __expf(-v));
+    else v = act_fwd(v, act, slope);
+    float f[8] = {v, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    stg16(out + i * C, pack8(f));
+  }
+}
+
+// dzc[n,y,x,tap] = dz[n, y - t/k, x - t%k, 0] (0 outside), taps < 16; the first 16 channels of every row are written
+__global__ void head_scatter_kernel(const __nv_bfloat16* __restrict__ dz, __nv_bfloat16* __restrict__ dzc, int N,
+                                    int Hi, int Wi, int Ho, int Wo, int k, int C) {
+  const size_t total = size_t(N) * Hi * Wi;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int x = int(i % Wi), y = int((i / Wi) % Hi), n = int(i / (size_t(Wi) * Hi));
+    float f[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      f[t] = 0.f;
+      if (t < k * k) {
+        const int oy = y - t / k, ox = x - t % k;
+        if (oy >= 0 && ox >= 0 && oy < Ho && ox < Wo)
+          f[t] = __bfloat162float(dz[((size_t(n) * Ho + oy) * Wo + ox) * C]);
+      }
+    }
+    float lo[8], hi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { lo[j] = f[j]; hi[j] = f[8 + j]; }
+    stg16(dzc + i * 64, pack8(lo));
+    stg16(dzc + i * 64 + 8, pack8(hi));
+  }
+}
+
+// nsq[n] += sum over an fp32 NCHW image gradient of (g + 1e-16)^2   (gradient penalty norm, util.py:92)
+__global__ void gp_normsq_img_kernel(const float* __restrict__ g, size_t per_img, float* __restrict__ nsq) {
+  __shared__ float sh[32];
+  const int n = blockIdx.y;
+  float acc = 0.f;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < per_img; i += size_t(gridDim.x) * blockDim.x) {
+    const float v = g[size_t(n) * per_img + i] + 1e-16f;
+    acc += v * v;
+  }
+  const float tot = block_sum(acc, sh);
+  if (threadIdx.x == 0) atomicAdd(nsq + n, tot);
+}
+
 // ------------------------------------------------------------------ InstanceNorm forward
 // partial: [N][T][C][2] (sum, sumsq) from the conv epilogue -> mr: [N][C][2] (mean, rstd)
 __global__ void in_finalize_kernel(const float* __restrict__ partial, float* __restrict__ mr, int T,
@@ -987,12 +1101,16 @@ __global__ void adam_kernel(const AdamTensor* __restrict__ tab, int ntensors, fl
       tap = int(i % taps);
       const size_t r = i / taps;
       const int d1 = int(r % t.dim1), d0 = int(r / t.dim1);
-      if (t.kind == 1) { o = d0; ic = d1; } else { ic = d0; o = d1; }
-      for (int sgi = 0; sgi < t.nseg; ++sgi)
-        if (ic < t.seg_end[sgi]) { ic += t.seg_shift[sgi]; break; }
-      // gradient lives in the packed forward layout [tap][rows_pad][cols_pad]
-      gi = t.kind == 1 ? (size_t(tap) * t.o_pad + o) * t.i_pad + ic
-                       : (size_t(tap) * t.i_pad + ic) * t.o_pad + o;
+      if (t.kind == 2) { ic = d0; o = d1; } else { o = d0; ic = d1; }
+      if (t.kind == 4) ic = tap * t.dim1 + ic;   // im2col column of the thin first layer
+      else
+        for (int sgi = 0; sgi < t.nseg; ++sgi)
+          if (ic < t.seg_end[sgi]) { ic += t.seg_shift[sgi]; break; }
+      // gradient lives in the packed forward layout [tap][rows_pad][cols_pad] (kind 3: rows = taps, kind 4: one tap)
+      gi = t.kind == 1   ? (size_t(tap) * t.o_pad + o) * t.i_pad + ic
+           : t.kind == 2 ? (size_t(tap) * t.i_pad + ic) * t.o_pad + o
+           : t.kind == 3 ? size_t(tap) * t.i_pad + ic
+                         : size_t(o) * t.i_pad + ic;
     }
     float p = t.param[i];
     if (t.grad) {
@@ -1010,14 +1128,18 @@ __global__ void adam_kernel(const AdamTensor* __restrict__ tab, int ntensors, fl
       const __nv_bfloat16 b = __float2bfloat16(p);
       if (t.pack_fwd) {
         // forward operand: [tap][rows][cols], cols contiguous = reduction channel of the forward op
-        const size_t k = t.kind == 1 ? (size_t(tap) * t.o_pad + o) * t.i_pad + ic
-                                     : (size_t(tap) * t.o_pad + o) * t.i_pad + ic;
+        const size_t k = t.kind <= 2   ? (size_t(tap) * t.o_pad + o) * t.i_pad + ic
+                         : t.kind == 3 ? size_t(tap) * t.i_pad + ic
+                                       : size_t(o) * t.i_pad + ic;
         t.pack_fwd[k] = b;
       }
       if (t.pack_bwd) {
         // backward-data operand: transposed roles, taps mirrored for Conv2d (flip), same for convT
         const int btap = t.kind == 1 ? (taps - 1 - tap) : tap;
-        t.pack_bwd[(size_t(btap) * t.i_pad + ic) * t.o_pad + o] = b;
+        const size_t k = t.kind <= 2   ? (size_t(btap) * t.i_pad + ic) * t.o_pad + o
+                         : t.kind == 3 ? size_t(ic) * t.o_pad + tap
+                                       : size_t(ic) * t.o_pad + o;
+        t.pack_bwd[k] = b;
       }
     }
   }
@@ -1051,6 +1173,48 @@ int tg_unpack_nhwc(const void* in, float* out, int N, int HW, int C, int c_off, 
                    void* stream) {
   unpack_nhwc_kernel<<<grid_for(size_t(N) * HW, 256), 256, 0, TG_STREAM(stream)>>>(
       (const __nv_bfloat16*)in, out, N, HW, C, c_off, cj, scale);
+  TG_RET();
+}
+
+int tg_im2col_pack(const float* A, const float* B, const float* B2, const float* wa, const float* wb, void* cols,
+                   int N, int ca, int cb, int H, int W, int k, int stride, void* stream) {
+  if (k * k * (ca + cb) > 64) return tg_set_error("tg_im2col_pack: k*k*(ca+cb) must be <= 64");
+  if (!B) return tg_set_error("tg_im2col_pack: B is required");
+  const int Ho = (H - k) / stride + 1, Wo = (W - k) / stride + 1;
+  im2col_pack_kernel<<<grid_for(size_t(N) * Ho * Wo, 128, 148 * 16), 128, 0, TG_STREAM(stream)>>>(
+      A, B, B2, wa, wb, (__nv_bfloat16*)cols, N, ca, cb, H, W, Ho, Wo, k, stride);
+  TG_RET();
+}
+
+int tg_col2im_grad(const void* dcols, float* g, int N, int ct, int c_off, int cj, int H, int W, int k, int stride,
+                   float scale, void* stream) {
+  if (cj > 8 || k * k * ct > 64) return tg_set_error("tg_col2im_grad: at most 8 channels, k*k*ct <= 64");
+  const int Ho = (H - k) / stride + 1, Wo = (W - k) / stride + 1;
+  col2im_grad_kernel<<<grid_for(size_t(N) * H * W, 256, 148 * 16), 256, 0, TG_STREAM(stream)>>>(
+      (const __nv_bfloat16*)dcols, g, N, ct, c_off, cj, H, W, Ho, Wo, k, stride, scale);
+  TG_RET();
+}
+
+int tg_head_gather(const void* hc, const float* bias, void* out, int N, int Hi, int Wi, int k, int C, int act,
+                   float slope, void* stream) {
+  if (k * k > 16) return tg_set_error("tg_head_gather: at most 16 taps");
+  const int Ho = Hi - k + 1, Wo = Wi - k + 1;
+  head_gather_kernel<<<grid_for(size_t(N) * Ho * Wo, 256, 148 * 8), 256, 0, TG_STREAM(stream)>>>(
+      (const __nv_bfloat16*)hc, bias, (__nv_bfloat16*)out, N, Hi, Wi, Ho, Wo, k, C, act, slope);
+  TG_RET();
+}
+
+int tg_head_scatter(const void* dz, void* dzc, int N, int Hi, int Wi, int k, int C, void* stream) {
+  if (k * k > 16) return tg_set_error("tg_head_scatter: at most 16 taps");
+  const int Ho = Hi - k + 1, Wo = Wi - k + 1;
+  head_scatter_kernel<<<grid_for(size_t(N) * Hi * Wi, 256, 148 * 8), 256, 0, TG_STREAM(stream)>>>(
+      (const __nv_bfloat16*)dz, (__nv_bfloat16*)dzc, N, Hi, Wi, Ho, Wo, k, C);
+  TG_RET();
+}
+
+int tg_gp_normsq_img(const float* g, int N, long long per_img, float* nsq, void* stream) {
+  dim3 grid(grid_for(size_t(per_img), 256, 64), N);
+  gp_normsq_img_kernel<<<grid, 256, 0, TG_STREAM(stream)>>>(g, size_t(per_img), nsq);
   TG_RET();
 }
 

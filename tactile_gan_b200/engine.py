@@ -215,6 +215,7 @@ class GraphEngine:
         """One ConvLayer per nn.Conv2d, shared by every engine built on the same module."""
         cache = self.store.layer_cache
         if isinstance(conv, torch.nn.ConvTranspose2d):
+            assert kind == "conv"
             kind = "convT"
         if name not in cache:
             l = ConvLayer(name, conv.weight, conv.bias, kind, conv.stride[0], conv.padding[0], in_split,
@@ -421,11 +422,20 @@ class PatchDInstance(GraphEngine):
         norms = [None, m[3], m[6], m[9], None]
         self.c_in = convs[0].in_channels
         self.has_sigmoid = len(m) > 12
-        self.x0 = Act("x0", bf16(n, h, w, pad64(self.c_in), device=dev), self.c_in)
+        # The first conv (thin input) runs on im2col rows written by pack_input, the single-output head as a
+        # 1x1 GEMM over its taps (layers.ConvLayer kinds "cols" / "head"): both are dense 1-tap problems.
+        c0 = convs[0]
+        self.k0, self.s0 = c0.kernel_size[0], c0.stride[0]
+        self.cols = self.k0 * self.k0 * self.c_in <= 64 and c0.padding[0] == 0
+        if not self.cols:
+            raise _C.TgError("PatchDiscriminator engine expects kernel^2 * in_channels <= 64 for the first conv")
+        self.h1, self.w1 = (h - self.k0) // self.s0 + 1, (w - self.k0) // self.s0 + 1
+        self.x0 = Act("x0cols", bf16(n, self.h1, self.w1, 64, device=dev), self.k0 * self.k0 * self.c_in)
         self.u = []
         src = self.x0
         for k, (conv, norm) in enumerate(zip(convs, norms)):
-            layer = self.conv_layer(f"model.{[0, 2, 5, 8, 11][k]}", conv, [conv.in_channels])
+            kind = "cols" if k == 0 else ("head" if (k == 4 and conv.out_channels == 1) else "conv")
+            layer = self.conv_layer(f"model.{[0, 2, 5, 8, 11][k]}", conv, [conv.in_channels], kind=kind)
             if norm is not None:
                 g, b = _affine(norm)
                 unit = ConvUnit(self, f"d{k + 1}", layer, [src], True, g, b, ACT_LRELU, 0.2)
@@ -443,7 +453,7 @@ class PatchDInstance(GraphEngine):
         self.pred = self.u[4].y.buf                      # [n, h5, w5, 64], channel 0 meaningful
         self.hw5 = self.u[4].ho * self.u[4].wo
         if backward:
-            self.dx0 = bf16(*self.x0.buf.shape, device=dev)
+            self.dx0 = bf16(*self.x0.buf.shape, device=dev)      # gradient w.r.t. the im2col rows
             self.x0.build_grad(self.dx0.view(-1))
         if second_order:
             self._build_second_order()
@@ -453,11 +463,11 @@ class PatchDInstance(GraphEngine):
         """x0[n0:n0+n, ..., :ca] = A ; x0[n0:n0+n, ..., ca:ca+cb] = wa*B (+ wb*B2)  (fp32 NCHW sources;
         wa / wb are per-sample weights, e.g. the gradient-penalty interpolation of util.py:79-83)."""
         n = self.n if n is None else n
-        hw, c = self.h * self.w, self.x0.buf.shape[3]
         dst = self.x0.buf[n0:n0 + n]
-        ca = img_a.shape[1]
-        _pack(img_a, None, None, None, dst, n, hw, c, 0)
-        _pack(img_b, b2, wa, wb, dst, n, hw, c, ca)
+        ca, cb = (img_a.shape[1] if img_a is not None else self.c_in - img_b.shape[1]), img_b.shape[1]
+        assert ca + cb == self.c_in
+        _C.call("im2col_pack", ptr(img_a), ptr(img_b), ptr(b2), ptr(wa), ptr(wb), ptr(dst), n, ca, cb, self.h,
+                self.w, self.k0, self.s0)
 
     def forward(self):
         self.store.refresh()
@@ -478,6 +488,13 @@ class PatchDInstance(GraphEngine):
             self.x0.run_grad()
         return self.dx0
 
+    def input_grad_image(self, c_off, cj, out, scale=1.0):
+        """d / d(input image channels [c_off, c_off+cj)) as fp32 NCHW, folded back from the im2col-row gradient
+        (valid after backward(input_grad=True) / gp_first_backward)."""
+        _C.call("col2im_grad", ptr(self.dx0), ptr(out), self.n, self.c_in, c_off, cj, self.h, self.w, self.k0,
+                self.s0, F(scale))
+        return out
+
     def features(self):
         return [unit.y for unit in self.u[:4]]
 
@@ -487,7 +504,8 @@ class PatchDInstance(GraphEngine):
         u1, u2, u3, u4, u5 = self.u
         L = [x.layer for x in self.u]
         so = self.so = {}
-        so["seed"] = bf16(*self.x0.buf.shape, device=dev)
+        so["seed"] = bf16(*self.x0.buf.shape, device=dev)      # im2col rows of the second-order seed image
+        so["g_img"] = None
         so["nsq"] = torch.zeros(self.n, device=dev)
         so["coef"] = torch.zeros(self.n, device=dev)
         so["U"] = [bf16(*x.dz.shape, device=dev) for x in self.u]      # adj(dz_k) (U[4] = adj(dz5))
@@ -500,12 +518,12 @@ class PatchDInstance(GraphEngine):
         so["red_dn"] = [None] + [torch.zeros(x.n, x.c, 2, device=dev) for x in self.u[1:4]]
         # upward: U_k = conv_k(no bias)(V_{k-1}), V_0 = seed ; wgrad(P = V_{k-1}, Q = dz_k)
         ins = [so["seed"]] + so["V"]
-        so["up_conv"] = [L[k].fwd_plan([ins[k]], so["U"][k], use_bias=False) for k in range(5)]
-        so["up_wgrad"] = [L[k].wgrad_plan([ins[k]], self.u[k].dz) for k in range(5)]
+        so["up_conv"] = [L[k].fwd_plans([ins[k]], so["U"][k], use_bias=False) for k in range(5)]
+        so["up_wgrad"] = [L[k].wgrad_plans([ins[k]], self.u[k].dz) for k in range(5)]
         # downward: wgrad(P = a_{k-1}, Q = Z_k / T5), E_{k-1} = dgrad(Z_k)
         acts_in = [self.x0.buf] + [x.y.buf for x in self.u[:4]]
         outs = so["Z"] + [so["T5"]]
-        so["dn_wgrad"] = [L[k].wgrad_plan([acts_in[k]], outs[k]) for k in range(5)]
+        so["dn_wgrad"] = [L[k].wgrad_plans([acts_in[k]], outs[k]) for k in range(5)]
         so["dn_dgrad"] = [None] + [L[k].dgrad_plans(outs[k], so["E"][k - 1]) for k in range(1, 5)]
 
     def gp_first_backward(self):
@@ -520,11 +538,18 @@ class PatchDInstance(GraphEngine):
     def gp_penalty(self, c_off, cj, lambda_gp, constant, loss_slot):
         """penalty value -> *loss_slot; builds the second-order seed coef_n * (g_n + 1e-16)."""
         so = self.so
-        n, hw, c = self.n, self.h * self.w, self.x0.buf.shape[3]
+        n = self.n
+        if so["g_img"] is None or so["g_img"].shape[1] != cj:
+            so["g_img"] = torch.zeros(n, cj, self.h, self.w, device=self.device)
+        g_img = self.input_grad_image(c_off, cj, so["g_img"])
         so["nsq"].zero_()
-        _C.call("gp_normsq", ptr(self.dx0), n, hw, c, c_off, cj, ptr(so["nsq"]))
+        _C.call("gp_normsq_img", ptr(g_img), n, LL(cj * self.h * self.w), ptr(so["nsq"]))
         _C.call("gp_finish", ptr(so["nsq"]), n, F(lambda_gp), F(constant), ptr(loss_slot), ptr(so["coef"]))
-        _C.call("gp_seed", ptr(self.dx0), ptr(so["coef"]), n, hw, c, c_off, cj, ptr(so["seed"]))
+        # seed image coef_n * g_n (the + 1e-16 of util.py:92 is far below bf16 resolution), as im2col rows with the
+        # conditioning-image channels zero
+        assert c_off + cj == self.c_in
+        _C.call("im2col_pack", None, ptr(g_img), None, ptr(so["coef"]), None, ptr(so["seed"]), n, c_off, cj, self.h,
+                self.w, self.k0, self.s0)
 
     def gp_second_backward(self):
         """Backward of the penalty through the first backward pass: accumulates weight gradients."""
@@ -532,8 +557,10 @@ class PatchDInstance(GraphEngine):
         u = self.u
         # ---------------- upward sweep through the (linearised) backward graph
         for k in range(5):
-            so["up_conv"][k].run()           # U_k = adj(dz_k)
-            so["up_wgrad"][k].run()          # from dX_{k-1} = W_k^T dz_k
+            for pl in so["up_conv"][k]:
+                pl.run()                     # U_k = adj(dz_k)
+            for pl in so["up_wgrad"][k]:
+                pl.run()                     # from dX_{k-1} = W_k^T dz_k
             if k == 0:
                 _C.call("act_bwd", ptr(so["U"][0]), ptr(u[0].y.buf), ptr(so["V"][0]), LL(so["U"][0].numel()),
                         ACT_LRELU, F(0.2))
@@ -551,7 +578,8 @@ class PatchDInstance(GraphEngine):
                 ptr(so["T5"]))
         # ---------------- downward sweep: ordinary backward with the injected adj(z_k)
         _C.call("bias_grad", ptr(so["T5"]), ptr(u5.layer.bias_grad), LL(u5.n * self.hw5), u5.c, u5.c_valid)
-        so["dn_wgrad"][4].run()
+        for pl in so["dn_wgrad"][4]:
+            pl.run()
         for k in range(4, 0, -1):
             for p in so["dn_dgrad"][k]:
                 p.run()                       # E_{k-1} = adj(a_{k-1})
@@ -572,18 +600,5 @@ class PatchDInstance(GraphEngine):
             else:
                 _C.call("act_bwd", ptr(e), ptr(x.y.buf), ptr(z), LL(z.numel()), ACT_LRELU, F(0.2))
                 _C.call("bias_grad", ptr(z), ptr(x.layer.bias_grad), LL(x.n * x.ho * x.wo), x.c, x.c_valid)
-            so["dn_wgrad"][k - 1].run()
-
-
-def _pack(a, b, wa, wb, out, n, hw, c, c_off):
-    """fp32 NCHW -> bf16 NHWC channel slice, split at 8-channel group boundaries."""
-    cj_total = a.shape[1]
-    j = 0
-    while j < cj_total:
-        room = 8 - ((c_off + j) & 7)
-        cj = min(room, cj_total - j)
-        if cj == cj_total and j == 0:
-            _C.call("pack_nchw", ptr(a), ptr(b), ptr(wa), ptr(wb), ptr(out), n, hw, cj, c, c_off)
-        else:
-            raise _C.TgError("channel slices that straddle an 8-channel group are not supported yet")
-        j += cj
+            for pl in so["dn_wgrad"][k - 1]:
+                pl.run()

@@ -64,7 +64,7 @@ class ConvLayer:
     def __init__(self, name, weight, bias, kind, stride, pad, in_split, device):
         self.name, self.weight, self.bias, self.kind = name, weight, bias, kind
         self.stride, self.pad = stride, pad
-        if kind == "conv":
+        if kind in ("conv", "head", "cols"):
             self.O, self.I, self.kh, self.kw = weight.shape
         else:
             self.I, self.O, self.kh, self.kw = weight.shape
@@ -76,15 +76,35 @@ class ConvLayer:
         self.o_pad = pad64(self.O)
         self.taps = self.kh * self.kw
         bf = dict(dtype=torch.bfloat16, device=device)
-        self.pack_fwd = torch.zeros(self.taps, self.o_pad, self.i_pad, **bf)
-        self.pack_bwd = torch.zeros(self.taps, self.i_pad, self.o_pad, **bf)
-        self.grad = None      # fp32 [taps][o_pad][i_pad] (conv) / [taps][i_pad][o_pad] (convT)
+        if kind == "head":
+            # single-output conv as a 1x1 GEMM whose output channels are the taps (tg_head_gather sums them)
+            assert self.O == 1 and self.taps <= 16 and pad == 0 and stride == 1
+            self.pack_shape, self.pack_bwd_shape = (1, 64, self.i_pad), (1, self.i_pad, 64)
+        elif kind == "cols":
+            # thin-input conv on im2col rows written by tg_im2col_pack: a 1x1 GEMM with K = taps * Cin <= 64
+            assert self.taps * self.I <= 64 and pad == 0 and len(in_split) == 1
+            self.pack_shape, self.pack_bwd_shape = (1, self.o_pad, 64), (1, 64, self.o_pad)
+        elif kind == "conv":
+            self.pack_shape = (self.taps, self.o_pad, self.i_pad)
+            self.pack_bwd_shape = (self.taps, self.i_pad, self.o_pad)
+        else:
+            self.pack_shape = (self.taps, self.o_pad, self.i_pad)
+            self.pack_bwd_shape = (self.taps, self.i_pad, self.o_pad)
+        self.pack_fwd = torch.zeros(*self.pack_shape, **bf)
+        self.pack_bwd = torch.zeros(*self.pack_bwd_shape, **bf)
+        # fp32 gradient, in the layout the weight-gradient kernel emits: pack_shape for conv / head / cols,
+        # [taps][i_pad][o_pad] for convT
+        self.grad_shape = self.pack_bwd_shape if kind == "convT" else self.pack_shape
+        self.grad = None
         self.bias_grad = None
+        self._scratch = {}
 
     # ---- plan factories -------------------------------------------------------------------
     def out_hw(self, h, w):
         k, s, p = self.kh, self.stride, self.pad
-        if self.kind == "conv":
+        if self.kind == "cols":
+            return h, w            # the source already is the im2col grid
+        if self.kind in ("conv", "head"):
             return (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
         return (h - 1) * s - 2 * p + k, (w - 1) * s - 2 * p + k
 
@@ -93,6 +113,21 @@ class ConvLayer:
         ConvTranspose2d (each output phase is a small stride-1 conv written to a strided view)."""
         if self.kind == "conv":
             return [self.fwd_plan(srcs, out, stats_partial, act, slope, use_bias)]
+        bias_t = self.bias.detach() if (use_bias and self.bias is not None) else None
+        if self.kind == "cols":
+            n, ho, wo, _ = out.shape
+            src = [dict(act=srcs[0], wgt=self.pack_fwd, k_off=0, c_real=self.taps * self.I)]
+            return [_C.conv_plan(src, out, [(0, 0, 0)], bias=bias_t, stats_partial=stats_partial, act=act, slope=slope,
+                                 cout_real=self.O)]
+        if self.kind == "head":
+            x = srcs[0]
+            n, hi, wi, _ = x.shape
+            hc = self._buf(("hc", out.data_ptr()), (n, hi, wi, 64), x.device)
+            ho, wo = hi - self.kh + 1, wi - self.kw + 1
+            gemm = _C.conv_plan([dict(act=x, wgt=self.pack_fwd, k_off=0)], hc, [(0, 0, 0)],
+                                flops=2.0 * n * ho * wo * self.taps * self.I)
+            return [gemm, TailCall("head_gather", (hc, bias_t, out), lambda: (
+                _C.ptr(hc), _C.ptr(bias_t), _C.ptr(out), n, hi, wi, self.kh, out.shape[3], act, _C.F(slope)))]
         assert len(srcs) == len(self.in_split)
         s = self.stride
         srcd = [dict(act=t, wgt=self.pack_fwd, k_off=o, c_real=c) for t, o, c in zip(srcs, self.k_off, self.in_split)]
@@ -129,13 +164,25 @@ class ConvLayer:
         if self.kind == "conv":
             return [_C.wgrad_plan(list(srcs), dy, conv_taps(self.kh, self.kw, self.pad), self.grad,
                                   stride=self.stride, p_real=self.I, q_real=self.O)]
+        if self.kind == "cols":
+            return [_C.wgrad_plan([srcs[0]], dy, [(0, 0, 0)], self.grad, p_real=self.taps * self.I, q_real=self.O)]
+        if self.kind == "head":
+            x = srcs[0]
+            n, hi, wi, _ = x.shape
+            dzc = self._buf(("dzc", dy.data_ptr()), (n, hi, wi, 64), x.device)
+            ho, wo = hi - self.kh + 1, wi - self.kw + 1
+            return [TailCall("head_scatter", (dy, dzc), lambda: (_C.ptr(dy), _C.ptr(dzc), n, hi, wi, self.kh,
+                                                                 dy.shape[3])),
+                    _C.wgrad_plan([x], dzc, [(0, 0, 0)], self.grad, flops=2.0 * n * ho * wo * self.taps * self.I)]
         taps = conv_taps(self.kh, self.kw, self.pad)
         return [_C.wgrad_plan([dy], x, taps, self.grad, stride=self.stride, p_real=self.O, q_real=c, dw_row_off=o)
                 for x, o, c in zip(srcs, self.k_off, self.in_split)]
 
-    def wgrad_plan(self, srcs, dy):
-        assert self.kind == "conv"
-        return self.wgrad_plans(srcs, dy)[0]
+    def _buf(self, key, shape, device):
+        """Scratch tensors of the restated layers (one per call site, keyed by the tensor they belong to)."""
+        if key not in self._scratch:
+            self._scratch[key] = torch.zeros(*shape, dtype=torch.bfloat16, device=device)
+        return self._scratch[key]
 
     def dgrad_src(self, dy, seg):
         """Operand descriptor for the input-gradient of concat segment `seg`."""
@@ -143,6 +190,17 @@ class ConvLayer:
 
     def dgrad_plans(self, dy, out, seg=0):
         """Input gradient w.r.t. concat segment `seg` -> list of plans (one per output phase)."""
+        if self.kind == "cols":
+            return [_C.conv_plan([dict(act=dy, wgt=self.pack_bwd, k_off=0, c_real=self.O)], out, [(0, 0, 0)],
+                                 cout_real=self.taps * self.I)]
+        if self.kind == "head":
+            n, hi, wi, _ = out.shape
+            dzc = self._buf(("dzc", dy.data_ptr()), (n, hi, wi, 64), out.device)
+            ho, wo = hi - self.kh + 1, wi - self.kw + 1
+            return [TailCall("head_scatter", (dy, dzc), lambda: (_C.ptr(dy), _C.ptr(dzc), n, hi, wi, self.kh,
+                                                                 dy.shape[3])),
+                    _C.conv_plan([dict(act=dzc, wgt=self.pack_bwd, k_off=0)], out, [(0, 0, 0)],
+                                 flops=2.0 * n * ho * wo * self.taps * self.I)]
         if self.kind == "convT":
             # d(input) of a transposed conv is an ordinary strided conv over dY with the [tap][ci][co] pack
             return [_C.conv_plan([self.dgrad_src(dy, seg)], out, conv_taps(self.kh, self.kw, self.pad),
@@ -163,6 +221,16 @@ class ConvLayer:
                     continue
                 plans.append(_C.conv_plan([self.dgrad_src(dy, seg)], sub, taps, cout_real=self.in_split[seg]))
         return plans
+
+
+class TailCall:
+    """A bandwidth kernel that sits in a plan list next to the implicit-GEMM plans (same .run() protocol)."""
+
+    def __init__(self, name, keep, args):
+        self.name, self.keep, self.args = name, keep, args
+
+    def run(self):
+        _C.call(self.name, *self.args())
 
 
 def multi_dgrad_plan(consumers, out):
@@ -203,7 +271,7 @@ class ParamStore:
         for i, p in enumerate(self.params):
             if i in self.conv_of:
                 l = self.conv_of[i]
-                sizes.append(l.taps * l.o_pad * l.i_pad)
+                sizes.append(l.grad_shape[0] * l.grad_shape[1] * l.grad_shape[2])
             elif i in self.bias_of:
                 sizes.append(self.bias_of[i].o_pad)
             else:
@@ -217,7 +285,7 @@ class ParamStore:
             g = self.grad_arena[offs[i]:offs[i] + sizes[i]]
             if i in self.conv_of:
                 l = self.conv_of[i]
-                l.grad = g.view(l.taps, l.o_pad, l.i_pad) if l.kind == "conv" else g.view(l.taps, l.i_pad, l.o_pad)
+                l.grad = g.view(*l.grad_shape)
             elif i in self.bias_of:
                 self.bias_of[i].bias_grad = g
             self.grad_views.append(g)
@@ -246,7 +314,7 @@ class ParamStore:
             r.numel = p.numel()
             if i in self.conv_of:
                 l = self.conv_of[i]
-                r.kind = 1 if l.kind == "conv" else 2
+                r.kind = {"conv": 1, "convT": 2, "head": 3, "cols": 4}[l.kind]
                 r.kh, r.kw = l.kh, l.kw
                 r.dim1 = p.shape[1]
                 r.o_pad, r.i_pad = l.o_pad, l.i_pad
@@ -304,6 +372,11 @@ class ParamStore:
             if l.kind == "conv":
                 parts = [l.grad[:, :l.O, o:o + c] for o, c in zip(l.k_off, l.in_split)]
                 return torch.cat(parts, 2).reshape(l.kh, l.kw, l.O, l.I).permute(2, 3, 0, 1).contiguous()
+            if l.kind == "head":      # [1][tap][ci] -> [1][I][kh][kw]
+                parts = [l.grad[0, :l.taps, o:o + c] for o, c in zip(l.k_off, l.in_split)]
+                return torch.cat(parts, 1).reshape(l.kh, l.kw, l.I).permute(2, 0, 1).unsqueeze(0).contiguous()
+            if l.kind == "cols":      # [1][o][tap*I + c] -> [O][I][kh][kw]
+                return l.grad[0, :l.O, :l.taps * l.I].reshape(l.O, l.kh, l.kw, l.I).permute(0, 3, 1, 2).contiguous()
             parts = [l.grad[:, o:o + c, :l.O] for o, c in zip(l.k_off, l.in_split)]
             return torch.cat(parts, 1).reshape(l.kh, l.kw, l.I, l.O).permute(2, 3, 0, 1).contiguous()
         if i in self.bias_of:

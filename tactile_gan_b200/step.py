@@ -128,8 +128,8 @@ class TrainStep:
         S1.forward()
         S1.u[4].dz.zero_()
         self._gan_loss(S1, 0, B, True, False, 1.0, SLOT["G_GAN"])
-        dx0 = S1.backward(wgrad=False, input_grad=True)
-        _C.call("unpack_nhwc", ptr(dx0), ptr(self.gan_grad), B, HW, dx0.shape[3], self.c_a, self.c_b, F(1.0))
+        S1.backward(wgrad=False, input_grad=True)
+        S1.input_grad_image(self.c_a, self.c_b, self.gan_grad)
         _C.call("l1_loss", ptr(fake), ptr(real_B), LL(fake.numel()), F(self.lambda_a),
                 ptr(self.losses[3:4]), ptr(self.l1_grad))
         if self.lambda_per != 0 and self.version == 2:
