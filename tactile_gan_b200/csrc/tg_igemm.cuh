@@ -66,7 +66,8 @@ struct IgemmCfg {
   static constexpr int kSmemStore = 2 * kStoreBytes;
   static constexpr int kSmemScratch = 4 * 64 * 2 * 4;  // [4 warps][64 ch][sum, sumsq]
   static constexpr int kSmemBars = 256;
-  static constexpr int kSmemTotal = 1024 + kSmemStages + kSmemStore + kSmemScratch + kSmemBars;
+  static constexpr int kSmemBias = 256;                // 64 fp32 bias values of the current output chunk
+  static constexpr int kSmemTotal = 1024 + kSmemStages + kSmemStore + kSmemScratch + kSmemBars + kSmemBias;
 };
 
 // Bounded spin so a protocol bug reports an error instead of hanging the GPU.
@@ -84,40 +85,67 @@ __device__ __forceinline__ void mbar_wait_guard(uint32_t bar, uint32_t parity, i
 // ---- epilogue helpers (one warp per scheduler runs these: keep the instruction count low) ----------
 // 64 fp32 accumulator columns -> 32 packed bf16x2 words, with the optional bias / activation hoisted
 // out of the common (InstanceNorm follows: no bias, no activation) path.
-__device__ __forceinline__ void epi_pack(const uint32_t (&v0)[32], const uint32_t (&v1)[32],
-                                         uint32_t (&packed)[32], int act, float slope,
-                                         const float* __restrict__ bias, int bias_len, int c_base) {
-  if (act == ACT_NONE && bias == nullptr) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      packed[j] = pack_bf16x2(__uint_as_float(v0[2 * j]), __uint_as_float(v0[2 * j + 1]));
-      packed[16 + j] = pack_bf16x2(__uint_as_float(v1[2 * j]), __uint_as_float(v1[2 * j + 1]));
-    }
-    return;
-  }
+template <int ACT, bool BIAS>
+__device__ __forceinline__ void epi_pack_as(const uint32_t (&v0)[32], const uint32_t (&v1)[32],
+                                            uint32_t (&packed)[32], float slope, const float* __restrict__ sbias) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     float x0 = __uint_as_float(j < 16 ? v0[2 * j] : v1[2 * (j - 16)]);
     float x1 = __uint_as_float(j < 16 ? v0[2 * j + 1] : v1[2 * (j - 16) + 1]);
-    if (bias) {
-      if (c_base + 2 * j < bias_len) x0 += __ldg(bias + c_base + 2 * j);
-      if (c_base + 2 * j + 1 < bias_len) x1 += __ldg(bias + c_base + 2 * j + 1);
+    if (BIAS) {   // this chunk's 64 bias values, staged in shared memory (zero past bias_len): broadcast reads
+      const float2 b = *reinterpret_cast<const float2*>(sbias + 2 * j);
+      x0 += b.x;
+      x1 += b.y;
     }
-    if (act == ACT_LRELU) {
+    if (ACT == ACT_LRELU) {
       x0 = x0 > 0.f ? x0 : x0 * slope;
       x1 = x1 > 0.f ? x1 : x1 * slope;
-    } else if (act == ACT_RELU) {
+    } else if (ACT == ACT_RELU) {
       x0 = fmaxf(x0, 0.f);
       x1 = fmaxf(x1, 0.f);
-    } else if (act == ACT_SIGMOID) {
+    } else if (ACT == ACT_SIGMOID) {
       x0 = 1.f / (1.f + __expf(-x0));
       x1 = 1.f / (1.f + __expf(-x1));
-    } else if (act == ACT_TANH) {
+    } else if (ACT == ACT_TANH) {
       x0 = tanhf(x0);
       x1 = tanhf(x1);
     }
     packed[j] = pack_bf16x2(x0, x1);
   }
+}
+
+// The activation switch sits OUTSIDE the 32-element loop: every variant is a tight straight-line block (with
+// the switch inside, the unrolled body is a chain of branches over several KB of code per tile row).
+__device__ __forceinline__ void epi_pack(const uint32_t (&v0)[32], const uint32_t (&v1)[32],
+                                         uint32_t (&packed)[32], int act, float slope,
+                                         const float* __restrict__ sbias) {
+  if (sbias == nullptr) {
+    switch (act) {
+      case ACT_NONE: epi_pack_as<ACT_NONE, false>(v0, v1, packed, slope, sbias); break;
+      case ACT_LRELU: epi_pack_as<ACT_LRELU, false>(v0, v1, packed, slope, sbias); break;
+      case ACT_RELU: epi_pack_as<ACT_RELU, false>(v0, v1, packed, slope, sbias); break;
+      case ACT_SIGMOID: epi_pack_as<ACT_SIGMOID, false>(v0, v1, packed, slope, sbias); break;
+      default: epi_pack_as<ACT_TANH, false>(v0, v1, packed, slope, sbias); break;
+    }
+  } else {
+    switch (act) {
+      case ACT_NONE: epi_pack_as<ACT_NONE, true>(v0, v1, packed, slope, sbias); break;
+      case ACT_LRELU: epi_pack_as<ACT_LRELU, true>(v0, v1, packed, slope, sbias); break;
+      case ACT_RELU: epi_pack_as<ACT_RELU, true>(v0, v1, packed, slope, sbias); break;
+      case ACT_SIGMOID: epi_pack_as<ACT_SIGMOID, true>(v0, v1, packed, slope, sbias); break;
+      default: epi_pack_as<ACT_TANH, true>(v0, v1, packed, slope, sbias); break;
+    }
+  }
+}
+
+// Stage bias[c_base .. c_base+64) (zero past bias_len) for the 128 epilogue threads; no-op when already staged.
+__device__ __forceinline__ void epi_stage_bias(float* sbias, const float* __restrict__ bias, int bias_len,
+                                               int c_base, int& staged_base, int et) {
+  if (bias == nullptr || staged_base == c_base) return;
+  named_bar_sync(1, 128);   // readers of the previously staged chunk are done
+  if (et < 64) sbias[et] = c_base + et < bias_len ? __ldg(bias + c_base + et) : 0.f;
+  named_bar_sync(1, 128);
+  staged_base = c_base;
 }
 
 // this thread's row (128 B = 64 bf16) of the staging tile, 128B-swizzled like the TMA store expects
@@ -285,6 +313,8 @@ igemm_conv_kernel(const __grid_constant__ IgemmParams p) {
     uint32_t aphase = 0;
     uint32_t chunk_ctr = 0;
     float* scratch = reinterpret_cast<float*>(smem_gen + (scratch_base - smem_base));
+    float* sbias = reinterpret_cast<float*>(smem_gen + (bar_base + Cfg::kSmemBars - smem_base));
+    int staged_base = -1;
     const int e_act = p.act, e_bias_len = p.bias_len;
     const float e_slope = p.slope;
     const float* e_bias = p.bias;
@@ -322,7 +352,8 @@ igemm_conv_kernel(const __grid_constant__ IgemmParams p) {
         }
         const int c_base = n_tile * BN + chunk * 64;
         uint32_t packed[32];
-        epi_pack(v0, v1, packed, e_act, e_slope, e_bias, e_bias_len, c_base);
+        epi_stage_bias(sbias, e_bias, e_bias_len, c_base, staged_base, et);
+        epi_pack(v0, v1, packed, e_act, e_slope, e_bias ? sbias : nullptr);
         // staging buffer `sb` must have been drained by the TMA store issued two chunks ago
         if (et == 0) tma_store_wait_read<1>();
         named_bar_sync(1, 128);

@@ -25,7 +25,7 @@ constexpr int kHaloAStages = 2;
 constexpr int kHaloBStage = 9 * 64 * 128;  // 72 KiB: up to 9 taps
 constexpr int kHaloBStages = 2;
 constexpr int kHaloSmem = 1024 + kHaloBStages * kHaloBStage + kHaloAStages * kHaloAStage + 2 * kStoreBytes +
-                          4 * 64 * 2 * 4 + 256;
+                          4 * 64 * 2 * 4 + 256 + 256;   // ... + barriers + staged bias chunk
 
 struct alignas(64) HaloParams {
   IgemmSrc src[kMaxSrc];  // act box {64, 8+ww, 16+hh, 1}; wgt box {64, 64, wgt_taps}
@@ -207,6 +207,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_halo_kernel(const __grid
     int set = 0;
     uint32_t tphase = 0, chunk_ctr = 0;
     float* scratch = reinterpret_cast<float*>(smem_gen + (scratch_base - smem_base));
+    float* sbias = reinterpret_cast<float*>(smem_gen + (bar_base + 256 - smem_base));
+    int staged_base = -1;
     const int e_act = p.act, e_bias_len = p.bias_len;
     const float e_slope = p.slope;
     const float* e_bias = p.bias;
@@ -235,7 +237,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_halo_kernel(const __grid
           mbar_arrive(tempty(set));
         }
         uint32_t packed[32];
-        epi_pack(v0, v1, packed, e_act, e_slope, e_bias, e_bias_len, c_base);
+        epi_stage_bias(sbias, e_bias, e_bias_len, c_base, staged_base, et);
+        epi_pack(v0, v1, packed, e_act, e_slope, e_bias ? sbias : nullptr);
         if (et == 0) tma_store_wait_read<1>();
         named_bar_sync(1, 128);
         epi_store_row(store_base + sb * kStoreBytes, row, packed);
