@@ -397,15 +397,21 @@ static int create_wgrad_taps_plan(const tg_wgrad_desc* d, tg_plan* pl) {
   memset(&p, 0, sizeof(p));
   p.num_src = d->num_src;
   memset(p.tap_w, -1, sizeof(p.tap_w));
-  for (int t = 0; t < d->taps; ++t) p.tap_w[d->tap_dy[t] + 1][d->tap_dx[t] + 1] = d->tap_w[t];
+  int ymin = 127, xmin = 127;
+  for (int t = 0; t < d->taps; ++t) {
+    ymin = d->tap_dy[t] < ymin ? d->tap_dy[t] : ymin;
+    xmin = d->tap_dx[t] < xmin ? d->tap_dx[t] : xmin;
+  }
+  p.org_y = ymin + 1; p.org_x = xmin + 1;     // window centre: taps become (dy, dx) in [-1, 1]
+  for (int t = 0; t < d->taps; ++t) p.tap_w[d->tap_dy[t] - ymin][d->tap_dx[t] - xmin] = d->tap_w[t];
   const int H = d->q.h, W = d->q.w;
   p.N = d->q.n;
   p.tiles_h = (H + tg::kWtTH - 1) / tg::kWtTH;
-  p.tiles_w = (W + tg::kWtTW - 1) / tg::kWtTW;
+  p.tiles_w = (W + 2 * p.org_x + tg::kWtTW - 1) / tg::kWtTW;
   int chunks = 0;
   for (int s = 0; s < d->num_src; ++s) {
     if (d->p[s].c % 64) return tg_set_error("tg_wgrad_plan_create: P channels must be a multiple of 64");
-    if (d->p[s].h != H || d->p[s].w != W || d->p[s].n != d->q.n)
+    if (d->p[s].h != d->p[0].h || d->p[s].w != d->p[0].w || d->p[s].n != d->q.n)
       return tg_set_error("tg_wgrad_plan_create: source size mismatch");
     if (make_act_map(&p.src[s].act, d->p[s], 0, d->p[s].c, tg::kWtTW, tg::kWtTH + 2, 1, 1)) return -1;
     p.src[s].c_chunks = d->p[s].c / 64;
@@ -457,10 +463,15 @@ int tg_wgrad_plan_create(const tg_wgrad_desc* d, tg_plan** out) {
     {
       static const bool use_old = getenv("TG_WGRAD_HALO") != nullptr;
       static const int max_qc = getenv("TG_WGRAD_TAPS_MAXC") ? atoi(getenv("TG_WGRAD_TAPS_MAXC")) : 128;
-      bool centred = d->taps <= 9;
-      for (int t = 0; t < d->taps && centred; ++t)
-        centred = d->tap_dy[t] >= -1 && d->tap_dy[t] <= 1 && d->tap_dx[t] >= -1 && d->tap_dx[t] <= 1;
-      if (!disabled && !use_old && d->stride == 1 && d->taps >= 2 && centred && same && d->q.c <= max_qc) {
+      // any <= 3x3 tap window of a stride-1 conv, padded (X grid == dY grid) or valid (X grid larger)
+      const bool window = d->taps <= 9 && ymax - ymin <= 2 && xmax - xmin <= 2;
+      const bool grids = ymin >= -1 && xmin >= -1 && ymin <= 0 && xmin <= 0;   // centre offset 0 (padded) or 1 (valid)
+      // wide outputs: the per-tap kernel re-streams both operands nine times, which only pays while they sit in L2
+      double op_bytes = double(d->q.n) * d->q.h * d->q.w * d->q.c * 2.0;
+      for (int s2 = 0; s2 < d->num_src; ++s2) op_bytes += double(d->p[s2].n) * d->p[s2].h * d->p[s2].w * d->p[s2].c * 2.0;
+      const bool big = op_bytes > 200.0 * 1024 * 1024;
+      (void)same;
+      if (!disabled && !use_old && d->stride == 1 && d->taps >= 2 && window && grids && (d->q.c <= max_qc || big)) {
         if (create_wgrad_taps_plan(d, pl)) { delete pl; return -1; }
         *out = pl;
         return 0;

@@ -1,4 +1,4 @@
-// Tap-tiled weight gradient for 3x3-window stride-1 same-size convolutions (sm_100a, tcgen05).
+// Tap-tiled weight gradient for 3x3-window stride-1 convolutions, padded or valid (sm_100a, tcgen05).
 //
 //   dW[(dy,dx)][co][ci] = sum_{r,c} X[r+dy, c+dx][ci] * dY[r, c][co]
 //                       = sum_{r,c'} X[r+dy, c'][ci] * dY[r, c'-dx][co]          (c' = c + dx)
@@ -32,6 +32,7 @@ struct alignas(64) WgradTapsParams {
   int num_src;
   int8_t tap_w[3][3];     // [dy+1][dx+1] -> index on dw's tap axis, or -1 if the tap is absent
   int tiles_h, tiles_w, N;
+  int org_y, org_x;       // X pixel of tap (dy, dx) = (0, 0) relative to the dY pixel (0 for pad = 1, 1 for pad = 0)
   int total_chunks, n_tiles, splits;
   float* dw;              // [taps_total][n_total][m_total] fp32
   int m_total, n_total;
@@ -100,11 +101,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) wgrad_taps_kernel(const __grid
         const int xc = j * 64;
         for (int kt = k0; kt < k1; ++kt) {
           const int img = kt / tiles_per_img, t_in = kt % tiles_per_img;
-          const int y0 = (t_in / p.tiles_w) * kWtTH, x0 = (t_in % p.tiles_w) * kWtTW;
+          // tile columns run over c' = c + dx in [-org_x, W + org_x): for a valid conv the shifted column can
+          // fall one pixel outside the dY grid on either side while still addressing a real X column
+          const int y0 = (t_in / p.tiles_w) * kWtTH, x0 = (t_in % p.tiles_w) * kWtTW - p.org_x;
           mbar_wait_guard(empty_bar(stage), phase ^ 1, p.err_flag, 41);
           const uint32_t xs = smem_base + stage * kWtStageBytes;
           mbar_arrive_expect_tx(full_bar(stage), uint32_t(kWtStageBytes));
-          tma_load_4d(xs, xmap, full_bar(stage), xc, x0, y0 - 1, img);
+          tma_load_4d(xs, xmap, full_bar(stage), xc, x0 + p.org_x, y0 - 1 + p.org_y, img);
           tma_load_4d(xs + kWtXBytes, &p.q, full_bar(stage), n_tile * 64, x0 - 1, y0, img);
           if (++stage == kWtStages) { stage = 0; phase ^= 1; }
         }

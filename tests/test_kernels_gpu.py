@@ -78,6 +78,7 @@ WGRAD_CASES = [
     (2, [3], 64, 64, 64, 3, 1, 1), (2, [128], 256, 61, 61, 3, 1, 0), (2, [64], 128, 127, 127, 3, 2, 0),
     (2, [64], 128, 64, 64, 4, 2, 1), (2, [24, 8], 24, 32, 32, 3, 1, 1), (1, [512], 1, 59, 59, 3, 1, 0),
     (3, [64], 128, 37, 29, 3, 1, 1), (2, [128, 64], 128, 48, 40, 3, 1, 1), (5, [64], 64, 16, 8, 3, 1, 1),
+    (2, [64], 128, 31, 29, 3, 1, 0), (3, [128], 64, 18, 10, 3, 1, 0),      # valid convs on the tap-tiled kernel
 ]
 
 

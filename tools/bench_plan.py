@@ -39,7 +39,26 @@ def conv_case(n, h, w, cin, cout, taps, stride=1, bias=False, act=0, pad=None):
           f"{fl/ms/1e9:8.1f} TF/s  {(x.numel()+out.numel())*2/ms/1e6:7.1f} GB/s")
 
 
+def wgrad_case(n, h, w, cin, cout, k=3, pad=1):
+    ho, wo = h + 2 * pad - k + 1, w + 2 * pad - k + 1
+    x = torch.randn(n, h, w, cin, device=dev).bfloat16()
+    dy = torch.randn(n, ho, wo, cout, device=dev).bfloat16()
+    dw = torch.zeros(k * k, cout, cin, device=dev)
+    tp = [(r - pad, s - pad, r * k + s) for r in range(k) for s in range(k)]
+    plan = _C.wgrad_plan([x], dy, tp, dw)
+    ms = timeit(plan)
+    fl = 2.0 * n * ho * wo * k * k * cin * cout
+    print(f"wgrad n{n} {h}x{w} cin{cin} cout{cout} k{k} p{pad}: {ms*1e3:8.1f} us {fl/ms/1e9:8.1f} TF/s")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "wgrad":
+        for n in (16, 32, 48, 64):
+            wgrad_case(n, 61, 61, 256, 512, pad=0)
+        wgrad_case(64, 63, 63, 128, 256, pad=0)
+        wgrad_case(32, 64, 64, 256, 256)
+        wgrad_case(32, 32, 32, 512, 512)
+        sys.exit(0)
     for args in [(32, 127, 127, 64, 64, 1), (32, 128, 128, 64, 64, 1), (32, 127, 127, 64, 128, 1),
                  (32, 59, 59, 512, 64, 1), (32, 59, 59, 64, 512, 1), (32, 256, 256, 64, 64, 1)]:
         conv_case(*args)
