@@ -140,6 +140,16 @@ int tg_fmap_fwd(const void* x, const float* w, const float* b, float* out, int N
 int tg_fmap_bwd(const void* x, const float* w, const float* out, const float* g1, const float* g2,
                 void* dx, float* dw, float* db, int N, int HW, int C, int co, int use_tanh, void* stream);
 
+/* ---- version-1 perceptual term, VGGPerceptualLoss (util.py:100-144): input transform (channel repeat,
+ *      ImageNet mean / std, bilinear resize align_corners=False) and its transpose, MaxPool2d(2) for layers without
+ *      a normalise pass, and the gradient of weight * L1-mean between two feature tensors */
+int tg_vgg_prep_fwd(const float* x, void* out, int N, int cs, int H, int W, int OH, int OW, int C, int resize,
+                    void* stream);
+int tg_vgg_prep_bwd(const void* g, float* grad, int N, int cs, int H, int W, int OH, int OW, int C, int resize,
+                    float scale, void* stream);
+int tg_pool_fwd(const void* y, void* pool, int N, int H, int W, int C, int mode, void* stream);
+int tg_feat_loss_grad(const void* a, const void* b, long long numel, float weight, void* g, void* stream);
+
 /* ---- losses: GANLoss (generators/generators.py:80-105), nn.L1Loss (train.py:145), pan_loss
  *      (util.py:41-70), gradient_penalty norm (util.py:92-93) */
 int tg_gan_loss(const void* pred, const float* label, float label_const, int mode, int target_is_real,

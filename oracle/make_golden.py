@@ -125,6 +125,37 @@ def run_case(gen_name, nf, size, batch, loss, steps, seed, lambda_gp=0.01, compa
     return fixture
 
 
+def vgg_blocks(seed):
+    """The reference's four VGG16 slices (util.py:104-107) with seeded random-init weights: the pretrained
+    ImageNet weights cannot be downloaded here (no network)."""
+    import torchvision
+    torch.manual_seed(seed)
+    feats = torchvision.models.vgg16(weights=None).features
+    return nn.ModuleList([feats[:4], feats[4:9], feats[9:16], feats[16:23]]).eval()
+
+
+def vgg_case(seed=31, batch=2, size=64, channels=3):
+    """VGGPerceptualLoss.forward (util.py:119-144) of the UNMODIFIED reference class, called unbound on a stand-in
+    `self`: the class's __init__ hard-codes .cuda() and pretrained=True (download), so it cannot be constructed
+    here, but forward only touches self.blocks / mean / std / transform / resize."""
+    import types
+    ref_util, _, _, _ = reference_modules()
+    blocks = vgg_blocks(seed)
+    stub = types.SimpleNamespace(blocks=blocks, mean=torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1),
+                                 std=torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1),
+                                 transform=torch.nn.functional.interpolate, resize=True)
+    g = torch.Generator().manual_seed(seed + 1000)
+    real_b = torch.rand(batch, channels, size, size, generator=g)
+    fake_b = torch.rand(batch, channels, size, size, generator=g).requires_grad_(True)
+    w_per = [0, .1, .3, .6]
+    loss = ref_util.VGGPerceptualLoss.forward(stub, real_b, fake_b, weights=w_per)
+    (grad,) = torch.autograd.grad(loss, fake_b)
+    return dict(meta=dict(seed=seed, batch=batch, size=size, channels=channels, w_per=w_per,
+                          torch=torch.__version__), loss=float(loss), grad_norm=float(grad.norm()),
+                grad_sub=grad[:, :, ::4, ::4].clone(),
+                weight_probe={k: float(v.flatten()[0]) for k, v in list(blocks.state_dict().items())[:4]})
+
+
 def state_dict_keys():
     """Key/shape inventory of all reference networks at nf=64 (the checkpoint-layout contract)."""
     _, create_gen, _, create_disc = reference_modules()
@@ -149,10 +180,16 @@ if __name__ == "__main__":
         ("unetpp_w", dict(gen_name="UNet++", nf=4, size=32, batch=2, loss="w", steps=1, compact=True, seed=26)),
     ]
     for name, kw in cases:
+        if len(sys.argv) > 1 and sys.argv[1] == "vgg":
+            break                       # `make_golden.py vgg`: only (re)write the VGG fixtures
         fx = run_case(**kw)
         path = os.path.join(OUT, f"{name}.pt")
         torch.save(fx, path)
         print(name, os.path.getsize(path) // 1024, "KiB", {k: round(v, 6) for k, v in fx["steps"][0].items()
                                                             if isinstance(v, float)})
+    for name, kw in (("vgg_v1_rgb", dict(channels=3)), ("vgg_v1_gray", dict(seed=32, channels=1))):
+        fx = vgg_case(**kw)
+        torch.save(fx, os.path.join(OUT, f"{name}.pt"))
+        print(name, fx["loss"], fx["grad_norm"])
     torch.save(state_dict_keys(), os.path.join(OUT, "state_dict_keys.pt"))
     print("wrote", OUT)

@@ -12,6 +12,7 @@ What follows which reference lines (all under /root/reference):
   gan_loss         generators/generators.py:80-105
   pan_loss         util.py:41-70 (mode='normal' only, as called from train.py:160)
   gradient_penalty util.py:72-97
+  vgg_perceptual   util.py:100-144 (VGGPerceptualLoss: 4 slices of torchvision VGG16.features[:23]; version 1 only)
   adam_update      torch.optim.Adam as configured at train.py:56-57 (betas=(beta1,0.99), eps=1e-8)
   train_step       train.py:99-168
 
@@ -192,6 +193,50 @@ def gradient_penalty(sd_d, real_a, real_b, fake_b, alpha, activation, lambda_gp,
     return (((g + 1e-16).norm(2, dim=1) - constant) ** 2).mean() * lambda_gp
 
 
+# --------------------------------------------------------------------------- version-1 perceptual term
+# torchvision VGG16.features[:23] in the reference's four slices (util.py:104-107). nn.Sequential slicing keeps the
+# original child names, so the ModuleList's state_dict keys are blocks.<slice>.<features index>.{weight,bias}.
+VGG_SLICES = ((0, 2), (5, 7), (10, 12, 14), (17, 19, 21))      # conv indices; slices 1..3 start with MaxPool2d(2)
+VGG_MEAN = (0.485, 0.456, 0.406)
+VGG_STD = (0.229, 0.224, 0.225)
+
+
+def vgg_features(sd, x):
+    """x: normalised (and resized) (B,3,h,w) -> the four slice outputs (util.py:133-135)."""
+    feats = []
+    for b, convs in enumerate(VGG_SLICES):
+        if b > 0:
+            x = F.max_pool2d(x, 2)
+        for i in convs:
+            x = _q(F.relu(F.conv2d(x, _q(sd[f"blocks.{b}.{i}.weight"]), sd[f"blocks.{b}.{i}.bias"], padding=1)))
+        feats.append(x)
+    return feats
+
+
+def vgg_transform(x, resize=True):
+    """util.py:120-129: repeat to 3 channels, ImageNet mean / std, bilinear resize to 224 (align_corners=False)."""
+    if x.shape[1] != 3:
+        x = x.repeat(1, 3, 1, 1)
+    mean = torch.tensor(VGG_MEAN, dtype=x.dtype).view(1, 3, 1, 1)
+    std = torch.tensor(VGG_STD, dtype=x.dtype).view(1, 3, 1, 1)
+    x = (x - mean) / std
+    if resize:
+        x = F.interpolate(x, mode="bilinear", size=(224, 224), align_corners=False)
+    return x
+
+
+def vgg_perceptual(sd, inp, target, weights=(0.25, 0.25, 0.25, 0.25), feature_layers=(0, 1, 2, 3), resize=True):
+    """VGGPerceptualLoss.forward with style_layers=[] (util.py:119-144): sum_i weights[i] * L1mean(x_i, y_i);
+    unlike pan_loss the weights are NOT normalised."""
+    fx = vgg_features(sd, _q(vgg_transform(inp, resize)))
+    fy = vgg_features(sd, _q(vgg_transform(target, resize)))
+    loss = 0.0
+    for i in range(4):
+        if i in feature_layers:
+            loss = loss + F.l1_loss(fx[i], fy[i]) * weights[i]
+    return loss
+
+
 # --------------------------------------------------------------------------- optimiser
 def adam_update(params, grads, state, lr, beta1, beta2=0.99, eps=1e-8):
     """In-place Adam on dicts keyed by parameter name; state[name] = dict(step, exp_avg, exp_avg_sq)."""
@@ -217,6 +262,7 @@ class StepConfig:
         self.lambda_a, self.lambda_gp, self.lambda_per = lambda_a, lambda_gp, lambda_per
         self.w_per, self.lr, self.beta1, self.regularize = tuple(w_per), lr, beta1, regularize
         self.activation = loss == "ls"  # train.py:33
+        self.vgg_sd = None              # version 1: state_dict of the four VGG16 slices (blocks.<b>.<i>.weight/bias)
 
 
 def _leaf(sd):
@@ -255,9 +301,12 @@ def train_step(sd_g, sd_d, opt_g, opt_d, real_a, real_b, real_label, alpha, cfg)
     l1 = F.l1_loss(real_b, fake_b)
     total_g = g_gan + l1 * cfg.lambda_a
     out["G_GAN"], out["L1"] = float(g_gan.detach()), float(l1.detach())
-    if cfg.lambda_per != 0:
-        if cfg.version != 2:
-            raise NotImplementedError("version 1 (VGG16) is handled by oracle.vgg_perceptual")
+    if cfg.lambda_per != 0 and cfg.version != 2:
+        # train.py:151-153,160: perceptual_loss(real_B, fake_B, weights=w_per) with frozen VGG16 weights
+        per = vgg_perceptual(cfg.vgg_sd, real_b, fake_b, cfg.w_per) * cfg.lambda_per
+        total_g = total_g + per
+        out["per"] = float(per.detach())
+    elif cfg.lambda_per != 0:
         _, feats_real = patchd_forward(pd2, real_a, real_b, act)
         # the reference stores detached clones of both feature lists: the term carries no gradient
         per = pan_loss([f.detach() for f in feats_real], [f.detach() for f in feats_fake], cfg.w_per) * cfg.lambda_per

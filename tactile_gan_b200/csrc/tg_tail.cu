@@ -1035,6 +1035,103 @@ __global__ void feat_loss_kernel(const __nv_bfloat16* __restrict__ a, const __nv
   if (threadIdx.x == 0) atomicAdd(loss, tot * weight / float(n8 * 8));
 }
 
+// d/da of  weight * mean|a - b|  as a bf16 tensor: g = sign(a - b) * weight / numel  (version-1 perceptual term)
+__global__ void feat_loss_grad_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                      size_t n8, float weight, __nv_bfloat16* __restrict__ g) {
+  const float s = weight / float(n8 * 8);
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n8; i += size_t(gridDim.x) * blockDim.x) {
+    float x[8], y[8];
+    unpack8(ldg16(a + i * 8), x);
+    unpack8(ldg16(b + i * 8), y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = x[j] > y[j] ? s : (x[j] < y[j] ? -s : 0.f);
+    stg16(g + i * 8, pack8(x));
+  }
+}
+
+// 2x2 pooling of a bf16 NHWC tensor (mode 1 average, 2 max) for layers without a normalise pass (VGG16)
+__global__ void pool_fwd_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ pool, int N, int H,
+                                int W, int C, int mode) {
+  const int CG = C >> 3, H2 = H >> 1, W2 = W >> 1;
+  const size_t total = size_t(N) * H2 * W2 * CG;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int cg = int(i % CG);
+    const size_t q = i / CG;
+    const int qx = int(q % W2), qy = int((q / W2) % H2), n = int(q / (size_t(W2) * H2));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = mode == 2 ? -3.0e38f : 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float f[8];
+      unpack8(ldg16(y + ((size_t(n) * H + 2 * qy + (k >> 1)) * W + 2 * qx + (k & 1)) * C + cg * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = mode == 2 ? fmaxf(acc[j], f[j]) : acc[j] + 0.25f * f[j];
+    }
+    stg16(pool + q * C + cg * 8, pack8(acc));
+  }
+}
+
+// VGGPerceptualLoss input transform (util.py:120-129): repeat a 1-channel image to 3, (x - mean) / std, bilinear
+// resize (align_corners = False, as F.interpolate) to OH x OW; fp32 NCHW -> bf16 NHWC (first 8-channel group).
+struct BilinTap { int i0, i1; float l0, l1; };
+__device__ __forceinline__ BilinTap bilin_tap(int o, int in_size, float scale) {
+  float src = scale * (float(o) + 0.5f) - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  BilinTap t;
+  t.i0 = min(int(src), in_size - 1);
+  t.i1 = t.i0 + (t.i0 < in_size - 1 ? 1 : 0);
+  t.l1 = src - float(t.i0);
+  t.l0 = 1.f - t.l1;
+  return t;
+}
+__constant__ float kVggMean[3] = {0.485f, 0.456f, 0.406f};
+__constant__ float kVggStd[3] = {0.229f, 0.224f, 0.225f};
+
+__global__ void vgg_prep_fwd_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int cs,
+                                    int H, int W, int OH, int OW, int C, int resize) {
+  const size_t total = size_t(N) * OH * OW;
+  const float sy = resize ? float(H) / float(OH) : 1.f, sx = resize ? float(W) / float(OW) : 1.f;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int ox = int(i % OW), oy = int((i / OW) % OH), n = int(i / (size_t(OW) * OH));
+    const BilinTap ty = bilin_tap(oy, H, sy), tx = bilin_tap(ox, W, sx);
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* p = x + (size_t(n) * cs + (cs == 3 ? c : 0)) * H * W;
+      const float m = kVggMean[c], is = 1.f / kVggStd[c];
+      const float v00 = (p[size_t(ty.i0) * W + tx.i0] - m) * is, v01 = (p[size_t(ty.i0) * W + tx.i1] - m) * is;
+      const float v10 = (p[size_t(ty.i1) * W + tx.i0] - m) * is, v11 = (p[size_t(ty.i1) * W + tx.i1] - m) * is;
+      f[c] = ty.l0 * (tx.l0 * v00 + tx.l1 * v01) + ty.l1 * (tx.l0 * v10 + tx.l1 * v11);
+    }
+    stg16(out + i * C, pack8(f));
+  }
+}
+
+// transpose of the transform above: grad[n, c, y, x] += scale * sum over output pixels of w * g[n, oy, ox, c] / std
+__global__ void vgg_prep_bwd_kernel(const __nv_bfloat16* __restrict__ g, float* __restrict__ grad, int N, int cs,
+                                    int H, int W, int OH, int OW, int C, int resize, float scale) {
+  const size_t total = size_t(N) * OH * OW;
+  const float sy = resize ? float(H) / float(OH) : 1.f, sx = resize ? float(W) / float(OW) : 1.f;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int ox = int(i % OW), oy = int((i / OW) % OH), n = int(i / (size_t(OW) * OH));
+    const BilinTap ty = bilin_tap(oy, H, sy), tx = bilin_tap(ox, W, sx);
+    float f[8];
+    unpack8(ldg16(g + i * C), f);
+    float gc[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) gc[c] = scale * f[c] / kVggStd[c];
+    if (cs != 3) { gc[0] += gc[1] + gc[2]; }
+    for (int c = 0; c < (cs == 3 ? 3 : 1); ++c) {
+      float* p = grad + (size_t(n) * cs + c) * H * W;
+      atomicAdd(p + size_t(ty.i0) * W + tx.i0, gc[c] * ty.l0 * tx.l0);
+      atomicAdd(p + size_t(ty.i0) * W + tx.i1, gc[c] * ty.l0 * tx.l1);
+      atomicAdd(p + size_t(ty.i1) * W + tx.i0, gc[c] * ty.l1 * tx.l0);
+      atomicAdd(p + size_t(ty.i1) * W + tx.i1, gc[c] * ty.l1 * tx.l1);
+    }
+  }
+}
+
 // Gradient penalty: nsq[n] = sum_{pix, j<cj} (g[n,pix,c_off+j] + 1e-16)^2
 __global__ void gp_normsq_kernel(const __nv_bfloat16* __restrict__ g, int HW, int C, int c_off, int cj,
                                  float* __restrict__ nsq) {
@@ -1395,6 +1492,36 @@ int tg_feat_loss(const void* a, const void* b, long long numel, float weight, in
                  void* stream) {
   feat_loss_kernel<<<grid_for(size_t(numel) / 8, 256, 148 * 8), 256, 0, TG_STREAM(stream)>>>(
       (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, size_t(numel) / 8, weight, l2, loss);
+  TG_RET();
+}
+
+int tg_feat_loss_grad(const void* a, const void* b, long long numel, float weight, void* g, void* stream) {
+  feat_loss_grad_kernel<<<grid_for(size_t(numel) / 8, 256, 148 * 16), 256, 0, TG_STREAM(stream)>>>(
+      (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, size_t(numel) / 8, weight, (__nv_bfloat16*)g);
+  TG_RET();
+}
+
+int tg_pool_fwd(const void* y, void* pool, int N, int H, int W, int C, int mode, void* stream) {
+  if ((H | W) & 1) return tg_set_error("tg_pool_fwd: H and W must be even");
+  if (mode != 1 && mode != 2) return tg_set_error("tg_pool_fwd: mode 1 (avg) or 2 (max)");
+  pool_fwd_kernel<<<grid_for(size_t(N) * (H / 2) * (W / 2) * (C / 8), 256, 148 * 16), 256, 0, TG_STREAM(stream)>>>(
+      (const __nv_bfloat16*)y, (__nv_bfloat16*)pool, N, H, W, C, mode);
+  TG_RET();
+}
+
+int tg_vgg_prep_fwd(const float* x, void* out, int N, int cs, int H, int W, int OH, int OW, int C, int resize,
+                    void* stream) {
+  if (cs != 1 && cs != 3) return tg_set_error("tg_vgg_prep: 1 or 3 source channels");
+  vgg_prep_fwd_kernel<<<grid_for(size_t(N) * OH * OW, 256, 148 * 16), 256, 0, TG_STREAM(stream)>>>(
+      x, (__nv_bfloat16*)out, N, cs, H, W, OH, OW, C, resize);
+  TG_RET();
+}
+
+int tg_vgg_prep_bwd(const void* g, float* grad, int N, int cs, int H, int W, int OH, int OW, int C, int resize,
+                    float scale, void* stream) {
+  if (cs != 1 && cs != 3) return tg_set_error("tg_vgg_prep: 1 or 3 source channels");
+  vgg_prep_bwd_kernel<<<grid_for(size_t(N) * OH * OW, 256, 148 * 16), 256, 0, TG_STREAM(stream)>>>(
+      (const __nv_bfloat16*)g, grad, N, cs, H, W, OH, OW, C, resize, scale);
   TG_RET();
 }
 

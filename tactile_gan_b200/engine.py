@@ -130,6 +130,8 @@ class ConvUnit:
             _C.call("in_act_fwd", ptr(self.raw), ptr(self.mr), g, b, ptr(self.y.buf),
                     ptr(self.pool.buf if self.pool else None), self.pool_mode,
                     ptr(self.up.buf if self.up else None), n, ho, wo, c, self.c_valid, self.act, F(self.slope))
+        elif self.pool:
+            _C.call("pool_fwd", ptr(self.y.buf), ptr(self.pool.buf), self.n, self.ho, self.wo, self.c, self.pool_mode)
 
     # ---- backward. The gradient of y = same-res consumers (+ explicit extra) + pooled copy + upsampled copy.
     def backward(self, g_extra=None, wgrad=True, keep_dn=False):
@@ -394,6 +396,87 @@ class BCDUNetEngine(SequentialGenEngine):
         self.last = self.units[-1]
         self.head = HeadUnit(self, "conv0", module.conv0.weight, module.conv0.bias, t, module.activation)
         self.finish()
+
+
+class VGGFeatEngine(GraphEngine):
+    """The four VGG16 slices of the reference's VGGPerceptualLoss (util.py:100-144; --version 1): input transform
+    (channel repeat, ImageNet mean / std, bilinear 224x224), 10 x [conv3x3 + bias -> ReLU] with MaxPool2d(2) in
+    front of slices 1-3. Weights are frozen (util.py:108-110): backward is the activation-gradient chain only,
+    seeded at the four slice outputs and ending in the gradient w.r.t. the input image."""
+    CONVS = ((0, 2), (5, 7), (10, 12, 14), (17, 19, 21))
+
+    def __init__(self, blocks, n, h, w, src_channels=3, resize=True, backward=True):
+        super().__init__(blocks, n, h, w, backward)
+        dev = self.device
+        self.cs, self.resize = src_channels, resize
+        self.oh, self.ow = (224, 224) if resize else (h, w)
+        if self.oh % 8 or self.ow % 8:
+            raise ValueError("VGG slices need H, W divisible by 8")
+        self.cin = 3
+        self.x_in = Act("vgg_in", bf16(n, self.oh, self.ow, 64, device=dev), 3)
+        t = self.x_in
+        self.taps = []
+        for b, convs in enumerate(self.CONVS):
+            for j, i in enumerate(convs):
+                conv = blocks[b][j * 2 + (1 if b > 0 else 0)]
+                assert isinstance(conv, torch.nn.Conv2d), "unexpected VGG slice layout"
+                layer = self.conv_layer(f"{b}.{i}", conv, [conv.in_channels])
+                last = j == len(convs) - 1
+                u = ConvUnit(self, f"vgg{b}_{i}", layer, [t], False, act=ACT_RELU, pool=2 if (last and b < 3) else 0)
+                t = u.y
+            self.taps.append(u)
+            if b < 3:
+                t = u.pool
+        self.finish()
+        if backward:
+            self.g_feat = [bf16(*u.y.buf.shape, device=dev) for u in self.taps]
+            self.dx_in = bf16(*self.x_in.buf.shape, device=dev)
+            self.x_in.build_grad(self.dx_in.view(-1))
+
+    def forward(self, x):
+        """x: fp32 NCHW (n, 1|3, h, w) -> list of the four slice outputs (Act)."""
+        assert x.shape == (self.n, self.cs, self.h, self.w) and x.dtype == torch.float32 and x.is_contiguous()
+        self.store.refresh()
+        _C.call("vgg_prep_fwd", ptr(x), ptr(self.x_in.buf), self.n, self.cs, self.h, self.w, self.oh, self.ow, 64,
+                int(self.resize))
+        for u in self.units:
+            u.forward()
+        return [u.y for u in self.taps]
+
+    def loss_and_seed(self, other, weights, scale, loss_slot, feature_layers=(0, 1, 2, 3)):
+        """*loss_slot += scale * sum_i weights[i] * L1mean(self_i, other_i); seeds d/d(self_i) for backward()."""
+        self.active = []
+        for i, (u, o) in enumerate(zip(self.taps, other.taps)):
+            wi = float(weights[i]) * scale if i in feature_layers else 0.0
+            self.active.append(wi != 0.0)
+            if wi == 0.0:
+                continue
+            numel = u.y.buf.numel()
+            _C.call("feat_loss", ptr(o.y.buf), ptr(u.y.buf), LL(numel), F(wi), 0, ptr(loss_slot))
+            if self.with_backward:
+                _C.call("feat_loss_grad", ptr(u.y.buf), ptr(o.y.buf), LL(numel), F(wi), ptr(self.g_feat[i]))
+
+    def backward(self, grad_image, scale=1.0):
+        """grad_image (fp32 NCHW, n x cs x h x w) += scale * d loss / d x. Units behind the last active tap are skipped."""
+        tap_of = {id(u): i for i, u in enumerate(self.taps)}
+        last = max([i for i, a in enumerate(self.active) if a], default=-1)
+        if last < 0:
+            return grad_image
+        started = False
+        for u in reversed(self.units):
+            i = tap_of.get(id(u))
+            if not started:
+                if i != last:
+                    continue
+                started = True
+            # slice outputs feed the next slice through their pooled copy only, so the loss gradient is the sole
+            # same-resolution route; an unweighted slice output just passes the pooled gradient on
+            g_extra = self.g_feat[i] if (i is not None and self.active[i]) else None
+            u.backward(g_extra=g_extra, wgrad=False)
+        self.x_in.run_grad()
+        _C.call("vgg_prep_bwd", ptr(self.dx_in), ptr(grad_image), self.n, self.cs, self.h, self.w, self.oh, self.ow, 64,
+                int(self.resize), F(scale))
+        return grad_image
 
 
 def build_generator_engine(kind, module, n, h, w, backward=True):

@@ -7,7 +7,8 @@ scalars accumulated in one device buffer. Differences from the reference that do
     wasted generator backward inside the D step (train.py:126,134 -> util.py:83) is not paid;
   * fake/real discriminator passes of the D step run as one 2B batch (InstanceNorm is per sample);
   * the version-2 perceptual term (pan_loss of detached D features, train.py:155-162) is evaluated
-    for logging only -- it has no gradient in the reference either.
+    for logging only -- it has no gradient in the reference either. Version 1 (VGG16 slices, frozen
+    weights) does back-propagate into fake_B: engine.VGGFeatEngine.
 Data parallel: one process per GPU; the flat fp32 gradient arenas of D and G are all-reduced (sum) with
 NCCL and scaled by 1/world inside the fused Adam kernel.
 """
@@ -23,7 +24,7 @@ SLOT = {"loss_D": 0, "gp": 1, "G_GAN": 2, "L1": 3, "per": 4}
 class TrainStep:
     def __init__(self, netG, netD, batch, height, width, loss="ls", version=2, lambda_a=1.0, lambda_gp=0.01,
                  lambda_per=1.0, w_per=(0, .1, .3, .6), lr=1e-3, beta1=0.9, label_smoothing=True, gen_kind=None,
-                 process_group=None):
+                 process_group=None, vgg_blocks=None):
         self.netG, self.netD = netG, netD
         self.B, self.H, self.W = batch, height, width
         self.loss, self.version = loss, version
@@ -41,7 +42,17 @@ class TrainStep:
             build_generator_engine(kind, netG, batch, height, width, True)
         self.DA = PatchDInstance(netD, 2 * batch, height, width, backward=True)
         self.S1 = PatchDInstance(netD, batch, height, width, backward=True, second_order=True)
-        self.S2 = PatchDInstance(netD, batch, height, width, backward=False)
+        # version 2 needs a fifth D forward for the real-pair features (train.py:156); version 1 replaces it with
+        # two passes through frozen VGG16 slices (train.py:48-49,151-153)
+        self.S2 = PatchDInstance(netD, batch, height, width, backward=False) if version == 2 else None
+        self.VR = self.VF = None
+        if version != 2 and self.lambda_per != 0:
+            if vgg_blocks is None:
+                raise ValueError("version 1 needs the VGG16 slices: TrainStep(..., vgg_blocks=VGGPerceptualLoss().blocks)")
+            from .engine import VGGFeatEngine
+            cb = netD.model[0].in_channels - self.G.cin
+            self.VR = VGGFeatEngine(vgg_blocks, batch, height, width, src_channels=cb, resize=True, backward=False)
+            self.VF = VGGFeatEngine(vgg_blocks, batch, height, width, src_channels=cb, resize=True, backward=True)
         self.c_in = netD.model[0].in_channels
         self.c_a = self.G.cin
         self.c_b = self.c_in - self.c_a
@@ -142,6 +153,13 @@ class TrainStep:
                 cpad = fr.buf.shape[3]
                 _C.call("feat_loss", ptr(fr.buf), ptr(ff.buf), LL(fr.buf.numel()),
                         F(self.lambda_per * w / wsum * cpad / fr.c), 0, ptr(self.losses[4:5]))
+        if self.VF is not None:
+            # version 1: per = lambda_per * sum_i w_i * L1mean(VGG_i(real_B), VGG_i(fake_B)) (util.py:119-144);
+            # its gradient w.r.t. fake_B is added to the L1 gradient buffer
+            self.VR.forward(real_B)
+            self.VF.forward(fake)
+            self.VF.loss_and_seed(self.VR, self.w_per, self.lambda_per, self.losses[4:5])
+            self.VF.backward(self.l1_grad)
         G.backward(self.gan_grad, self.l1_grad)
         self._allreduce(gs)
         gs.adam_step(self.lr, self.beta1, grad_scale=1.0 / self.world)

@@ -75,11 +75,16 @@ class Train_GAN:
 
     def _build_step(self, h, w):
         o = self.opt
+        vgg_blocks = None
         if o.version != 2 and o.lambda_per != 0:
-            raise NotImplementedError("--version 1 (VGG16 perceptual term) is not built yet; use --version 2")
+            # train.py:48-49: VGGPerceptualLoss(resize=True) -- frozen VGG16 slices (ImageNet weights when available)
+            from .util import VGGPerceptualLoss
+            self.perceptual = VGGPerceptualLoss(resize=True)
+            vgg_blocks = self.perceptual.blocks
         self.step = TrainStep(self.netG, self.netD, o.batch_size, h, w, loss=o.loss, version=o.version,
                               lambda_a=o.lambda_a, lambda_gp=o.lambda_gp, lambda_per=o.lambda_per, w_per=o.w_per,
-                              lr=o.lr, beta1=o.beta1, label_smoothing=not o.no_label_smoothing)
+                              lr=o.lr, beta1=o.beta1, label_smoothing=not o.no_label_smoothing,
+                              vgg_blocks=vgg_blocks)
         if self._pending_opt_state is not None:
             self.optimizer_G.load_state_dict(self._pending_opt_state[0])
             self.optimizer_D.load_state_dict(self._pending_opt_state[1])

@@ -128,3 +128,82 @@ def gradient_penalty(disc, real_img, real_mask, fake_mask, device, ver=2, type='
     inst.gp_second_backward()
     params = list(disc.parameters())
     return _GradientPenaltyFn.apply(inst, out, len(params), *params)[0]
+
+
+class _VGGLossFn(torch.autograd.Function):
+    """Value and input-gradients of the perceptual term in one fused pass through engine.VGGFeatEngine."""
+
+    @staticmethod
+    def forward(ctx, inp, target, owner, weights, feature_layers):
+        n, c, h, w = inp.shape
+        e_in = owner._engine(n, c, h, w, "input", inp.requires_grad)
+        e_tg = owner._engine(n, c, h, w, "target", target.requires_grad)
+        xi, xt = inp.detach().contiguous().float(), target.detach().contiguous().float()
+        e_in.forward(xi)
+        e_tg.forward(xt)
+        out = torch.zeros(1, device=inp.device)
+        spare = torch.zeros(1, device=inp.device)
+        gi = gt = None
+        counted = False
+        if target.requires_grad:
+            e_tg.loss_and_seed(e_in, weights, 1.0, out, feature_layers)
+            gt = e_tg.backward(torch.zeros(n, c, h, w, device=inp.device))
+            counted = True
+        if inp.requires_grad:
+            e_in.loss_and_seed(e_tg, weights, 1.0, spare if counted else out, feature_layers)
+            gi = e_in.backward(torch.zeros(n, c, h, w, device=inp.device))
+            counted = True
+        if not counted:
+            e_tg.loss_and_seed(e_in, weights, 1.0, out, feature_layers)
+        ctx.grads = (gi, gt)
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        gi, gt = ctx.grads
+        return (None if gi is None else gi * g, None if gt is None else gt * g, None, None, None)
+
+
+class VGGPerceptualLoss(torch.nn.Module):
+    """reference util.py:100-144 (the --version 1 perceptual term): L1 distances between the outputs of four
+    frozen VGG16 slices. Same constructor / forward signature; the slices run on the sm_100a engine. The
+    reference loads torchvision's ImageNet weights; without network access they cannot be downloaded, so
+    the slices fall back to torchvision's random init (load a state_dict with keys blocks.<b>.<i>.* to
+    use real weights). The gram / style branch (style_layers, unused by train.py) is not built."""
+
+    def __init__(self, resize=True):
+        super().__init__()
+        import torchvision
+        try:
+            feats = torchvision.models.vgg16(weights=torchvision.models.VGG16_Weights.IMAGENET1K_V1).features
+        except Exception as e:   # no network / no cached checkpoint
+            import warnings
+            warnings.warn(f"VGG16 ImageNet weights unavailable ({type(e).__name__}); using random-init VGG16")
+            feats = torchvision.models.vgg16(weights=None).features
+        blocks = [feats[:4], feats[4:9], feats[9:16], feats[16:23]]
+        for bl in blocks:
+            for p in bl.parameters():
+                p.requires_grad = False
+        self.blocks = torch.nn.ModuleList(blocks).eval()
+        self.resize = resize
+        self.register_buffer("mean", torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1))
+        self.register_buffer("std", torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1))
+        if torch.cuda.is_available():
+            self.cuda()
+
+    def _engine(self, n, c, h, w, role, backward):
+        from .engine import VGGFeatEngine
+        cache = self.__dict__.setdefault("_tg_engines", {})
+        key = (n, c, h, w, role)
+        if key not in cache or (backward and not cache[key].with_backward):
+            cache[key] = VGGFeatEngine(self.blocks, n, h, w, src_channels=c, resize=self.resize, backward=backward)
+        return cache[key]
+
+    def forward(self, input, target, feature_layers=[0, 1, 2, 3], style_layers=[], weights=[0.25, 0.25, 0.25, 0.25]):
+        if len(style_layers):
+            raise NotImplementedError("the gram / style branch of VGGPerceptualLoss is not built (unused by train.py)")
+        if not input.is_cuda:
+            raise _C.TgError("tactile_gan_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if input.shape[1] not in (1, 3):
+            raise ValueError("VGGPerceptualLoss expects 1- or 3-channel images")
+        return _VGGLossFn.apply(input, target, self, [float(v) for v in weights], tuple(feature_layers))

@@ -236,3 +236,82 @@ def test_two_step_trajectory_and_checkpoint_roundtrip(tmp_path):
     plain.load_state_dict(ck["optimizerD_state_dict"])     # loads into the stock optimizer unchanged
     optD.load_state_dict(ref_opt)                          # and the reference's state loads into ours
     assert netD._tg_store.step_count == int(ref_opt["state"][0]["step"])
+
+
+def _vgg_loss_module(seed):
+    """VGGPerceptualLoss with the seeded random-init slices of tests/test_oracle_golden.vgg_state_dict."""
+    import warnings
+    from test_oracle_golden import vgg_state_dict
+    from tactile_gan_b200.util import VGGPerceptualLoss
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mod = VGGPerceptualLoss(resize=True)
+    sd = vgg_state_dict(seed)
+    mod.load_state_dict(sd, strict=False)
+    return mod, sd
+
+
+@pytest.mark.parametrize("channels,size", [(3, 64), (1, 96)])
+def test_vgg_perceptual_loss_against_oracle(channels, size):
+    """--version 1 perceptual term (reference util.py:100-144): value within 2 %, gradient w.r.t. the generated
+    image within 6 % rel-l2 of the bf16-storage oracle (max-pool / ReLU routing flips on near-ties)."""
+    orc, _C = _setup()
+    mod, sd = _vgg_loss_module(41)
+    g = torch.Generator().manual_seed(7)
+    real_b = torch.rand(2, channels, size, size, generator=g)
+    fake_b = torch.rand(2, channels, size, size, generator=g)
+    w = [0, .1, .3, .6]
+    orc.QUANT["on"] = True
+    try:
+        fb = fake_b.clone().requires_grad_(True)
+        ref = orc.vgg_perceptual(sd, real_b, fb, w)
+        (gref,) = torch.autograd.grad(ref, fb)
+    finally:
+        orc.QUANT["on"] = False
+    fk = fake_b.cuda().requires_grad_(True)
+    got = mod.forward(real_b.cuda(), fk, weights=w)
+    got.backward()
+    torch.cuda.synchronize()
+    assert _C.error_flag() == 0
+    assert float(got) == pytest.approx(float(ref), rel=2e-2)
+    assert rel(fk.grad, gref) < 0.06 and cos(fk.grad, gref) > 0.99
+    with pytest.raises(NotImplementedError):
+        mod.forward(real_b.cuda(), fk, style_layers=[1])
+
+
+def test_train_step_version1_vgg_against_oracle():
+    """One --version 1 iteration (LSGAN + L1 + VGG16 perceptual + GP) against oracle.train_step."""
+    orc, _C = _setup()
+    from tactile_gan_b200.discriminators.discriminators import create_disc
+    from tactile_gan_b200.generators.generators import create_gen
+    from tactile_gan_b200.step import TrainStep
+    from tactile_gan_b200.util import init_weights
+    torch.manual_seed(3)
+    nf, size, n = 16, 64, 2
+    netG = create_gen("UNet++", 3, 3, nf, True)
+    netD = create_disc("patch", 3, 3, nf, False, True)
+    init_weights(netG)
+    init_weights(netD)
+    sd_g = OrderedDict((k, v.detach().clone()) for k, v in netG.state_dict().items())
+    sd_d = OrderedDict((k, v.detach().clone()) for k, v in netD.state_dict().items())
+    mod, vsd = _vgg_loss_module(43)
+    g = torch.Generator().manual_seed(9)
+    a, b = orc.synthetic_batch(g, n, size)
+    alpha = torch.rand(n, 1, generator=g)
+    netG, netD = netG.cuda(), netD.cuda()
+    ts = TrainStep(netG, netD, n, size, size, version=1, vgg_blocks=mod.blocks)
+    label = ts.ensure_label(generator=g).cpu()
+    ts.step(a.cuda(), b.cuda(), regularize=True, alpha=alpha)
+    got = ts.loss_dict()
+    assert _C.error_flag() == 0
+    cfg = orc.StepConfig(version=1)
+    cfg.vgg_sd = vsd
+    ref = orc.train_step(sd_g, sd_d, {}, {}, a, b, label, alpha, cfg)
+    for k in got:
+        assert abs(got[k] - ref[k]) <= 0.03 * abs(ref[k]) + 2e-3, (k, got[k], ref[k])
+    fused = ts.G.store.grads_by_name()
+    gg, rr = [], []
+    for k, v in ref["grads_G"].items():
+        gg.append(fused[k].flatten().cpu())
+        rr.append(v.flatten())
+    assert cos(torch.cat(gg), torch.cat(rr)) > 0.9

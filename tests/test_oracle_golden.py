@@ -70,3 +70,31 @@ def test_state_dict_key_inventory(golden_dir):
     """Checkpoint-layout contract: 92 / 86 / 66 / 13 keys."""
     inv = _load(golden_dir, "state_dict_keys")
     assert len(inv["UNet++"]) == 92 and len(inv["UNet"]) == 86 and len(inv["BCDUNet"]) == 66 and len(inv["patch"]) == 13
+
+
+def vgg_state_dict(seed):
+    """Seeded random-init VGG16 slices, keyed like the reference's VGGPerceptualLoss.state_dict()
+    (same recipe as oracle/make_golden.py:vgg_blocks; pretrained weights are not available offline)."""
+    import torchvision
+    torch.manual_seed(seed)
+    f = torchvision.models.vgg16(weights=None).features
+    blocks = torch.nn.ModuleList([f[:4], f[4:9], f[9:16], f[16:23]])
+    return OrderedDict(("blocks." + k, v.detach().clone()) for k, v in blocks.state_dict().items())
+
+
+@pytest.mark.parametrize("name", ["vgg_v1_rgb", "vgg_v1_gray"])
+def test_oracle_vgg_perceptual_matches_reference_forward(golden_dir, name):
+    """oracle.vgg_perceptual against the fixture produced by the reference's own VGGPerceptualLoss.forward."""
+    fx = _load(golden_dir, name)
+    m = fx["meta"]
+    sd = vgg_state_dict(m["seed"])
+    for k, v in fx["weight_probe"].items():
+        assert float(sd["blocks." + k].flatten()[0]) == v, "seeded VGG init differs from the fixture's"
+    g = torch.Generator().manual_seed(m["seed"] + 1000)
+    real_b = torch.rand(m["batch"], m["channels"], m["size"], m["size"], generator=g)
+    fake_b = torch.rand(m["batch"], m["channels"], m["size"], m["size"], generator=g).requires_grad_(True)
+    loss = orc.vgg_perceptual(sd, real_b, fake_b, m["w_per"])
+    (grad,) = torch.autograd.grad(loss, fake_b)
+    assert float(loss) == pytest.approx(fx["loss"], rel=1e-5)
+    assert float(grad.norm()) == pytest.approx(fx["grad_norm"], rel=1e-4)
+    torch.testing.assert_close(grad[:, :, ::4, ::4], fx["grad_sub"], rtol=1e-3, atol=1e-9)
