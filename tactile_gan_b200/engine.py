@@ -226,9 +226,23 @@ class GraphEngine:
             cache[name] = l
         return cache[name]
 
+    def completion_order(self):
+        """Parameter indices in the order backward() finalises their gradients (head first, then the units in
+        reverse execution order)."""
+        idx = self.store.index
+        out = []
+        head = getattr(self, "head", None)
+        if head is not None:
+            out += [idx[id(head.weight)], idx[id(head.bias)]]
+        for u in reversed([u for u in self.units if isinstance(u, ConvUnit)]):
+            for p in (u.layer.weight, u.layer.bias, u.gamma, u.beta):
+                if p is not None and id(p) in idx:
+                    out.append(idx[id(p)])
+        return out
+
     def finish(self):
         if self.own_store:
-            self.store.finalize()
+            self.store.finalize(self.completion_order())
             self.module._tg_store = self.store
         cu = [u for u in self.units if isinstance(u, ConvUnit)]
         if self.with_backward:
@@ -306,13 +320,18 @@ class UNetPPEngine(GraphEngine):
             u1.forward()
         return self.head.forward()
 
-    def backward(self, g1, g2=None):
-        """g1 (+ g2): gradients w.r.t. the fp32 NCHW output. Accumulates into the store's grad arena."""
+    def backward(self, g1, g2=None, after_unit=None):
+        """g1 (+ g2): gradients w.r.t. the fp32 NCHW output. Accumulates into the store's grad arena.
+        after_unit(unit) is called once a unit's parameter gradients are final (data-parallel overlap)."""
         dx = self.head.backward(g1, g2)
         for (i, j) in reversed(self.order):
             u0, u1 = self.X[i, j]
             u1.backward(g_extra=dx if (i, j) == (0, 4) else None)
+            if after_unit:
+                after_unit(u1)
             u0.backward()
+            if after_unit:
+                after_unit(u0)
 
 
 class SequentialGenEngine(GraphEngine):
@@ -327,10 +346,12 @@ class SequentialGenEngine(GraphEngine):
             u.forward()
         return self.head.forward()
 
-    def backward(self, g1, g2=None):
+    def backward(self, g1, g2=None, after_unit=None):
         dx = self.head.backward(g1, g2)
         for u in reversed(self.units):
             u.backward(g_extra=dx if u is self.last else None)
+            if after_unit:
+                after_unit(u)
 
     def _double(self, name, block, srcs, pool=0):
         """[conv | convT] -> IN -> ReLU -> conv3x3 -> IN -> ReLU (reference ConvDown / DeconvUp / conv_block)."""

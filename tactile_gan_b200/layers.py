@@ -233,6 +233,26 @@ class TailCall:
         _C.call(self.name, *self.args())
 
 
+def plan_buckets(layout, bucket_elems):
+    """Split an arena layout [(param, offset, size), ...] (completion order) into contiguous buckets of at
+    least `bucket_elems` elements: returns [(start, end, last_param), ...]; a bucket may be all-reduced as soon
+    as the gradient of `last_param` is final."""
+    buckets, start, last = [], None, None
+    for i, off, size in layout:
+        if size == 0:
+            continue
+        if start is None:
+            start = off
+        last = i
+        if off + size - start >= bucket_elems:
+            buckets.append((start, off + size, last))
+            start = None
+    if start is not None:
+        i, off, size = layout[-1]
+        buckets.append((start, off + size, last))
+    return buckets
+
+
 def multi_dgrad_plan(consumers, out):
     """d(out) = sum over consumers (layer, dY, segment) of the stride-1 input gradients -- one
     multi-source implicit GEMM (the K loop walks the consumers)."""
@@ -264,8 +284,10 @@ class ParamStore:
         if layer.bias is not None:
             self.bias_of[self.index[id(layer.bias)]] = layer
 
-    def finalize(self):
-        """Allocate arenas once every conv is registered."""
+    def finalize(self, order=None):
+        """Allocate arenas once every conv is registered. `order`: parameter indices in the order their
+        gradients become final during backward; the gradient arena is laid out in that order, so the buckets
+        of the overlapped data-parallel allreduce are contiguous ranges that complete front to back."""
         dev = self.device
         sizes = []
         for i, p in enumerate(self.params):
@@ -276,10 +298,15 @@ class ParamStore:
                 sizes.append(self.bias_of[i].o_pad)
             else:
                 sizes.append(p.numel())
-        offs = [0]
-        for s in sizes:
-            offs.append(offs[-1] + (s + 3) // 4 * 4)
-        self.grad_arena = torch.zeros(offs[-1], dtype=torch.float32, device=dev)
+        seen = set()
+        layout = [i for i in (order or []) if not (i in seen or seen.add(i))]
+        layout += [i for i in range(len(self.params)) if i not in seen]
+        offs, total = {}, 0
+        for i in layout:
+            offs[i] = total
+            total += (sizes[i] + 3) // 4 * 4
+        self.arena_layout = [(i, offs[i], (sizes[i] + 3) // 4 * 4) for i in layout]   # (param, offset, padded size)
+        self.grad_arena = torch.zeros(total, dtype=torch.float32, device=dev)
         self.grad_views = []
         for i, p in enumerate(self.params):
             g = self.grad_arena[offs[i]:offs[i] + sizes[i]]

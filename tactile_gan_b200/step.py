@@ -77,6 +77,8 @@ class TrainStep:
         return self.real_label
 
     def set_label(self, label):
+        if label is not None and tuple(label.shape) != (self.B, 1, self.h5, self.w5):
+            raise ValueError(f"real-label tensor must be {(self.B, 1, self.h5, self.w5)}, got {tuple(label.shape)}")
         self.real_label = None if label is None else label.to(self.device).float().contiguous()
 
     def draw_alpha(self, alpha=None):
@@ -100,6 +102,53 @@ class TrainStep:
     def _allreduce(self, store):
         if self.world > 1:
             torch.distributed.all_reduce(store.grad_arena, group=self.pg)
+
+    # ---- generator gradients: bucketed allreduce overlapped with the rest of backward -----------------
+    BUCKET_BYTES = 32 << 20
+
+    def _plan_g_buckets(self):
+        """The gradient arena is laid out in backward-completion order (ParamStore.finalize), so bucket k is a
+        contiguous range that is final once the unit owning its last parameter has run."""
+        from .layers import plan_buckets
+        store = self.G.store
+        buckets = plan_buckets(store.arena_layout, self.BUCKET_BYTES // 4)
+        owner = {}
+        for u in self.G.units:
+            for p in (getattr(u, "gamma", None), getattr(u, "beta", None), getattr(getattr(u, "layer", None), "weight", None),
+                      getattr(getattr(u, "layer", None), "bias", None)):
+                if p is not None and id(p) in store.index:
+                    owner[store.index[id(p)]] = u
+        self._g_buckets = [(a, b, owner.get(last)) for a, b, last in buckets]
+        self._comm_stream = torch.cuda.Stream(device=self.device)
+
+    def _g_backward(self):
+        G, gs = self.G, self.G.store
+        if self.world == 1:
+            G.backward(self.gan_grad, self.l1_grad)
+            return
+        if not hasattr(self, "_g_buckets"):
+            self._plan_g_buckets()
+        pending = list(self._g_buckets)
+        works = []
+        main = torch.cuda.current_stream()
+
+        def launch(a, b):
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(self._comm_stream):
+                self._comm_stream.wait_event(ev)
+                works.append(torch.distributed.all_reduce(gs.grad_arena[a:b], group=self.pg, async_op=True))
+
+        def after_unit(u):
+            while pending and pending[0][2] is u:
+                a, b, _ = pending.pop(0)
+                launch(a, b)
+
+        G.backward(self.gan_grad, self.l1_grad, after_unit=after_unit)
+        for a, b, _ in pending:          # buckets whose last parameter has no unit (head-only / dead parameters)
+            launch(a, b)
+        for w in works:
+            w.wait()                     # the compute stream waits for the collectives; the host does not block
 
     # ------------------------------------------------------------------ the iteration
     def step(self, real_A, real_B, regularize=True, alpha=None):
@@ -160,8 +209,7 @@ class TrainStep:
             self.VF.forward(fake)
             self.VF.loss_and_seed(self.VR, self.w_per, self.lambda_per, self.losses[4:5])
             self.VF.backward(self.l1_grad)
-        G.backward(self.gan_grad, self.l1_grad)
-        self._allreduce(gs)
+        self._g_backward()
         gs.adam_step(self.lr, self.beta1, grad_scale=1.0 / self.world)
         return self.losses
 

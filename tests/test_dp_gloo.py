@@ -55,3 +55,55 @@ def test_two_rank_gradient_average_matches_single_process():
         p.join(300)
         assert p.exitcode == 0
     assert out.get() < 1e-4
+
+
+def test_bucket_plan_covers_the_arena_in_completion_order():
+    """layers.plan_buckets: contiguous, gap-free, front-to-back buckets whose 'ready' parameter is the last one
+    of the bucket in backward-completion order."""
+    sys.path.insert(0, ROOT)
+    from tactile_gan_b200.layers import plan_buckets
+    sizes = [12, 4, 40, 8, 100, 4, 4, 60]
+    layout, off = [], 0
+    for i, sz in zip([5, 3, 7, 0, 2, 1, 6, 4], sizes):      # (param index, offset, padded size)
+        layout.append((i, off, sz))
+        off += sz
+    buckets = plan_buckets(layout, 50)
+    assert buckets[0][0] == 0 and buckets[-1][1] == off
+    for (a0, b0, _), (a1, _, _) in zip(buckets, buckets[1:]):
+        assert b0 == a1
+    assert [b[2] for b in buckets] == [7, 2, 4]              # ready after params 7, 2 and (tail) 4
+    assert all(b - a >= 50 for a, b, _ in buckets[:-1])
+    assert plan_buckets(layout, 10 ** 9) == [(0, off, 4)]
+
+
+def _bucketed(rank, world, port, out):
+    """What TrainStep._g_backward does on the comm stream, on CPU: all-reduce contiguous slices of the flat
+    gradient arena asynchronously, bucket by bucket, and wait for all of them before the optimiser step."""
+    sys.path.insert(0, ROOT)
+    from tactile_gan_b200.layers import plan_buckets
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(100 + rank)
+    arena = torch.randn(10_000, generator=g)
+    whole = arena.clone()
+    layout = [(i, i * 1000, 1000) for i in range(10)]
+    works = [dist.all_reduce(arena[a:b], async_op=True) for a, b, _ in plan_buckets(layout, 2500)]
+    for w in works:
+        w.wait()
+    dist.all_reduce(whole)
+    if rank == 0:
+        out.put(float((arena - whole).abs().max()))
+    dist.destroy_process_group()
+
+
+def test_bucketed_async_allreduce_equals_one_allreduce():
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = 31000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_bucketed, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert out.get() == 0.0
