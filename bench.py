@@ -7,8 +7,12 @@
 One "step" = one full G+D iteration (reference train.py:99-168) on a per-GPU batch of 32 synthetic
 256x256 pairs (configs[1]); N > 1 = one rank per GPU, NCCL gradient allreduce, weak scaling.
 `value` is timed with inputs resident in HBM; `e2e` goes through TrainStep.step_from_host (pinned host
-batch -> H2D -> step -> D2H of the loss scalars). `roofline` is measured live with CUDA events around
-every implicit-GEMM launch of the timed steps.
+batch -> H2D -> step -> D2H of the loss scalars). `roofline*` are measured live with CUDA events around
+every implicit-GEMM launch (tensor roofline) and every InstanceNorm tail launch (HBM roofline) of the
+timed steps; `traffic` is the DRAM byte count of one representative launch from the committed ncu capture.
+
+Other workloads (not bench lines; for DESIGN.md / profiles): --gen UNet|BCDUNet, --version 1,
+--workload infer (generator forward only, configs[4]).
 """
 import argparse
 import json
@@ -24,7 +28,19 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-GFLOP_PER_IMG = {True: 994.0, False: 927.2}   # 2*(3*MAC_G + 15*MAC_D) with GP / without
+# algorithmic GMAC per 256^2 image. Training = 2*(3*MAC_G + 15*MAC_D) FLOP with GP (9 without);
+# version 1 drops the fifth D forward and adds 6 VGG16 forward-equivalents at 224^2; inference = 2*MAC_G.
+MAC_G = {"UNet++": 137.833218048, "UNet": 15.717105664, "BCDUNet": 36.767268864}
+MAC_D = 5.567061888
+MAC_VGG = 13.96
+
+
+def gflop_per_image(gen, workload, version, regularize=True, size=256):
+    s = (size / 256.0) ** 2
+    if workload == "infer":
+        return 2 * MAC_G[gen] * s
+    d = (15 if regularize else 9) - (0 if version == 2 else 1)
+    return 2 * ((3 * MAC_G[gen] + d * MAC_D) * s + (6 * MAC_VGG if version != 2 else 0))
 
 
 def peaks():
@@ -36,25 +52,29 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons every 200 ms while the timed regions run (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.proc = index, [], None
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                f = [x.strip() for x in line.strip().split(",")]
                 if len(f) >= 6:
                     self.samples.append(f)
-            except Exception:
-                pass
-            time.sleep(0.2)
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
 
     def summary(self):
         if not self.samples:
@@ -101,40 +121,47 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 6)), max(0, min(args.warmup, 1))
-    cb = cpu_baseline(steps, warmup, 1)
+    steps, warmup = max(1, min(args.steps, 8)), max(0, min(args.warmup, 1))
+    cb = cpu_baseline(steps, warmup, 2)
     line = {"impl": "reference", "metric": "train images/sec (G+D step) UNet++ 256^2", "value": cb["value"],
             "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": cb["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "UNet++ nf=64 + PatchDiscriminator, version-2 loss stack with GP every step, "
-                                   "256x256; CPU arm samples batch 1 per step (GPU arm: batch 32 per GPU)"},
+                                   "256x256; CPU arm samples batch 2 per step (GPU arm: batch 32 per GPU)"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def layer_table(ts, batch, path):
-    """Diagnostic (not a bench number): two more steps with a CUDA-event pair around every launch;
-    per-shape implicit-GEMM TFLOP/s and per-kernel tail time go to `path` as JSON."""
+def layer_table(fn, path, reps=2):
+    """Diagnostic (not a bench number): `reps` steps with a CUDA-event pair around every tail launch, then `reps`
+    with one around every implicit-GEMM launch; per-shape TFLOP/s and per-kernel tail time go to `path` (JSON)."""
     from tactile_gan_b200 import _C
     _C.TIMING["records"].clear()
     _C.TIMING["tail_records"].clear()
-    _C.TIMING["on"] = _C.TIMING["tail"] = True
-    reps = 2
+    _C.TIMING["on"], _C.TIMING["tail"] = False, True
     for _ in range(reps):
-        ts.step(*batch)
+        fn()
     torch.cuda.synchronize()
-    _C.TIMING["on"] = _C.TIMING["tail"] = False
-    gemm, tail = {}, {}
-    for kind, flops, a, b, tag in _C.TIMING["records"]:
-        t, f, c = gemm.get(tag, (0.0, 0.0, 0))
-        gemm[tag] = (t + a.elapsed_time(b), f + flops, c + 1)
+    _C.TIMING["tail"] = False
+    tail = {}
     for name, a, b in _C.TIMING["tail_records"]:
         t, c = tail.get(name, (0.0, 0))
         tail[name] = (t + a.elapsed_time(b), c + 1)
-    _C.TIMING["records"].clear()
     _C.TIMING["tail_records"].clear()
+    _C.TIMING["on"] = True
+    for _ in range(reps):
+        fn()
+    torch.cuda.synchronize()
+    _C.TIMING["on"] = False
+    gemm = {}
+    for kind, flops, a, b, tag in _C.TIMING["records"]:
+        if kind.startswith("tail:"):
+            continue
+        t, f, c = gemm.get(tag, (0.0, 0.0, 0))
+        gemm[tag] = (t + a.elapsed_time(b), f + flops, c + 1)
+    _C.TIMING["records"].clear()
     out = {"gemm": [{"tag": k, "ms_per_step": t / reps, "launches_per_step": c / reps,
                      "tflops": (f / (t / 1e3) / 1e12) if t > 0 else 0.0, "gflop_per_step": f / reps / 1e9}
                     for k, (t, f, c) in sorted(gemm.items(), key=lambda kv: -kv[1][0])],
@@ -144,6 +171,18 @@ def layer_table(ts, batch, path):
     out["tail_ms_per_step"] = sum(r["ms_per_step"] for r in out["tail"])
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
     json.dump(out, open(path, "w"), indent=1)
+
+
+def ncu_traffic():
+    """DRAM bytes of one representative launch of the dominant kernel, from the committed `ncu --set full`
+    summary (profiles/r01_ncu_top_kernels.json, written by tools/ncu_summary.py --json)."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_top_kernels.json")
+    if not os.path.exists(p):
+        return None, None
+    top = json.load(open(p)).get("roofline_launch")
+    if not top:
+        return None, None
+    return top.get("dram_bytes"), top
 
 
 def run_ours(args):
@@ -162,17 +201,48 @@ def run_ours(args):
         torch.distributed.init_process_group("nccl", device_id=dev)
     B, S = args.batch, args.size
     torch.manual_seed(21)
-    netG = create_gen("UNet++", 3, 3, 64, True).to(dev)
+    netG = create_gen(args.gen, 3, 3, 64, True).to(dev)
     init_weights(netG)
-    netD = create_disc("patch", 3, 3, 64, return_filter=True, activation=True).to(dev)
-    init_weights(netD)
-    ts = TrainStep(netG, netD, B, S, S, loss="ls", version=2, lambda_a=1.0, lambda_gp=0.01, lambda_per=1.0,
-                   w_per=(0, .1, .3, .6), lr=1e-3, beta1=0.9, label_smoothing=True)
     g = torch.Generator().manual_seed(21 + rank)
     pool = 2
     host = [(torch.rand(B, 3, S, S, generator=g).mul_(2).sub_(1).pin_memory(),
              torch.rand(B, 3, S, S, generator=g).pin_memory()) for _ in range(pool)]
     devb = [(a.to(dev), b.to(dev)) for a, b in host]
+    train = args.workload == "train"
+    ts = None
+    if train:
+        netD = create_disc("patch", 3, 3, 64, return_filter=args.version == 2, activation=True).to(dev)
+        init_weights(netD)
+        vgg_blocks = None
+        if args.version != 2:
+            import warnings
+            from tactile_gan_b200.util import VGGPerceptualLoss
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                vgg_blocks = VGGPerceptualLoss(resize=True).blocks
+        ts = TrainStep(netG, netD, B, S, S, loss="ls", version=args.version, lambda_a=1.0, lambda_gp=0.01,
+                       lambda_per=1.0, w_per=(0, .1, .3, .6), lr=1e-3, beta1=0.9, label_smoothing=True,
+                       vgg_blocks=vgg_blocks)
+
+        def step_dev(i):
+            ts.step(*devb[i % pool])
+
+        def step_host(i):
+            ts.step_from_host(*host[i % pool])
+        h2d, d2h = 2 * B * 3 * S * S * 4, 32
+    else:
+        eng = netG._engine(B, S, S, False)
+        dev_in = torch.empty(B, 3, S, S, device=dev)
+        host_out = torch.empty(B, 3, S, S).pin_memory()
+
+        def step_dev(i):
+            eng.forward(devb[i % pool][0])
+
+        def step_host(i):       # test.py:202-203: out = model(real_A.to(device)).cpu()
+            dev_in.copy_(host[i % pool][0], non_blocking=True)
+            host_out.copy_(eng.forward(dev_in), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        h2d = d2h = B * 3 * S * S * 4
 
     def barrier():
         if world > 1:
@@ -193,61 +263,79 @@ def run_ours(args):
         return ms.item()
 
     for i in range(args.warmup):
-        ts.step(*devb[i % pool])
+        step_dev(i)
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
     sampler.start()
+    time.sleep(0.3)
     _C.COUNTERS["launches"] = 0
     _C.TIMING["records"].clear()
     _C.TIMING["on"] = True
-    ms = timed(lambda i: ts.step(*devb[i % pool]), args.steps)
+    ms = timed(step_dev, args.steps)
     _C.TIMING["on"] = False
     launches = _C.COUNTERS["launches"]
-    sampler.stop_flag = True
-    losses = ts.loss_dict()
-    # per-kernel-kind roofline from the CUDA events recorded around every implicit-GEMM launch
+    losses = ts.loss_dict() if train else {}
+    # per-kernel-family rooflines from the CUDA events recorded around the launches of the timed steps
     agg = {}
-    for kind, flops, a, b, _tag in _C.TIMING["records"]:
-        t, f, c = agg.get(kind, (0.0, 0.0, 0))
-        agg[kind] = (t + a.elapsed_time(b), f + flops, c + 1)
+    for kind, work, a, b, _tag in _C.TIMING["records"]:
+        fam = "tail" if kind.startswith("tail:") else kind
+        t, f, c = agg.get(fam, (0.0, 0.0, 0))
+        agg[fam] = (t + a.elapsed_time(b), f + work, c + 1)
     _C.TIMING["records"].clear()
-    if args.layers and rank == 0:
-        layer_table(ts, devb[0], args.layers)
     # end-to-end through the public call with host buffers
     for i in range(min(2, args.warmup)):
-        ts.step_from_host(*host[i % pool])
-    ms_e2e = timed(lambda i: ts.step_from_host(*host[i % pool]), args.steps)
-    sampler.join(timeout=2)
+        step_host(i)
+    ms_e2e = timed(step_host, args.steps)
+    sampler.stop()
+    if args.layers and rank == 0:
+        layer_table(lambda: step_dev(0), args.layers)
 
     if rank == 0:
         hbm, tf_burst, tf_sus, which = peaks()
         imgs = B * world * args.steps
-        line = {"metric": "train images/sec (G+D step) UNet++ 256^2", "value": imgs / (ms / 1e3), "unit": "images/s",
+        gfl = gflop_per_image(args.gen, args.workload, args.version, True, S)
+        if train:
+            what = (f"{args.gen} nf=64 + PatchDiscriminator, version-{args.version} loss stack (LSGAN + L1 + "
+                    f"{'pan' if args.version == 2 else 'VGG16 perceptual'} + GP every step)")
+        else:
+            what = f"{args.gen} nf=64 generator forward (test.py:202-203)"
+        headline = train and args.gen == "UNet++" and args.version == 2
+        line = {"metric": "train images/sec (G+D step) UNet++ 256^2" if headline else
+                f"{'train' if train else 'inference'} images/sec {args.gen} {S}^2 (v{args.version})",
+                "value": imgs / (ms / 1e3), "unit": "images/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic",
-                "config": {"workload": f"UNet++ nf=64 + PatchDiscriminator, version-2 loss stack (LSGAN + L1 + pan + GP "
-                                       f"every step), batch {B}/GPU, {S}x{S}, random-init weights",
+                "config": {"workload": f"{what}, batch {B}/GPU, {S}x{S}, random-init weights",
                            "global_batch": B * world, "parallelism": f"dp{world}",
                            "l2": "per-step working set (>10 GB of activations) exceeds the 126 MB L2; no explicit flush"},
                 "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "images/s",
-                        "h2d_bytes_per_step": 2 * B * 3 * S * S * 4, "d2h_bytes_per_step": 32},
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": sampler.summary(), "losses_last_step": losses,
-                "step_tflops": GFLOP_PER_IMG[True] * B * args.steps / (ms / 1e3) / 1e3}
+                "step_tflops": gfl * B * args.steps / (ms / 1e3) / 1e3, "gflop_per_image": gfl}
         if "conv" in agg:
             t, f, c = agg["conv"]
             ach = f / (t / 1e3) / 1e12
-            line["roofline"] = {"bound": "tensor", "kernel": "igemm_conv_kernel (conv fwd + dgrad, all shapes)",
-                                "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus,
-                                "peak_source": f"bf16_tflops_sustained, {which}", "traffic": None,
-                                "launches": c, "share_of_step": t / ms}
+            traffic, top = ncu_traffic()
+            line["roofline"] = {"bound": "tensor", "kernel": "igemm_halo_kernel / igemm_conv_kernel (conv forward + "
+                                "input gradient, all shapes)", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s",
+                                "frac": ach / tf_sus, "peak_source": f"bf16_tflops_sustained, {which}",
+                                "traffic": traffic, "traffic_launch": top, "launches": c, "share_of_step": t / ms}
         if "wgrad" in agg:
             t, f, c = agg["wgrad"]
             ach = f / (t / 1e3) / 1e12
-            line["roofline_wgrad"] = {"bound": "tensor", "kernel": "wgrad_kernel", "achieved": ach, "peak": tf_sus,
-                                      "unit": "TFLOP/s", "frac": ach / tf_sus, "launches": c, "share_of_step": t / ms}
+            line["roofline_wgrad"] = {"bound": "tensor", "kernel": "wgrad_taps_kernel / wgrad_kernel", "achieved": ach,
+                                      "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "launches": c,
+                                      "share_of_step": t / ms}
+        if "tail" in agg:
+            t, f, c = agg["tail"]
+            ach = f / (t / 1e3) / 1e9
+            line["roofline_tail"] = {"bound": "hbm", "kernel": "in_act_fwd / in_bwd_reduce / in_bwd_apply "
+                                     "(InstanceNorm + activation forward / backward)", "achieved": ach, "peak": hbm,
+                                     "unit": "GB/s", "frac": ach / hbm, "peak_source": f"hbm_gbs, {which}",
+                                     "launches": c, "share_of_step": t / ms}
         if world == 1 and not args.no_cpu:
-            cb = cpu_baseline(2, 1, 1)
+            cb = cpu_baseline(4, 1, 2)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
     if world > 1:
@@ -262,6 +350,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch (configs[1]: 32)")
     ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--gen", default="UNet++", choices=["UNet++", "UNet", "BCDUNet"])
+    ap.add_argument("--version", type=int, default=2, choices=[1, 2])
+    ap.add_argument("--workload", default="train", choices=["train", "infer"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--layers", default="", help="diagnostic: write a per-shape / per-kernel timing table (JSON)")
     args = ap.parse_args()

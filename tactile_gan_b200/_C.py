@@ -211,10 +211,19 @@ def error_flag():
     return int(lib().tg_error_flag_read())
 
 
-def call(name, *args):
-    """Call a tail kernel launcher `tg_<name>(..., stream)`."""
+def call(name, *args, nbytes=None):
+    """Call a tail kernel launcher `tg_<name>(..., stream)`. `nbytes`: algorithmic HBM bytes of the launch
+    (what it must read + write once), recorded with its CUDA-event timing while bench.py measures."""
     fn = getattr(lib(), "tg_" + name)
     COUNTERS["launches"] += _KERNELS_PER_CALL.get(name, 1)
+    if TIMING["on"] and nbytes is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(fn(*args, stream_ptr()), "tg_" + name)
+        e1.record()
+        TIMING["records"].append(("tail:" + name, float(nbytes), e0, e1, name))
+        return
     if TIMING["tail"]:
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)

@@ -127,9 +127,12 @@ class ConvUnit:
                 _C.call("in_finalize", ptr(self.partial), ptr(self.mr), n, self.tpi, c, ho * wo, F(EPS_IN))
             else:
                 _C.call("in_stats_direct", ptr(self.raw), ptr(self.mr), n, ho * wo, c, F(EPS_IN))
+            # algorithmic traffic: raw in, y out (+ the pooled quarter-size / upsampled 4x-size copies)
+            nb = 2.0 * n * ho * wo * c * (2 + (0.25 if self.pool else 0) + (4 if self.up else 0))
             _C.call("in_act_fwd", ptr(self.raw), ptr(self.mr), g, b, ptr(self.y.buf),
                     ptr(self.pool.buf if self.pool else None), self.pool_mode,
-                    ptr(self.up.buf if self.up else None), n, ho, wo, c, self.c_valid, self.act, F(self.slope))
+                    ptr(self.up.buf if self.up else None), n, ho, wo, c, self.c_valid, self.act, F(self.slope),
+                    nbytes=nb)
         elif self.pool:
             _C.call("pool_fwd", ptr(self.y.buf), ptr(self.pool.buf), self.n, self.ho, self.wo, self.c, self.pool_mode)
 
@@ -147,11 +150,14 @@ class ConvUnit:
         g, b = self._aff()
         if self.norm:
             self.red.zero_()
+            elems = 2.0 * n * ho * wo * c      # bytes of one bf16 tensor of this unit
+            nb = elems * (2 + (1 if g_same is not None else 0) + (0.25 if g_pool is not None else 0) +
+                          (4 if g_up is not None else 0))
             _C.call("in_bwd_reduce", ptr(self.raw), ptr(self.y.buf), ptr(self.mr), g, b, ptr(g_same), ptr(g_pool),
                     self.pool_mode, ptr(g_up), ptr(dn), ptr(self.red), n, ho, wo, c, self.c_valid,
-                    self.act, F(self.slope))
+                    self.act, F(self.slope), nbytes=nb)
             _C.call("in_bwd_apply", ptr(dn), ptr(self.raw), ptr(self.mr), g, ptr(self.red),
-                    ptr(self.dz), n, ho * wo, c, self.c_valid)
+                    ptr(self.dz), n, ho * wo, c, self.c_valid, nbytes=3 * elems)
             if wgrad and self.gamma is not None:
                 _C.call("affine_grad", ptr(self.red), ptr(eng.store.grad_of(self.gamma)),
                         ptr(eng.store.grad_of(self.beta)), n, c, self.c_valid)
