@@ -195,6 +195,10 @@ int create_halo_plan(const tg_conv_desc* d, tg_plan* pl, int dy0, int dx0, int e
   if (p.stats_partial && p.stats_tiles_total < p.stats_tile_off + p.tiles_h * p.tiles_w)
     return tg_set_error("tg_conv_plan_create: stats buffer has too few tile slots");
   p.cout = cout;
+  {
+    static const int pf = getenv("TG_HALO_PREFETCH") ? atoi(getenv("TG_HALO_PREFETCH")) : 1;
+    p.prefetch = pf;
+  }
   p.err_flag = tg_error_flag_device_ptr();
   for (int s = 0; s < d->num_src; ++s) {
     const tg_conv_src& cs = d->src[s];

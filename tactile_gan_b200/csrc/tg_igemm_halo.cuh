@@ -46,6 +46,7 @@ struct alignas(64) HaloParams {
   float* stats_partial;
   int stats_tiles_total, stats_tile_off;
   int cout;
+  int prefetch;   // issue L2 prefetches one chunk ahead
   int* err_flag;
 };
 
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_halo_kernel(const __grid
   // of n_tiles), the weights are loaded ONCE per CTA instead of once per item -- for the single-chunk layers
   // that is 44 % of the bytes staged through shared memory.
   const bool resident = chunks <= kHaloBStages && (int(gridDim.x) % p.n_tiles) == 0;
+  const bool prefetch = p.prefetch != 0;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -127,6 +129,24 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_halo_kernel(const __grid
               mbar_arrive_expect_tx(bfull(bs), uint32_t(p.b_bytes));
               tma_load_3d(b_base + bs * kHaloBStage, &src.wgt, bfull(bs), cc * kChunkK, n_tile * kHaloBN, 0);
               if (++bs == kHaloBStages) { bs = 0; bphase ^= 1; }
+            }
+            if (prefetch) {
+              // the shared-memory ring holds only two halo tiles (~1 tile = 0.6 us of MMA work ahead), less than
+              // an HBM round trip: pull the NEXT chunk's tiles (next source / next item at the end) into L2 now
+              int ps = s, pcc = cc + 1, pt0 = t0, pcnt = cnt;
+              if (pcc == src.c_chunks) { pcc = 0; ++ps; }
+              if (ps == p.num_src) {
+                ps = 0;
+                const int nitem = item + int(gridDim.x);
+                pt0 = (nitem / p.n_tiles) * kHaloR;
+                pcnt = nitem < total_items ? min(kHaloR, m_tiles - pt0) : 0;
+              }
+              for (int r = 0; r < pcnt; ++r) {
+                const int mt = pt0 + r;
+                const int img = mt / tiles_per_img, t_in = mt % tiles_per_img;
+                tma_prefetch_4d(&p.src[ps].act, pcc * kChunkK, (t_in % p.tiles_w) * kHaloTW + p.org_dx,
+                                (t_in / p.tiles_w) * kHaloTH + p.org_dy, img);
+              }
             }
             for (int r = 0; r < cnt; ++r) {
               const int mt = t0 + r;
