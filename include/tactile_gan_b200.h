@@ -122,8 +122,10 @@ int tg_in_bwd_reduce(const void* raw, const void* y, const float* mr, const floa
                      const float* beta, const void* g_same, const void* g_pool, int pool_mode,
                      const void* g_up, void* dn, float* red, int N, int H, int W, int C, int c_valid,
                      int act, float slope, void* stream);
+/* dgamma / dbeta (optional, fp32 [c_valid]): += the affine gradients, i.e. what tg_affine_grad computes */
 int tg_in_bwd_apply(const void* dn, const void* raw, const float* mr, const float* gamma,
-                    const float* red, void* dz, int N, int HW, int C, int c_valid, void* stream);
+                    const float* red, void* dz, int N, int HW, int C, int c_valid, float* dgamma, float* dbeta,
+                    void* stream);
 int tg_affine_grad(const float* red, float* dgamma, float* dbeta, int N, int C, int c_valid, void* stream);
 int tg_bias_grad(const void* dz, float* db, long long rows, int C, int c_valid, void* stream);
 /* InstanceNorm double backward for the gradient penalty (util.py:88-93, create_graph=True) */

@@ -572,8 +572,20 @@ __global__ void __launch_bounds__(256)
 in_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dn, const __nv_bfloat16* __restrict__ raw,
                     const float* __restrict__ mr, const float* __restrict__ gamma,
                     const float* __restrict__ red, __nv_bfloat16* __restrict__ dz, int HW, int C,
-                    int c_valid) {
+                    int c_valid, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   const int n = blockIdx.y;
+  // affine gradients ride along (one block): dgamma[c] += sum_n red[n][c][1], dbeta[c] += sum_n red[n][c][0]
+  if ((dgamma || dbeta) && blockIdx.x == 0 && blockIdx.y == 0) {
+    for (int c = threadIdx.x; c < c_valid; c += blockDim.x) {
+      float g = 0.f, b = 0.f;
+      for (int k = 0; k < int(gridDim.y); ++k) {
+        b += red[(size_t(k) * C + c) * 2];
+        g += red[(size_t(k) * C + c) * 2 + 1];
+      }
+      if (dgamma) dgamma[c] += g;
+      if (dbeta) dbeta[c] += b;
+    }
+  }
   const StripIdx t = strip_index(C, HW);
   if (t.pl >= t.PL) return;
   const float inv = 1.f / float(HW);
@@ -1382,10 +1394,12 @@ int tg_in_bwd_reduce(const void* raw, const void* y, const float* mr, const floa
 }
 
 int tg_in_bwd_apply(const void* dn, const void* raw, const float* mr, const float* gamma,
-                    const float* red, void* dz, int N, int HW, int C, int c_valid, void* stream) {
+                    const float* red, void* dz, int N, int HW, int C, int c_valid, float* dgamma, float* dbeta,
+                    void* stream) {
   dim3 grid(strip_count(HW, C, N, 16), N);
   in_bwd_apply_kernel<<<grid, strip_block(C), 0, TG_STREAM(stream)>>>(
-      (const __nv_bfloat16*)dn, (const __nv_bfloat16*)raw, mr, gamma, red, (__nv_bfloat16*)dz, HW, C, c_valid);
+      (const __nv_bfloat16*)dn, (const __nv_bfloat16*)raw, mr, gamma, red, (__nv_bfloat16*)dz, HW, C, c_valid,
+      dgamma, dbeta);
   TG_RET();
 }
 

@@ -156,11 +156,11 @@ class ConvUnit:
             _C.call("in_bwd_reduce", ptr(self.raw), ptr(self.y.buf), ptr(self.mr), g, b, ptr(g_same), ptr(g_pool),
                     self.pool_mode, ptr(g_up), ptr(dn), ptr(self.red), n, ho, wo, c, self.c_valid,
                     self.act, F(self.slope), nbytes=nb)
+            aff = wgrad and self.gamma is not None
             _C.call("in_bwd_apply", ptr(dn), ptr(self.raw), ptr(self.mr), g, ptr(self.red),
-                    ptr(self.dz), n, ho * wo, c, self.c_valid, nbytes=3 * elems)
-            if wgrad and self.gamma is not None:
-                _C.call("affine_grad", ptr(self.red), ptr(eng.store.grad_of(self.gamma)),
-                        ptr(eng.store.grad_of(self.beta)), n, c, self.c_valid)
+                    ptr(self.dz), n, ho * wo, c, self.c_valid,
+                    ptr(eng.store.grad_of(self.gamma)) if aff else None,
+                    ptr(eng.store.grad_of(self.beta)) if aff else None, nbytes=3 * elems)
         else:
             _C.call("in_bwd_reduce", None, ptr(self.y.buf), None, None, None, ptr(g_same), ptr(g_pool),
                     self.pool_mode, ptr(g_up), ptr(self.dz), None, n, ho, wo, c, self.c_valid, self.act,
@@ -701,12 +701,11 @@ class PatchDInstance(GraphEngine):
                 red.zero_()
                 _C.call("in_bwd_reduce", ptr(x.raw), ptr(x.y.buf), ptr(x.mr), g, b, ptr(e), None, 0, None,
                         ptr(self.dn_scratch), ptr(red), x.n, x.ho, x.wo, x.c, x.c_valid, ACT_LRELU, F(0.2))
+                aff = x.gamma is not None
                 _C.call("in_bwd_apply", ptr(self.dn_scratch), ptr(x.raw), ptr(x.mr), g, ptr(red), ptr(z), x.n,
-                        x.ho * x.wo, x.c, x.c_valid)
+                        x.ho * x.wo, x.c, x.c_valid, ptr(st.grad_of(x.gamma)) if aff else None,
+                        ptr(st.grad_of(x.beta)) if aff else None)
                 _C.call("add", ptr(z), ptr(so["INJ"][k - 1]), ptr(z), LL(z.numel()))
-                if x.gamma is not None:
-                    _C.call("affine_grad", ptr(red), ptr(st.grad_of(x.gamma)), ptr(st.grad_of(x.beta)), x.n, x.c,
-                            x.c_valid)
             else:
                 _C.call("act_bwd", ptr(e), ptr(x.y.buf), ptr(z), LL(z.numel()), ACT_LRELU, F(0.2))
                 _C.call("bias_grad", ptr(z), ptr(x.layer.bias_grad), LL(x.n * x.ho * x.wo), x.c, x.c_valid)

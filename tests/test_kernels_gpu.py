@@ -149,9 +149,13 @@ def test_instance_norm_forward_backward_pool_upsample():
     gs_p, gp_p, gu_p = nhwc_pad(gs), nhwc_pad(gp), nhwc_pad(gu)   # keep alive: the launch is asynchronous
     C.call("in_bwd_reduce", ptr(raw), ptr(y), ptr(mr), ptr(gamma), ptr(beta), ptr(gs_p), ptr(gp_p), 1,
            ptr(gu_p), ptr(dn), ptr(red), n, h, w, cp, c, 3, f32(0.0))
-    C.call("in_bwd_apply", ptr(dn), ptr(raw), ptr(mr), ptr(gamma), ptr(red), ptr(dz), n, h * w, cp, c)
     dgam, dbet = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
-    C.call("affine_grad", ptr(red), ptr(dgam), ptr(dbet), n, cp, c)
+    C.call("in_bwd_apply", ptr(dn), ptr(raw), ptr(mr), ptr(gamma), ptr(red), ptr(dz), n, h * w, cp, c, ptr(dgam),
+           ptr(dbet))
+    dgam2, dbet2 = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
+    C.call("affine_grad", ptr(red), ptr(dgam2), ptr(dbet2), n, cp, c)     # stand-alone form of the same sums
+    torch.cuda.synchronize()
+    assert torch.allclose(dgam, dgam2) and torch.allclose(dbet, dbet2)
     torch.cuda.synchronize()
     assert rel(dz[..., :c].permute(0, 3, 1, 2), dx_ref) < 1e-2   # dn is stored as bf16
     assert rel(dgam, dg_ref) < 5e-3 and rel(dbet, db_ref) < 5e-3
