@@ -152,6 +152,16 @@ int tg_vgg_prep_bwd(const void* g, float* grad, int N, int cs, int H, int W, int
 int tg_pool_fwd(const void* y, void* pool, int N, int H, int W, int C, int mode, void* stream);
 int tg_feat_loss_grad(const void* a, const void* b, long long numel, float weight, void* g, void* stream);
 
+/* ---- input pipeline on the device (datasets/PairedDataset.py:30-44,80-92): HorizontalFlip + Affine of a uint8 HWC
+ *      image / mask pair (image bilinear, mask nearest, zero border), then ToTensor (+ Normalize(.5,.5) on the image)
+ *      into fp32 NCHW. params[n] = {flip, a00, a01, a02, a10, a11, a12, 0}: the inverse map in 16.16 fixed point */
+int tg_augment_pair(const void* img_u8, const void* mask_u8, const long long* params, float* out_a, float* out_b,
+                    int N, int H, int W, int ca, int cb, void* stream);
+
+/* ---- evaluation (test.py:113-124, eval_pair fuzzy=True): per image stats[n][4] += (sum o*r, sum o^2 + r^2,
+ *      sum min(o, r), sum r); accuracy = s2/s3, dice = 2 s0/s1, jaccard = s0/(s1 - s0) */
+int tg_eval_fuzzy(const float* out, const float* real, int N, long long per_img, float* stats, void* stream);
+
 /* ---- losses: GANLoss (generators/generators.py:80-105), nn.L1Loss (train.py:145), pan_loss
  *      (util.py:41-70), gradient_penalty norm (util.py:92-93) */
 int tg_gan_loss(const void* pred, const float* label, float label_const, int mode, int target_is_real,

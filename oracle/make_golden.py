@@ -156,6 +156,21 @@ def vgg_case(seed=31, batch=2, size=64, channels=3):
                 weight_probe={k: float(v.flatten()[0]) for k, v in list(blocks.state_dict().items())[:4]})
 
 
+def eval_case(seed=51):
+    """eval_pair of the reference's test.py (lines 113-146). test.py cannot be imported (matplotlib / seaborn are
+    not installed), so the function's own source is cut out of the file with ast and executed unmodified."""
+    import ast
+    import numpy as np
+    src = open(os.path.join(REF, "test.py")).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "eval_pair")
+    ns = {"np": np}
+    exec(compile(ast.Module([fn], []), os.path.join(REF, "test.py"), "exec"), ns)
+    g = torch.Generator().manual_seed(seed)
+    real = (torch.rand(3, 3, 64, 64, generator=g) > 0.7).float() * torch.rand(3, 3, 64, 64, generator=g)
+    out = (real + 0.2 * torch.randn(3, 3, 64, 64, generator=g)).clamp(0, 1)
+    return dict(meta=dict(seed=seed), results=[ns["eval_pair"](real[i], out[i]) for i in range(3)])
+
+
 def state_dict_keys():
     """Key/shape inventory of all reference networks at nf=64 (the checkpoint-layout contract)."""
     _, create_gen, _, create_disc = reference_modules()
@@ -191,5 +206,6 @@ if __name__ == "__main__":
         fx = vgg_case(**kw)
         torch.save(fx, os.path.join(OUT, f"{name}.pt"))
         print(name, fx["loss"], fx["grad_norm"])
+    torch.save(eval_case(), os.path.join(OUT, "eval_pair_fuzzy.pt"))
     torch.save(state_dict_keys(), os.path.join(OUT, "state_dict_keys.pt"))
     print("wrote", OUT)

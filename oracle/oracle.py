@@ -13,6 +13,10 @@ What follows which reference lines (all under /root/reference):
   pan_loss         util.py:41-70 (mode='normal' only, as called from train.py:160)
   gradient_penalty util.py:72-97
   vgg_perceptual   util.py:100-144 (VGGPerceptualLoss: 4 slices of torchvision VGG16.features[:23]; version 1 only)
+  eval_pair_fuzzy  test.py:113-124 (eval_pair, fuzzy=True: the accuracy / Dice / Jaccard test_model reports)
+  augment_pair     datasets/PairedDataset.py:30-44,80-92 (flip + affine + ToTensor/Normalize). PARITY UNPINNED: the
+                   arithmetic belongs to albumentations (unpinned, not installed); this restates the transform
+                   tactile_gan_b200/augment.py specifies (inverse map in 16.16 fixed point), not albumentations' own.
   adam_update      torch.optim.Adam as configured at train.py:56-57 (betas=(beta1,0.99), eps=1e-8)
   train_step       train.py:99-168
 
@@ -235,6 +239,52 @@ def vgg_perceptual(sd, inp, target, weights=(0.25, 0.25, 0.25, 0.25), feature_la
         if i in feature_layers:
             loss = loss + F.l1_loss(fx[i], fy[i]) * weights[i]
     return loss
+
+
+# --------------------------------------------------------------------------- input pipeline (PairedDataset.py:30-92)
+def augment_pair(img_u8, mask_u8, params):
+    """numpy restatement of tg_augment_pair: img (N,H,W,ca) / mask (N,H,W,cb) uint8, params (N,8) int64
+    {flip, a00..a12 in 16.16 fixed point (inverse map)} -> (fp32 NCHW in [-1,1], fp32 NCHW in [0,1])."""
+    import numpy as np
+    img, mask, q = img_u8.numpy(), mask_u8.numpy(), params.numpy().astype(np.int64)
+    n, h, w, ca = img.shape
+    cb = mask.shape[3]
+    ys, xs = np.meshgrid(np.arange(h, dtype=np.int64), np.arange(w, dtype=np.int64), indexing="ij")
+    out_a = np.zeros((n, ca, h, w), np.float32)
+    out_b = np.zeros((n, cb, h, w), np.float32)
+    for i in range(n):
+        sx = q[i, 1] * xs + q[i, 2] * ys + q[i, 3]
+        sy = q[i, 4] * xs + q[i, 5] * ys + q[i, 6]
+        if q[i, 0]:
+            sx = ((w - 1) << 16) - sx
+        x0, y0 = sx >> 16, sy >> 16
+        fx = ((sx & 0xFFFF).astype(np.float32) * np.float32(1 / 65536))[..., None]
+        fy = ((sy & 0xFFFF).astype(np.float32) * np.float32(1 / 65536))[..., None]
+
+        def tap(yy, xx, src):
+            ok = (xx >= 0) & (xx < w) & (yy >= 0) & (yy < h)
+            v = src[np.clip(yy, 0, h - 1), np.clip(xx, 0, w - 1)].astype(np.float32)
+            return np.where(ok[..., None], v, np.float32(0))
+        v00, v01 = tap(y0, x0, img[i]), tap(y0, x0 + 1, img[i])
+        v10, v11 = tap(y0 + 1, x0, img[i]), tap(y0 + 1, x0 + 1, img[i])
+        top, bot = v00 + fx * (v01 - v00), v10 + fx * (v11 - v10)
+        val = (top + fy * (bot - top)) / np.float32(255)
+        out_a[i] = ((val - np.float32(0.5)) / np.float32(0.5)).transpose(2, 0, 1)
+        xn, yn = (sx + 32768) >> 16, (sy + 32768) >> 16
+        out_b[i] = (tap(yn, xn, mask[i]) / np.float32(255)).transpose(2, 0, 1)
+    return torch.from_numpy(out_a), torch.from_numpy(out_b)
+
+
+# --------------------------------------------------------------------------- evaluation (test.py:113-124)
+def eval_pair_fuzzy(real, out):
+    """eval_pair(real, out, fuzzy=True) for one (C,H,W) pair, in float64 numpy like the reference."""
+    o = out.detach().cpu().numpy().astype("float64")
+    r = real.detach().cpu().numpy().astype("float64")
+    inter = (o * r).sum()
+    denom = (o ** 2 + r ** 2).sum()
+    import numpy as np
+    return {"accuracy": float(np.minimum(o, r).sum() / r.sum()), "dice": float(2 * inter / denom),
+            "jaccard": float(inter / (denom - inter))}
 
 
 # --------------------------------------------------------------------------- optimiser

@@ -1144,6 +1144,67 @@ __global__ void vgg_prep_bwd_kernel(const __nv_bfloat16* __restrict__ g, float* 
   }
 }
 
+// Device-side augmentation + ToTensor / Normalize of one uint8 HWC pair (PairedDataset.py:30-44,80-92): optional
+// horizontal flip, then an affine warp given as the INVERSE map in 16.16 fixed point (so the index math is exact
+// integer arithmetic, identical on host and device); source image bilinear, target mask nearest, zero border.
+//   q[n] = {flip, a00, a01, a02, a10, a11, a12, 0}: src_x = (a00*x + a01*y + a02) / 65536, src_y likewise.
+// out_a[n,c,y,x] = (img/255 - 0.5) / 0.5 (fp32 NCHW), out_b[n,c,y,x] = mask/255.
+__global__ void augment_pair_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask,
+                                    const long long* __restrict__ q, float* __restrict__ out_a,
+                                    float* __restrict__ out_b, int N, int H, int W, int ca, int cb) {
+  const size_t total = size_t(N) * H * W;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int x = int(i % W), y = int((i / W) % H), n = int(i / (size_t(W) * H));
+    const long long* p = q + size_t(n) * 8;
+    long long sx = p[1] * x + p[2] * y + p[3];
+    const long long sy = p[4] * x + p[5] * y + p[6];
+    if (p[0]) sx = ((long long)(W - 1) << 16) - sx;
+    // ---- image: bilinear, zero outside
+    const long long x0 = sx >> 16, y0 = sy >> 16;
+    const float fx = float(sx & 0xFFFF) * (1.f / 65536.f), fy = float(sy & 0xFFFF) * (1.f / 65536.f);
+    const uint8_t* ib = img + size_t(n) * H * W * ca;
+    for (int c = 0; c < ca; ++c) {
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const long long xx = x0 + (k & 1), yy = y0 + (k >> 1);
+        v[k] = (xx >= 0 && xx < W && yy >= 0 && yy < H) ? float(ib[(size_t(yy) * W + xx) * ca + c]) : 0.f;
+      }
+      const float top = v[0] + fx * (v[1] - v[0]), bot = v[2] + fx * (v[3] - v[2]);
+      const float val = (top + fy * (bot - top)) / 255.f;   // ToTensor divides by 255
+      out_a[(size_t(n) * ca + c) * H * W + size_t(y) * W + x] = (val - 0.5f) / 0.5f;
+    }
+    // ---- mask: nearest (round half up), zero outside
+    const long long xn = (sx + 32768) >> 16, yn = (sy + 32768) >> 16;
+    const bool in = xn >= 0 && xn < W && yn >= 0 && yn < H;
+    const uint8_t* mb = mask + size_t(n) * H * W * cb;
+    for (int c = 0; c < cb; ++c)
+      out_b[(size_t(n) * cb + c) * H * W + size_t(y) * W + x] =
+          in ? float(mb[(size_t(yn) * W + xn) * cb + c]) / 255.f : 0.f;
+  }
+}
+
+// Fuzzy evaluation sums of test.py:113-124 per image: stats[n] = (sum o*r, sum o^2 + r^2, sum min(o, r), sum r)
+// for the generator output o and the target r (fp32, any layout, per_img elements each).
+__global__ void eval_fuzzy_kernel(const float* __restrict__ o, const float* __restrict__ r, size_t per_img,
+                                  float* __restrict__ stats) {
+  __shared__ float sh[32];
+  const int n = blockIdx.y;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < per_img; i += size_t(gridDim.x) * blockDim.x) {
+    const float x = o[size_t(n) * per_img + i], y = r[size_t(n) * per_img + i];
+    a0 = fmaf(x, y, a0);
+    a1 += x * x + y * y;
+    a2 += fminf(x, y);
+    a3 += y;
+  }
+  float t;
+  t = block_sum(a0, sh); if (threadIdx.x == 0) atomicAdd(stats + n * 4 + 0, t);
+  t = block_sum(a1, sh); if (threadIdx.x == 0) atomicAdd(stats + n * 4 + 1, t);
+  t = block_sum(a2, sh); if (threadIdx.x == 0) atomicAdd(stats + n * 4 + 2, t);
+  t = block_sum(a3, sh); if (threadIdx.x == 0) atomicAdd(stats + n * 4 + 3, t);
+}
+
 // Gradient penalty: nsq[n] = sum_{pix, j<cj} (g[n,pix,c_off+j] + 1e-16)^2
 __global__ void gp_normsq_kernel(const __nv_bfloat16* __restrict__ g, int HW, int C, int c_off, int cj,
                                  float* __restrict__ nsq) {
@@ -1536,6 +1597,19 @@ int tg_vgg_prep_bwd(const void* g, float* grad, int N, int cs, int H, int W, int
   if (cs != 1 && cs != 3) return tg_set_error("tg_vgg_prep: 1 or 3 source channels");
   vgg_prep_bwd_kernel<<<grid_for(size_t(N) * OH * OW, 256, 148 * 16), 256, 0, TG_STREAM(stream)>>>(
       (const __nv_bfloat16*)g, grad, N, cs, H, W, OH, OW, C, resize, scale);
+  TG_RET();
+}
+
+int tg_augment_pair(const void* img_u8, const void* mask_u8, const long long* params, float* out_a, float* out_b,
+                    int N, int H, int W, int ca, int cb, void* stream) {
+  augment_pair_kernel<<<grid_for(size_t(N) * H * W, 256, 148 * 16), 256, 0, TG_STREAM(stream)>>>(
+      (const uint8_t*)img_u8, (const uint8_t*)mask_u8, params, out_a, out_b, N, H, W, ca, cb);
+  TG_RET();
+}
+
+int tg_eval_fuzzy(const float* out, const float* real, int N, long long per_img, float* stats, void* stream) {
+  dim3 grid(grid_for(size_t(per_img), 256, 32), N);
+  eval_fuzzy_kernel<<<grid, 256, 0, TG_STREAM(stream)>>>(out, real, size_t(per_img), stats);
   TG_RET();
 }
 

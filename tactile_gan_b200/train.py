@@ -64,6 +64,7 @@ class Train_GAN:
         self.schedulers = [self.get_scheduler(x) for x in self.optimizers]
         self.gen_loss, self.disc_loss, self.l1_loss, self.per_loss, self.gp_loss = [], [], [], [], []
         self.step = None
+        self.aug_rng = torch.Generator().manual_seed(21)       # util.py:8-11 seeds everything with 21
         if o.continue_training:
             ckpt = torch.load(os.path.join(f"{o.data.rsplit('/', 1)[0]}/models", o.folder_load, "final_model.pth"),
                               map_location=self.device)
@@ -98,8 +99,18 @@ class Train_GAN:
             regularize = (o.reg_every != 0) and (epoch % o.reg_every == 0) and (o.lambda_gp != 0)
             accum, steps = None, 0
             for batch in self.dataset:
-                real_A = batch[0].to(self.device, non_blocking=True).float().contiguous()
-                real_B = batch[1].to(self.device, non_blocking=True).float().contiguous()
+                if batch[0].dtype == torch.uint8:
+                    # raw uint8 HWC pair from datasets.PairedDataset(raw=True): ToTensor / Normalize and -- with
+                    # augmentation on -- HorizontalFlip + Affine run on the device (augment.py; PairedDataset.py:80-92)
+                    from .augment import augment_pair, identity_params, sample_params
+                    n, h, w = batch[0].shape[:3]
+                    aug = getattr(self.dataset.dataset, "aug", False)
+                    q = sample_params(n, h, w, generator=self.aug_rng) if aug else identity_params(n)
+                    real_A, real_B = augment_pair(batch[0].to(self.device, non_blocking=True),
+                                                  batch[1].to(self.device, non_blocking=True), q)
+                else:
+                    real_A = batch[0].to(self.device, non_blocking=True).float().contiguous()
+                    real_B = batch[1].to(self.device, non_blocking=True).float().contiguous()
                 if self.step is None:
                     self._build_step(real_A.shape[2], real_A.shape[3])
                     accum = torch.zeros_like(self.step.losses)
@@ -189,7 +200,7 @@ def main(argv=None):
         train_set = SyntheticPairs(opt.synthetic, opt.image_size, opt.input_dim, opt.output_dim)
     else:
         from .datasets.datasets import get_dataset
-        train_set = get_dataset(os.path.join(opt.data, "train", "source"), opt, mode='train')
+        train_set = get_dataset(os.path.join(opt.data, "train", "source"), opt, mode='train', raw=True)
     experiment = Train_GAN(opt, train_set)
     root = opt.data.rsplit('/', 1)[0]
     mkdir(os.path.join(f"{root}/checkpoints", opt.folder_save))

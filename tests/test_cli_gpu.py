@@ -43,6 +43,32 @@ def test_train_and_test_cli(tmp_path, monkeypatch):
     out = np.load(tmp_path / "Outputs" / "run1" / "out" / "1.npy")
     assert out.shape == (3, 256, 256) or out.shape == (3, 64, 64)
     assert np.isfinite(out).all() and np.abs(out).max() <= 1.0
+    ev = (tmp_path / "Outputs" / "run1" / "eval.txt").read_text().splitlines()     # reference format, test.py:175-181
+    assert ev[0].startswith("Pixel Accuracy => min:") and ev[1].startswith("Dice Coeff") and ev[2].startswith("Jaccard")
+
+
+def test_train_cli_on_image_folder_with_device_augmentation(tmp_path, monkeypatch):
+    """The reference's directory convention (train/source/s_*.png + train/tactile/t_*.tiff) through the uint8 ->
+    device pipeline with augmentation on, --version 1 (VGG16 term) and --target ch (three grayscale masks)."""
+    Image = pytest.importorskip("PIL.Image")
+    from tactile_gan_b200 import train as tg_train
+    monkeypatch.chdir(tmp_path)
+    rng = np.random.default_rng(0)
+    for kind in ("source", "tactile"):
+        (tmp_path / "data" / "train" / kind).mkdir(parents=True)
+    for i in range(4):
+        Image.fromarray(rng.integers(0, 256, (64, 64, 3), dtype=np.uint8)).save(tmp_path / "data/train/source" / f"s_{i}.png")
+        Image.fromarray(rng.integers(0, 256, (64, 64, 3), dtype=np.uint8)).save(tmp_path / "data/train/tactile" / f"t_{i}.tiff")
+        for part in ("axes", "grids", "content"):
+            Image.fromarray(rng.integers(0, 256, (64, 64), dtype=np.uint8)).save(
+                tmp_path / "data/train/tactile" / f"t_{i}_{part}.tiff")
+    for extra, name in ((["--version", "2"], "rgb"), (["--version", "1", "--target", "ch"], "ch")):
+        tg_train.opt = None
+        tg_train.main(["--data", str(tmp_path / "data"), "--batch_size", "2", "--nf", "8", "--total_epochs", "1",
+                       "--epoch_constant", "1", "--threads", "0", "--folder_save", name] + extra)
+        losses = [np.load(tmp_path / "models" / name / f"{k}.npy") for k in ("genloss", "discloss", "l1loss", "perloss")]
+        assert all(np.isfinite(v).all() and v.shape == (1,) for v in losses)
+        assert losses[3][0] > 0          # the perceptual term is live in both versions
 
 
 def test_reference_style_loop_on_autograd_bridge():

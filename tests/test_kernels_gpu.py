@@ -312,3 +312,41 @@ def test_maxpool_forward_backward():
     pos = (F.max_pool2d(yq, 2) > 0).float()
     pos_full = F.interpolate(pos, scale_factor=2, mode="nearest")
     assert rel(dn.permute(0, 3, 1, 2).float() * pos_full, g_y * mask.detach() * pos_full) < 1e-2
+
+
+def test_eval_fuzzy_sums_match_oracle():
+    """tg_eval_fuzzy (test.py:113-124 on the device, batched) against the oracle's float64 numpy restatement;
+    fp32 accumulation of 12k terms: 1e-5 relative."""
+    import oracle as orc
+    from test_oracle_golden import eval_inputs
+    from tactile_gan_b200.test import eval_pair, fuzzy_sums, metrics_from_sums
+    real, out = eval_inputs(51)
+    m = metrics_from_sums(fuzzy_sums(out.cuda(), real.cuda()))
+    for i in range(3):
+        ref = orc.eval_pair_fuzzy(real[i], out[i])
+        one = eval_pair(real[i].cuda(), out[i].cuda())
+        for k in ref:
+            assert float(m[k][i]) == pytest.approx(ref[k], rel=1e-5) and one[k] == pytest.approx(ref[k], rel=1e-5)
+    with pytest.raises(NotImplementedError):
+        eval_pair(real[0].cuda(), out[0].cuda(), fuzzy=False)
+
+
+@pytest.mark.parametrize("n,h,w,cb", [(6, 64, 96, 3), (3, 37, 29, 1)])
+def test_device_augmentation_matches_oracle(n, h, w, cb):
+    """tg_augment_pair against oracle.augment_pair on the same sampled parameters: the nearest-neighbour mask (pure
+    index math) must be bit-exact; the bilinear image agrees to fp32 rounding of the three lerps (FMA contraction)."""
+    import oracle as orc
+    from tactile_gan_b200.augment import augment_pair, identity_params, sample_params
+    g = torch.Generator().manual_seed(17)
+    img = torch.randint(0, 256, (n, h, w, 3), generator=g, dtype=torch.uint8)
+    mask = torch.randint(0, 256, (n, h, w, cb), generator=g, dtype=torch.uint8)
+    q = sample_params(n, h, w, generator=g, p_flip=0.5, p_affine=0.8)
+    q[0, 0], q[1, 0] = 0, 1                                # both flipped and unflipped samples are exercised
+    ra, rb = orc.augment_pair(img, mask, q)
+    a, b = augment_pair(img.cuda(), mask.cuda(), q)
+    assert torch.equal(b.cpu(), rb)
+    assert (a.cpu() - ra).abs().max().item() < 2e-6
+    # identity parameters = ToTensor / Normalize only (PairedDataset.py:52-58,86)
+    a0, b0 = augment_pair(img.cuda(), mask.cuda(), identity_params(n))
+    assert torch.equal(b0.cpu(), mask.permute(0, 3, 1, 2).float() / 255)
+    assert (a0.cpu() - (img.permute(0, 3, 1, 2).float() / 255 - 0.5) / 0.5).abs().max().item() < 1e-6

@@ -98,3 +98,20 @@ def test_oracle_vgg_perceptual_matches_reference_forward(golden_dir, name):
     assert float(loss) == pytest.approx(fx["loss"], rel=1e-5)
     assert float(grad.norm()) == pytest.approx(fx["grad_norm"], rel=1e-4)
     torch.testing.assert_close(grad[:, :, ::4, ::4], fx["grad_sub"], rtol=1e-3, atol=1e-9)
+
+
+def eval_inputs(seed):
+    g = torch.Generator().manual_seed(seed)
+    real = (torch.rand(3, 3, 64, 64, generator=g) > 0.7).float() * torch.rand(3, 3, 64, 64, generator=g)
+    out = (real + 0.2 * torch.randn(3, 3, 64, 64, generator=g)).clamp(0, 1)
+    return real, out
+
+
+def test_oracle_eval_pair_matches_reference_function(golden_dir):
+    """oracle.eval_pair_fuzzy against the fixture produced by executing the reference's own eval_pair source."""
+    fx = _load(golden_dir, "eval_pair_fuzzy")
+    real, out = eval_inputs(fx["meta"]["seed"])
+    for i, ref in enumerate(fx["results"]):
+        got = orc.eval_pair_fuzzy(real[i], out[i])
+        for k in ("accuracy", "dice", "jaccard"):
+            assert got[k] == pytest.approx(float(ref[k]), rel=1e-6), k
