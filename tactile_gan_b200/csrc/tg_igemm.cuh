@@ -185,7 +185,7 @@ __device__ __forceinline__ void epi_stats_rows(uint32_t sbuf, int r0, int lane, 
 }
 
 template <int BN>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(kNumThreads, 2)
 igemm_conv_kernel(const __grid_constant__ IgemmParams p) {
   using Cfg = IgemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];

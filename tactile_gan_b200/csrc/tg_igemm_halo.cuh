@@ -50,7 +50,7 @@ struct alignas(64) HaloParams {
   int* err_flag;
 };
 
-__global__ void __launch_bounds__(kNumThreads, 1) igemm_halo_kernel(const __grid_constant__ HaloParams p) {
+__global__ void __launch_bounds__(kNumThreads, 2) igemm_halo_kernel(const __grid_constant__ HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_base = smem_base;

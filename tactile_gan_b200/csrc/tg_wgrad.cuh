@@ -50,7 +50,7 @@ struct WgradCfg {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(kNumThreads, 2)
 wgrad_kernel(const __grid_constant__ WgradParams p) {
   using Cfg = WgradCfg<BN>;
   extern __shared__ uint8_t smem_raw[];

@@ -35,7 +35,7 @@ struct alignas(64) WgradHaloParams {
   int* err_flag;
 };
 
-__global__ void __launch_bounds__(kNumThreads, 1) wgrad_halo_kernel(const __grid_constant__ WgradHaloParams p) {
+__global__ void __launch_bounds__(kNumThreads, 2) wgrad_halo_kernel(const __grid_constant__ WgradHaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + kWhStages * kWhStageBytes;

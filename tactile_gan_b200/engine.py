@@ -166,10 +166,25 @@ class ConvUnit:
                     self.pool_mode, ptr(g_up), ptr(self.dz), None, n, ho, wo, c, self.c_valid, self.act,
                     F(self.slope))
         if wgrad:
-            if self.layer.bias is not None:
-                _C.call("bias_grad", ptr(self.dz), ptr(self.layer.bias_grad), LL(n * ho * wo), c, self.c_valid)
-            for p in self.wgrad_plans:
-                p.run()
+            ws = getattr(eng, "wgrad_stream", None)
+            if ws is None:
+                self._weight_grads()
+            else:
+                # the weight gradient only needs dz (final now) and the unit's inputs: it leaves the dependency
+                # chain of backward and runs on a side stream, where it overlaps the bandwidth-bound passes of the
+                # following units (a persistent GEMM CTA leaves room for one or two normalise / apply blocks per SM)
+                ev = torch.cuda.Event()
+                ev.record()
+                with torch.cuda.stream(ws):
+                    ws.wait_event(ev)
+                    self._weight_grads()
+
+    def _weight_grads(self):
+        if self.layer.bias is not None:
+            _C.call("bias_grad", ptr(self.dz), ptr(self.layer.bias_grad), LL(self.n * self.ho * self.wo), self.c,
+                    self.c_valid)
+        for p in self.wgrad_plans:
+            p.run()
 
 
 class HeadUnit:
@@ -231,6 +246,22 @@ class GraphEngine:
             self.store.register_conv(l)
             cache[name] = l
         return cache[name]
+
+    def _unit_done(self, unit, after_unit):
+        """after_unit(unit) runs in the stream that finalises the unit's parameter gradients."""
+        if after_unit is None:
+            return
+        ws = getattr(self, "wgrad_stream", None)
+        if ws is None:
+            after_unit(unit)
+        else:
+            with torch.cuda.stream(ws):
+                after_unit(unit)
+
+    def _join_wgrad(self):
+        ws = getattr(self, "wgrad_stream", None)
+        if ws is not None:
+            torch.cuda.current_stream().wait_stream(ws)
 
     def completion_order(self):
         """Parameter indices in the order backward() finalises their gradients (head first, then the units in
@@ -333,11 +364,10 @@ class UNetPPEngine(GraphEngine):
         for (i, j) in reversed(self.order):
             u0, u1 = self.X[i, j]
             u1.backward(g_extra=dx if (i, j) == (0, 4) else None)
-            if after_unit:
-                after_unit(u1)
+            self._unit_done(u1, after_unit)
             u0.backward()
-            if after_unit:
-                after_unit(u0)
+            self._unit_done(u0, after_unit)
+        self._join_wgrad()
 
 
 class SequentialGenEngine(GraphEngine):
@@ -356,8 +386,8 @@ class SequentialGenEngine(GraphEngine):
         dx = self.head.backward(g1, g2)
         for u in reversed(self.units):
             u.backward(g_extra=dx if u is self.last else None)
-            if after_unit:
-                after_unit(u)
+            self._unit_done(u, after_unit)
+        self._join_wgrad()
 
     def _double(self, name, block, srcs, pool=0):
         """[conv | convT] -> IN -> ReLU -> conv3x3 -> IN -> ReLU (reference ConvDown / DeconvUp / conv_block)."""

@@ -63,6 +63,9 @@ class TrainStep:
         self.one_minus_alpha = torch.zeros(batch, device=dev)
         self.gan_grad = torch.zeros(batch, self.c_b, height, width, device=dev)
         self.l1_grad = torch.zeros(batch, self.c_b, height, width, device=dev)
+        import os
+        if os.environ.get("TG_WGRAD_STREAM", "1") != "0":
+            self.G.wgrad_stream = torch.cuda.Stream(device=dev)
         self.real_label = None
         self.label_smoothing = label_smoothing
         self.fake_B = None
@@ -130,11 +133,10 @@ class TrainStep:
             self._plan_g_buckets()
         pending = list(self._g_buckets)
         works = []
-        main = torch.cuda.current_stream()
 
         def launch(a, b):
             ev = torch.cuda.Event()
-            ev.record(main)
+            ev.record()          # on the stream that finalised the bucket (the generator's weight-gradient stream)
             with torch.cuda.stream(self._comm_stream):
                 self._comm_stream.wait_event(ev)
                 works.append(torch.distributed.all_reduce(gs.grad_arena[a:b], group=self.pg, async_op=True))
