@@ -582,8 +582,9 @@ in_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dn, const __nv_bfloat16* _
         b += red[(size_t(k) * C + c) * 2];
         g += red[(size_t(k) * C + c) * 2 + 1];
       }
-      if (dgamma) dgamma[c] += g;
-      if (dbeta) dbeta[c] += b;
+      // atomic: sub-batch engines of the same network run this concurrently on their own streams
+      if (dgamma) atomicAdd(dgamma + c, g);
+      if (dbeta) atomicAdd(dbeta + c, b);
     }
   }
   const StripIdx t = strip_index(C, HW);
