@@ -50,7 +50,7 @@ class EngineModule(nn.Module):
         eng = self._engine(n, h, w, need_grad)
         if need_grad:
             return _EngineFn.apply(x, eng, *params)
-        return eng.forward(x.detach().contiguous().float()).clone()
+        return eng.forward_graphed(x.detach().contiguous().float()).clone()
 
 
 # ------------------------------------------------------------------------------- discriminator bridge
