@@ -64,6 +64,9 @@ typedef struct tg_conv_desc {
   int stats_tile_off;     /* first tile slot this launch writes (phase-decomposed outputs share a buffer) */
   int act;
   float slope;
+  int pool_out;           /* 1: `out` is the half-resolution tensor and the epilogue stores the 2x2 SUM of the
+                           * (2*out.h x 2*out.w) result -- the input gradient of a conv that read a nearest-
+                           * upsampled tensor (nn.Upsample, UNet_plusplus.py:40), folded back without materialising it */
 } tg_conv_desc;
 
 /* Weight gradient (split-K implicit GEMM over pixels, fp32 accumulation into dw with red.add):
@@ -118,10 +121,12 @@ int tg_in_stats_direct(const void* raw, float* mr, int N, int HW, int C, float e
 int tg_in_act_fwd(const void* raw, const float* mr, const float* gamma, const float* beta, void* y,
                   void* pool, int pool_mode, void* up, int N, int H, int W, int C, int c_valid, int act,
                   float slope, void* stream);
+/* g_up: gradient arriving through the 2x nearest-upsampled copy -- at the upsampled resolution (gathered 2x2 here)
+ * or, with g_up_pooled, already summed to this tensor's resolution by a pool_out conv */
 int tg_in_bwd_reduce(const void* raw, const void* y, const float* mr, const float* gamma,
                      const float* beta, const void* g_same, const void* g_pool, int pool_mode,
-                     const void* g_up, void* dn, float* red, int N, int H, int W, int C, int c_valid,
-                     int act, float slope, void* stream);
+                     const void* g_up, int g_up_pooled, void* dn, float* red, int N, int H, int W, int C,
+                     int c_valid, int act, float slope, void* stream);
 /* dgamma / dbeta (optional, fp32 [c_valid]): += the affine gradients, i.e. what tg_affine_grad computes */
 int tg_in_bwd_apply(const void* dn, const void* raw, const float* mr, const float* gamma,
                     const float* red, void* dz, int N, int HW, int C, int c_valid, float* dgamma, float* dbeta,

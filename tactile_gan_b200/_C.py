@@ -38,7 +38,7 @@ class ConvDesc(Structure):
                 ("stride", c_int), ("tap_dy", c_int8 * TG_MAX_TAPS), ("tap_dx", c_int8 * TG_MAX_TAPS),
                 ("tap_w", c_int8 * TG_MAX_TAPS), ("bias", c_void_p), ("bias_len", c_int),
                 ("stats_partial", c_void_p), ("stats_tiles_total", c_int), ("stats_tile_off", c_int),
-                ("act", c_int), ("slope", c_float)]
+                ("act", c_int), ("slope", c_float), ("pool_out", c_int)]
 
 
 class WgradDesc(Structure):
@@ -136,7 +136,7 @@ def conv_query_tiles(n, ho, wo, want_stats):
 
 
 def conv_plan(srcs, out, taps, stride=1, bias=None, stats_partial=None, act=ACT_NONE, slope=0.2,
-              stats_tiles_total=0, stats_tile_off=0, cout_real=None, flops=None):
+              stats_tiles_total=0, stats_tile_off=0, cout_real=None, flops=None, pool_out=False):
     """srcs: list of dict(act=tensor NHWC, wgt=packed bf16 [taps][rows][k], k_off=0, row_off=0)
     taps: list of (dy, dx, w_index)."""
     d = ConvDesc()
@@ -166,17 +166,20 @@ def conv_plan(srcs, out, taps, stride=1, bias=None, stats_partial=None, act=ACT_
     d.stats_tile_off = stats_tile_off
     d.act = act
     d.slope = slope
+    d.pool_out = int(pool_out)
     h = c_void_p()
     check(lib().tg_conv_plan_create(byref(d), byref(h)), "tg_conv_plan_create")
     # algorithmic FLOPs of this launch: real (unpadded) channels, every output pixel, every tap
     n, ho, wo, _ = out.shape
+    if pool_out:
+        ho, wo = 2 * ho, 2 * wo
     if flops is None:
         flops = 0.0
         for s in srcs:
             flops += 2.0 * n * ho * wo * len(taps) * s.get("c_real", s["act"].shape[3]) * (cout_real or out.shape[3])
     tag = "conv n%d %dx%d cin[%s] cout%d taps%d s%d%s" % (
         n, ho, wo, ",".join(str(s["act"].shape[3]) for s in srcs), out.shape[3], len(taps), stride,
-        " stats" if stats_partial is not None else "")
+        (" stats" if stats_partial is not None else "") + (" pool" if pool_out else ""))
     return Plan(h, keep, "conv", flops, tag)
 
 

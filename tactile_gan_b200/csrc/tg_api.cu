@@ -9,7 +9,6 @@
 #include "tg_igemm.cuh"
 #include "tg_wgrad.cuh"
 #include "tg_igemm_halo.cuh"
-#include "tg_wgrad_halo.cuh"
 #include "tg_wgrad_taps.cuh"
 #include <cstdlib>
 
@@ -143,7 +142,6 @@ struct tg_plan {
   tg::IgemmParams conv;
   tg::WgradParams wg;
   tg::HaloParams halo;
-  tg::WgradHaloParams wgh;
   tg::WgradTapsParams wgt;
 };
 
@@ -152,6 +150,7 @@ namespace {
 bool halo_eligible(const tg_conv_desc* d, int* dy0, int* dx0, int* eh, int* ew) {
   static const bool disabled = getenv("TG_DISABLE_HALO") != nullptr;
   if (disabled || d->stride != 1 || d->taps > 9 || d->taps < 2) return false;
+  if (d->pool_out && (d->stats_partial || d->bias || d->act != 0)) return false;
   if (d->out.c != 64 && d->out.c != 128) return false;
   int ymin = 127, ymax = -127, xmin = 127, xmax = -127;
   for (int t = 0; t < d->taps; ++t) {
@@ -183,7 +182,9 @@ int create_halo_plan(const tg_conv_desc* d, tg_plan* pl, int dy0, int dx0, int e
   p.halo_w = tg::kHaloTW + ew;
   p.a_bytes = (tg::kHaloTW + ew) * (tg::kHaloTH + eh) * 128;
   p.b_bytes = d->src[0].wgt_taps * tg::kHaloBN * 128;
-  p.Ho = d->out.h; p.Wo = d->out.w; p.N = d->out.n;
+  const int up = d->pool_out ? 2 : 1;
+  p.pool_out = d->pool_out;
+  p.Ho = d->out.h * up; p.Wo = d->out.w * up; p.N = d->out.n;
   p.tiles_h = (p.Ho + tg::kHaloTH - 1) / tg::kHaloTH;
   p.tiles_w = (p.Wo + tg::kHaloTW - 1) / tg::kHaloTW;
   p.n_tiles = cout / tg::kHaloBN;
@@ -210,7 +211,7 @@ int create_halo_plan(const tg_conv_desc* d, tg_plan* pl, int dy0, int dx0, int e
       return -1;
     p.src[s].c_chunks = cs.act.c / 64;
   }
-  if (make_act_map(&p.out, d->out, 0, cout, tg::kHaloTW, tg::kHaloTH, 1, 1)) return -1;
+  if (make_act_map(&p.out, d->out, 0, cout, tg::kHaloTW / up, tg::kHaloTH / up, 1, 1)) return -1;
   const int m_tiles = p.N * p.tiles_h * p.tiles_w;
   const int total = ((m_tiles + tg::kHaloR - 1) / tg::kHaloR) * p.n_tiles;
   pl->grid = total < sm_count() ? total : sm_count();
@@ -280,14 +281,24 @@ int tg_conv_plan_create(const tg_conv_desc* d, tg_plan** out) {
   const int bn = cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64);
   pl->bn = bn;
   int th, tw, tn;
-  choose_tile(d->out.n, d->out.h, d->out.w, tg::kTileM, d->stats_partial != nullptr, &th, &tw, &tn);
+  const int up = d->pool_out ? 2 : 1;
+  if (d->pool_out) {
+    if (d->stats_partial || d->bias || d->act != 0 || d->stride != 1) {
+      delete pl;
+      return tg_set_error("tg_conv_plan_create: pool_out is a plain stride-1 input-gradient mode (no bias/act/stats)");
+    }
+    th = 16; tw = 8; tn = 1;       // the pooled epilogue pairs lanes of a 16x8 tile
+  } else {
+    choose_tile(d->out.n, d->out.h, d->out.w, tg::kTileM, d->stats_partial != nullptr, &th, &tw, &tn);
+  }
+  p.pool_out = d->pool_out;
   p.num_src = d->num_src;
   p.taps = d->taps;
   p.stride = d->stride;
   memcpy(p.tap_dy, d->tap_dy, 16);
   memcpy(p.tap_dx, d->tap_dx, 16);
   memcpy(p.tap_w, d->tap_w, 16);
-  p.Ho = d->out.h; p.Wo = d->out.w; p.N = d->out.n;
+  p.Ho = d->out.h * up; p.Wo = d->out.w * up; p.N = d->out.n;
   p.th = th; p.tw = tw; p.tn = tn;
   p.tiles_h = (p.Ho + th - 1) / th;
   p.tiles_w = (p.Wo + tw - 1) / tw;
@@ -313,7 +324,7 @@ int tg_conv_plan_create(const tg_conv_desc* d, tg_plan** out) {
     }
     p.src[s].c_chunks = cs.act.c / 64;
   }
-  if (make_act_map(&p.out, d->out, 0, cout, tw, th, tn, 1)) { delete pl; return -1; }
+  if (make_act_map(&p.out, d->out, 0, cout, tw / up, th / up, tn, 1)) { delete pl; return -1; }
   const int total = p.tiles_img * p.tiles_h * p.tiles_w * p.n_tiles;
   pl->grid = total < sm_count() ? total : sm_count();
   cudaError_t e;
@@ -333,64 +344,6 @@ int tg_conv_plan_create(const tg_conv_desc* d, tg_plan** out) {
     return -1;
   }
   *out = pl;
-  return 0;
-}
-
-static int create_wgrad_halo_plan(const tg_wgrad_desc* d, tg_plan* pl, int ymin, int ymax, int xmin, int xmax) {
-  pl->kind = 3;
-  tg::WgradHaloParams& p = pl->wgh;
-  memset(&p, 0, sizeof(p));
-  const int eh = ymax - ymin, ew = xmax - xmin;
-  p.num_src = d->num_src;
-  p.taps = d->taps;
-  for (int t = 0; t < d->taps; ++t) {
-    p.tap_dy[t] = int8_t(ymax - d->tap_dy[t]);   // dY pixel = X pixel - tap offset
-    p.tap_dx[t] = int8_t(xmax - d->tap_dx[t]);
-    p.tap_w[t] = d->tap_w[t];
-  }
-  p.org_dy = -ymax; p.org_dx = -xmax;
-  p.halo_w = tg::kHaloTW + ew;
-  p.y_bytes = (tg::kHaloTW + ew) * (tg::kHaloTH + eh) * 128;
-  // pixel domain = the X (input) grid, which for stride-1 convs covers every pixel any tap touches
-  const int H = d->p[0].h, W = d->p[0].w;
-  p.N = d->q.n;
-  p.tiles_h = (H + tg::kHaloTH - 1) / tg::kHaloTH;
-  p.tiles_w = (W + tg::kHaloTW - 1) / tg::kHaloTW;
-  int chunks = 0;
-  for (int s = 0; s < d->num_src; ++s) {
-    if (d->p[s].c % 64) return tg_set_error("tg_wgrad_plan_create: P channels must be a multiple of 64");
-    if (d->p[s].h != H || d->p[s].w != W) return tg_set_error("tg_wgrad_plan_create: source size mismatch");
-    if (make_act_map(&p.src[s].act, d->p[s], 0, d->p[s].c, tg::kHaloTW, tg::kHaloTH, 1, 1)) return -1;
-    p.src[s].c_chunks = d->p[s].c / 64;
-    chunks += p.src[s].c_chunks;
-  }
-  if (make_act_map(&p.q, d->q, 0, d->q.c, tg::kHaloTW + ew, tg::kHaloTH + eh, 1, 1)) return -1;
-  p.total_chunks = chunks;
-  p.m_tiles = (chunks + 1) / 2;
-  p.n_tiles = d->q.c / 64;
-  p.tap_groups = (d->taps + tg::kWhTaps - 1) / tg::kWhTaps;
-  p.dw = d->dw;
-  p.m_total = d->dw_cols;
-  p.n_total = d->dw_rows;
-  if (p.m_total != chunks * 64) return tg_set_error("tg_wgrad_plan_create: dw_cols != sum of P channels");
-  if (p.n_total < d->q.c) return tg_set_error("tg_wgrad_plan_create: dw_rows < Q channels");
-  p.err_flag = tg_error_flag_device_ptr();
-  const int k_tiles = p.N * p.tiles_h * p.tiles_w;
-  const int items0 = p.tap_groups * p.m_tiles * p.n_tiles;
-  int splits = (2 * sm_count() + items0 - 1) / items0;
-  const int max_splits = k_tiles / 4 > 1 ? k_tiles / 4 : 1;
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
-  while (splits > 1 && ((k_tiles + splits - 1) / splits) * (splits - 1) >= k_tiles) --splits;
-  p.splits = splits;
-  const int total = items0 * splits;
-  pl->grid = total < sm_count() ? total : sm_count();
-  pl->smem = tg::kWhSmem;
-  cudaError_t e = cudaFuncSetAttribute(tg::wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl->smem));
-  if (e != cudaSuccess) {
-    snprintf(g_err, sizeof(g_err), "cudaFuncSetAttribute(wgrad halo): %s", cudaGetErrorString(e));
-    return -1;
-  }
   return 0;
 }
 
@@ -462,28 +415,16 @@ int tg_wgrad_plan_create(const tg_wgrad_desc* d, tg_plan** out) {
       ymin = d->tap_dy[t] < ymin ? d->tap_dy[t] : ymin; ymax = d->tap_dy[t] > ymax ? d->tap_dy[t] : ymax;
       xmin = d->tap_dx[t] < xmin ? d->tap_dx[t] : xmin; xmax = d->tap_dx[t] > xmax ? d->tap_dx[t] : xmax;
     }
-    // same-size (pad = (k-1)/2) stride-1 windows only: the X grid then equals the dY grid
-    const bool same = d->p[0].h == d->q.h && d->p[0].w == d->q.w;
-    {
-      static const bool use_old = getenv("TG_WGRAD_HALO") != nullptr;
-      static const int max_qc = getenv("TG_WGRAD_TAPS_MAXC") ? atoi(getenv("TG_WGRAD_TAPS_MAXC")) : 128;
-      // any <= 3x3 tap window of a stride-1 conv, padded (X grid == dY grid) or valid (X grid larger)
-      const bool window = d->taps <= 9 && ymax - ymin <= 2 && xmax - xmin <= 2;
-      const bool grids = ymin >= -1 && xmin >= -1 && ymin <= 0 && xmin <= 0;   // centre offset 0 (padded) or 1 (valid)
-      // wide outputs: the per-tap kernel re-streams both operands nine times, which only pays while they sit in L2
-      double op_bytes = double(d->q.n) * d->q.h * d->q.w * d->q.c * 2.0;
-      for (int s2 = 0; s2 < d->num_src; ++s2) op_bytes += double(d->p[s2].n) * d->p[s2].h * d->p[s2].w * d->p[s2].c * 2.0;
-      const bool big = op_bytes > 200.0 * 1024 * 1024;
-      (void)same;
-      if (!disabled && !use_old && d->stride == 1 && d->taps >= 2 && window && grids && (d->q.c <= max_qc || big)) {
-        if (create_wgrad_taps_plan(d, pl)) { delete pl; return -1; }
-        *out = pl;
-        return 0;
-      }
-    }
-    if (!disabled && d->stride == 1 && d->taps >= 2 && d->taps <= 9 && ymax - ymin <= 2 && xmax - xmin <= 2 && same &&
-        (d->q.c == 64 || d->q.c == 128)) {
-      if (create_wgrad_halo_plan(d, pl, ymin, ymax, xmin, xmax)) { delete pl; return -1; }
+    static const int max_qc = getenv("TG_WGRAD_TAPS_MAXC") ? atoi(getenv("TG_WGRAD_TAPS_MAXC")) : 128;
+    // any <= 3x3 tap window of a stride-1 conv, padded (X grid == dY grid) or valid (X grid larger)
+    const bool window = d->taps <= 9 && ymax - ymin <= 2 && xmax - xmin <= 2;
+    const bool grids = ymin >= -1 && xmin >= -1 && ymin <= 0 && xmin <= 0;   // centre offset 0 (padded) or 1 (valid)
+    // wide outputs: the per-tap kernel re-streams both operands nine times, which only pays while they sit in L2
+    double op_bytes = double(d->q.n) * d->q.h * d->q.w * d->q.c * 2.0;
+    for (int s2 = 0; s2 < d->num_src; ++s2) op_bytes += double(d->p[s2].n) * d->p[s2].h * d->p[s2].w * d->p[s2].c * 2.0;
+    const bool big = op_bytes > 200.0 * 1024 * 1024;
+    if (!disabled && d->stride == 1 && d->taps >= 2 && window && grids && (d->q.c <= max_qc || big)) {
+      if (create_wgrad_taps_plan(d, pl)) { delete pl; return -1; }
       *out = pl;
       return 0;
     }
@@ -568,8 +509,6 @@ int tg_plan_run(tg_plan* pl, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (pl->kind == 2) {
     tg::igemm_halo_kernel<<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->halo);
-  } else if (pl->kind == 3) {
-    tg::wgrad_halo_kernel<<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->wgh);
   } else if (pl->kind == 4) {
     tg::wgrad_taps_kernel<<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->wgt);
   } else if (pl->kind == 0) {

@@ -53,6 +53,7 @@ struct alignas(64) IgemmParams {
   float* stats_partial;   // [N][stats_tiles_total][Cout][2] or nullptr (requires tn == 1)
   int stats_tiles_total, stats_tile_off;
   int cout;               // padded Cout (row pitch of stats)
+  int pool_out;           // epilogue stores the 2x2 sum (tile is 16x8, `out` map is the half-resolution tensor)
   int* err_flag;
 };
 
@@ -136,6 +137,24 @@ __device__ __forceinline__ void epi_pack(const uint32_t (&v0)[32], const uint32_
       default: epi_pack_as<ACT_TANH, true>(v0, v1, packed, slope, sbias); break;
     }
   }
+}
+
+// 2x2 SUM over a 16x8-pixel tile held one pixel row per thread (tile row = ty*8 + tx = TMEM lane, 32 rows per
+// warp = 4 image rows): the x neighbour is lane^1, the y neighbour lane^8. Every lane takes part; returns true on
+// the 8 lanes per warp that end up holding a pooled pixel, `prow` = its row in the 8x4 pooled tile.
+__device__ __forceinline__ bool epi_pool2x2(uint32_t (&v0)[32], uint32_t (&v1)[32], int q, int lane, int& prow) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float a = __uint_as_float(v0[j]), b = __uint_as_float(v1[j]);
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    b += __shfl_xor_sync(0xffffffffu, b, 1);
+    a += __shfl_xor_sync(0xffffffffu, a, 8);
+    b += __shfl_xor_sync(0xffffffffu, b, 8);
+    v0[j] = __float_as_uint(a);
+    v1[j] = __float_as_uint(b);
+  }
+  prow = (2 * q + (lane >> 4)) * 4 + ((lane >> 1) & 3);
+  return (lane & 9) == 0;
 }
 
 // Stage bias[c_base .. c_base+64) (zero past bias_len) for the 128 epilogue threads; no-op when already staged.
@@ -352,6 +371,21 @@ igemm_conv_kernel(const __grid_constant__ IgemmParams p) {
         }
         const int c_base = n_tile * BN + chunk * 64;
         uint32_t packed[32];
+        if (p.pool_out) {
+          int prow;
+          const bool keep = epi_pool2x2(v0, v1, q, lane, prow);
+          epi_pack(v0, v1, packed, ACT_NONE, 0.f, nullptr);
+          if (et == 0) tma_store_wait_read<1>();
+          named_bar_sync(1, 128);
+          if (keep) epi_store_row(store_base + sb * kStoreBytes, prow, packed);
+          fence_proxy_async();
+          named_bar_sync(1, 128);
+          if (et == 0) {
+            tma_store_4d(&p.out, store_base + sb * kStoreBytes, c_base, wo0 >> 1, ho0 >> 1, n0);
+            tma_store_commit();
+          }
+          continue;
+        }
         epi_stage_bias(sbias, e_bias, e_bias_len, c_base, staged_base, et);
         epi_pack(v0, v1, packed, e_act, e_slope, e_bias ? sbias : nullptr);
         // staging buffer `sb` must have been drained by the TMA store issued two chunks ago

@@ -47,6 +47,7 @@ struct alignas(64) HaloParams {
   int stats_tiles_total, stats_tile_off;
   int cout;
   int prefetch;   // issue L2 prefetches one chunk ahead
+  int pool_out;   // epilogue stores the 2x2 sum of the tile (`out` map = half-resolution tensor, box {64,4,8,1})
   int* err_flag;
 };
 
@@ -257,6 +258,21 @@ __global__ void __launch_bounds__(kNumThreads, 2) igemm_halo_kernel(const __grid
           mbar_arrive(tempty(set));
         }
         uint32_t packed[32];
+        if (p.pool_out) {
+          int prow;
+          const bool keep = epi_pool2x2(v0, v1, q, lane, prow);
+          epi_pack(v0, v1, packed, ACT_NONE, 0.f, nullptr);
+          if (et == 0) tma_store_wait_read<1>();
+          named_bar_sync(1, 128);
+          if (keep) epi_store_row(store_base + sb * kStoreBytes, prow, packed);
+          fence_proxy_async();
+          named_bar_sync(1, 128);
+          if (et == 0) {
+            tma_store_4d(&p.out, store_base + sb * kStoreBytes, c_base, wo0 >> 1, ho0 >> 1, img);
+            tma_store_commit();
+          }
+          continue;
+        }
         epi_stage_bias(sbias, e_bias, e_bias_len, c_base, staged_base, et);
         epi_pack(v0, v1, packed, e_act, e_slope, e_bias ? sbias : nullptr);
         if (et == 0) tma_store_wait_read<1>();

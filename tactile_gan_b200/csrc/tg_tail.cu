@@ -400,13 +400,19 @@ struct InBwdArgs {
   __nv_bfloat16* dn;
   float* red;                 // [N][C][2]
   int N, H, W, C, c_valid, act, pool_mode;
+  int up_pooled;              // g_up is already summed to this tensor's resolution (pool_out conv epilogue)
   float slope;
 };
 
 // Per-pixel work of the backward reduce for the general case (pooled / upsampled gradient routes).
 __device__ __forceinline__ void in_bwd_gather(const InBwdArgs& a, int n, int pix, int c0, float (&g)[8]) {
   const int yy = pix / a.W, xx = pix % a.W;
-  if (a.g_up) {
+  if (a.g_up && a.up_pooled) {
+    float f[8];
+    unpack8(ldg16(a.g_up + (size_t(n) * a.H * a.W + pix) * a.C + c0), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] += f[j];
+  } else if (a.g_up) {
     const int WU = 2 * a.W;
     const size_t ub = (size_t(n) * 2 * a.H + 2 * yy) * WU + 2 * xx;
     const uint4 u0 = ldg16(a.g_up + ub * a.C + c0), u1 = ldg16(a.g_up + (ub + 1) * a.C + c0);
@@ -1437,9 +1443,10 @@ int tg_in_act_fwd(const void* raw, const float* mr, const float* gamma, const fl
 
 int tg_in_bwd_reduce(const void* raw, const void* y, const float* mr, const float* gamma,
                      const float* beta, const void* g_same, const void* g_pool, int pool_mode,
-                     const void* g_up, void* dn, float* red, int N, int H, int W, int C, int c_valid,
-                     int act, float slope, void* stream) {
+                     const void* g_up, int g_up_pooled, void* dn, float* red, int N, int H, int W, int C,
+                     int c_valid, int act, float slope, void* stream) {
   InBwdArgs a;
+  a.up_pooled = g_up_pooled;
   a.raw = (const __nv_bfloat16*)raw; a.y = (const __nv_bfloat16*)y; a.mr = mr; a.gamma = gamma;
   a.beta = beta; a.g_same = (const __nv_bfloat16*)g_same; a.g_pool = (const __nv_bfloat16*)g_pool;
   a.g_up = (const __nv_bfloat16*)g_up; a.dn = (__nv_bfloat16*)dn; a.red = red;

@@ -32,18 +32,25 @@ class Act:
     def shape(self):
         return self.buf.shape
 
-    def build_grad(self, scratch, scratch2=None):
+    def build_grad(self, scratch, scratch2=None, pooled=False):
         """Plan d(self) = sum of the input-gradients of all consuming convs. All stride-1 Conv2d consumers
         share ONE launch (the K loop of the implicit GEMM walks the consumers); a strided Conv2d or a
-        ConvTranspose2d consumer gets its own launch(es) into a second buffer that is then added."""
+        ConvTranspose2d consumer gets its own launch(es) into a second buffer that is then added.
+        pooled (nearest-upsampled copies): the gradient is produced directly at the source's resolution -- the
+        conv epilogue sums each 2x2 block -- instead of at this 4x larger tensor's."""
         if not self.consumers:
             return
         n, h, w, c = self.buf.shape
-        self.grad_buf = scratch[: n * h * w * c].view(n, h, w, c)
         units = [(u.layer, u.dz, seg) for u, seg in self.consumers]
         same = [x for x in units if x[0].kind == "conv" and x[0].stride == 1]
         other = [x for x in units if not (x[0].kind == "conv" and x[0].stride == 1)]
         self.grad_plans, self.grad_adds = [], []
+        self.grad_pooled = bool(pooled and same and not other and h % 2 == 0 and w % 2 == 0)
+        if self.grad_pooled:
+            self.grad_buf = scratch[: n * (h // 2) * (w // 2) * c].view(n, h // 2, w // 2, c)
+            self.grad_plans.append(multi_dgrad_plan(same, self.grad_buf, pool_out=True))
+            return
+        self.grad_buf = scratch[: n * h * w * c].view(n, h, w, c)
         if same:
             self.grad_plans.append(multi_dgrad_plan(same, self.grad_buf))
         for i, (l, dz, seg) in enumerate(other):
@@ -109,7 +116,7 @@ class ConvUnit:
             if self.pool:
                 self.pool.build_grad(eng.gp_scratch)
             if self.up:
-                self.up.build_grad(eng.gu_scratch)
+                self.up.build_grad(eng.gu_scratch, pooled=True)
 
     def _aff(self):
         g = self.gamma.detach() if self.gamma is not None else None
@@ -147,14 +154,15 @@ class ConvUnit:
             g_same = g_extra
         g_pool = self.pool.run_grad() if (self.pool and self.pool.consumers) else None
         g_up = self.up.run_grad() if (self.up and self.up.consumers) else None
+        up_pooled = int(bool(g_up is not None and self.up.grad_pooled))
         g, b = self._aff()
         if self.norm:
             self.red.zero_()
             elems = 2.0 * n * ho * wo * c      # bytes of one bf16 tensor of this unit
             nb = elems * (2 + (1 if g_same is not None else 0) + (0.25 if g_pool is not None else 0) +
-                          (4 if g_up is not None else 0))
+                          ((1 if up_pooled else 4) if g_up is not None else 0))
             _C.call("in_bwd_reduce", ptr(self.raw), ptr(self.y.buf), ptr(self.mr), g, b, ptr(g_same), ptr(g_pool),
-                    self.pool_mode, ptr(g_up), ptr(dn), ptr(self.red), n, ho, wo, c, self.c_valid,
+                    self.pool_mode, ptr(g_up), up_pooled, ptr(dn), ptr(self.red), n, ho, wo, c, self.c_valid,
                     self.act, F(self.slope), nbytes=nb)
             aff = wgrad and self.gamma is not None
             _C.call("in_bwd_apply", ptr(dn), ptr(self.raw), ptr(self.mr), g, ptr(self.red),
@@ -163,7 +171,7 @@ class ConvUnit:
                     ptr(eng.store.grad_of(self.beta)) if aff else None, nbytes=3 * elems)
         else:
             _C.call("in_bwd_reduce", None, ptr(self.y.buf), None, None, None, ptr(g_same), ptr(g_pool),
-                    self.pool_mode, ptr(g_up), ptr(self.dz), None, n, ho, wo, c, self.c_valid, self.act,
+                    self.pool_mode, ptr(g_up), up_pooled, ptr(self.dz), None, n, ho, wo, c, self.c_valid, self.act,
                     F(self.slope))
         if wgrad:
             ws = getattr(eng, "wgrad_stream", None)
@@ -760,7 +768,7 @@ class PatchDInstance(GraphEngine):
                 g, b = x._aff()
                 red = so["red_dn"][k - 1]
                 red.zero_()
-                _C.call("in_bwd_reduce", ptr(x.raw), ptr(x.y.buf), ptr(x.mr), g, b, ptr(e), None, 0, None,
+                _C.call("in_bwd_reduce", ptr(x.raw), ptr(x.y.buf), ptr(x.mr), g, b, ptr(e), None, 0, None, 0,
                         ptr(self.dn_scratch), ptr(red), x.n, x.ho, x.wo, x.c, x.c_valid, ACT_LRELU, F(0.2))
                 aff = x.gamma is not None
                 _C.call("in_bwd_apply", ptr(self.dn_scratch), ptr(x.raw), ptr(x.mr), g, ptr(red), ptr(z), x.n,

@@ -253,14 +253,16 @@ def plan_buckets(layout, bucket_elems):
     return buckets
 
 
-def multi_dgrad_plan(consumers, out):
+def multi_dgrad_plan(consumers, out, pool_out=False):
     """d(out) = sum over consumers (layer, dY, segment) of the stride-1 input gradients -- one
-    multi-source implicit GEMM (the K loop walks the consumers)."""
+    multi-source implicit GEMM (the K loop walks the consumers). pool_out: `out` is the half-resolution
+    tensor and the kernel stores the 2x2 sum (gradient through a nearest-upsampled copy)."""
     l0 = consumers[0][0]
     for layer, _, _ in consumers:
         assert layer.stride == 1 and (layer.kh, layer.kw, layer.pad) == (l0.kh, l0.kw, l0.pad)
     srcs = [layer.dgrad_src(dy, seg) for layer, dy, seg in consumers]
-    return _C.conv_plan(srcs, out, dgrad_taps_s1(l0.kh, l0.kw, l0.pad), cout_real=l0.in_split[consumers[0][2]])
+    return _C.conv_plan(srcs, out, dgrad_taps_s1(l0.kh, l0.kw, l0.pad), cout_real=l0.in_split[consumers[0][2]],
+                        pool_out=pool_out)
 
 
 class ParamStore:

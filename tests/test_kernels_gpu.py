@@ -73,6 +73,24 @@ def test_conv_forward(case):
     run_conv(**case)
 
 
+@pytest.mark.parametrize("cin,cout,h,w", [(64, 128, 32, 48), (64, 64, 16, 16), (128, 256, 32, 32), (192, 512, 16, 32)])
+def test_conv_pool_out_sums_2x2_blocks(cin, cout, h, w):
+    """pool_out: the epilogue stores the 2x2 sum of the (h x w) result into an (h/2 x w/2) tensor -- the input
+    gradient through a nearest-upsampled copy -- on the halo kernel (cout 64/128) and the generic one."""
+    C = _C()
+    g = torch.Generator().manual_seed(4)
+    n = 2
+    x = torch.randn(n, cin, h, w, generator=g).to(dev)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) * 0.05).to(dev)
+    ref = F.avg_pool2d(F.conv2d(x.bfloat16().float(), wt.bfloat16().float(), padding=1), 2) * 4
+    wp = wt.permute(2, 3, 0, 1).reshape(9, cout, cin).bfloat16().contiguous()
+    out = torch.full((n, h // 2, w // 2, cout), 7.0, dtype=torch.bfloat16, device=dev)
+    C.conv_plan([dict(act=nhwc_pad(x), wgt=wp)], out, conv_taps(3, 3, 1), pool_out=True).run()
+    torch.cuda.synchronize()
+    assert C.error_flag() == 0
+    assert rel(out.permute(0, 3, 1, 2), ref) < 5e-3
+
+
 WGRAD_CASES = [
     (2, [64], 64, 16, 16, 1, 1, 0), (2, [128], 256, 32, 32, 3, 1, 1), (2, [64, 64, 128], 64, 64, 64, 3, 1, 1),
     (2, [3], 64, 64, 64, 3, 1, 1), (2, [128], 256, 61, 61, 3, 1, 0), (2, [64], 128, 127, 127, 3, 2, 0),
@@ -148,7 +166,14 @@ def test_instance_norm_forward_backward_pool_upsample():
     red = torch.zeros(n, cp, 2, device=dev)
     gs_p, gp_p, gu_p = nhwc_pad(gs), nhwc_pad(gp), nhwc_pad(gu)   # keep alive: the launch is asynchronous
     C.call("in_bwd_reduce", ptr(raw), ptr(y), ptr(mr), ptr(gamma), ptr(beta), ptr(gs_p), ptr(gp_p), 1,
-           ptr(gu_p), ptr(dn), ptr(red), n, h, w, cp, c, 3, f32(0.0))
+           ptr(gu_p), 0, ptr(dn), ptr(red), n, h, w, cp, c, 3, f32(0.0))
+    # the same gradient with the upsample route pre-summed to this resolution (what a pool_out conv stores)
+    gu_lo = nhwc_pad(F.avg_pool2d(q(gu), 2) * 4)
+    dn_b, red_b = torch.zeros_like(raw), torch.zeros(n, cp, 2, device=dev)
+    C.call("in_bwd_reduce", ptr(raw), ptr(y), ptr(mr), ptr(gamma), ptr(beta), ptr(gs_p), ptr(gp_p), 1,
+           ptr(gu_lo), 1, ptr(dn_b), ptr(red_b), n, h, w, cp, c, 3, f32(0.0))
+    torch.cuda.synchronize()
+    assert rel(dn_b, dn) < 6e-3 and rel(red_b, red) < 6e-3
     dgam, dbet = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
     C.call("in_bwd_apply", ptr(dn), ptr(raw), ptr(mr), ptr(gamma), ptr(red), ptr(dz), n, h * w, cp, c, ptr(dgam),
            ptr(dbet))
@@ -304,7 +329,7 @@ def test_maxpool_forward_backward():
     gpp = nhwc_pad(gp)
     dn = torch.zeros_like(raw)
     red = torch.zeros(n, c, 2, device=dev)
-    C.call("in_bwd_reduce", ptr(raw), ptr(y), ptr(mr), None, None, None, ptr(gpp), 2, None, ptr(dn), ptr(red), n, h, w,
+    C.call("in_bwd_reduce", ptr(raw), ptr(y), ptr(mr), None, None, None, ptr(gpp), 2, None, 0, ptr(dn), ptr(red), n, h, w,
            c, c, 3, f32(0.0))
     torch.cuda.synchronize()
     # ties (several zeros in a window) are routed to the first element by both implementations only when
