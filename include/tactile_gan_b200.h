@@ -144,8 +144,10 @@ int tg_act_bwd(const void* g, const void* y, void* out, long long numel, int act
 /* ---- FeatureMapBlock: 1x1 conv + bias (+Tanh) (UNet_plusplus.py:5-16) forward / backward */
 int tg_fmap_fwd(const void* x, const float* w, const float* b, float* out, int N, int HW, int C, int co,
                 int use_tanh, void* stream);
+/* dw: fp32 [dw_replicas][co][64] accumulated with atomics (blocks spread over the replicas; the caller sums them) */
 int tg_fmap_bwd(const void* x, const float* w, const float* out, const float* g1, const float* g2,
-                void* dx, float* dw, float* db, int N, int HW, int C, int co, int use_tanh, void* stream);
+                void* dx, float* dw, int dw_replicas, float* db, int N, int HW, int C, int co, int use_tanh,
+                void* stream);
 
 /* ---- version-1 perceptual term, VGGPerceptualLoss (util.py:100-144): input transform (channel repeat,
  *      ImageNet mean / std, bilinear resize align_corners=False) and its transpose, MaxPool2d(2) for layers without

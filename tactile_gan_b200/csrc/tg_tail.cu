@@ -110,27 +110,41 @@ __global__ void unpack_nhwc_kernel(const __nv_bfloat16* __restrict__ in, float* 
 //                z[n,oy,ox] = sum_tap hc[n,oy+dy,ox+dx,tap]; the backward scatters dz to dzc[n,y,x,tap] = dz[n,y-dy,x-dx].
 
 // cols <- im2col of cat(A, wa*B + wb*B2) (fp32 NCHW sources), k x k taps, stride s, no padding. One thread per
-// output pixel writes its 128-byte row.
-__global__ void im2col_pack_kernel(const float* __restrict__ A, const float* __restrict__ B,
-                                   const float* __restrict__ B2, const float* __restrict__ wa,
-                                   const float* __restrict__ wb, __nv_bfloat16* __restrict__ cols, int N, int ca,
-                                   int cb, int H, int W, int Ho, int Wo, int k, int stride) {
+// output pixel writes its 128-byte row. KK / CA / CB > 0: compile-time shape (the row lives in registers);
+// 0: run-time shape (generic fallback, row in local memory).
+template <int KK, int CA, int CB>
+__global__ void __launch_bounds__(128)
+im2col_pack_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                   const float* __restrict__ B2, const float* __restrict__ wa,
+                   const float* __restrict__ wb, __nv_bfloat16* __restrict__ cols, int N, int ca_,
+                   int cb_, int H, int W, int Ho, int Wo, int k_, int stride) {
+  const int k = KK ? KK : k_, ca = KK ? CA : ca_, cb = KK ? CB : cb_;
   const size_t total = size_t(N) * Ho * Wo;
   const int ct = ca + cb;
+  const size_t HW = size_t(H) * W;
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
     const int ox = int(i % Wo), oy = int((i / Wo) % Ho), n = int(i / (size_t(Wo) * Ho));
     const float fa = wa ? wa[n] : 1.f, fb = wb ? wb[n] : 0.f;
     __align__(16) __nv_bfloat16 row[64];
 #pragma unroll
     for (int j = 0; j < 64; ++j) row[j] = __float2bfloat16(0.f);
-    for (int t = 0; t < k * k; ++t) {
-      const int y = oy * stride + t / k, x = ox * stride + t % k;
-      const size_t pix = size_t(y) * W + x;
-      for (int c = 0; c < ca; ++c)
-        if (A) row[t * ct + c] = __float2bfloat16(__ldg(A + (size_t(n) * ca + c) * H * W + pix));
-      for (int c = 0; c < cb; ++c) {
-        float v = fa * __ldg(B + (size_t(n) * cb + c) * H * W + pix);
-        if (B2) v += fb * __ldg(B2 + (size_t(n) * cb + c) * H * W + pix);
+    const float* An = A ? A + size_t(n) * ca * HW : nullptr;
+    const float* Bn = B + size_t(n) * cb * HW;
+    const float* B2n = B2 ? B2 + size_t(n) * cb * HW : nullptr;
+#pragma unroll
+    for (int t = 0; t < (KK ? KK * KK : 16); ++t) {
+      if (t >= k * k) break;
+      const size_t pix = size_t(oy * stride + t / k) * W + ox * stride + t % k;
+#pragma unroll
+      for (int c = 0; c < (KK ? CA : 8); ++c) {
+        if (c >= ca) break;
+        if (An) row[t * ct + c] = __float2bfloat16(__ldg(An + c * HW + pix));
+      }
+#pragma unroll
+      for (int c = 0; c < (KK ? CB : 8); ++c) {
+        if (c >= cb) break;
+        float v = fa * __ldg(Bn + c * HW + pix);
+        if (B2n) v += fb * __ldg(B2n + c * HW + pix);
         row[t * ct + ca + c] = __float2bfloat16(v);
       }
     }
@@ -219,24 +233,26 @@ __global__ void gp_normsq_img_kernel(const float* __restrict__ g, size_t per_img
 // partial: [N][T][C][2] (sum, sumsq) from the conv epilogue -> mr: [N][C][2] (mean, rstd)
 __global__ void in_finalize_kernel(const float* __restrict__ partial, float* __restrict__ mr, int T,
                                    int C, float inv_count, float eps) {
-  __shared__ float sh[16][64][2];
+  // block = 16 channels x 64 tile lanes (grid (C/16, N)): a (tile, 16-channel) row is one 128-byte line
+  __shared__ float sh[64][16][2];
   const int n = blockIdx.y;
-  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
-  const int tl = threadIdx.x >> 6;  // 0..15
+  const int cl = threadIdx.x & 15;
+  const int c = blockIdx.x * 16 + cl;
+  const int tl = threadIdx.x >> 4;  // 0..63
   float s = 0.f, q = 0.f;
   const float2* src = reinterpret_cast<const float2*>(partial) + (size_t(n) * T) * C + c;
-  for (int t = tl; t < T; t += 16) {
+  for (int t = tl; t < T; t += 64) {
     const float2 v = __ldg(src + size_t(t) * C);
     s += v.x;
     q += v.y;
   }
-  sh[tl][threadIdx.x & 63][0] = s;
-  sh[tl][threadIdx.x & 63][1] = q;
+  sh[tl][cl][0] = s;
+  sh[tl][cl][1] = q;
   __syncthreads();
   if (tl == 0) {
-    for (int k = 1; k < 16; ++k) {
-      s += sh[k][threadIdx.x][0];
-      q += sh[k][threadIdx.x][1];
+    for (int k = 1; k < 64; ++k) {
+      s += sh[k][cl][0];
+      q += sh[k][cl][1];
     }
     const float mean = s * inv_count;
     const float var = fmaxf(q * inv_count - mean * mean, 0.f);
@@ -507,18 +523,28 @@ __global__ void __launch_bounds__(256, 2) in_bwd_reduce_kernel(const InBwdArgs a
     const size_t img = size_t(n) * HW;
     int pix = t.p0 + t.pl;
     if (PLAIN) {
+      // same-resolution routes only: g_same and / or the pre-summed upsample route (either may be absent)
+      const __nv_bfloat16* ga = a.g_same ? a.g_same : a.g_up;
+      const __nv_bfloat16* gb = (a.g_same && a.g_up) ? a.g_up : nullptr;
       for (; pix + 3 * t.PL < t.p1; pix += 4 * t.PL) {
-        uint4 vr[4], vg[4];
+        uint4 vr[4], vg[4], vu[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const size_t lin = (img + pix + k * t.PL) * a.C + c0;
           vr[k] = ldg16(src + lin);
-          vg[k] = ldg16(a.g_same + lin);
+          vg[k] = ldg16(ga + lin);
+          if (gb) vu[k] = ldg16(gb + lin);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           float g[8];
           unpack8(vg[k], g);
+          if (gb) {
+            float f[8];
+            unpack8(vu[k], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] += f[j];
+          }
           finish(vr[k], g, (img + pix + k * t.PL) * a.C + c0);
         }
       }
@@ -526,7 +552,13 @@ __global__ void __launch_bounds__(256, 2) in_bwd_reduce_kernel(const InBwdArgs a
         const size_t lin = (img + pix) * a.C + c0;
         float g[8];
         const uint4 vr = ldg16(src + lin);
-        unpack8(ldg16(a.g_same + lin), g);
+        unpack8(ldg16(ga + lin), g);
+        if (gb) {
+          float f[8];
+          unpack8(ldg16(gb + lin), f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] += f[j];
+        }
         finish(vr, g, lin);
       }
     } else {
@@ -869,11 +901,14 @@ __global__ void fmap_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float
 
 // dz[o] = (g1 + g2)[n,o,pix] * (1 - out^2) ; dx[n,pix,c] = sum_o dz[o] w[o][c];
 // dw[o][c] += sum dz[o] x[c]; db[o] += sum dz[o]
-__global__ void fmap_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
-                                const float* __restrict__ out, const float* __restrict__ g1,
-                                const float* __restrict__ g2, __nv_bfloat16* __restrict__ dx,
-                                float* __restrict__ dw, float* __restrict__ db, int N, int HW, int C,
-                                int co, int use_tanh) {
+// grid (strips, N): a block walks a strip of one image's pixels, thread = (pixel lane, 8-channel group), two pixels
+// per iteration so ~20 independent loads are in flight per thread.
+__global__ void __launch_bounds__(256)
+fmap_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                const float* __restrict__ out, const float* __restrict__ g1,
+                const float* __restrict__ g2, __nv_bfloat16* __restrict__ dx,
+                float* __restrict__ dw, float* __restrict__ db, int N, int HW, int C,
+                int co, int use_tanh, int replicas) {
   __shared__ float sw[4 * 64];
   __shared__ float sacc[4 * 64 + 4];
   for (int i = threadIdx.x; i < co * C; i += blockDim.x) sw[i] = w[i];
@@ -885,46 +920,67 @@ __global__ void fmap_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float
   for (int o = 0; o < 4; ++o)
 #pragma unroll
     for (int j = 0; j < 8; ++j) lw[o][j] = 0.f;
-  const int grp = threadIdx.x & 7;  // C == 64 -> 8 groups of 8 channels
-  const size_t total = size_t(N) * HW * 8;
-  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total;
-       i += size_t(gridDim.x) * blockDim.x) {
-    const size_t p = i >> 3;
-    const int n = int(p / HW), pix = int(p % HW);
-    float dz[4];
+  const int grp = threadIdx.x & 7, pl = threadIdx.x >> 3;  // C == 64 -> 8 groups of 8 channels, 32 pixel lanes
+  const int n = blockIdx.y;
+  const int strip = (HW + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * strip, p1 = min(HW, p0 + strip);
+  float wreg[4][8];
+#pragma unroll
+  for (int o = 0; o < 4; ++o)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wreg[o][j] = o < co ? sw[o * C + grp * 8 + j] : 0.f;
+
+  // branch-free loads (a null g1 / g2 reads the other operand with weight 0), so all of an iteration's loads issue
+  // back to back instead of one dependent round trip per `if`
+  const float* ga = g1 ? g1 : g2;
+  const float* gb = g2 ? g2 : g1;
+  const float wa = g1 ? 1.f : 0.f, wb = g2 ? 1.f : 0.f, wt = use_tanh ? 1.f : 0.f;
+  auto load_dz = [&](int pix, float (&dz)[4]) {
+    float a[4], b[4], t[4];
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
-      dz[o] = 0.f;
-      if (o < co) {
-        const size_t k = (size_t(n) * co + o) * HW + pix;
-        float g = g1 ? g1[k] : 0.f;
-        if (g2) g += g2[k];
-        if (use_tanh) {
-          const float t = out[k];
-          g *= 1.f - t * t;
-        }
-        dz[o] = g;
-      }
+      const size_t k = (size_t(n) * co + (o < co ? o : 0)) * HW + pix;
+      a[o] = __ldg(ga + k);
+      b[o] = __ldg(gb + k);
+      t[o] = __ldg(out + k);
     }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) dz[o] = o < co ? (wa * a[o] + wb * b[o]) * (1.f - wt * t[o] * t[o]) : 0.f;
+  };
+  auto emit = [&](int pix, const uint4& vx, const float (&dz)[4]) {
     float f[8], d[8];
-    unpack8(ldg16(x + p * C + grp * 8), f);
+    unpack8(vx, f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float a = 0.f;
+      float acc = 0.f;
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
-        if (o < co) {
-          a += dz[o] * sw[o * C + grp * 8 + j];
-          lw[o][j] += dz[o] * f[j];
-        }
+        acc = fmaf(dz[o], wreg[o][j], acc);
+        lw[o][j] = fmaf(dz[o], f[j], lw[o][j]);
       }
-      d[j] = a;
+      d[j] = acc;
     }
     if (grp == 0) {
 #pragma unroll
       for (int o = 0; o < 4; ++o) lb[o] += dz[o];
     }
-    if (dx) stg16(dx + p * C + grp * 8, pack8(d));
+    if (dx) stg16(dx + (size_t(n) * HW + pix) * C + grp * 8, pack8(d));
+  };
+  int pix = p0 + pl;
+  for (; pix + 32 < p1; pix += 64) {
+    float dza[4], dzb[4];
+    const uint4 xa = ldg16(x + (size_t(n) * HW + pix) * C + grp * 8);
+    const uint4 xb = ldg16(x + (size_t(n) * HW + pix + 32) * C + grp * 8);
+    load_dz(pix, dza);
+    load_dz(pix + 32, dzb);
+    emit(pix, xa, dza);
+    emit(pix + 32, xb, dzb);
+  }
+  for (; pix < p1; pix += 32) {
+    float dza[4];
+    const uint4 xa = ldg16(x + (size_t(n) * HW + pix) * C + grp * 8);
+    load_dz(pix, dza);
+    emit(pix, xa, dza);
   }
   // lanes with equal grp are 8 apart: reduce over them with shuffles, then smem, then atomics
 #pragma unroll
@@ -949,7 +1005,9 @@ __global__ void fmap_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < co * 64; i += blockDim.x) atomicAdd(dw + i, sacc[i]);
+  // ~1200 blocks adding into the same 6 cache lines serialise in L2: spread them over `replicas` copies of dw
+  float* dwr = dw + size_t((blockIdx.y * gridDim.x + blockIdx.x) % replicas) * co * 64;
+  for (int i = threadIdx.x; i < co * 64; i += blockDim.x) atomicAdd(dwr + i, sacc[i]);
   if (threadIdx.x < co) atomicAdd(db + threadIdx.x, sacc[256 + threadIdx.x]);
 }
 
@@ -1358,8 +1416,14 @@ int tg_im2col_pack(const float* A, const float* B, const float* B2, const float*
   if (k * k * (ca + cb) > 64) return tg_set_error("tg_im2col_pack: k*k*(ca+cb) must be <= 64");
   if (!B) return tg_set_error("tg_im2col_pack: B is required");
   const int Ho = (H - k) / stride + 1, Wo = (W - k) / stride + 1;
-  im2col_pack_kernel<<<grid_for(size_t(N) * Ho * Wo, 128, 148 * 16), 128, 0, TG_STREAM(stream)>>>(
-      A, B, B2, wa, wb, (__nv_bfloat16*)cols, N, ca, cb, H, W, Ho, Wo, k, stride);
+  if (ca > 8 || cb > 8 || k > 4) return tg_set_error("tg_im2col_pack: at most 8 + 8 channels and 4x4 taps");
+  const int grid = grid_for(size_t(N) * Ho * Wo, 128, 148 * 16);
+  if (k == 3 && ca == 3 && cb == 3)
+    im2col_pack_kernel<3, 3, 3><<<grid, 128, 0, TG_STREAM(stream)>>>(A, B, B2, wa, wb, (__nv_bfloat16*)cols, N, ca, cb,
+                                                                      H, W, Ho, Wo, k, stride);
+  else
+    im2col_pack_kernel<0, 0, 0><<<grid, 128, 0, TG_STREAM(stream)>>>(A, B, B2, wa, wb, (__nv_bfloat16*)cols, N, ca, cb,
+                                                                      H, W, Ho, Wo, k, stride);
   TG_RET();
 }
 
@@ -1397,7 +1461,7 @@ int tg_gp_normsq_img(const float* g, int N, long long per_img, float* nsq, void*
 
 int tg_in_finalize(const float* partial, float* mr, int N, int T, int C, int count, float eps,
                    void* stream) {
-  dim3 grid(C / 64, N);
+  dim3 grid(C / 16, N);
   in_finalize_kernel<<<grid, 1024, 0, TG_STREAM(stream)>>>(partial, mr, T, C, 1.f / float(count), eps);
   TG_RET();
 }
@@ -1457,7 +1521,8 @@ int tg_in_bwd_reduce(const void* raw, const void* y, const float* mr, const floa
   const int PL = block / (C / 8);
   const size_t smem = red ? size_t(PL) * C * 2 * sizeof(float) : 0;
   dim3 grid(strip_count(H * W, C, N, 16), N);
-  if (g_same && !g_pool && !g_up) in_bwd_reduce_kernel<true><<<grid, block, smem, TG_STREAM(stream)>>>(a);
+  const bool plain = !g_pool && (g_same || g_up) && (!g_up || g_up_pooled);
+  if (plain) in_bwd_reduce_kernel<true><<<grid, block, smem, TG_STREAM(stream)>>>(a);
   else in_bwd_reduce_kernel<false><<<grid, block, smem, TG_STREAM(stream)>>>(a);
   TG_RET();
 }
@@ -1534,10 +1599,16 @@ int tg_fmap_fwd(const void* x, const float* w, const float* b, float* out, int N
 }
 
 int tg_fmap_bwd(const void* x, const float* w, const float* out, const float* g1, const float* g2,
-                void* dx, float* dw, float* db, int N, int HW, int C, int co, int use_tanh, void* stream) {
+                void* dx, float* dw, int dw_replicas, float* db, int N, int HW, int C, int co, int use_tanh,
+                void* stream) {
+  if (dw_replicas < 1) return tg_set_error("tg_fmap_bwd: dw_replicas >= 1");
   if (C != 64 || co > 4) return tg_set_error("tg_fmap_bwd: expects C == 64, co <= 4");
-  fmap_bwd_kernel<<<grid_for(size_t(N) * HW * 8, 256, 148 * 8), 256, 0, TG_STREAM(stream)>>>(
-      (const __nv_bfloat16*)x, w, out, g1, g2, (__nv_bfloat16*)dx, dw, db, N, HW, C, co, use_tanh);
+  int strips = (HW + 1023) / 1024;                 // >= 32 pixels per lane per block
+  const int cap = (148 * 8 + N - 1) / N;
+  if (strips > cap) strips = cap;
+  if (strips < 1) strips = 1;
+  fmap_bwd_kernel<<<dim3(strips, N), 256, 0, TG_STREAM(stream)>>>(
+      (const __nv_bfloat16*)x, w, out, g1, g2, (__nv_bfloat16*)dx, dw, db, N, HW, C, co, use_tanh, dw_replicas);
   TG_RET();
 }
 

@@ -207,7 +207,7 @@ class HeadUnit:
         self.out = torch.zeros(n, self.co, h, w, device=eng.device)
         self.dx = bf16(n, h, w, c, device=eng.device)
         self.wpad = torch.zeros(self.co, 64, device=eng.device)     # fp32 [co][64]
-        self.dwpad = torch.zeros(self.co, 64, device=eng.device)
+        self.dwpad = torch.zeros(32, self.co, 64, device=eng.device)   # 32 replicas: see tg_fmap_bwd
 
     def forward(self):
         self.wpad[:, :self.ci].copy_(self.weight.detach().view(self.co, self.ci))
@@ -219,9 +219,10 @@ class HeadUnit:
         st = self.eng.store
         self.dwpad.zero_()
         _C.call("fmap_bwd", ptr(self.src.buf), ptr(self.wpad), ptr(self.out), ptr(g1), ptr(g2), ptr(self.dx),
-                ptr(self.dwpad), ptr(st.grad_of(self.bias)), self.n, self.hw, 64, self.co, int(self.use_tanh))
+                ptr(self.dwpad), self.dwpad.shape[0], ptr(st.grad_of(self.bias)), self.n, self.hw, 64, self.co,
+                int(self.use_tanh))
         if wgrad:
-            st.grad_of(self.weight).view(self.co, self.ci).add_(self.dwpad[:, :self.ci])
+            st.grad_of(self.weight).view(self.co, self.ci).add_(self.dwpad.sum(0)[:, :self.ci])
         return self.dx
 
 
