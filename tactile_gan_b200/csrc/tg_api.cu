@@ -385,7 +385,10 @@ static int create_wgrad_taps_plan(const tg_wgrad_desc* d, tg_plan* pl) {
   p.err_flag = tg_error_flag_device_ptr();
   const int k_tiles = p.N * p.tiles_h * p.tiles_w;
   const int items0 = chunks * p.n_tiles;
-  int splits = (2 * sm_count() + items0 - 1) / items0;
+  static const int waves = getenv("TG_WGRAD_WAVES") ? atoi(getenv("TG_WGRAD_WAVES")) : 2;
+  // items are dealt round-robin to one persistent CTA per SM: keep items0 * splits just BELOW a whole number of
+  // rounds (rounding up leaves a nearly empty extra round: 300 items on 148 SMs take 3 item-times, 294 take 2)
+  int splits = waves * sm_count() / items0;
   const int max_splits = k_tiles / 4 > 1 ? k_tiles / 4 : 1;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
@@ -466,7 +469,8 @@ int tg_wgrad_plan_create(const tg_wgrad_desc* d, tg_plan** out) {
   p.err_flag = tg_error_flag_device_ptr();
   const int k_blocks = p.tiles_img * p.tiles_h * p.tiles_w;
   const int items0 = p.taps * p.m_tiles * p.n_tiles;
-  int splits = (2 * sm_count() + items0 - 1) / items0;
+  static const int waves = getenv("TG_WGRAD_WAVES") ? atoi(getenv("TG_WGRAD_WAVES")) : 2;
+  int splits = waves * sm_count() / items0;   // whole rounds of the persistent grid, see create_wgrad_taps_plan
   {
     // the pixel ranges being streamed at any one time (one per concurrently active split) should stay
     // L2-resident, because every (tap, m, n) item of a split re-reads them

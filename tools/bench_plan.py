@@ -58,6 +58,10 @@ if __name__ == "__main__":
         wgrad_case(64, 63, 63, 128, 256, pad=0)
         wgrad_case(32, 64, 64, 256, 256)
         wgrad_case(32, 32, 32, 512, 512)
+        wgrad_case(32, 256, 256, 64, 64)
+        wgrad_case(32, 256, 256, 384, 64)
+        wgrad_case(32, 128, 128, 128, 128)
+        wgrad_case(32, 128, 128, 640, 128)
         sys.exit(0)
     for args in [(32, 127, 127, 64, 64, 1), (32, 128, 128, 64, 64, 1), (32, 127, 127, 64, 128, 1),
                  (32, 59, 59, 512, 64, 1), (32, 59, 59, 64, 512, 1), (32, 256, 256, 64, 64, 1)]:
