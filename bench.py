@@ -7,9 +7,10 @@
 One "step" = one full G+D iteration (reference train.py:99-168) on a per-GPU batch of 32 synthetic
 256x256 pairs (configs[1]); N > 1 = one rank per GPU, NCCL gradient allreduce, weak scaling.
 `value` is timed with inputs resident in HBM; `e2e` goes through TrainStep.step_from_host (pinned host
-batch -> H2D -> step -> D2H of the loss scalars). `roofline*` are measured live with CUDA events around
-every implicit-GEMM launch (tensor roofline) and every InstanceNorm tail launch (HBM roofline) of the
-timed steps; `traffic` is the DRAM byte count of one representative launch from the committed ncu capture.
+batch -> H2D -> step -> D2H of the loss scalars). `roofline*` are measured live in the same process with CUDA
+events around every implicit-GEMM launch (tensor roofline) and every InstanceNorm tail launch (HBM roofline) of
+K further steps run with serialised launches; `traffic` is the DRAM byte count of one representative launch
+from the committed ncu capture.
 
 Other workloads (not bench lines; for DESIGN.md / profiles): --gen UNet|BCDUNet, --version 1,
 --workload infer (generator forward only, configs[4]).
@@ -269,13 +270,22 @@ def run_ours(args):
     sampler.start()
     time.sleep(0.3)
     _C.COUNTERS["launches"] = 0
-    _C.TIMING["records"].clear()
-    _C.TIMING["on"] = True
     ms = timed(step_dev, args.steps)
-    _C.TIMING["on"] = False
     launches = _C.COUNTERS["launches"]
     losses = ts.loss_dict() if train else {}
-    # per-kernel-family rooflines from the CUDA events recorded around the launches of the timed steps
+    # Per-kernel-family rooflines: the same K steps again with a CUDA-event pair around every implicit-GEMM and
+    # InstanceNorm-tail launch. The product path overlaps weight gradients (side stream) with the bandwidth-bound
+    # passes, which would fold contention and double counting into per-launch durations, so this pass runs the
+    # launches serialised on one stream; `value` above is the uninstrumented, overlapped path.
+    side = getattr(ts.G, "wgrad_stream", None) if train else None
+    if side is not None:
+        ts.G.wgrad_stream = None
+    _C.TIMING["records"].clear()
+    _C.TIMING["on"] = True
+    ms_roof = timed(step_dev, args.steps)
+    _C.TIMING["on"] = False
+    if side is not None:
+        ts.G.wgrad_stream = side
     agg = {}
     for kind, work, a, b, _tag in _C.TIMING["records"]:
         fam = "tail" if kind.startswith("tail:") else kind
@@ -320,20 +330,23 @@ def run_ours(args):
             line["roofline"] = {"bound": "tensor", "kernel": "igemm_halo_kernel / igemm_conv_kernel (conv forward + "
                                 "input gradient, all shapes)", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s",
                                 "frac": ach / tf_sus, "peak_source": f"bf16_tflops_sustained, {which}",
-                                "traffic": traffic, "traffic_launch": top, "launches": c, "share_of_step": t / ms}
+                                "traffic": traffic, "traffic_launch": top, "launches": c,
+                                "share_of_step": t / ms_roof,
+                                "measured": f"{args.steps} further steps, CUDA events around every launch, launches "
+                                            f"serialised on one stream ({ms_roof / args.steps:.2f} ms/step)"}
         if "wgrad" in agg:
             t, f, c = agg["wgrad"]
             ach = f / (t / 1e3) / 1e12
             line["roofline_wgrad"] = {"bound": "tensor", "kernel": "wgrad_taps_kernel / wgrad_kernel", "achieved": ach,
                                       "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "launches": c,
-                                      "share_of_step": t / ms}
+                                      "share_of_step": t / ms_roof}
         if "tail" in agg:
             t, f, c = agg["tail"]
             ach = f / (t / 1e3) / 1e9
             line["roofline_tail"] = {"bound": "hbm", "kernel": "in_act_fwd / in_bwd_reduce / in_bwd_apply "
                                      "(InstanceNorm + activation forward / backward)", "achieved": ach, "peak": hbm,
                                      "unit": "GB/s", "frac": ach / hbm, "peak_source": f"hbm_gbs, {which}",
-                                     "launches": c, "share_of_step": t / ms}
+                                     "launches": c, "share_of_step": t / ms_roof}
         if world == 1 and not args.no_cpu:
             cb = cpu_baseline(4, 1, 2)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -153,7 +153,7 @@ class TrainStep:
             w.wait()                     # the compute stream waits for the collectives; the host does not block
 
     # ------------------------------------------------------------------ the iteration
-    def step(self, real_A, real_B, regularize=True, alpha=None):
+    def step(self, real_A, real_B, regularize=True, alpha=None, real_B_ready=None):
         """real_A (B,in,H,W) in [-1,1], real_B (B,out,H,W) in [0,1]: fp32, contiguous, on the device.
         Returns the device tensor of loss slots (see SLOT); reading it is the caller's only sync."""
         B, HW = self.B, self.H * self.W
@@ -168,6 +168,8 @@ class TrainStep:
         fake = G.forward(real_A)
         self.fake_B = fake
         # ---- D step (train.py:107-135)
+        if real_B_ready is not None:      # real_B is still arriving on a copy stream (step_from_host)
+            torch.cuda.current_stream().wait_event(real_B_ready)
         ds.zero_grad()
         DA.pack_input(real_A, fake, n0=0, n=B)
         DA.pack_input(real_A, real_B, n0=B, n=B)
@@ -221,9 +223,15 @@ class TrainStep:
         if not hasattr(self, "_dev_A"):
             self._dev_A = torch.empty(host_A.shape, device=self.device)
             self._dev_B = torch.empty(host_B.shape, device=self.device)
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        # the generator forward only needs real_A: the target's H2D copy runs beside it on a copy stream
         self._dev_A.copy_(host_A, non_blocking=True)
-        self._dev_B.copy_(host_B, non_blocking=True)
-        self.step(self._dev_A, self._dev_B, regularize=regularize)
+        ready = torch.cuda.Event()
+        self._copy_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._copy_stream):
+            self._dev_B.copy_(host_B, non_blocking=True)
+            ready.record()
+        self.step(self._dev_A, self._dev_B, regularize=regularize, real_B_ready=ready)
         return self.loss_dict()
 
     def loss_dict(self):
