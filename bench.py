@@ -343,7 +343,7 @@ def run_ours(args):
         if "tail" in agg:
             t, f, c = agg["tail"]
             ach = f / (t / 1e3) / 1e9
-            line["roofline_tail"] = {"bound": "hbm", "kernel": "in_act_fwd / in_bwd_reduce / in_bwd_apply "
+            line["roofline_tail"] = {"bound": "hbm", "kernel": "in_act_fwd / in_bwd_reduce / in_bwd_apply_re "
                                      "(InstanceNorm + activation forward / backward)", "achieved": ach, "peak": hbm,
                                      "unit": "GB/s", "frac": ach / hbm, "peak_source": f"hbm_gbs, {which}",
                                      "launches": c, "share_of_step": t / ms_roof}

@@ -127,6 +127,12 @@ int tg_in_bwd_reduce(const void* raw, const void* y, const float* mr, const floa
                      const float* beta, const void* g_same, const void* g_pool, int pool_mode,
                      const void* g_up, int g_up_pooled, void* dn, float* red, int N, int H, int W, int C,
                      int c_valid, int act, float slope, void* stream);
+/* second pass without a stored dn: re-reads raw and the gradient routes of tg_in_bwd_reduce (dn may be NULL there),
+ * recomputes dn in fp32 and writes dz -- 5 instead of 6 tensor-sizes of HBM traffic per unit */
+int tg_in_bwd_apply_re(const void* raw, const void* y, const float* mr, const float* gamma, const float* beta,
+                       const void* g_same, const void* g_pool, int pool_mode, const void* g_up, int g_up_pooled,
+                       const float* red, void* dz, int N, int H, int W, int C, int c_valid, int act, float slope,
+                       float* dgamma, float* dbeta, void* stream);
 /* dgamma / dbeta (optional, fp32 [c_valid]): += the affine gradients, i.e. what tg_affine_grad computes */
 int tg_in_bwd_apply(const void* dn, const void* raw, const float* mr, const float* gamma,
                     const float* red, void* dz, int N, int HW, int C, int c_valid, float* dgamma, float* dbeta,

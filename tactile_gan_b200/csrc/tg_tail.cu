@@ -418,6 +418,10 @@ struct InBwdArgs {
   int N, H, W, C, c_valid, act, pool_mode;
   int up_pooled;              // g_up is already summed to this tensor's resolution (pool_out conv epilogue)
   float slope;
+  // second pass (PASS == 1): dz = P*dn + Q*raw + R with dn recomputed from the same loads; optional affine gradients
+  __nv_bfloat16* dz;
+  float* dgamma;
+  float* dbeta;
 };
 
 // Per-pixel work of the backward reduce for the general case (pooled / upsampled gradient routes).
@@ -479,13 +483,30 @@ __device__ __forceinline__ void in_bwd_gather(const InBwdArgs& a, int n, int pix
 
 // PLAIN: the only gradient route is g_same (no pooled / upsampled copies) -> four pixels per iteration with
 // all eight 16-byte loads in flight before the first use.
-template <bool PLAIN>
+// PASS 0: statistics pass -- red[n][c] += (sum dn, sum dn*xhat); dn is stored only if a.dn is given (the GP double
+//         backward keeps it) or the layer has no norm (then dn IS dz).
+// PASS 1: apply pass -- the same loads again (raw + the gradient routes, 2 tensors for a plain unit), dn recomputed
+//         in fp32 and dz = rstd*gamma*(dn - mean(dn) - xhat*mean(dn*xhat)) written: the backward of a unit moves
+//         5 tensor-sizes through HBM instead of the 6 of "store dn, re-read dn".
+template <bool PLAIN, int PASS>
 __global__ void __launch_bounds__(256, 2) in_bwd_reduce_kernel(const InBwdArgs a) {
   extern __shared__ float shm[];  // [PL][C][2]
   const int n = blockIdx.y;
   const int HW = a.H * a.W;
   const StripIdx t = strip_index(a.C, HW);
   const int c0 = t.c0;
+  if (PASS == 1 && (a.dgamma || a.dbeta) && blockIdx.x == 0 && blockIdx.y == 0) {
+    // affine gradients ride along (one block): dgamma[c] += sum_n red[n][c][1], dbeta[c] += sum_n red[n][c][0]
+    for (int c = threadIdx.x; c < a.c_valid; c += blockDim.x) {
+      float g = 0.f, b = 0.f;
+      for (int k = 0; k < a.N; ++k) {
+        b += a.red[(size_t(k) * a.C + c) * 2];
+        g += a.red[(size_t(k) * a.C + c) * 2 + 1];
+      }
+      if (a.dgamma) atomicAdd(a.dgamma + c, g);
+      if (a.dbeta) atomicAdd(a.dbeta + c, b);
+    }
+  }
   // n = A*raw + B (pre-activation); xhat = (raw - mean)*rstd is folded into the finalisation:
   // sum dn*xhat = rstd * (sum dn*raw - mean * sum dn)
   float A[8], B[8];
@@ -499,6 +520,20 @@ __global__ void __launch_bounds__(256, 2) in_bwd_reduce_kernel(const InBwdArgs a
     B[j] = b - mean * A[j];
   }
   float s0[8] = {0}, s1[8] = {0};
+  float P[8], Q[8], R[8];
+  if (PASS == 1) {
+    const float inv = 1.f / float(HW);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const size_t k = size_t(n) * a.C + c0 + j;
+      const float g = ld_aff(a.gamma, c0 + j, a.c_valid, 1.f);
+      const float mean = a.mr[k * 2], rstd = a.mr[k * 2 + 1];
+      const float am = a.red[k * 2] * inv, bm = a.red[k * 2 + 1] * inv;
+      P[j] = g * rstd;
+      Q[j] = -g * rstd * rstd * bm;
+      R[j] = -P[j] * am - Q[j] * mean;
+    }
+  }
   const __nv_bfloat16* src = a.raw ? a.raw : a.y;
   const bool has_raw = a.raw != nullptr;
   const int act = a.act;
@@ -506,6 +541,15 @@ __global__ void __launch_bounds__(256, 2) in_bwd_reduce_kernel(const InBwdArgs a
   auto finish = [&](const uint4& vr, float (&g)[8], size_t lin) {
     float r[8];
     unpack8(vr, r);
+    if (PASS == 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dn = g[j] * act_grad(fmaf(r[j], A[j], B[j]), act, slope);
+        g[j] = fmaf(P[j], dn, fmaf(Q[j], r[j], R[j]));
+      }
+      stg16(a.dz + lin, pack8(g));
+      return;
+    }
     if (has_raw) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -517,7 +561,7 @@ __global__ void __launch_bounds__(256, 2) in_bwd_reduce_kernel(const InBwdArgs a
 #pragma unroll
       for (int j = 0; j < 8; ++j) g[j] *= act_grad(r[j], act, slope);
     }
-    stg16(a.dn + lin, pack8(g));
+    if (a.dn) stg16(a.dn + lin, pack8(g));
   };
   if (t.pl < t.PL) {
     const size_t img = size_t(n) * HW;
@@ -586,7 +630,7 @@ __global__ void __launch_bounds__(256, 2) in_bwd_reduce_kernel(const InBwdArgs a
       }
     }
   }
-  if (!a.red) return;
+  if (PASS == 1 || !a.red) return;
   float* shp = shm + (size_t(t.pl) * a.C + c0) * 2;
   if (t.pl < t.PL) {
 #pragma unroll
@@ -1511,6 +1555,7 @@ int tg_in_bwd_reduce(const void* raw, const void* y, const float* mr, const floa
                      int c_valid, int act, float slope, void* stream) {
   InBwdArgs a;
   a.up_pooled = g_up_pooled;
+  a.dz = nullptr; a.dgamma = nullptr; a.dbeta = nullptr;
   a.raw = (const __nv_bfloat16*)raw; a.y = (const __nv_bfloat16*)y; a.mr = mr; a.gamma = gamma;
   a.beta = beta; a.g_same = (const __nv_bfloat16*)g_same; a.g_pool = (const __nv_bfloat16*)g_pool;
   a.g_up = (const __nv_bfloat16*)g_up; a.dn = (__nv_bfloat16*)dn; a.red = red;
@@ -1521,9 +1566,33 @@ int tg_in_bwd_reduce(const void* raw, const void* y, const float* mr, const floa
   const int PL = block / (C / 8);
   const size_t smem = red ? size_t(PL) * C * 2 * sizeof(float) : 0;
   dim3 grid(strip_count(H * W, C, N, 16), N);
+  if (!raw && !dn) return tg_set_error("tg_in_bwd_reduce: a layer without norm needs the dn (= dz) output");
   const bool plain = !g_pool && (g_same || g_up) && (!g_up || g_up_pooled);
-  if (plain) in_bwd_reduce_kernel<true><<<grid, block, smem, TG_STREAM(stream)>>>(a);
-  else in_bwd_reduce_kernel<false><<<grid, block, smem, TG_STREAM(stream)>>>(a);
+  if (plain) in_bwd_reduce_kernel<true, 0><<<grid, block, smem, TG_STREAM(stream)>>>(a);
+  else in_bwd_reduce_kernel<false, 0><<<grid, block, smem, TG_STREAM(stream)>>>(a);
+  TG_RET();
+}
+
+// Second pass of the InstanceNorm backward without a stored dn: re-reads raw and the gradient routes, recomputes
+// dn and writes dz (see in_bwd_reduce_kernel PASS 1). red must hold the sums of tg_in_bwd_reduce on the same inputs.
+int tg_in_bwd_apply_re(const void* raw, const void* y, const float* mr, const float* gamma, const float* beta,
+                       const void* g_same, const void* g_pool, int pool_mode, const void* g_up, int g_up_pooled,
+                       const float* red, void* dz, int N, int H, int W, int C, int c_valid, int act, float slope,
+                       float* dgamma, float* dbeta, void* stream) {
+  if (!raw || !mr || !red || !dz) return tg_set_error("tg_in_bwd_apply_re: null argument");
+  InBwdArgs a;
+  a.raw = (const __nv_bfloat16*)raw; a.y = (const __nv_bfloat16*)y; a.mr = mr; a.gamma = gamma;
+  a.beta = beta; a.g_same = (const __nv_bfloat16*)g_same; a.g_pool = (const __nv_bfloat16*)g_pool;
+  a.g_up = (const __nv_bfloat16*)g_up; a.dn = nullptr; a.red = const_cast<float*>(red);
+  a.N = N; a.H = H; a.W = W; a.C = C; a.c_valid = c_valid; a.act = act; a.pool_mode = pool_mode; a.slope = slope;
+  a.up_pooled = g_up_pooled;
+  a.dz = (__nv_bfloat16*)dz; a.dgamma = dgamma; a.dbeta = dbeta;
+  const int block = strip_block(C);
+  if (block > 1024) return tg_set_error("tg_in_bwd_apply_re: C too large");
+  dim3 grid(strip_count(H * W, C, N, 16), N);
+  const bool plain = !g_pool && (g_same || g_up) && (!g_up || g_up_pooled);
+  if (plain) in_bwd_reduce_kernel<true, 1><<<grid, block, 0, TG_STREAM(stream)>>>(a);
+  else in_bwd_reduce_kernel<false, 1><<<grid, block, 0, TG_STREAM(stream)>>>(a);
   TG_RET();
 }
 

@@ -159,16 +159,19 @@ class ConvUnit:
         if self.norm:
             self.red.zero_()
             elems = 2.0 * n * ho * wo * c      # bytes of one bf16 tensor of this unit
-            nb = elems * (2 + (1 if g_same is not None else 0) + (0.25 if g_pool is not None else 0) +
-                          ((1 if up_pooled else 4) if g_up is not None else 0))
+            routes = ((1 if g_same is not None else 0) + (0.25 if g_pool is not None else 0) +
+                      ((1 if up_pooled else 4) if g_up is not None else 0))
+            keep = keep_dn and self.norm
+            # pass 1: statistics of dn = g * act'(n) (dn itself is stored only for the GP double backward);
+            # pass 2: the same loads again, dn recomputed, dz written -- 5 tensor-sizes instead of 6
             _C.call("in_bwd_reduce", ptr(self.raw), ptr(self.y.buf), ptr(self.mr), g, b, ptr(g_same), ptr(g_pool),
-                    self.pool_mode, ptr(g_up), up_pooled, ptr(dn), ptr(self.red), n, ho, wo, c, self.c_valid,
-                    self.act, F(self.slope), nbytes=nb)
+                    self.pool_mode, ptr(g_up), up_pooled, ptr(dn) if keep else None, ptr(self.red), n, ho, wo, c,
+                    self.c_valid, self.act, F(self.slope), nbytes=elems * (1 + routes + (1 if keep else 0)))
             aff = wgrad and self.gamma is not None
-            _C.call("in_bwd_apply", ptr(dn), ptr(self.raw), ptr(self.mr), g, ptr(self.red),
-                    ptr(self.dz), n, ho * wo, c, self.c_valid,
-                    ptr(eng.store.grad_of(self.gamma)) if aff else None,
-                    ptr(eng.store.grad_of(self.beta)) if aff else None, nbytes=3 * elems)
+            _C.call("in_bwd_apply_re", ptr(self.raw), ptr(self.y.buf), ptr(self.mr), g, b, ptr(g_same), ptr(g_pool),
+                    self.pool_mode, ptr(g_up), up_pooled, ptr(self.red), ptr(self.dz), n, ho, wo, c, self.c_valid,
+                    self.act, F(self.slope), ptr(eng.store.grad_of(self.gamma)) if aff else None,
+                    ptr(eng.store.grad_of(self.beta)) if aff else None, nbytes=elems * (2 + routes))
         else:
             _C.call("in_bwd_reduce", None, ptr(self.y.buf), None, None, None, ptr(g_same), ptr(g_pool),
                     self.pool_mode, ptr(g_up), up_pooled, ptr(self.dz), None, n, ho, wo, c, self.c_valid, self.act,
@@ -770,11 +773,11 @@ class PatchDInstance(GraphEngine):
                 red = so["red_dn"][k - 1]
                 red.zero_()
                 _C.call("in_bwd_reduce", ptr(x.raw), ptr(x.y.buf), ptr(x.mr), g, b, ptr(e), None, 0, None, 0,
-                        ptr(self.dn_scratch), ptr(red), x.n, x.ho, x.wo, x.c, x.c_valid, ACT_LRELU, F(0.2))
+                        None, ptr(red), x.n, x.ho, x.wo, x.c, x.c_valid, ACT_LRELU, F(0.2))
                 aff = x.gamma is not None
-                _C.call("in_bwd_apply", ptr(self.dn_scratch), ptr(x.raw), ptr(x.mr), g, ptr(red), ptr(z), x.n,
-                        x.ho * x.wo, x.c, x.c_valid, ptr(st.grad_of(x.gamma)) if aff else None,
-                        ptr(st.grad_of(x.beta)) if aff else None)
+                _C.call("in_bwd_apply_re", ptr(x.raw), ptr(x.y.buf), ptr(x.mr), g, b, ptr(e), None, 0, None, 0,
+                        ptr(red), ptr(z), x.n, x.ho, x.wo, x.c, x.c_valid, ACT_LRELU, F(0.2),
+                        ptr(st.grad_of(x.gamma)) if aff else None, ptr(st.grad_of(x.beta)) if aff else None)
                 _C.call("add", ptr(z), ptr(so["INJ"][k - 1]), ptr(z), LL(z.numel()))
             else:
                 _C.call("act_bwd", ptr(e), ptr(x.y.buf), ptr(z), LL(z.numel()), ACT_LRELU, F(0.2))

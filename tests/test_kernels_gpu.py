@@ -184,6 +184,17 @@ def test_instance_norm_forward_backward_pool_upsample():
     torch.cuda.synchronize()
     assert rel(dz[..., :c].permute(0, 3, 1, 2), dx_ref) < 1e-2   # dn is stored as bf16
     assert rel(dgam, dg_ref) < 5e-3 and rel(dbet, db_ref) < 5e-3
+    # the path the engines use: statistics pass without a dn store, then the recomputing apply pass
+    for up_ptr, up_pooled in ((ptr(gu_p), 0), (ptr(gu_lo), 1)):
+        red_c, dz_c = torch.zeros(n, cp, 2, device=dev), torch.zeros_like(raw)
+        dgam_c, dbet_c = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
+        C.call("in_bwd_reduce", ptr(raw), ptr(y), ptr(mr), ptr(gamma), ptr(beta), ptr(gs_p), ptr(gp_p), 1, up_ptr,
+               up_pooled, None, ptr(red_c), n, h, w, cp, c, 3, f32(0.0))
+        C.call("in_bwd_apply_re", ptr(raw), ptr(y), ptr(mr), ptr(gamma), ptr(beta), ptr(gs_p), ptr(gp_p), 1, up_ptr,
+               up_pooled, ptr(red_c), ptr(dz_c), n, h, w, cp, c, 3, f32(0.0), ptr(dgam_c), ptr(dbet_c))
+        torch.cuda.synchronize()
+        assert rel(dz_c[..., :c].permute(0, 3, 1, 2), dx_ref) < 1e-2
+        assert rel(dgam_c, dg_ref) < 6e-3 and rel(dbet_c, db_ref) < 6e-3
 
 
 def test_adam_kernel_matches_torch_adam():
