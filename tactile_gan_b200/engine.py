@@ -161,17 +161,25 @@ class ConvUnit:
             elems = 2.0 * n * ho * wo * c      # bytes of one bf16 tensor of this unit
             routes = ((1 if g_same is not None else 0) + (0.25 if g_pool is not None else 0) +
                       ((1 if up_pooled else 4) if g_up is not None else 0))
-            keep = keep_dn and self.norm
+            # max-pool routing re-reads the 2x2 window of y per pixel: too dear to do twice, keep dn for that route
+            stored = g_pool is not None and self.pool_mode == 2
+            keep = (keep_dn and self.norm) or stored
+            routes += 4 if stored else 0
             # pass 1: statistics of dn = g * act'(n) (dn itself is stored only for the GP double backward);
             # pass 2: the same loads again, dn recomputed, dz written -- 5 tensor-sizes instead of 6
             _C.call("in_bwd_reduce", ptr(self.raw), ptr(self.y.buf), ptr(self.mr), g, b, ptr(g_same), ptr(g_pool),
                     self.pool_mode, ptr(g_up), up_pooled, ptr(dn) if keep else None, ptr(self.red), n, ho, wo, c,
                     self.c_valid, self.act, F(self.slope), nbytes=elems * (1 + routes + (1 if keep else 0)))
             aff = wgrad and self.gamma is not None
-            _C.call("in_bwd_apply_re", ptr(self.raw), ptr(self.y.buf), ptr(self.mr), g, b, ptr(g_same), ptr(g_pool),
-                    self.pool_mode, ptr(g_up), up_pooled, ptr(self.red), ptr(self.dz), n, ho, wo, c, self.c_valid,
-                    self.act, F(self.slope), ptr(eng.store.grad_of(self.gamma)) if aff else None,
-                    ptr(eng.store.grad_of(self.beta)) if aff else None, nbytes=elems * (2 + routes))
+            dg = ptr(eng.store.grad_of(self.gamma)) if aff else None
+            db = ptr(eng.store.grad_of(self.beta)) if aff else None
+            if stored:
+                _C.call("in_bwd_apply", ptr(dn), ptr(self.raw), ptr(self.mr), g, ptr(self.red), ptr(self.dz), n,
+                        ho * wo, c, self.c_valid, dg, db, nbytes=3 * elems)
+            else:
+                _C.call("in_bwd_apply_re", ptr(self.raw), ptr(self.y.buf), ptr(self.mr), g, b, ptr(g_same),
+                        ptr(g_pool), self.pool_mode, ptr(g_up), up_pooled, ptr(self.red), ptr(self.dz), n, ho, wo, c,
+                        self.c_valid, self.act, F(self.slope), dg, db, nbytes=elems * (2 + routes))
         else:
             _C.call("in_bwd_reduce", None, ptr(self.y.buf), None, None, None, ptr(g_same), ptr(g_pool),
                     self.pool_mode, ptr(g_up), up_pooled, ptr(self.dz), None, n, ho, wo, c, self.c_valid, self.act,
