@@ -175,6 +175,21 @@ int tg_augment_pair(const void* img_u8, const void* mask_u8, const long long* pa
  *      sum min(o, r), sum r); accuracy = s2/s3, dice = 2 s0/s1, jaccard = s0/(s1 - s0) */
 int tg_eval_fuzzy(const float* out, const float* real, int N, long long per_img, float* stats, void* stream);
 
+/* ---- ConvLSTM / ConvBLSTM skip modules of BCDUNet (generators/BCDUNet.py:6-103; constructed at :145-152, never
+ *      called by the reference forward -- SURVEY 8f row 4). The gate conv over cat[X, H_prev] is an ordinary
+ *      two-source implicit GEMM (tg_conv_plan_create, 4*C output channels + bias); these two finish the cell:
+ *      tg_pack_nchw_tiled: fp32 NCHW time slice (image stride in elements) -> bf16 NHWC, any channel count;
+ *      tg_convlstm_gates: i/f/g/o peephole gates (BCDUNet.py:36-45) on z = bf16 NHWC [N][HW][zc] with the gate
+ *      groups at channel offsets 0, C, 2C, 3C; W_c* fp32 [C][HW]; cell state and H in fp32 NCHW (image strides in
+ *      elements; c_prev NULL = zero state, may alias c_out); H also as bf16 NHWC [N][HW][hc] for the next step's
+ *      conv (h_out or h_nhwc may be NULL). act: 3 relu, 4 tanh. */
+int tg_pack_nchw_tiled(const float* in, long long in_stride_n, void* out, int N, int C, int HW, int Cpad,
+                       void* stream);
+int tg_convlstm_gates(const void* z, int zc, const float* w_ci, const float* w_cf, const float* w_co,
+                      const float* c_prev, long long c_prev_stride_n, float* c_out, long long c_out_stride_n,
+                      float* h_out, long long h_out_stride_n, void* h_nhwc, int hc, int N, int HW, int C, int act,
+                      void* stream);
+
 /* ---- losses: GANLoss (generators/generators.py:80-105), nn.L1Loss (train.py:145), pan_loss
  *      (util.py:41-70), gradient_penalty norm (util.py:92-93) */
 int tg_gan_loss(const void* pred, const float* label, float label_const, int mode, int target_is_real,

@@ -171,6 +171,46 @@ def eval_case(seed=51):
     return dict(meta=dict(seed=seed), results=[ns["eval_pair"](real[i], out[i]) for i in range(3)])
 
 
+def convlstm_case(seed=61):
+    """The reference's own ConvLSTMCell / ConvLSTM / ConvBLSTM classes (generators/BCDUNet.py:6-103), run on the CPU
+    (their `self.device` falls back to cpu when CUDA is absent). Conv weights N(0, 0.1) so the gates leave the linear
+    region; peepholes keep the reference's Xavier init."""
+    sys.path.insert(0, REF)
+    from generators import BCDUNet as ref
+    out = dict(meta=dict(seed=seed, torch=torch.__version__), cases=OrderedDict())
+    specs = [("cell_tanh", "cell", 24, 16, "tanh", 1), ("lstm_tanh", "lstm", 16, 8, "tanh", 3),
+             ("lstm_relu", "lstm", 8, 8, "relu", 2), ("blstm_tanh", "blstm", 16, 16, "tanh", 3)]
+    for name, kind, cin, cout, act, t in specs:
+        torch.manual_seed(seed)
+        frame, b = (16, 24), 2
+        if kind == "cell":
+            m = ref.ConvLSTMCell(cin, cout, (3, 3), (1, 1), act, frame)
+        elif kind == "lstm":
+            m = ref.ConvLSTM(cin, cout, (3, 3), (1, 1), act, frame, return_sequence=True)
+        else:
+            m = ref.ConvBLSTM(cin, cout, (3, 3), (1, 1), act, frame, return_sequence=True)
+        with torch.no_grad():
+            for k, p in m.named_parameters():
+                if k.endswith("conv.weight"):
+                    p.normal_(0, 0.1)
+                elif k.endswith("conv.bias"):
+                    p.normal_(0, 0.2)
+        g = torch.Generator().manual_seed(seed + 1)
+        with torch.no_grad():
+            if kind == "cell":
+                x = torch.randn(b, cin, *frame, generator=g)
+                h0 = torch.randn(b, cout, *frame, generator=g) * 0.5
+                c0 = torch.randn(b, cout, *frame, generator=g)
+                h, c = m(x, h0, c0)
+                io = dict(x=x, h0=h0, c0=c0, h=h, c=c)
+            else:
+                x = torch.randn(b, t, cin, *frame, generator=g)
+                io = dict(x=x, out=m(x))
+        out["cases"][name] = dict(kind=kind, cin=cin, cout=cout, act=act, frame=frame,
+                                  sd=OrderedDict((k, v.clone()) for k, v in m.state_dict().items()), **io)
+    return out
+
+
 def state_dict_keys():
     """Key/shape inventory of all reference networks at nf=64 (the checkpoint-layout contract)."""
     _, create_gen, _, create_disc = reference_modules()
@@ -207,5 +247,6 @@ if __name__ == "__main__":
         torch.save(fx, os.path.join(OUT, f"{name}.pt"))
         print(name, fx["loss"], fx["grad_norm"])
     torch.save(eval_case(), os.path.join(OUT, "eval_pair_fuzzy.pt"))
+    torch.save(convlstm_case(), os.path.join(OUT, "convlstm.pt"))
     torch.save(state_dict_keys(), os.path.join(OUT, "state_dict_keys.pt"))
     print("wrote", OUT)

@@ -17,6 +17,9 @@ What follows which reference lines (all under /root/reference):
   augment_pair     datasets/PairedDataset.py:30-44,80-92 (flip + affine + ToTensor/Normalize). PARITY UNPINNED: the
                    arithmetic belongs to albumentations (unpinned, not installed); this restates the transform
                    tactile_gan_b200/augment.py specifies (inverse map in 16.16 fixed point), not albumentations' own.
+  convlstm_cell / convlstm / convblstm   generators/BCDUNet.py:32-47 (cell), :61-84 (unrolled sequence, zero initial
+                   state), :96-103 (bidirectional: second cell on the reversed frames, channel concat). Constructed by
+                   BCDUNet but never called by its forward; pinned by tests/golden/convlstm.pt (reference classes run here)
   adam_update      torch.optim.Adam as configured at train.py:56-57 (betas=(beta1,0.99), eps=1e-8)
   train_step       train.py:99-168
 
@@ -288,6 +291,41 @@ def eval_pair_fuzzy(real, out):
 
 
 # --------------------------------------------------------------------------- optimiser
+def convlstm_cell(sd, x, h_prev, c_prev, activation="tanh", prefix=""):
+    """BCDUNet.py:32-47. sd keys: conv.weight [4C, Cin+C, k, k], conv.bias, W_ci / W_cf / W_co [C, H, W]."""
+    act = torch.tanh if activation == "tanh" else torch.relu
+    w = sd[prefix + "conv.weight"]
+    z = F.conv2d(torch.cat([_q(x), _q(h_prev)], 1), _q(w), sd[prefix + "conv.bias"], padding=w.shape[2] // 2)
+    zi, zf, zg, zo = torch.chunk(_q(z), 4, dim=1)
+    i = torch.sigmoid(zi + sd[prefix + "W_ci"] * c_prev)
+    f = torch.sigmoid(zf + sd[prefix + "W_cf"] * c_prev)
+    c = f * c_prev + i * act(zg)
+    o = torch.sigmoid(zo + sd[prefix + "W_co"] * c)
+    return o * act(c), c
+
+
+def convlstm(sd, x, activation="tanh", prefix="convLSTMcell.", return_sequence=True):
+    """BCDUNet.py:61-84: x (B,T,Cin,H,W) -> (B,T,C,H,W) (or the last frame)."""
+    b, t, _, hh, ww = x.shape
+    c_out = sd[prefix + "W_ci"].shape[0]
+    h = x.new_zeros(b, c_out, hh, ww)
+    c = x.new_zeros(b, c_out, hh, ww)
+    outs = []
+    for k in range(t):
+        h, c = convlstm_cell(sd, x[:, k], h, c, activation, prefix)
+        outs.append(h)
+    out = torch.stack(outs, 1)
+    return out if return_sequence else out[:, -1]
+
+
+def convblstm(sd, x, activation="tanh", return_sequence=True):
+    """BCDUNet.py:96-103."""
+    fwd = convlstm(sd, x, activation, "forward_cell.convLSTMcell.")
+    bwd = convlstm(sd, x.flip(1), activation, "backward_cell.convLSTMcell.").flip(1)
+    out = torch.cat((fwd, bwd), dim=2)
+    return out if return_sequence else out[:, -1]
+
+
 def adam_update(params, grads, state, lr, beta1, beta2=0.99, eps=1e-8):
     """In-place Adam on dicts keyed by parameter name; state[name] = dict(step, exp_avg, exp_avg_sq)."""
     for k, p in params.items():

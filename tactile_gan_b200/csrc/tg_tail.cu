@@ -1314,6 +1314,93 @@ __global__ void eval_fuzzy_kernel(const float* __restrict__ o, const float* __re
   t = block_sum(a3, sh); if (threadIdx.x == 0) atomicAdd(stats + n * 4 + 3, t);
 }
 
+// ------------------------------------------------------------------ ConvLSTM (generators/BCDUNet.py:6-103)
+// fp32 NCHW (image stride sn elements, so a time slice X[:, t] of a (B,T,C,H,W) sequence needs no copy) ->
+// bf16 NHWC [N][HW][Cpad]; channels >= C of the row are written as zero. One 64-pixel x 64-channel tile per block
+// through shared memory: coalesced 256-byte reads along pixels, 16-byte vector writes along channels.
+__global__ void __launch_bounds__(256)
+pack_nchw_tiled_kernel(const float* __restrict__ in, long long sn, __nv_bfloat16* __restrict__ out, int C, int HW,
+                       int Cpad) {
+  __shared__ float t[64][65];
+  const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+  for (int i = threadIdx.x; i < 4096; i += 256) {
+    const int cl = i >> 6, pl = i & 63;
+    const int c = c0 + cl, p = p0 + pl;
+    t[cl][pl] = (c < C && p < HW) ? __ldg(in + size_t(n) * sn + size_t(c) * HW + p) : 0.f;
+  }
+  __syncthreads();
+  for (int v = threadIdx.x; v < 512; v += 256) {
+    const int pl = v >> 3, k = v & 7;
+    const int p = p0 + pl, c = c0 + 8 * k;
+    if (p < HW && c < Cpad) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = t[8 * k + j][pl];
+      stg16(out + (size_t(n) * HW + p) * Cpad + c, pack8(f));
+    }
+  }
+}
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// Peephole gates of one ConvLSTM time step (BCDUNet.py:32-47). z = conv(cat[X, H_prev]) + bias arrives from the
+// implicit-GEMM kernel as bf16 NHWC with the four gate groups i | f | g | o at channel offsets 0, C, 2C, 3C; the
+// cell state, the peepholes W_c* [C][H][W] and the returned H live in the module's own fp32 NCHW layout. A block
+// owns 32 pixels x 32 channels: the z tile is transposed through shared memory so that phase 1 reads NHWC rows with
+// 16-byte vectors and phase 2 walks pixel-fastest over the NCHW tensors (128-byte segments per channel row).
+//   i = s(zi + W_ci*c)   f = s(zf + W_cf*c)   c' = f*c + i*act(zg)   o = s(zo + W_co*c')   h = o*act(c')
+// h is written twice: fp32 NCHW (module output / sequence slot, image stride h_sn) and bf16 NHWC (the next step's
+// conv operand). c_prev == nullptr: zero state (first step). c_prev may alias c_out.
+__global__ void __launch_bounds__(256)
+convlstm_gates_kernel(const __nv_bfloat16* __restrict__ z, int zc, const float* __restrict__ w_ci,
+                      const float* __restrict__ w_cf, const float* __restrict__ w_co, const float* c_prev,
+                      long long cp_sn, float* c_out, long long co_sn, float* __restrict__ h_out, long long h_sn,
+                      __nv_bfloat16* __restrict__ h_nhwc, int hc, int HW, int C, int act) {
+  __shared__ float zt[4][32][33];
+  __shared__ float ht[32][33];
+  const int n = blockIdx.z, cb = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  for (int v = threadIdx.x; v < 512; v += 256) {
+    const int g = v >> 7, pl = (v >> 2) & 31, k = v & 3;
+    const int p = p0 + pl, c = cb + 8 * k;
+    if (p < HW && c < C) {
+      float f[8];
+      unpack8(ldg16(z + (size_t(n) * HW + p) * zc + g * C + c), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) zt[g][pl][8 * k + j] = f[j];
+    }
+  }
+  __syncthreads();
+  const int pl = threadIdx.x & 31, p = p0 + pl;
+  for (int cl = threadIdx.x >> 5; cl < 32; cl += 8) {
+    const int c = cb + cl;
+    float h = 0.f;
+    if (c < C && p < HW) {
+      const size_t idx = size_t(c) * HW + p;
+      const float cp = c_prev ? c_prev[size_t(n) * cp_sn + idx] : 0.f;
+      const float gi = sigmoid_f(zt[0][pl][cl] + __ldg(w_ci + idx) * cp);
+      const float gf = sigmoid_f(zt[1][pl][cl] + __ldg(w_cf + idx) * cp);
+      const float zg = zt[2][pl][cl];
+      const float cn = gf * cp + gi * (act == 4 ? tanhf(zg) : fmaxf(zg, 0.f));
+      const float go = sigmoid_f(zt[3][pl][cl] + __ldg(w_co + idx) * cn);
+      h = go * (act == 4 ? tanhf(cn) : fmaxf(cn, 0.f));
+      c_out[size_t(n) * co_sn + idx] = cn;
+      if (h_out) h_out[size_t(n) * h_sn + idx] = h;
+    }
+    ht[pl][cl] = h;
+  }
+  __syncthreads();
+  if (h_nhwc && threadIdx.x < 128) {
+    const int ql = threadIdx.x >> 2, k = threadIdx.x & 3;
+    const int q = p0 + ql, c = cb + 8 * k;
+    if (q < HW && c < C) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = ht[ql][8 * k + j];
+      stg16(h_nhwc + (size_t(n) * HW + q) * hc + c, pack8(f));
+    }
+  }
+}
+
 // Gradient penalty: nsq[n] = sum_{pix, j<cj} (g[n,pix,c_off+j] + 1e-16)^2
 __global__ void gp_normsq_kernel(const __nv_bfloat16* __restrict__ g, int HW, int C, int c_off, int cj,
                                  float* __restrict__ nsq) {
@@ -1758,6 +1845,28 @@ int tg_augment_pair(const void* img_u8, const void* mask_u8, const long long* pa
 int tg_eval_fuzzy(const float* out, const float* real, int N, long long per_img, float* stats, void* stream) {
   dim3 grid(grid_for(size_t(per_img), 256, 32), N);
   eval_fuzzy_kernel<<<grid, 256, 0, TG_STREAM(stream)>>>(out, real, size_t(per_img), stats);
+  TG_RET();
+}
+
+int tg_pack_nchw_tiled(const float* in, long long in_stride_n, void* out, int N, int C, int HW, int Cpad,
+                       void* stream) {
+  if (Cpad % 8 || C > Cpad) return tg_set_error("tg_pack_nchw_tiled: Cpad must be a multiple of 8 and >= C");
+  dim3 grid((HW + 63) / 64, (Cpad + 63) / 64, N);
+  pack_nchw_tiled_kernel<<<grid, 256, 0, TG_STREAM(stream)>>>(in, in_stride_n, (__nv_bfloat16*)out, C, HW, Cpad);
+  TG_RET();
+}
+
+int tg_convlstm_gates(const void* z, int zc, const float* w_ci, const float* w_cf, const float* w_co,
+                      const float* c_prev, long long c_prev_stride_n, float* c_out, long long c_out_stride_n,
+                      float* h_out, long long h_out_stride_n, void* h_nhwc, int hc, int N, int HW, int C, int act,
+                      void* stream) {
+  if (C % 8 || zc < 4 * C || zc % 8) return tg_set_error("tg_convlstm_gates: C % 8 == 0 and zc >= 4*C required");
+  if (h_nhwc && (hc < C || hc % 8)) return tg_set_error("tg_convlstm_gates: hc must be a multiple of 8 and >= C");
+  if (act != 3 && act != 4) return tg_set_error("tg_convlstm_gates: activation must be relu (3) or tanh (4)");
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, N);
+  convlstm_gates_kernel<<<grid, 256, 0, TG_STREAM(stream)>>>(
+      (const __nv_bfloat16*)z, zc, w_ci, w_cf, w_co, c_prev, c_prev_stride_n, c_out, c_out_stride_n, h_out,
+      h_out_stride_n, (__nv_bfloat16*)h_nhwc, hc, HW, C, act);
   TG_RET();
 }
 

@@ -1,8 +1,9 @@
 """BCDUNet generator with the reference's constructor and parameter names (reference:
 generators/BCDUNet.py). The reference constructs ConvLSTM / ConvBLSTM skip modules but never calls them
-in forward (BCDUNet.py:154-181): they are kept here as parameter holders (30 state_dict keys,
-Xavier-initialised peepholes) and as plain callable modules, outside the engine's hot path.
-forward() runs engine.BCDUNetEngine."""
+in forward (BCDUNet.py:154-181): inside BCDUNet they are parameter holders (30 state_dict keys,
+Xavier-initialised peepholes). Called on their own they run the device engine of
+tactile_gan_b200/convlstm.py (two-source implicit GEMM + fused gate kernel, forward only, no eager fallback).
+BCDUNet.forward() runs engine.BCDUNetEngine."""
 import numpy as np
 import torch
 import torch.nn as nn
@@ -23,10 +24,8 @@ class ConvLSTMCell(nn.Module):
             setattr(self, name, w)
 
     def forward(self, X, H_prev, C_prev):
-        i, f, g, o = torch.chunk(self.conv(torch.cat([X, H_prev], dim=1)), 4, dim=1)
-        C = torch.sigmoid(f + self.W_cf * C_prev) * C_prev + torch.sigmoid(i + self.W_ci * C_prev) * self.activation(g)
-        H = torch.sigmoid(o + self.W_co * C) * self.activation(C)
-        return H, C
+        from ..convlstm import cell_forward
+        return cell_forward(self, X, H_prev, C_prev)
 
 
 class ConvLSTM(nn.Module):
@@ -36,15 +35,10 @@ class ConvLSTM(nn.Module):
         self.convLSTMcell = ConvLSTMCell(in_channels, out_channels, kernel_size, padding, activation, frame_size)
 
     def forward(self, X):
-        b, t, _, h, w = X.shape
-        H = X.new_zeros(b, self.out_channels, h, w)
-        C = X.new_zeros(b, self.out_channels, h, w)
-        outs = []
-        for step in range(t):
-            H, C = self.convLSTMcell(X[:, step], H, C)
-            outs.append(H)
-        out = torch.stack(outs, 1)
-        return out if self.return_sequence else out[:, -1]
+        """X: (batch, seq_len, channels, height, width) -> (batch, seq_len, out_channels, H, W), or the last frame's
+        H when return_sequence is False (reference BCDUNet.py:61-84)."""
+        from ..convlstm import lstm_forward
+        return lstm_forward(self, X)
 
 
 class ConvBLSTM(nn.Module):
@@ -56,10 +50,8 @@ class ConvBLSTM(nn.Module):
         self.backward_cell = ConvLSTM(*args, return_sequence=True)
 
     def forward(self, x):
-        fwd = self.forward_cell(x)
-        bwd = self.backward_cell(x.flip(1)).flip(1)
-        out = torch.cat((fwd, bwd), dim=2)
-        return out if self.return_sequence else out[:, -1]
+        from ..convlstm import blstm_forward
+        return blstm_forward(self, x)
 
 
 class BCDUNet(EngineModule):

@@ -386,3 +386,60 @@ def test_device_augmentation_matches_oracle(n, h, w, cb):
     a0, b0 = augment_pair(img.cuda(), mask.cuda(), identity_params(n))
     assert torch.equal(b0.cpu(), mask.permute(0, 3, 1, 2).float() / 255)
     assert (a0.cpu() - (img.permute(0, 3, 1, 2).float() / 255 - 0.5) / 0.5).abs().max().item() < 1e-6
+
+
+def _convlstm_module(c):
+    from tactile_gan_b200.generators.BCDUNet import ConvBLSTM, ConvLSTM, ConvLSTMCell
+    cls = {"cell": ConvLSTMCell, "lstm": ConvLSTM, "blstm": ConvBLSTM}[c["kind"]]
+    kw = {} if c["kind"] == "cell" else dict(return_sequence=True)
+    m = cls(c["cin"], c["cout"], (3, 3), (1, 1), c["act"], c["frame"], **kw)
+    m.load_state_dict(c["sd"])
+    return m.cuda()
+
+
+def test_convlstm_modules_match_reference_fixture(golden_dir):
+    """ConvLSTMCell / ConvLSTM / ConvBLSTM on the device (two-source tcgen05 gate conv + tg_convlstm_gates) against
+    the outputs of the reference's own classes (tests/golden/convlstm.pt). bf16 operands / bf16 gate pre-activations,
+    fp32 cell state: rel-l2 <= 1e-2 on H and C after up to 3 recurrent steps."""
+    import os
+    fx = torch.load(os.path.join(golden_dir, "convlstm.pt"), weights_only=False)
+    for name, c in fx["cases"].items():
+        m = _convlstm_module(c)
+        if c["kind"] == "cell":
+            h, cc = m(c["x"].cuda(), c["h0"].cuda(), c["c0"].cuda())
+            assert rel(h, c["h"]) < 1e-2 and rel(cc, c["c"]) < 1e-2, (name, rel(h, c["h"]), rel(cc, c["c"]))
+        else:
+            out = m(c["x"].cuda())
+            assert out.shape == c["out"].shape
+            assert rel(out, c["out"]) < 1e-2, (name, rel(out, c["out"]))
+            for t in range(out.shape[1]):                    # every frame on its own, not just the aggregate
+                assert rel(out[:, t], c["out"][:, t]) < 1.5e-2, (name, t)
+            m.return_sequence = False
+            assert torch.equal(m(c["x"].cuda()), out[:, -1])
+    with pytest.raises(_C().TgError):
+        _convlstm_module(fx["cases"]["lstm_tanh"])(fx["cases"]["lstm_tanh"]["x"])    # CPU tensor: no fallback
+
+
+def test_bcdunet_convlstm_skip_module_full_size():
+    """create_gen("BCDUNet", nf=64).clstm3 -- the skip module at the full 256x256 frame (BCDUNet.py:152; a ConvBLSTM
+    of two 64 -> 16 channel cells as create_gen builds it), two frames, against the oracle on the same parameters."""
+    from collections import OrderedDict
+    import oracle as orc
+    from tactile_gan_b200.generators.BCDUNet import ConvBLSTM
+    from tactile_gan_b200.generators.generators import create_gen
+    torch.manual_seed(3)
+    net = create_gen("BCDUNet", 3, 3, 64, True)
+    lstm = net.clstm3
+    with torch.no_grad():
+        for k, p in lstm.named_parameters():
+            if k.endswith("conv.weight"):
+                p.normal_(0, 0.05)
+            elif k.endswith("conv.bias"):
+                p.normal_(0, 0.2)
+    sd = OrderedDict((k, v.detach().clone()) for k, v in lstm.state_dict().items())
+    x = torch.randn(2, 2, 64, 256, 256)
+    fn = orc.convblstm if isinstance(lstm, ConvBLSTM) else orc.convlstm
+    ref = fn(sd, x, "tanh", return_sequence=False)
+    got = lstm.cuda()(x.cuda())
+    assert got.shape == ref.shape and got.shape[2:] == (256, 256)
+    assert rel(got, ref) < 1e-2, rel(got, ref)

@@ -115,3 +115,19 @@ def test_oracle_eval_pair_matches_reference_function(golden_dir):
         got = orc.eval_pair_fuzzy(real[i], out[i])
         for k in ("accuracy", "dice", "jaccard"):
             assert got[k] == pytest.approx(float(ref[k]), rel=1e-6), k
+
+
+def test_oracle_convlstm_matches_reference_classes(golden_dir):
+    """oracle.convlstm_cell / convlstm / convblstm against the reference's own ConvLSTMCell / ConvLSTM / ConvBLSTM
+    (generators/BCDUNet.py:6-103) run by oracle/make_golden.py; same fp32 torch ops -> tight tolerance."""
+    fx = _load(golden_dir, "convlstm")
+    for name, c in fx["cases"].items():
+        if c["kind"] == "cell":
+            h, cc = orc.convlstm_cell(c["sd"], c["x"], c["h0"], c["c0"], c["act"])
+            torch.testing.assert_close(h, c["h"], rtol=1e-5, atol=1e-6)
+            torch.testing.assert_close(cc, c["c"], rtol=1e-5, atol=1e-6)
+        else:
+            fn = orc.convlstm if c["kind"] == "lstm" else orc.convblstm
+            torch.testing.assert_close(fn(c["sd"], c["x"], c["act"]), c["out"], rtol=1e-5, atol=1e-6)
+            last = fn(c["sd"], c["x"], c["act"], return_sequence=False)
+            assert torch.equal(last, fn(c["sd"], c["x"], c["act"])[:, -1])
