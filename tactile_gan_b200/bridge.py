@@ -6,6 +6,8 @@ import torch.nn as nn
 
 from . import _C
 
+INFER_CHUNK_PIXELS = 64 * 256 * 256
+
 
 class _EngineFn(torch.autograd.Function):
     """Whole-network autograd node: forward = engine forward; backward = engine backward, returning the
@@ -41,16 +43,32 @@ class EngineModule(nn.Module):
             cache[key] = build_generator_engine(self.engine_kind, self, n, h, w, backward)
         return cache[key]
 
+    @staticmethod
+    def infer_chunk(h, w):
+        """Images per inference engine: activations are ~0.4 GB per 256x256 image (UNet++), so a batch-512 sweep
+        (BASELINE.json configs[4]) runs as chunks of 64 images' worth of pixels; throughput is flat beyond that."""
+        return max(1, INFER_CHUNK_PIXELS // (h * w))
+
     def forward(self, x):
         if not x.is_cuda:
             raise _C.TgError("tactile_gan_b200 modules run on CUDA (sm_100a) only; there is no CPU fallback")
         n, _, h, w = x.shape
         params = list(self.parameters())
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        eng = self._engine(n, h, w, need_grad)
         if need_grad:
-            return _EngineFn.apply(x, eng, *params)
-        return eng.forward_graphed(x.detach().contiguous().float()).clone()
+            return _EngineFn.apply(x, self._engine(n, h, w, True), *params)
+        chunk = self.infer_chunk(h, w)
+        xs = x.detach().contiguous().float()
+        if n <= chunk:
+            return self._engine(n, h, w, False).forward_graphed(xs).clone()
+        out = None
+        for i in range(0, n, chunk):
+            m = min(chunk, n - i)
+            y = self._engine(m, h, w, False).forward_graphed(xs[i:i + m])
+            if out is None:
+                out = torch.empty(n, *y.shape[1:], device=y.device)
+            out[i:i + m].copy_(y)
+        return out
 
 
 # ------------------------------------------------------------------------------- discriminator bridge

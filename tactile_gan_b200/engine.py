@@ -82,7 +82,7 @@ class ConvUnit:
         self.n, self.c, self.c_valid = n, layer.o_pad, layer.O
         shp = (n, self.ho, self.wo, self.c)
         self.y = Act(name + ".y", bf16(*shp, device=dev), layer.O)
-        self.dz = bf16(*shp, device=dev)
+        self.dz = bf16(*shp, device=dev) if eng.with_backward else None   # gradient w.r.t. raw: training engines only
         self.pool_mode, self.pool, self.up = pool, None, None
         if pool:
             self.pool = Act(name + ".pool", bf16(n, self.ho // 2, self.wo // 2, self.c, device=dev), layer.O)

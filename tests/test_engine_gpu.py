@@ -315,3 +315,22 @@ def test_train_step_version1_vgg_against_oracle():
         gg.append(fused[k].flatten().cpu())
         rr.append(v.flatten())
     assert cos(torch.cat(gg), torch.cat(rr)) > 0.9
+
+
+def test_inference_forward_in_chunks_equals_one_engine(monkeypatch):
+    """test.py's forward at batches past the per-engine activation budget (BASELINE configs[4]: up to 512) runs as
+    fixed-size chunks (+ one ragged tail engine); InstanceNorm is per sample, so the result must be bit-identical to
+    the single-engine forward."""
+    from tactile_gan_b200 import bridge
+    from tactile_gan_b200.generators.generators import create_gen
+    torch.manual_seed(4)
+    net = create_gen("UNet++", 3, 3, 16, True).cuda()
+    randomize(net, 7)
+    x = torch.rand(5, 3, 64, 64, device="cuda") * 2 - 1
+    with torch.no_grad():
+        whole = net(x)
+        monkeypatch.setattr(bridge, "INFER_CHUNK_PIXELS", 2 * 64 * 64)
+        assert net.infer_chunk(64, 64) == 2
+        chunks = net(x)
+    assert whole.shape == chunks.shape == (5, 3, 64, 64)
+    assert torch.equal(whole, chunks)
