@@ -335,7 +335,7 @@ def run_ours(args):
             t, f, c = agg["conv"]
             ach = f / (t / 1e3) / 1e12
             traffic, top = ncu_traffic()
-            line["roofline"] = {"bound": "tensor", "kernel": "igemm_halo_kernel / igemm_conv_kernel (conv forward + "
+            line["roofline"] = {"bound": "tensor", "kernel": "igemm_rows_kernel / igemm_halo_kernel / igemm_conv_kernel (conv forward + "
                                 "input gradient, all shapes)", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s",
                                 "frac": ach / tf_sus, "peak_source": f"bf16_tflops_sustained, {which}",
                                 "traffic": traffic, "traffic_launch": top, "launches": c,

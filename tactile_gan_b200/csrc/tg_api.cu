@@ -9,6 +9,7 @@
 #include "tg_igemm.cuh"
 #include "tg_wgrad.cuh"
 #include "tg_igemm_halo.cuh"
+#include "tg_igemm_rows.cuh"
 #include "tg_wgrad_taps.cuh"
 #include <cstdlib>
 
@@ -135,13 +136,14 @@ void choose_tile(int n, int h, int w, int pixels, bool single_image, int* th, in
 }  // namespace
 
 struct tg_plan {
-  int kind;  // 0 conv, 1 wgrad, 2 halo-resident conv
+  int kind;  // 0 conv, 1 wgrad, 2 halo-resident conv, 3 row-resident conv, 4 tap-tiled wgrad
   int bn;
   int grid;
   size_t smem;
   tg::IgemmParams conv;
   tg::WgradParams wg;
   tg::HaloParams halo;
+  tg::RowsParams rows;
   tg::WgradTapsParams wgt;
 };
 
@@ -223,6 +225,70 @@ int create_halo_plan(const tg_conv_desc* d, tg_plan* pl, int dy0, int dx0, int e
   }
   return 0;
 }
+// Full 3x3 stride-1 same-size convolutions on maps with W % 128 == 0 and H % 4 == 0 run the row-resident kernel
+// (N = 192 vertical-scatter UMMAs, tg_igemm_rows.cuh). TG_ROWS=0 keeps them on the halo kernel.
+bool rows_eligible(const tg_conv_desc* d, int dy0, int dx0, int eh, int ew) {
+  static const bool enabled = !(getenv("TG_ROWS") && atoi(getenv("TG_ROWS")) == 0);
+  if (!enabled || d->taps != 9 || eh != 2 || ew != 2) return false;
+  const int up = d->pool_out ? 2 : 1;
+  const int ho = d->out.h * up, wo = d->out.w * up;
+  if (wo % tg::kTileM || ho % tg::kRowsG) return false;
+  bool seen[3][3] = {};
+  for (int t = 0; t < 9; ++t) seen[d->tap_dy[t] - dy0][d->tap_dx[t] - dx0] = true;
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b)
+      if (!seen[a][b]) return false;
+  for (int s = 0; s < d->num_src; ++s)
+    if (d->src[s].act.h != ho || d->src[s].act.w != wo) return false;
+  return true;
+}
+
+int create_rows_plan(const tg_conv_desc* d, tg_plan* pl, int dy0, int dx0) {
+  pl->kind = 3;
+  tg::RowsParams& p = pl->rows;
+  memset(&p, 0, sizeof(p));
+  const int cout = d->out.c;
+  p.num_src = d->num_src;
+  for (int t = 0; t < 9; ++t) p.tap_w[d->tap_dy[t] - dy0][d->tap_dx[t] - dx0] = d->tap_w[t];
+  p.org_dy = dy0; p.org_dx = dx0;
+  const int up = d->pool_out ? 2 : 1;
+  p.pool_out = d->pool_out;
+  p.Ho = d->out.h * up; p.Wo = d->out.w * up; p.N = d->out.n;
+  p.segs = p.Wo / tg::kTileM;
+  p.groups_h = p.Ho / tg::kRowsG;
+  p.n_tiles = cout / 64;
+  p.act = d->act; p.slope = d->slope;
+  p.bias = d->bias; p.bias_len = d->bias_len;
+  p.stats_partial = d->stats_partial;
+  p.stats_tiles_total = d->stats_tiles_total > 0 ? d->stats_tiles_total : p.Ho * p.segs;
+  p.stats_tile_off = d->stats_tile_off;
+  if (p.stats_partial && p.stats_tiles_total < p.stats_tile_off + p.Ho * p.segs)
+    return tg_set_error("tg_conv_plan_create: stats buffer has too few tile slots");
+  p.cout = cout;
+  {
+    static const int pf = getenv("TG_HALO_PREFETCH") ? atoi(getenv("TG_HALO_PREFETCH")) : 1;
+    p.prefetch = pf;
+  }
+  p.err_flag = tg_error_flag_device_ptr();
+  for (int s = 0; s < d->num_src; ++s) {
+    const tg_conv_src& cs = d->src[s];
+    if (cs.act.c % 64) return tg_set_error("tg_conv_plan_create: source C must be a multiple of 64");
+    if (make_act_map(&p.src[s].act, cs.act, 0, cs.act.c, tg::kRowsPix, 1, 1, 1)) return -1;
+    const char* wbase = static_cast<const char*>(cs.wgt) + (size_t(cs.row_off) * cs.wgt_k + cs.k_off) * 2;
+    if (make_wgt_map_taps(&p.src[s].wgt, wbase, cs.act.c, cout, cs.wgt_taps, cs.wgt_k, cs.wgt_rows, 64, 1)) return -1;
+    p.src[s].c_chunks = cs.act.c / 64;
+  }
+  if (make_act_map(&p.out, d->out, 0, cout, tg::kTileM / up, 1, 1, 1)) return -1;
+  const int total = p.N * p.groups_h * p.segs * p.n_tiles;
+  pl->grid = total < sm_count() ? total : sm_count();
+  pl->smem = tg::kRowsSmem;
+  cudaError_t e = cudaFuncSetAttribute(tg::igemm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl->smem));
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "cudaFuncSetAttribute(rows): %s", cudaGetErrorString(e));
+    return -1;
+  }
+  return 0;
+}
 }  // namespace
 
 extern "C" {
@@ -269,7 +335,9 @@ int tg_conv_plan_create(const tg_conv_desc* d, tg_plan** out) {
     if (halo_eligible(d, &dy0, &dx0, &eh, &ew)) {
       for (int s = 0; s < d->num_src; ++s)
         if (d->src[s].act.n != d->out.n) { delete pl; return tg_set_error("tg_conv_plan_create: batch mismatch"); }
-      if (create_halo_plan(d, pl, dy0, dx0, eh, ew)) { delete pl; return -1; }
+      if (rows_eligible(d, dy0, dx0, eh, ew)) {
+        if (create_rows_plan(d, pl, dy0, dx0)) { delete pl; return -1; }
+      } else if (create_halo_plan(d, pl, dy0, dx0, eh, ew)) { delete pl; return -1; }
       *out = pl;
       return 0;
     }
@@ -513,6 +581,8 @@ int tg_plan_run(tg_plan* pl, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (pl->kind == 2) {
     tg::igemm_halo_kernel<<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->halo);
+  } else if (pl->kind == 3) {
+    tg::igemm_rows_kernel<<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->rows);
   } else if (pl->kind == 4) {
     tg::wgrad_taps_kernel<<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->wgt);
   } else if (pl->kind == 0) {

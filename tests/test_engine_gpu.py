@@ -24,7 +24,9 @@ def _setup():
 
 @pytest.mark.parametrize("kind,nf,size,n,linear", [("UNet++", 64, 64, 2, True), ("UNet++", 64, 64, 2, False),
                                                    ("UNet", 16, 256, 1, True), ("UNet", 16, 256, 1, False),
-                                                   ("BCDUNet", 16, 64, 2, True), ("BCDUNet", 16, 64, 2, False)])
+                                                   ("BCDUNet", 16, 64, 2, True), ("BCDUNet", 16, 64, 2, False),
+                                                   # 128-wide level 0: the row-resident conv kernel inside an engine
+                                                   ("UNet++", 16, 128, 2, True), ("BCDUNet", 16, 128, 1, False)])
 def test_generator_forward_backward(kind, nf, size, n, linear):
     orc, _C = _setup()
     from tactile_gan_b200.generators.generators import create_gen
@@ -59,7 +61,11 @@ def test_generator_forward_backward(kind, nf, size, n, linear):
             continue
         if linear:
             # UNet normalises 2x2 .. 8x8 maps (4..64 samples per statistic), which amplifies bf16 noise
-            assert rel(p.grad, rg[k]) < (0.10 if kind == "UNet" else 0.04), k
+            # (the nf=16 128x128 case: 16-element affine gradients are sums of bf16 dz over 16384 pixels with heavy
+            # cancellation -- 4-6 % on single bias vectors with either conv kernel, TG_ROWS=0 or 1; conv weights,
+            # which carry the kernel logic, stay under 4 %)
+            small = size >= 128 and p.numel() < 4096
+            assert rel(p.grad, rg[k]) < (0.10 if (kind == "UNet" or small) else 0.04), k
         else:
             # ReLU masks (and, in UNet, InstanceNorm over tiny maps) make single tensors noisy: every sizeable
             # tensor must point the right way, the whole gradient must agree in direction

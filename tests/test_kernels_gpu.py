@@ -65,6 +65,12 @@ CONV_CASES = [
     dict(n=2, cins=[512], cout=1, h=59, w=59, k=3, stride=1, pad=0, bias=True, act=2),        # D head
     dict(n=2, cins=[64], cout=128, h=64, w=64, k=4, stride=2, pad=1),                         # UNet down conv
     dict(n=1, cins=[64], cout=64, h=16, w=16, k=3, stride=1, pad=1, stats=True),              # single image
+    # W % 128 == 0, H % 4 == 0: the row-resident kernel (N = 192 vertical-scatter UMMAs, tg_igemm_rows.cuh)
+    dict(n=2, cins=[64], cout=64, h=8, w=128, k=3, stride=1, pad=1, stats=True),              # resident weights
+    dict(n=3, cins=[64, 128], cout=128, h=12, w=256, k=3, stride=1, pad=1, stats=True),       # 3 chunks, 2 segments, 2 n-tiles
+    dict(n=1, cins=[24, 8], cout=24, h=4, w=128, k=3, stride=1, pad=1, bias=True, act=3),     # one strip, ragged channels
+    dict(n=8, cins=[64, 64], cout=64, h=128, w=128, k=3, stride=1, pad=1, stats=True),        # several items per CTA
+    dict(n=8, cins=[64], cout=128, h=128, w=128, k=3, stride=1, pad=1, stats=True),           # resident, 512 items
 ]
 
 
@@ -73,10 +79,12 @@ def test_conv_forward(case):
     run_conv(**case)
 
 
-@pytest.mark.parametrize("cin,cout,h,w", [(64, 128, 32, 48), (64, 64, 16, 16), (128, 256, 32, 32), (192, 512, 16, 32)])
+@pytest.mark.parametrize("cin,cout,h,w", [(64, 128, 32, 48), (64, 64, 16, 16), (128, 256, 32, 32), (192, 512, 16, 32),
+                                          (64, 128, 8, 128), (128, 64, 16, 256)])   # row-resident kernel
 def test_conv_pool_out_sums_2x2_blocks(cin, cout, h, w):
     """pool_out: the epilogue stores the 2x2 sum of the (h x w) result into an (h/2 x w/2) tensor -- the input
-    gradient through a nearest-upsampled copy -- on the halo kernel (cout 64/128) and the generic one."""
+    gradient through a nearest-upsampled copy -- on the halo kernel (cout 64/128), the row-resident one (W % 128 == 0)
+    and the generic one."""
     C = _C()
     g = torch.Generator().manual_seed(4)
     n = 2
@@ -264,6 +272,8 @@ LAYER_CASES = [
     ("convT", [128, 128], 128, 4, 2, 1, 8, 8, False),      # UNet deconv on a skip concat
     ("convT", [40], 24, 4, 2, 1, 16, 16, False),           # ragged channels, 4 sub-pixel phases
     ("convT", [64, 64], 64, 4, 2, 1, 64, 64, False),       # large enough for epilogue statistics
+    ("conv", [64, 128], 64, 3, 1, 1, 8, 128, True),        # row-resident kernel: forward + mirrored-tap input gradients
+    ("conv", [128], 128, 3, 1, 1, 16, 256, False),         # row-resident kernel, two segments, Cout 128
 ]
 
 

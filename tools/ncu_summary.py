@@ -64,7 +64,8 @@ def main():
                   d["kernel"][:44], d["dur"], d["dram_rd"] / 1e6, d["dram_wr"] / 1e6, d["dram%"], d["l2%"],
                   d.get("l2hit%") or 0, d["tensor%"], d.get("smem_tc%") or 0, d["sm%"], d["ghz"], d["grid"], d["regs"]))
     if out_json:
-        halo = [d for d in allrows if "igemm_halo" in d["kernel"]]
+        # the dominant kernel: the row-resident conv (round 1, second half) if captured, else the halo kernel
+        halo = [d for d in allrows if "igemm_rows" in d["kernel"]] or [d for d in allrows if "igemm_halo" in d["kernel"]]
         top = max(halo, key=lambda d: d["dur"]) if halo else None
         doc = {"source": "ncu --set full --clock-control none (cold-cache, serialised replays)", "launches": allrows}
         if top:
