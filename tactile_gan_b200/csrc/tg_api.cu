@@ -582,7 +582,7 @@ int tg_plan_run(tg_plan* pl, void* stream) {
   if (pl->kind == 2) {
     tg::igemm_halo_kernel<<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->halo);
   } else if (pl->kind == 3) {
-    tg::igemm_rows_kernel<<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->rows);
+    tg::igemm_rows_kernel<<<pl->grid, tg::kRowsThreads, pl->smem, s>>>(pl->rows);
   } else if (pl->kind == 4) {
     tg::wgrad_taps_kernel<<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->wgt);
   } else if (pl->kind == 0) {

@@ -159,11 +159,11 @@ __device__ __forceinline__ bool epi_pool2x2(uint32_t (&v0)[32], uint32_t (&v1)[3
 
 // Stage bias[c_base .. c_base+64) (zero past bias_len) for the 128 epilogue threads; no-op when already staged.
 __device__ __forceinline__ void epi_stage_bias(float* sbias, const float* __restrict__ bias, int bias_len,
-                                               int c_base, int& staged_base, int et) {
+                                               int c_base, int& staged_base, int et, uint32_t bar_id = 1) {
   if (bias == nullptr || staged_base == c_base) return;
-  named_bar_sync(1, 128);   // readers of the previously staged chunk are done
+  named_bar_sync(bar_id, 128);   // readers of the previously staged chunk are done
   if (et < 64) sbias[et] = c_base + et < bias_len ? __ldg(bias + c_base + et) : 0.f;
-  named_bar_sync(1, 128);
+  named_bar_sync(bar_id, 128);
   staged_base = c_base;
 }
 

@@ -29,7 +29,8 @@ constexpr int kRowsAStage = 17 * 1024;       // >= 130 * 128 B, 1 KiB aligned
 constexpr int kRowsABytes = kRowsPix * 128;
 constexpr int kRowsBBlock = 64 * 128;        // one tap: 64 co x 64 ci
 constexpr int kRowsBGroup = 3 * kRowsBBlock; // one dx: [dy=2 | dy=1 | dy=0]
-constexpr int kRowsSmem = 1024 + 3 * kRowsBGroup + kRowsIn * kRowsAStage + 2 * kStoreBytes + 4 * 64 * 2 * 4 + 256 + 256;
+constexpr int kRowsThreads = 64 + 2 * 128;   // TMA warp, MMA warp, two epilogue groups of four warps
+constexpr int kRowsSmem = 1024 + 3 * kRowsBGroup + kRowsIn * kRowsAStage + 2 * kStoreBytes + 2 * (4 * 64 * 2 * 4) + 256 + 512;
 
 struct alignas(64) RowsParams {
   IgemmSrc src[kMaxSrc];  // act box {64, 130, 1, 1}; wgt box {64, 64, 1}
@@ -52,14 +53,14 @@ struct alignas(64) RowsParams {
   int* err_flag;
 };
 
-__global__ void __launch_bounds__(kNumThreads, 2) igemm_rows_kernel(const __grid_constant__ RowsParams p) {
+__global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __grid_constant__ RowsParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_base = smem_base;
   const uint32_t a_base = b_base + 3 * kRowsBGroup;
   const uint32_t store_base = a_base + kRowsIn * kRowsAStage;
   const uint32_t scratch_base = store_base + 2 * kStoreBytes;
-  const uint32_t bar_base = scratch_base + 4 * 64 * 2 * 4;
+  const uint32_t bar_base = scratch_base + 2 * (4 * 64 * 2 * 4);
   auto bfull = [&](int s) { return bar_base + 8u * s; };              // 3
   auto bempty = [&](int s) { return bar_base + 8u * (3 + s); };       // 3
   auto afull = [&](int s) { return bar_base + 8u * (6 + s); };        // 6
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(kNumThreads, 2) igemm_rows_kernel(const __grid
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(tfull(s), 1);
-        mbar_init(tempty(s), 128);
+        mbar_init(tempty(s), 256);
       }
       fence_mbar_init();
     }
@@ -222,15 +223,21 @@ __global__ void __launch_bounds__(kNumThreads, 2) igemm_rows_kernel(const __grid
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (128 threads)
-    const int et = threadIdx.x - 64;
+    // ------------------------------------------------------------ epilogue: two groups of 128 threads
+    // One epilogue warp per scheduler is latency-bound (~1800 cycles per tile against 1152 tensor cycles per
+    // tile-chunk), which capped the one- and two-chunk layers; group e drains output rows e and e+2 of every item
+    // with its own staging tile, barrier, statistics scratch and bulk-store group.
+    const int e = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64 - e * 128;
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int ew = et >> 5;
+    const uint32_t bar_id = 1u + uint32_t(e);
+    const uint32_t stage = store_base + uint32_t(e) * kStoreBytes;
     int set = 0;
-    uint32_t tphase = 0, chunk_ctr = 0;
-    float* scratch = reinterpret_cast<float*>(smem_gen + (scratch_base - smem_base));
-    float* sbias = reinterpret_cast<float*>(smem_gen + (bar_base + 256 - smem_base));
+    uint32_t tphase = 0;
+    float* scratch = reinterpret_cast<float*>(smem_gen + (scratch_base - smem_base)) + e * 512;
+    float* sbias = reinterpret_cast<float*>(smem_gen + (bar_base + 256 - smem_base)) + e * 64;
     int staged_base = -1;
     const int e_act = p.act, e_bias_len = p.bias_len;
     const float e_slope = p.slope;
@@ -244,83 +251,76 @@ __global__ void __launch_bounds__(kNumThreads, 2) igemm_rows_kernel(const __grid
       mbar_wait_guard(tfull(set), tphase, p.err_flag, 36);
       tc_fence_after();
       if (p.pool_out) {
-        // input gradient through a nearest-upsampled copy: rows (2rp, 2rp+1) are two accumulators on the SAME lanes,
+        // input gradient through a nearest-upsampled copy: rows (2e, 2e+1) are two accumulators on the SAME lanes,
         // so the vertical pair is a register add and the horizontal pair one lane shuffle; even lanes keep the pixel
-#pragma unroll 1
-        for (int rp = 0; rp < kRowsG / 2; ++rp, ++chunk_ctr) {
-          const uint32_t sb = chunk_ctr & 1;
-          const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t((set * kRowsG + 2 * rp) * 64);
-          uint32_t v0[32], v1[32], t[32];
-          tmem_ld_32x32(taddr, v0);
-          tmem_ld_32x32(taddr + 64, t);
-          tmem_ld_wait();
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t((set * kRowsG + 2 * e) * 64);
+        uint32_t v0[32], v1[32], t[32];
+        tmem_ld_32x32(taddr, v0);
+        tmem_ld_32x32(taddr + 64, t);
+        tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v0[j] = __float_as_uint(__uint_as_float(v0[j]) + __uint_as_float(t[j]));
-          tmem_ld_32x32(taddr + 32, v1);
-          tmem_ld_32x32(taddr + 96, t);
-          tmem_ld_wait();
-          if (rp == kRowsG / 2 - 1) {
-            tc_fence_before();
-            mbar_arrive(tempty(set));
-          }
+        for (int j = 0; j < 32; ++j) v0[j] = __float_as_uint(__uint_as_float(v0[j]) + __uint_as_float(t[j]));
+        tmem_ld_32x32(taddr + 32, v1);
+        tmem_ld_32x32(taddr + 96, t);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(tempty(set));
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float a = __uint_as_float(v0[j]), b = __uint_as_float(v1[j]) + __uint_as_float(t[j]);
-            a += __shfl_xor_sync(0xffffffffu, a, 1);
-            b += __shfl_xor_sync(0xffffffffu, b, 1);
-            v0[j] = __float_as_uint(a);
-            v1[j] = __float_as_uint(b);
-          }
-          uint32_t packed[32];
-          epi_pack(v0, v1, packed, ACT_NONE, 0.f, nullptr);
-          if (et == 0) tma_store_wait_read<1>();
-          named_bar_sync(1, 128);
-          if ((lane & 1) == 0) epi_store_row(store_base + sb * kStoreBytes, row >> 1, packed);
-          fence_proxy_async();
-          named_bar_sync(1, 128);
-          if (et == 0) {
-            tma_store_4d(&p.out, store_base + sb * kStoreBytes, c_base, seg * (kTileM / 2), yg * (kRowsG / 2) + rp, img);
-            tma_store_commit();
-          }
+        for (int j = 0; j < 32; ++j) {
+          float a = __uint_as_float(v0[j]), b = __uint_as_float(v1[j]) + __uint_as_float(t[j]);
+          a += __shfl_xor_sync(0xffffffffu, a, 1);
+          b += __shfl_xor_sync(0xffffffffu, b, 1);
+          v0[j] = __float_as_uint(a);
+          v1[j] = __float_as_uint(b);
+        }
+        uint32_t packed[32];
+        epi_pack(v0, v1, packed, ACT_NONE, 0.f, nullptr);
+        if (et == 0) tma_store_wait_read<0>();
+        named_bar_sync(bar_id, 128);
+        if ((lane & 1) == 0) epi_store_row(stage, row >> 1, packed);
+        fence_proxy_async();
+        named_bar_sync(bar_id, 128);
+        if (et == 0) {
+          tma_store_4d(&p.out, stage, c_base, seg * (kTileM / 2), yg * (kRowsG / 2) + e, img);
+          tma_store_commit();
         }
         set ^= 1;
         if (set == 0) tphase ^= 1u;
         continue;
       }
 #pragma unroll 1
-      for (int r = 0; r < kRowsG; ++r, ++chunk_ctr) {
+      for (int r = e; r < kRowsG; r += 2) {
         const int y = yg * kRowsG + r;
-        const uint32_t sb = chunk_ctr & 1;
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t((set * kRowsG + r) * 64);
         uint32_t v0[32], v1[32];
         tmem_ld_32x32(taddr, v0);
         tmem_ld_32x32(taddr + 32, v1);
         tmem_ld_wait();
-        if (r == kRowsG - 1) {
+        if (r + 2 >= kRowsG) {
           tc_fence_before();
           mbar_arrive(tempty(set));
         }
         uint32_t packed[32];
-        epi_stage_bias(sbias, e_bias, e_bias_len, c_base, staged_base, et);
+        epi_stage_bias(sbias, e_bias, e_bias_len, c_base, staged_base, et, bar_id);
         epi_pack(v0, v1, packed, e_act, e_slope, e_bias ? sbias : nullptr);
-        if (et == 0) tma_store_wait_read<1>();
-        named_bar_sync(1, 128);
-        epi_store_row(store_base + sb * kStoreBytes, row, packed);
+        if (et == 0) tma_store_wait_read<0>();
+        named_bar_sync(bar_id, 128);
+        epi_store_row(stage, row, packed);
         fence_proxy_async();
-        named_bar_sync(1, 128);
+        named_bar_sync(bar_id, 128);
         if (et == 0) {
-          tma_store_4d(&p.out, store_base + sb * kStoreBytes, c_base, seg * kTileM, y, img);
+          tma_store_4d(&p.out, stage, c_base, seg * kTileM, y, img);
           tma_store_commit();
         }
         if (e_stats) {
           float s0, s1, q0, q1;
-          epi_stats_rows(store_base + sb * kStoreBytes, ew * 32, lane, 0xffffffffu, s0, s1, q0, q1);
+          epi_stats_rows(stage, ew * 32, lane, 0xffffffffu, s0, s1, q0, q1);
           float* sc = scratch + ew * 128;
           sc[(2 * lane) * 2 + 0] = s0;
           sc[(2 * lane) * 2 + 1] = q0;
           sc[(2 * lane + 1) * 2 + 0] = s1;
           sc[(2 * lane + 1) * 2 + 1] = q1;
-          named_bar_sync(1, 128);
+          named_bar_sync(bar_id, 128);
           const float tot = scratch[et] + scratch[128 + et] + scratch[256 + et] + scratch[384 + et];
           const size_t tile_lin = size_t(img) * p.stats_tiles_total + p.stats_tile_off + size_t(y) * p.segs + seg;
           e_stats[(tile_lin * p.cout + c_base) * 2 + et] = tot;
