@@ -228,8 +228,8 @@ def run_ours(args):
         def step_dev(i):
             ts.step(*devb[i % pool])
 
-        def step_host(i):
-            ts.step_from_host(*host[i % pool])
+        def step_host(i):       # every step copies its batch from pinned memory; the next batch's copy is in flight
+            ts.step_from_host(*host[i % pool], prefetch=host[(i + 1) % pool])
         h2d, d2h = 2 * B * 3 * S * S * 4, 32
     else:
         chunked = B > netG.infer_chunk(S, S)     # batch-512 sweeps: the module runs them as fixed-size chunks

@@ -217,21 +217,55 @@ class TrainStep:
         gs.adam_step(self.lr, self.beta1, grad_scale=1.0 / self.world)
         return self.losses
 
-    def step_from_host(self, host_A, host_B, regularize=True):
+    def step_from_host(self, host_A, host_B, regularize=True, prefetch=None):
         """End-to-end iteration as a training loop issues it (reference train.py:101-168): pinned host
-        batch -> H2D copy -> fused step -> D2H read of the five loss scalars (the only sync)."""
-        if not hasattr(self, "_dev_A"):
-            self._dev_A = torch.empty(host_A.shape, device=self.device)
-            self._dev_B = torch.empty(host_B.shape, device=self.device)
+        batch -> H2D copy -> fused step -> D2H read of the five loss scalars (the only sync).
+        prefetch: the NEXT iteration's pinned (host_A, host_B). Its H2D copy is issued now, on the copy stream, into
+        the second pair of device buffers and runs under this step's kernels -- the one-batch lookahead of a
+        DataLoader; the next call recognises the batch (same tensors) and only waits for the copy's event."""
+        if not hasattr(self, "_dev"):
+            self._dev = [(torch.empty(host_A.shape, device=self.device), torch.empty(host_B.shape, device=self.device))
+                         for _ in range(2)]
             self._copy_stream = torch.cuda.Stream(device=self.device)
-        # the generator forward only needs real_A: the target's H2D copy runs beside it on a copy stream
-        self._dev_A.copy_(host_A, non_blocking=True)
-        ready = torch.cuda.Event()
-        self._copy_stream.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(self._copy_stream):
-            self._dev_B.copy_(host_B, non_blocking=True)
-            ready.record()
-        self.step(self._dev_A, self._dev_B, regularize=regularize, real_B_ready=ready)
+            self._slot_free = [None, None]       # event: the last step that read the slot has finished
+            self._inflight = None                # (host_A, host_B, slot, ready_A, ready_B)
+            self._slot = 0
+        cur = torch.cuda.current_stream()
+        cs = self._copy_stream
+        fl = self._inflight
+        self._inflight = None
+        if fl is not None and fl[0] is host_A and fl[1] is host_B:
+            slot, ready_a, ready_b = fl[2], fl[3], fl[4]
+            cur.wait_event(ready_a)
+        else:
+            # no lookahead: the generator forward only needs real_A, the target's copy runs beside it
+            slot = self._slot
+            if fl is not None:                   # a lookahead copy of some other batch may still be writing this slot
+                cur.wait_event(fl[4])
+            if self._slot_free[slot] is not None:
+                cs.wait_event(self._slot_free[slot])
+            self._dev[slot][0].copy_(host_A, non_blocking=True)
+            ready_b = torch.cuda.Event()
+            cs.wait_stream(cur)
+            with torch.cuda.stream(cs):
+                self._dev[slot][1].copy_(host_B, non_blocking=True)
+                ready_b.record()
+        if prefetch is not None:
+            nslot = slot ^ 1
+            ra, rb = torch.cuda.Event(), torch.cuda.Event()
+            if self._slot_free[nslot] is not None:
+                cs.wait_event(self._slot_free[nslot])
+            with torch.cuda.stream(cs):
+                self._dev[nslot][0].copy_(prefetch[0], non_blocking=True)
+                ra.record()
+                self._dev[nslot][1].copy_(prefetch[1], non_blocking=True)
+                rb.record()
+            self._inflight = (prefetch[0], prefetch[1], nslot, ra, rb)
+        self.step(self._dev[slot][0], self._dev[slot][1], regularize=regularize, real_B_ready=ready_b)
+        done = torch.cuda.Event()
+        done.record()
+        self._slot_free[slot] = done
+        self._slot = slot ^ 1
         return self.loss_dict()
 
     def loss_dict(self):

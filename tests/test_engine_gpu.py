@@ -340,3 +340,47 @@ def test_inference_forward_in_chunks_equals_one_engine(monkeypatch):
         chunks = net(x)
     assert whole.shape == chunks.shape == (5, 3, 64, 64)
     assert torch.equal(whole, chunks)
+
+
+def test_step_from_host_with_prefetch_matches_device_resident_steps():
+    """The end-to-end entry point (pinned host batch -> H2D -> step -> loss read) with the one-batch lookahead copy must
+    produce what TrainStep.step produces on device-resident copies of the same batches: three iterations, the
+    prefetched, the non-prefetched and the mismatched-prefetch paths. The GP alpha is the only RNG consumer; both
+    runs are handed the same draws."""
+    orc, _C = _setup()
+    from tactile_gan_b200.discriminators.discriminators import create_disc
+    from tactile_gan_b200.generators.generators import create_gen
+    from tactile_gan_b200.step import TrainStep
+
+    def build():
+        torch.manual_seed(9)
+        netG = create_gen("UNet++", 3, 3, 16, True)
+        netD = create_disc("patch", 3, 3, 16, True, True)
+        randomize(netG, 1)
+        randomize(netD, 2)
+        ts = TrainStep(netG.cuda(), netD.cuda(), 2, 64, 64)
+        ts.ensure_label(generator=torch.Generator().manual_seed(3))
+        # lr = 0: the weights stay put, so every iteration depends on its own batch only and the comparison is not
+        # blurred by the run-to-run noise of the fp32 atomics in the weight gradients (1.5 % on gp one step later)
+        ts.lr = 0.0
+        return ts
+
+    g = torch.Generator().manual_seed(5)
+    host = [tuple(t.pin_memory() for t in orc.synthetic_batch(g, 2, 64)) for _ in range(3)]
+    alphas = [torch.rand(2, 1, generator=g) for _ in range(3)]
+    ref = build()
+    want = []
+    for (a, b), al in zip(host, alphas):
+        ref.step(a.cuda(), b.cuda(), regularize=True, alpha=al)
+        want.append(ref.loss_dict())
+    ts = build()
+    real_draw = ts.draw_alpha
+    it = iter(alphas)
+    ts.draw_alpha = lambda alpha=None: real_draw(next(it))
+    got = [ts.step_from_host(*host[0], prefetch=host[1]),      # issues the lookahead copy of batch 1
+           ts.step_from_host(*host[1], prefetch=host[0]),      # consumes it; prefetches a batch that is NOT used next
+           ts.step_from_host(*host[2])]                        # falls back to the in-line copy
+    assert _C.error_flag() == 0
+    for i, (w, gt) in enumerate(zip(want, got)):
+        for k in w:
+            assert gt[k] == pytest.approx(w[k], rel=1e-3, abs=1e-6), (i, k, gt[k], w[k])
