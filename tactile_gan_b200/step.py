@@ -217,12 +217,16 @@ class TrainStep:
         gs.adam_step(self.lr, self.beta1, grad_scale=1.0 / self.world)
         return self.losses
 
-    def step_from_host(self, host_A, host_B, regularize=True, prefetch=None):
+    def step_from_host(self, host_A, host_B, regularize=True, prefetch=None, lag=False):
         """End-to-end iteration as a training loop issues it (reference train.py:101-168): pinned host
         batch -> H2D copy -> fused step -> D2H read of the five loss scalars (the only sync).
         prefetch: the NEXT iteration's pinned (host_A, host_B). Its H2D copy is issued now, on the copy stream, into
         the second pair of device buffers and runs under this step's kernels -- the one-batch lookahead of a
-        DataLoader; the next call recognises the batch (same tensors) and only waits for the copy's event."""
+        DataLoader; the next call recognises the batch (same tensors) and only waits for the copy's event.
+        lag: read the loss scalars back with a one-iteration lag -- this call enqueues a pinned D2H copy of its own
+        losses and returns the PREVIOUS iteration's (None on the first call), so the host can queue the next iteration
+        while this one runs instead of draining the device every step (train.py itself syncs once per epoch). A call
+        with lag=False returns its own losses synchronously, as before."""
         if not hasattr(self, "_dev"):
             self._dev = [(torch.empty(host_A.shape, device=self.device), torch.empty(host_B.shape, device=self.device))
                          for _ in range(2)]
@@ -266,7 +270,24 @@ class TrainStep:
         done.record()
         self._slot_free[slot] = done
         self._slot = slot ^ 1
-        return self.loss_dict()
+        if not lag:
+            self._loss_pending = None
+            return self.loss_dict()
+        if not hasattr(self, "_loss_host"):
+            self._loss_host = [torch.empty(self.losses.shape, dtype=self.losses.dtype).pin_memory() for _ in range(2)]
+            self._loss_k = 0
+        prev = getattr(self, "_loss_pending", None)
+        self._loss_k ^= 1
+        buf = self._loss_host[self._loss_k]
+        buf.copy_(self.losses, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._loss_pending = (buf, ev)
+        if prev is None:
+            return None
+        prev[1].synchronize()
+        v = prev[0].tolist()
+        return {"loss_D": v[0], "gp": v[1], "G_GAN": v[2], "L1": v[3], "per": v[4]}
 
     def loss_dict(self):
         """Host copy of the loss slots with the reference's logging conventions (train.py:121-163):

@@ -375,12 +375,16 @@ def test_step_from_host_with_prefetch_matches_device_resident_steps():
         want.append(ref.loss_dict())
     ts = build()
     real_draw = ts.draw_alpha
-    it = iter(alphas)
+    it = iter(alphas + alphas[:2])
     ts.draw_alpha = lambda alpha=None: real_draw(next(it))
     got = [ts.step_from_host(*host[0], prefetch=host[1]),      # issues the lookahead copy of batch 1
            ts.step_from_host(*host[1], prefetch=host[0]),      # consumes it; prefetches a batch that is NOT used next
            ts.step_from_host(*host[2])]                        # falls back to the in-line copy
     assert _C.error_flag() == 0
+    # lagged loss read: the call returns the previous iteration's scalars (None first), its own arrive one call later
+    assert ts.step_from_host(*host[0], prefetch=host[1], lag=True) is None
+    got.append(ts.step_from_host(*host[1], lag=True))
+    want.append(want[0])
     for i, (w, gt) in enumerate(zip(want, got)):
         for k in w:
             assert gt[k] == pytest.approx(w[k], rel=1e-3, abs=1e-6), (i, k, gt[k], w[k])
