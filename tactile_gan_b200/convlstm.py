@@ -81,9 +81,15 @@ class ConvLSTMCellEngine(GraphEngine):
         return out
 
 
-def _check(x):
+def _check(x, module=None):
     if not x.is_cuda:
         raise _C.TgError("tactile_gan_b200 modules run on CUDA (sm_100a) only; there is no CPU fallback")
+    if torch.is_grad_enabled() and (x.requires_grad or (module is not None and
+                                                        any(p.requires_grad for p in module.parameters()))):
+        # no training path reaches these modules (BCDUNet.forward never calls them), so only the forward exists:
+        # refuse to hand back tensors that silently carry no graph
+        raise NotImplementedError("the ConvLSTM engine is forward-only: call it under torch.no_grad() "
+                                  "(or with requires_grad_(False) parameters)")
 
 
 def _engine(cell, n, h, w):
@@ -95,7 +101,7 @@ def _engine(cell, n, h, w):
 
 def cell_forward(cell, X, H_prev, C_prev):
     """ConvLSTMCell.forward(X, H_prev, C_prev) -> (H, C), all fp32 NCHW (BCDUNet.py:32-47). Forward only."""
-    _check(X)
+    _check(X, cell)
     n, _, h, w = X.shape
     eng = _engine(cell, n, h, w)
     X = X.detach().contiguous().float()
@@ -112,7 +118,7 @@ def cell_forward(cell, X, H_prev, C_prev):
 
 def lstm_forward(lstm, X):
     """ConvLSTM.forward (BCDUNet.py:61-84): zero initial state, unrolled over dim 1."""
-    _check(X)
+    _check(X, lstm)
     b, t, _, h, w = X.shape
     eng = _engine(lstm.convLSTMcell, b, h, w)
     X = X.detach().contiguous().float()
@@ -124,7 +130,7 @@ def lstm_forward(lstm, X):
 def blstm_forward(blstm, x):
     """ConvBLSTM.forward (BCDUNet.py:96-103): forward cell on the frames, backward cell on the reversed frames
     (un-reversed again), concatenated on the channel axis -- both cells write straight into their channel halves."""
-    _check(x)
+    _check(x, blstm)
     b, t, _, h, w = x.shape
     ef = _engine(blstm.forward_cell.convLSTMcell, b, h, w)
     eb = _engine(blstm.backward_cell.convLSTMcell, b, h, w)

@@ -413,19 +413,22 @@ def test_convlstm_modules_match_reference_fixture(golden_dir):
     fp32 cell state: rel-l2 <= 1e-2 on H and C after up to 3 recurrent steps."""
     import os
     fx = torch.load(os.path.join(golden_dir, "convlstm.pt"), weights_only=False)
-    for name, c in fx["cases"].items():
-        m = _convlstm_module(c)
-        if c["kind"] == "cell":
-            h, cc = m(c["x"].cuda(), c["h0"].cuda(), c["c0"].cuda())
-            assert rel(h, c["h"]) < 1e-2 and rel(cc, c["c"]) < 1e-2, (name, rel(h, c["h"]), rel(cc, c["c"]))
-        else:
-            out = m(c["x"].cuda())
-            assert out.shape == c["out"].shape
-            assert rel(out, c["out"]) < 1e-2, (name, rel(out, c["out"]))
-            for t in range(out.shape[1]):                    # every frame on its own, not just the aggregate
-                assert rel(out[:, t], c["out"][:, t]) < 1.5e-2, (name, t)
-            m.return_sequence = False
-            assert torch.equal(m(c["x"].cuda()), out[:, -1])
+    with pytest.raises(NotImplementedError):                 # forward-only: refuses to run under autograd
+        _convlstm_module(fx["cases"]["lstm_relu"])(fx["cases"]["lstm_relu"]["x"].cuda())
+    with torch.no_grad():
+        for name, c in fx["cases"].items():
+            m = _convlstm_module(c)
+            if c["kind"] == "cell":
+                h, cc = m(c["x"].cuda(), c["h0"].cuda(), c["c0"].cuda())
+                assert rel(h, c["h"]) < 1e-2 and rel(cc, c["c"]) < 1e-2, (name, rel(h, c["h"]), rel(cc, c["c"]))
+            else:
+                out = m(c["x"].cuda())
+                assert out.shape == c["out"].shape
+                assert rel(out, c["out"]) < 1e-2, (name, rel(out, c["out"]))
+                for t in range(out.shape[1]):                    # every frame on its own, not just the aggregate
+                    assert rel(out[:, t], c["out"][:, t]) < 1.5e-2, (name, t)
+                m.return_sequence = False
+                assert torch.equal(m(c["x"].cuda()), out[:, -1])
     with pytest.raises(_C().TgError):
         _convlstm_module(fx["cases"]["lstm_tanh"])(fx["cases"]["lstm_tanh"]["x"])    # CPU tensor: no fallback
 
@@ -450,6 +453,7 @@ def test_bcdunet_convlstm_skip_module_full_size():
     x = torch.randn(2, 2, 64, 256, 256)
     fn = orc.convblstm if isinstance(lstm, ConvBLSTM) else orc.convlstm
     ref = fn(sd, x, "tanh", return_sequence=False)
-    got = lstm.cuda()(x.cuda())
+    with torch.no_grad():
+        got = lstm.cuda()(x.cuda())
     assert got.shape == ref.shape and got.shape[2:] == (256, 256)
     assert rel(got, ref) < 1e-2, rel(got, ref)
