@@ -186,6 +186,21 @@ def ncu_traffic():
     return top.get("dram_bytes"), top
 
 
+def ncu_tensor_pipe():
+    """Time-weighted tensor-pipe utilisation of all conv GEMM launches of the step (BASELINE.json's second metric), from
+    the committed ncu pass profiles/r01_ncu_tensor_pipe.txt (sm__pipe_tensor_cycles_active over every launch)."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_tensor_pipe.txt")
+    if not os.path.exists(p):
+        return None
+    for line in open(p):
+        if line.startswith("# all conv GEMMs"):
+            try:
+                return float(line.split(":")[1].split("%")[0])
+            except ValueError:
+                return None
+    return None
+
+
 def run_ours(args):
     from tactile_gan_b200 import _C
     from tactile_gan_b200.discriminators.discriminators import create_disc
@@ -352,6 +367,8 @@ def run_ours(args):
                                 "input gradient, all shapes)", "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s",
                                 "frac": ach / tf_sus, "peak_source": f"bf16_tflops_sustained, {which}",
                                 "traffic": traffic, "traffic_launch": top, "launches": c,
+                                "frac_of_nominal_dense_peak": ach / 2250.0,
+                                "ncu_tensor_pipe_active_pct_all_conv_gemms": ncu_tensor_pipe() if headline else None,
                                 "share_of_step": t / ms_roof,
                                 "measured": f"{args.steps} further steps, CUDA events around every launch, launches "
                                             f"serialised on one stream ({ms_roof / args.steps:.2f} ms/step)"}
