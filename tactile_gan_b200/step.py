@@ -217,7 +217,7 @@ class TrainStep:
         gs.adam_step(self.lr, self.beta1, grad_scale=1.0 / self.world)
         return self.losses
 
-    def step_from_host(self, host_A, host_B, regularize=True, prefetch=None, lag=False):
+    def step_from_host(self, host_A, host_B, regularize=True, prefetch=None, lag=False, read=True):
         """End-to-end iteration as a training loop issues it (reference train.py:101-168): pinned host
         batch -> H2D copy -> fused step -> D2H read of the five loss scalars (the only sync).
         prefetch: the NEXT iteration's pinned (host_A, host_B). Its H2D copy is issued now, on the copy stream, into
@@ -226,7 +226,8 @@ class TrainStep:
         lag: read the loss scalars back with a one-iteration lag -- this call enqueues a pinned D2H copy of its own
         losses and returns the PREVIOUS iteration's (None on the first call), so the host can queue the next iteration
         while this one runs instead of draining the device every step (train.py itself syncs once per epoch). A call
-        with lag=False returns its own losses synchronously, as before."""
+        with lag=False returns its own losses synchronously, as before. read=False: no D2H at all, the device tensor of
+        loss slots is returned (train.py accumulates it on the device and syncs once per epoch)."""
         if not hasattr(self, "_dev"):
             self._dev = [(torch.empty(host_A.shape, device=self.device), torch.empty(host_B.shape, device=self.device))
                          for _ in range(2)]
@@ -270,6 +271,8 @@ class TrainStep:
         done.record()
         self._slot_free[slot] = done
         self._slot = slot ^ 1
+        if not read:
+            return self.losses
         if not lag:
             self._loss_pending = None
             return self.loss_dict()

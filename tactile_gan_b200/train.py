@@ -98,7 +98,26 @@ class Train_GAN:
             print("==training epoch ", epoch)
             regularize = (o.reg_every != 0) and (epoch % o.reg_every == 0) and (o.lambda_gp != 0)
             accum, steps = None, 0
-            for batch in self.dataset:
+            it = iter(self.dataset)
+            nxt = next(it, None)
+            while nxt is not None:
+                # one-batch lookahead: the next batch's H2D copy is issued before this step's kernels and runs under them
+                batch, nxt = nxt, next(it, None)
+                host_path = batch[0].dtype == torch.float32 and batch[1].dtype == torch.float32
+                if host_path:
+                    a, b = batch[0].contiguous(), batch[1].contiguous()
+                    if self.step is None:
+                        self._build_step(a.shape[2], a.shape[3])
+                    if accum is None:
+                        accum = torch.zeros_like(self.step.losses)
+                    self.step.lr = self.optimizer_G.param_groups[0]['lr']
+                    ahead = None
+                    if nxt is not None and nxt[0].dtype == torch.float32 and nxt[0].is_contiguous() \
+                            and nxt[1].dtype == torch.float32 and nxt[1].is_contiguous():
+                        ahead = (nxt[0], nxt[1])
+                    accum += self.step.step_from_host(a, b, regularize=regularize, prefetch=ahead, read=False)
+                    steps += 1
+                    continue
                 if batch[0].dtype == torch.uint8:
                     # raw uint8 HWC pair from datasets.PairedDataset(raw=True): ToTensor / Normalize and -- with
                     # augmentation on -- HorizontalFlip + Affine run on the device (augment.py; PairedDataset.py:80-92)
