@@ -143,3 +143,28 @@ def test_ganloss_class_matches_oracle(mode):
     a = sm.get_target_tensor(pred, True)
     assert a.shape == pred.shape and float(a.max()) <= 1.0 and sm.get_target_tensor(pred, True) is not None
     assert torch.equal(sm.real_label_tensor, a)     # cached: drawn once
+
+
+def test_convlstm_modules_keep_reference_parameter_names(golden_dir):
+    """ConvLSTMCell / ConvLSTM / ConvBLSTM expose exactly the reference's state_dict keys and shapes (generators/
+    BCDUNet.py:6-103; the fixture holds the reference modules' own state_dicts) and refuse CPU tensors."""
+    import os
+    import torch
+    from tactile_gan_b200 import _C
+    from tactile_gan_b200.generators.BCDUNet import ConvBLSTM, ConvLSTM, ConvLSTMCell
+    fx = torch.load(os.path.join(golden_dir, "convlstm.pt"), weights_only=False)
+    cls = {"cell": ConvLSTMCell, "lstm": ConvLSTM, "blstm": ConvBLSTM}
+    for name, c in fx["cases"].items():
+        m = cls[c["kind"]](c["cin"], c["cout"], (3, 3), (1, 1), c["act"], c["frame"])
+        sd = m.state_dict()
+        assert list(sd.keys()) == list(c["sd"].keys()), name
+        assert all(sd[k].shape == c["sd"][k].shape for k in sd), name
+        m.load_state_dict(c["sd"])
+    with pytest.raises(_C.TgError):
+        m(fx["cases"]["blstm_tanh"]["x"])
+
+
+def test_inference_chunk_size():
+    from tactile_gan_b200 import bridge
+    assert bridge.EngineModule.infer_chunk(256, 256) == 64 and bridge.EngineModule.infer_chunk(512, 512) == 16
+    assert bridge.EngineModule.infer_chunk(4096, 4096) == 1
