@@ -61,14 +61,19 @@ template <int BN>
 struct IgemmCfg {
   static constexpr int kBBytes = BN * kChunkK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = BN == 256 ? 3 : (BN == 128 ? 5 : 6);
+  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 5 : 6);
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
   static constexpr int kSmemStages = kStages * kStageBytes;
   static constexpr int kSmemStore = 2 * kStoreBytes;
   static constexpr int kSmemScratch = 4 * 64 * 2 * 4;  // [4 warps][64 ch][sum, sumsq]
   static constexpr int kSmemBars = 256;
   static constexpr int kSmemBias = 256;                // 64 fp32 bias values of the current output chunk
-  static constexpr int kSmemTotal = 1024 + kSmemStages + kSmemStore + kSmemScratch + kSmemBars + kSmemBias;
+  // The small regions (statistics scratch, barriers, bias) sit FIRST and the 1 KiB-aligned stage / store buffers
+  // follow at the next 1 KiB boundary: with the dynamic window starting 1 KiB-aligned (it does: the driver's reserved
+  // 1 KiB precedes it) BN = 256 fits FOUR 48 KiB stages in exactly 227 KiB. The kernel traps if the carve-up would
+  // run past the window.
+  static constexpr int kSmemMisc = kSmemScratch + kSmemBars + kSmemBias;
+  static constexpr int kSmemTotal = ((kSmemMisc + 1023) / 1024) * 1024 + kSmemStages + kSmemStore;
 };
 
 // Bounded spin so a protocol bug reports an error instead of hanging the GPU.
@@ -208,11 +213,19 @@ __global__ void __launch_bounds__(kNumThreads, 2)
 igemm_conv_kernel(const __grid_constant__ IgemmParams p) {
   using Cfg = IgemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stage_base = smem_base;
-  const uint32_t store_base = stage_base + Cfg::kSmemStages;
-  const uint32_t scratch_base = store_base + Cfg::kSmemStore;
+  const uint32_t smem_base = smem_u32(smem_raw);
+  const uint32_t scratch_base = smem_base;
   const uint32_t bar_base = scratch_base + Cfg::kSmemScratch;
+  const uint32_t stage_base = (smem_base + uint32_t(Cfg::kSmemMisc) + 1023u) & ~1023u;
+  const uint32_t store_base = stage_base + Cfg::kSmemStages;
+  {
+    uint32_t dyn;
+    asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+    if (store_base + Cfg::kSmemStore - smem_base > dyn) {
+      if (threadIdx.x == 0 && p.err_flag) atomicExch(p.err_flag, 20);
+      __trap();
+    }
+  }
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
