@@ -89,41 +89,103 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def cpu_baseline(steps, warmup, batch, threads=None):
-    """The oracle port (oracle/oracle.py, a restatement of the reference's PyTorch CPU path) on the host
-    cores: UNet++ nf=64 + PatchD, version-2 stack with GP, `batch` images of 256^2 per step."""
+def _port_runner(gen, batch):
+    """Fallback when baseline/_ref did not travel: the oracle port (oracle/oracle.py) of the same step."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as orc
-    threads = threads or os.cpu_count() or 1
-    torch.set_num_threads(threads)
     shapes = torch.load(os.path.join(ROOT, "tests", "golden", "state_dict_keys.pt"))
     g = torch.Generator().manual_seed(21)
-    sd_g = orc.init_state_dict(shapes["UNet++"], g)
+    sd_g = orc.init_state_dict(shapes[gen], g)
     sd_d = orc.init_state_dict(shapes["patch"], g)
-    cfg = orc.StepConfig(gen="UNet++", loss="ls", version=2)
+    cfg = orc.StepConfig(gen=gen, loss="ls", version=2)
     label = orc.make_real_label((batch, 1, 57, 57), True, generator=g)
     og, od = {}, {}
+
+    def run(a, b):
+        alpha = torch.rand(batch, 1, generator=g)
+        orc.train_step(sd_g, sd_d, og, od, a, b, label, alpha, cfg)
+    return run, "port"
+
+
+def cpu_baseline(steps, warmup, batch, threads=None, gen="UNet++"):
+    """The reference's own CPU path on the host cores: the UNMODIFIED reference modules from baseline/_ref driven
+    through train.py:99-168 (baseline/ref_step.py; kind "reference"), or the oracle port when baseline/_ref is absent
+    (kind "port"). `gen` nf=64 + PatchD, version-2 stack with GP, `batch` images of 256^2 per step, fp32."""
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    from baseline import ref_step
+    if ref_step.available():
+        rs = ref_step.RefStep(gen, 64, "cpu")
+        run, kind = (lambda a, b: rs.step(a, b)), "reference"
+    else:
+        run, kind = _port_runner(gen, batch)
+    g = torch.Generator().manual_seed(21)
     times = []
     for i in range(warmup + steps):
-        a, b = orc.synthetic_batch(g, batch, 256)
-        alpha = torch.rand(batch, 1, generator=g)
+        a = torch.rand(batch, 3, 256, 256, generator=g) * 2 - 1
+        b = torch.rand(batch, 3, 256, 256, generator=g)
         t = time.perf_counter()
-        orc.train_step(sd_g, sd_d, og, od, a, b, label, alpha, cfg)
+        run(a, b)
         dt = time.perf_counter() - t
         if i >= warmup:
             times.append(dt)
-    per_step = sum(times) / len(times)
-    return {"value": batch / per_step, "unit": "images/s", "cores": threads, "kind": "port",
-            "sample": f"{steps} G+D steps of UNet++(nf=64)+PatchD, version-2 losses + GP, batch {batch}, 256x256, "
-                      f"fp32 torch CPU after {warmup} warm-up", "s_per_step": per_step}
+    per_step = statistics.median(times)
+    return {"value": batch / per_step, "unit": "images/s", "cores": threads, "kind": kind,
+            "sample": f"{steps} G+D steps of {gen}(nf=64)+PatchD, version-2 losses + GP, batch {batch}, 256x256, "
+                      f"fp32 torch CPU after {warmup} warm-up (median step)", "s_per_step": per_step}
+
+
+def cudnn_baseline(dev, batch, size, steps=3, warmup=2, gen="UNet++"):
+    """The bar that matters: the reference's own modules on THIS GPU under PyTorch
+    eager + cuDNN, same step / batch / size, inputs resident in HBM, CUDA events over `steps` iterations.
+    Modes: stock (fp32 storage, cuDNN TF32 convolutions -- torch's default, what `python train.py` runs), strict fp32,
+    and bf16 autocast. Baseline leg only: none of this repo's kernels run here and the product path never imports it."""
+    from baseline import ref_step
+    if not ref_step.available():
+        return {"unavailable": "baseline/_ref not present on this box"}
+    out = {"kind": "reference modules, torch %s eager + cuDNN %s" % (torch.__version__, torch.backends.cudnn.version()),
+           "batch": batch, "size": size, "steps": steps, "warmup": warmup}
+    g = torch.Generator().manual_seed(21)
+    a = (torch.rand(batch, 3, size, size, generator=g) * 2 - 1).to(dev)
+    b = torch.rand(batch, 3, size, size, generator=g).to(dev)
+    keep = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    for mode, tf32, amp in (("bf16_autocast", True, torch.bfloat16), ("tf32_stock", True, None), ("fp32_strict", False, None)):
+        try:
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            rs = ref_step.RefStep(gen, 64, dev, autocast=amp)
+            for _ in range(warmup):
+                rs.step(a, b)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                losses = rs.step(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[mode] = {"images_per_s": batch / (ms / 1e3), "ms_per_step": ms,
+                         "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30, "losses_last_step": losses}
+        except Exception as e:  # e.g. out of memory at this batch: reported, never fatal for the bench line
+            out[mode] = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
+        finally:
+            rs = None
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = keep
+            torch.cuda.empty_cache()
+            torch.cuda.reset_peak_memory_stats()
+    return out
 
 
 def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the step on the host cores, on the GPU arm's metric and
+    config; each step is a bounded sample of the workload (batch 2 instead of 32 per step -- a batch-32 fp32 CPU step
+    takes ~25 s and ~50 GB). Also reports BASELINE.md section 4's prescribed cfg1 (UNet, batch 4)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 8)), max(0, min(args.warmup, 1))
+    steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
     cb = cpu_baseline(steps, warmup, 2)
+    cfg1 = cpu_baseline(3, 1, 4, gen="UNet")
     line = {"impl": "reference", "metric": "train images/sec (G+D step) UNet++ 256^2", "value": cb["value"],
             "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": cb["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -131,6 +193,7 @@ def run_reference(args):
             "config": {"workload": "UNet++ nf=64 + PatchDiscriminator, version-2 loss stack with GP every step, "
                                    "256x256; CPU arm samples batch 2 per step (GPU arm: batch 32 per GPU)"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cfg1_unet_b4": {k: cfg1[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -388,6 +451,13 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             cb = cpu_baseline(4, 1, 2)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if world == 1 and train and not args.no_cudnn:
+            # the reference's own GPU path on this box (eager + cuDNN): run after every timing of ours, our engines freed
+            ts = step_dev = step_host = None
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            line["cudnn_baseline"] = cudnn_baseline(dev, B, S, gen=args.gen)
         print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
@@ -405,6 +475,7 @@ def main():
     ap.add_argument("--version", type=int, default=2, choices=[1, 2])
     ap.add_argument("--workload", default="train", choices=["train", "infer"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cudnn", action="store_true", help="skip the reference-on-cuDNN leg (same GPU, eager PyTorch)")
     ap.add_argument("--layers", default="", help="diagnostic: write a per-shape / per-kernel timing table (JSON)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -58,6 +58,14 @@ class _RoundBF16(torch.autograd.Function):
 ACT = {"relu": F.relu}   # tests may linearise the generators (ACT["relu"] = identity) to remove mask flips
 
 
+def max_pool_2x2(t):
+    return F.max_pool2d(t, 2, 2)
+
+
+# tests may pin the arg-max routes (and ACT["relu"] the masks) to the pattern the CUDA forward took: tests/parity_util.py
+POOL = {"max": max_pool_2x2}
+
+
 def _q(x):
     return _RoundBF16.apply(x) if QUANT["on"] else x
 
@@ -119,7 +127,7 @@ def unet_forward(sd, x, activation=True):
 
 def bcdunet_forward(sd, x, activation=True):
     blk = lambda name, inp: _double_conv(inp, sd, name)
-    pool = lambda t: F.max_pool2d(t, 2, 2)
+    pool = lambda t: POOL["max"](t)
     c1 = blk("conv1", _q(x))
     c2 = blk("conv2", pool(c1))
     c3 = blk("conv3", pool(c2))
