@@ -359,6 +359,11 @@ class StepConfig:
         self.w_per, self.lr, self.beta1, self.regularize = tuple(w_per), lr, beta1, regularize
         self.activation = loss == "ls"  # train.py:33
         self.vgg_sd = None              # version 1: state_dict of the four VGG16 slices (blocks.<b>.<i>.weight/bias)
+        # tests only: discriminator weights to run the G step with INSTEAD of the oracle's own post-Adam weights. The
+        # first Adam step moves every weight by ~lr*sign(grad); gradients near zero flip sign under bf16 noise, so the
+        # two sides' updated discriminators differ by 2*lr on those weights. Handing the oracle the other side's
+        # updated D isolates the G-step comparison from that (the D step is compared on its own gradients).
+        self.sd_d_after = None
 
 
 def _leaf(sd):
@@ -391,7 +396,7 @@ def train_step(sd_g, sd_d, opt_g, opt_d, real_a, real_b, real_label, alpha, cfg)
     adam_update(sd_d, grads_d, opt_d, cfg.lr, cfg.beta1)
 
     # ---- G step (train.py:138-168), D already updated
-    pd2 = OrderedDict((k, v.detach()) for k, v in sd_d.items())
+    pd2 = OrderedDict((k, v.detach()) for k, v in (cfg.sd_d_after if cfg.sd_d_after is not None else sd_d).items())
     pred_fake, feats_fake = patchd_forward(pd2, real_a, fake_b, act)
     g_gan = gan_loss(pred_fake, True, cfg.loss, real_label, for_discriminator=False)
     l1 = F.l1_loss(real_b, fake_b)

@@ -213,7 +213,9 @@ class HeadUnit:
         self.eng, self.src, self.weight, self.bias, self.use_tanh = eng, src, weight, bias, use_tanh
         n, h, w, c = src.shape
         self.co, self.ci = weight.shape[0], weight.shape[1]
-        assert c == 64 and self.co <= 4, "head kernel expects <= 64 input and <= 4 output channels"
+        if c != 64 or self.co > 4:
+            raise ValueError(f"the FeatureMapBlock kernel serves num_filter <= 64 and output_dim <= 4 "
+                             f"(got {self.ci} -> {self.co})")
         self.n, self.hw = n, h * w
         self.out = torch.zeros(n, self.co, h, w, device=eng.device)
         self.dx = bf16(n, h, w, c, device=eng.device)
@@ -273,6 +275,8 @@ class GraphEngine:
         0.6 ms of kernels at batch 1. The weight re-pack check stays outside the graph."""
         assert x.shape == (self.n, self.cin, self.h, self.w) and x.dtype == torch.float32
         self.store.refresh()
+        if getattr(self, "_graph", None) is not None and self._graph_gen != self.store.generation:
+            self._graph = None       # parameters were re-allocated (.to(), .float(), p.data = ...): the graph's pointers are stale
         if getattr(self, "_graph", None) is None:
             if _C.TIMING["on"] or _C.TIMING["tail"]:
                 return self._forward_launches(x.contiguous())     # per-launch events cannot be captured
@@ -288,6 +292,7 @@ class GraphEngine:
             with torch.cuda.graph(graph):
                 self._graph_out = self._forward_launches(self._static_in)
             self._graph = graph
+            self._graph_gen = self.store.generation
         self._static_in.copy_(x)
         self._graph.replay()
         return self._graph_out

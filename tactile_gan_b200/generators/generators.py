@@ -10,6 +10,13 @@ def create_gen(name, in_nc, out_nc, num_filter, activation=True, multigpu=False)
     parallelism is one process per GPU with NCCL gradient allreduce (tactile_gan_b200/step.py), not
     nn.DataParallel."""
     key = name.lower()
+    if key in ("unet", "unet++", "bcdunet"):
+        # limits of the sm_100a engines the reference does not have (fail here, not deep inside an engine build)
+        if not 1 <= num_filter <= 64:
+            raise ValueError(f"num_filter must be in 1..64 for the sm_100a generators (got {num_filter}): the "
+                             f"FeatureMapBlock kernel reads one 64-channel row")
+        if not 1 <= out_nc <= 4 or not 1 <= in_nc <= 64:
+            raise ValueError(f"supported channel counts: input 1..64, output 1..4 (got {in_nc} -> {out_nc})")
     if key == "unet":
         from .UNet import UNet
         return UNet(input_dim=in_nc, output_dim=out_nc, num_filter=num_filter, activation=activation)

@@ -280,6 +280,7 @@ class ParamStore:
         self.layer_cache = {}  # name -> ConvLayer (shared by every engine built on this module)
         self.table = None
         self.step_count = 0
+        self.generation = 0    # bumped whenever parameter storage moved: captured CUDA graphs hold raw pointers
 
     def register_conv(self, layer):
         self.conv_of[self.index[id(layer.weight)]] = layer
@@ -372,6 +373,7 @@ class ParamStore:
             self.table_nograd = self._build_table(False)
             self._ptrs = ptrs
             self._versions = None
+            self.generation += 1
         if vers != self._versions:
             self.repack()
             self._versions = vers
@@ -414,3 +416,37 @@ class ParamStore:
 
     def grads_by_name(self):
         return {n: self.grad_as_torch(i) for i, n in enumerate(self.names)}
+
+    def set_grad_from_torch(self, i, grad):
+        """Inverse of grad_as_torch: write a torch-layout gradient (what autograd accumulated in p.grad on the
+        bridge path) into the arena slot the fused Adam kernel reads; padded rows / columns stay zero."""
+        g = self.grad_views[i]
+        grad = grad.detach().to(device=g.device, dtype=torch.float32)
+        if i in self.conv_of:
+            l = self.conv_of[i]
+            l.grad.zero_()
+            if l.kind == "conv":
+                t = grad.permute(2, 3, 0, 1).reshape(l.taps, l.O, l.I)
+                c0 = 0
+                for o, c in zip(l.k_off, l.in_split):
+                    l.grad[:, :l.O, o:o + c] = t[:, :, c0:c0 + c]
+                    c0 += c
+            elif l.kind == "head":
+                t = grad[0].permute(1, 2, 0).reshape(l.taps, l.I)
+                c0 = 0
+                for o, c in zip(l.k_off, l.in_split):
+                    l.grad[0, :l.taps, o:o + c] = t[:, c0:c0 + c]
+                    c0 += c
+            elif l.kind == "cols":
+                l.grad[0, :l.O, :l.taps * l.I] = grad.permute(0, 2, 3, 1).reshape(l.O, l.taps * l.I)
+            else:
+                t = grad.permute(2, 3, 0, 1).reshape(l.taps, l.I, l.O)
+                c0 = 0
+                for o, c in zip(l.k_off, l.in_split):
+                    l.grad[:, o:o + c, :l.O] = t[:, c0:c0 + c, :]
+                    c0 += c
+        elif i in self.bias_of:
+            g.zero_()
+            g[:self.bias_of[i].O] = grad
+        else:
+            g.view_as(self.params[i]).copy_(grad)

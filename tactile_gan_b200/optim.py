@@ -37,9 +37,20 @@ class FusedAdam(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale=1.0):
-        """Consumes the gradients the engines accumulated in the store's arena (not p.grad)."""
+        """Fused path (TrainStep): consumes the gradients the engines accumulated in the store's arena; p.grad is
+        None there. Bridge path (reference-style loop: several netD(...) / gradient_penalty(...) autograd nodes, then
+        loss.backward()): every node returns only ITS gradients and autograd sums them in p.grad, while the arena
+        holds whatever node ran last -- so when p.grad exists it is the truth and is re-packed into the arena first.
+        A parameter without p.grad on that path got no gradient: torch.optim.Adam skips it, here it steps on zero."""
         g = self.param_groups[0]
-        self.store.adam_step(g["lr"], g["betas"][0], g["betas"][1], g["eps"], grad_scale)
+        st = self.store
+        if any(p.grad is not None for p in st.params):
+            for i, p in enumerate(st.params):
+                if p.grad is not None:
+                    st.set_grad_from_torch(i, p.grad)
+                else:
+                    st.grad_views[i].zero_()
+        st.adam_step(g["lr"], g["betas"][0], g["betas"][1], g["eps"], grad_scale)
 
     def zero_grad(self, set_to_none=True):
         st = getattr(self.module, "_tg_store", None)

@@ -217,7 +217,7 @@ class TrainStep:
         gs.adam_step(self.lr, self.beta1, grad_scale=1.0 / self.world)
         return self.losses
 
-    def step_from_host(self, host_A, host_B, regularize=True, prefetch=None, lag=False, read=True):
+    def step_from_host(self, host_A, host_B, regularize=True, prefetch=None, lag=False, read=True, alpha=None):
         """End-to-end iteration as a training loop issues it (reference train.py:101-168): pinned host
         batch -> H2D copy -> fused step -> D2H read of the five loss scalars (the only sync).
         prefetch: the NEXT iteration's pinned (host_A, host_B). Its H2D copy is issued now, on the copy stream, into
@@ -266,7 +266,7 @@ class TrainStep:
                 self._dev[nslot][1].copy_(prefetch[1], non_blocking=True)
                 rb.record()
             self._inflight = (prefetch[0], prefetch[1], nslot, ra, rb)
-        self.step(self._dev[slot][0], self._dev[slot][1], regularize=regularize, real_B_ready=ready_b)
+        self.step(self._dev[slot][0], self._dev[slot][1], regularize=regularize, alpha=alpha, real_B_ready=ready_b)
         done = torch.cuda.Event()
         done.record()
         self._slot_free[slot] = done

@@ -116,6 +116,7 @@ def run_step_case(gen="UNet++", batch=2, size=256, nf=64, loss="ls", regularize=
     gd = ts.DA.store.grads_by_name()
     gg = ts.G.store.grads_by_name()
     masks, pools = forward_pattern(ts.G) if matched else (None, None)
+    d_after = OrderedDict((k, v.detach().cpu().clone()) for k, v in netD.state_dict().items())
     t_cuda = time.time() - t0
     cfg = orc.StepConfig(gen=gen, loss=loss, lambda_gp=lambda_gp, lambda_per=lambda_per, regularize=regularize)
     clone = lambda sd: OrderedDict((k, v.clone()) for k, v in sd.items())
@@ -135,6 +136,7 @@ def run_step_case(gen="UNet++", batch=2, size=256, nf=64, loss="ls", regularize=
         orc.QUANT["on"] = True
         orc.ACT["relu"] = MaskFeed(masks)
         orc.POOL["max"] = PoolFeed(pools)
+        cfg.sd_d_after = d_after          # G step from the SAME updated discriminator (see oracle.StepConfig)
         try:
             refm = orc.train_step(clone(sd_g), clone(sd_d), {}, {}, a, b, label, alpha, cfg)
         finally:

@@ -168,3 +168,48 @@ def test_inference_chunk_size():
     from tactile_gan_b200 import bridge
     assert bridge.EngineModule.infer_chunk(256, 256) == 64 and bridge.EngineModule.infer_chunk(512, 512) == 16
     assert bridge.EngineModule.infer_chunk(4096, 4096) == 1
+
+
+def test_lr_schedule_milestones_match_the_reference_formula():
+    """SURVEY 8 a13 / reference train.py:191-195: MultiStepLR, gamma 0.8, milestones
+    int16(linspace(epoch_constant, total_epochs, 11)[:-1]) = 25, 36, ..., 124 for the default 135-epoch run."""
+    import argparse
+    import torch
+    from tactile_gan_b200 import train as tg_train
+    old = tg_train.opt
+    try:
+        for const, total, want in ((25, 135, [25, 36, 47, 58, 69, 80, 91, 102, 113, 124]),
+                                   (1, 2, [1] * 10), (10, 50, [10, 14, 18, 22, 26, 30, 34, 38, 42, 46])):
+            tg_train.opt = argparse.Namespace(epoch_constant=const, total_epochs=total)
+            p = torch.nn.Parameter(torch.zeros(1))
+            opt_ = torch.optim.SGD([p], lr=1e-3)
+            sched = tg_train.Train_GAN.get_scheduler(opt_)
+            assert sorted(sched.milestones.elements()) == want
+            lrs = []
+            for _ in range(total):
+                lrs.append(opt_.param_groups[0]["lr"])
+                opt_.step()
+                sched.step()
+            # epoch e (1-based, train.py:85-87) runs with lr * 0.8^(number of milestones <= e - 1)
+            for e, lr in enumerate(lrs, start=1):
+                assert lr == pytest.approx(1e-3 * 0.8 ** sum(1 for m in want if m <= e - 1), rel=1e-12), (const, total, e)
+    finally:
+        tg_train.opt = old
+
+
+def test_factories_reject_shapes_the_engines_cannot_serve():
+    """limits the reference does not have are raised at construction with a clear message."""
+    from tactile_gan_b200.discriminators.discriminators import create_disc
+    from tactile_gan_b200.generators.generators import create_gen
+    for name in ("UNet", "UNet++", "BCDUNet"):
+        with pytest.raises(ValueError):
+            create_gen(name, 3, 3, 128)
+        with pytest.raises(ValueError):
+            create_gen(name, 3, 5, 16)
+    with pytest.raises(ValueError):
+        create_disc("patch", 4, 4, 16, True)
+    with pytest.raises(NameError):
+        create_gen("resnet", 3, 3, 16)
+    with pytest.raises(NameError):
+        create_disc("pixel", 3, 3, 16, True)
+    assert create_gen("unet++", 3, 3, 8) is not None and create_disc("patch", 3, 3, 8, True) is not None

@@ -120,3 +120,66 @@ def test_reference_style_loop_on_autograd_bridge():
         # both sides run the same kernels; fp32 atomics make their summation order (and so a few bf16 roundings that
         # the ReLU / InstanceNorm backward amplifies) differ between two launches
         assert r < 5e-2, (k, r)
+
+
+def test_reference_loop_with_fused_adam_steps_on_the_summed_gradient():
+    """in the reference-style loop several autograd nodes of the same network (netD(a, fake), netD(a, b),
+    gradient_penalty) contribute to loss_D; each bridge node returns only its own gradient and autograd sums them in
+    p.grad. FusedAdam.step() must step on that sum (it re-packs p.grad into the arena), i.e. land where the fused
+    TrainStep lands from the same weights -- not on the gradient of whichever node ran last."""
+    import copy
+    import oracle as orc
+    from tactile_gan_b200.discriminators.discriminators import create_disc
+    from tactile_gan_b200.generators.generators import GANLoss, create_gen
+    from tactile_gan_b200.optim import FusedAdam
+    from tactile_gan_b200.step import TrainStep
+    from tactile_gan_b200.util import gradient_penalty, init_weights, pan_loss, set_requires_grad
+    torch.manual_seed(0)
+    nf, size, n, lr = 8, 64, 2, 1e-3
+    netG = create_gen("UNet++", 3, 3, nf, True)
+    netD = create_disc("patch", 3, 3, nf, True, True)
+    init_weights(netG)
+    init_weights(netD)
+    netG2, netD2 = copy.deepcopy(netG).cuda(), copy.deepcopy(netD).cuda()
+    netG, netD = netG.cuda(), netD.cuda()
+    before_D = {k: v.clone() for k, v in netD.state_dict().items()}
+    g = torch.Generator().manual_seed(2)
+    a, b = orc.synthetic_batch(g, n, size)
+    a, b = a.cuda(), b.cuda()
+    gan = GANLoss("ls", label_smoothing=False)
+    # ---- the reference's loop body (train.py:104-168) on the bridge, with optimizer steps
+    fake = netG(a)
+    optD, optG = FusedAdam(netD, lr=lr, betas=(0.9, 0.99)), FusedAdam(netG, lr=lr, betas=(0.9, 0.99))
+    set_requires_grad(netD, True)
+    optD.zero_grad()
+    loss_D = (gan(netD(a, fake.detach()), False) + gan(netD(a, b), True)) / 2
+    torch.manual_seed(5)
+    loss_D = loss_D + gradient_penalty(netD, a, b, fake, "cuda", 2, lambda_gp=0.01)
+    loss_D.backward()
+    gsum = {k: p.grad.clone() for k, p in netD.named_parameters()}
+    optD.step()
+    set_requires_grad(netD, False)
+    optG.zero_grad()
+    pred = netD(a, fake)
+    feats_fake = netD.get_intermediate_output()
+    loss_G = gan(pred, True, for_discriminator=False) + torch.nn.L1Loss()(b, fake)
+    netD(a, b)
+    pan_loss(netD.get_intermediate_output(), feats_fake, weights=[0, .1, .3, .6])
+    loss_G.backward()
+    optG.step()
+    # ---- the fused step from the same start
+    ts = TrainStep(netG2, netD2, n, size, size, lr=lr, label_smoothing=False)
+    torch.manual_seed(5)
+    ts.step(a, b, regularize=True)
+    fusedD = ts.DA.store.grads_by_name()
+    for k, v in gsum.items():
+        assert ((fusedD[k] - v).norm() / (v.norm() + 1e-20)).item() < 5e-2, k       # p.grad really is the full sum
+    for net_a, net_b in ((netD, netD2), (netG, netG2)):
+        sa, sb = net_a.state_dict(), net_b.state_dict()
+        d = torch.cat([(sa[k] - sb[k]).flatten() for k in sa if not k.startswith("clstm")])
+        # the first Adam step moves every weight by ~lr*sign(grad): a flipped sign of a near-zero gradient costs
+        # 2*lr; the bulk must agree (stepping on a partial gradient moves O(half) of the weights the other way)
+        assert (d.abs() > 0.5 * lr).float().mean().item() < 0.03
+        assert d.abs().mean().item() < 0.05 * lr
+    moved = torch.cat([(netD.state_dict()[k] - before_D[k]).flatten() for k in before_D])
+    assert moved.abs().mean().item() > 0.5 * lr

@@ -107,3 +107,50 @@ def test_bucketed_async_allreduce_equals_one_allreduce():
         p.join(120)
         assert p.exitcode == 0
     assert out.get() == 0.0
+
+
+def _train_host_logic(rank, world, port, out):
+    """Product code of tactile_gan_b200.train's data-parallel host side (no CUDA needed): every rank draws the GLOBAL
+    smoothed-label tensor from the same seed and keeps its rows; the DistributedSampler shards are disjoint and
+    cover the set; the per-epoch loss reduction averages the rank means."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from tactile_gan_b200 import train as tg_train
+    from torch.utils.data.distributed import DistributedSampler
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    assert tg_train.dp_env() == (rank, world, rank)
+    per = 3
+    lab = tg_train.global_real_label(world, per, 5, 5, generator=torch.Generator().manual_seed(21))
+    mine = tg_train.rank_rows(lab, rank, per)
+    parts = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    ds = tg_train.SyntheticPairs(12, 8)
+    sampler = DistributedSampler(ds, num_replicas=world, rank=rank, shuffle=True, seed=21, drop_last=False)
+    sampler.set_epoch(3)
+    idx = torch.tensor(list(sampler))
+    allidx = [torch.zeros_like(idx) for _ in range(world)]
+    dist.all_gather(allidx, idx)
+    mean = torch.full((8,), float(rank + 1))
+    dist.all_reduce(mean)
+    mean /= world
+    if rank == 0:
+        single = tg_train.global_real_label(world, per, 5, 5, generator=torch.Generator().manual_seed(21))
+        out.put((bool(torch.equal(torch.cat(parts), single)), sorted(torch.cat(allidx).tolist()), mean[0].item()))
+    dist.destroy_process_group()
+
+
+def test_train_cli_data_parallel_host_logic():
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    port = 27000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_train_host_logic, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    same_label, covered, mean = out.get()
+    assert same_label
+    assert covered == list(range(12))
+    assert mean == 1.5

@@ -82,3 +82,31 @@ def test_two_gpu_bucketed_allreduce_matches_global_batch():
     assert buckets >= 2
     # bf16 storage + atomics: two launches of the same step differ at this level too
     assert err_g < 5e-2 and err_d < 2e-2
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_gpu_train_cli_matches_single_process_global_batch(tmp_path):
+    """`python -m torch.distributed.run --nproc-per-node 2 -m tactile_gan_b200.train` (BASELINE configs[2] in small):
+    NCCL init, sharded sampler, rank-0-only files, identical replicas (train.main raises if they diverge), and the
+    weights of one epoch = one global batch agree with the single-process run on that global batch."""
+    import subprocess
+    common = ["--synthetic", "4", "--image_size", "64", "--nf", "8", "--total_epochs", "1", "--epoch_constant", "1",
+              "--version", "2", "--threads", "0", "--no_label_smoothing", "--lambda_gp", "0"]
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    for name, launch, bs in (("dp", [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                                     "--master-addr", "127.0.0.1", "--master-port", str(35000 + os.getpid() % 2000),
+                                     "-m", "tactile_gan_b200.train"], "2"),
+                             ("one", [sys.executable, "-m", "tactile_gan_b200.train"], "4")):
+        (tmp_path / name / "data").mkdir(parents=True)
+        r = subprocess.run(launch + ["--data", str(tmp_path / name / "data"), "--batch_size", bs, "--folder_save", "run"]
+                           + common, cwd=tmp_path / name, env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+        assert r.stdout.count("==training epoch") == 1                     # only rank 0 logs
+    dp = torch.load(tmp_path / "dp" / "models" / "run" / "final_model.pth", weights_only=False)
+    one = torch.load(tmp_path / "one" / "models" / "run" / "final_model.pth", weights_only=False)
+    assert float(dp["optimizerG_state_dict"]["state"][0]["step"]) == 1.0
+    for key in ("gen", "disc"):
+        d = torch.cat([(dp[key][k] - one[key][k]).flatten().cpu() for k in dp[key] if not k.startswith("clstm")])
+        # one Adam step of lr 1e-3 from identical weights: sign flips of near-zero gradients cost 2*lr, the bulk agrees
+        assert (d.abs() > 0.5e-3).float().mean().item() < 0.03, key
+        assert d.abs().mean().item() < 0.05e-3, key

@@ -20,7 +20,7 @@ if __name__ == "__main__":
              dict(gen="BCDUNet", batch=2), dict(gen="BCDUNet", batch=2, binary_target=True),
              dict(gen="UNet++", batch=2, regularize=False), dict(gen="UNet++", batch=2, lambda_gp=0.0),
              dict(gen="UNet++", batch=2, lambda_per=0.0), dict(gen="UNet++", batch=2, label_smoothing=False),
-             dict(gen="UNet++", batch=2, loss="ce", label_smoothing=False),
+             dict(gen="UNet++", batch=2, loss="ce", label_smoothing=False), dict(gen="UNet++", batch=2, loss="ce"),
              dict(gen="UNet++", batch=2, loss="hinge"), dict(gen="UNet++", batch=2, loss="w")]
     if quick:
         cases = [dict(c, size=64, nf=16) for c in cases[:4]]
@@ -31,7 +31,7 @@ if __name__ == "__main__":
           % pu.run_forward_case("BCDUNet", 64, 256, samples=(0, 31, 63)), flush=True)
     print("forward UNet B=4 256^2 nf=64: rel-l2 %.5f max-abs %.5f" % pu.run_forward_case("UNet", 4, 256), flush=True)
     for resync in (True, False):
-        print("trajectory UNet++ nf=16 64^2 B=2, 8 steps, resync=%s (cuda/oracle)" % resync)
-        print(pu.fmt_traj(pu.run_trajectory(resync=resync)), flush=True)
+        print("trajectory UNet++ nf=32 128^2 B=2, 8 steps, resync=%s (cuda/oracle)" % resync)
+        print(pu.fmt_traj(pu.run_trajectory(nf=32, size=128, resync=resync)), flush=True)
     print("trajectory UNet++ nf=64 256^2 B=2, 4 steps, resync=True")
     print(pu.fmt_traj(pu.run_trajectory(nf=64, size=256, steps=4, resync=True)), flush=True)
