@@ -1,0 +1,232 @@
+// Streaming form of the InstanceNorm passes whose gradient routes all sit at the unit's own resolution (the common
+// case: 26 of UNet++'s 30 units backward, every forward without pooled / upsampled copies, the discriminator's
+// units): normalise+activation forward, backward statistics, backward apply.
+//
+// Why: the register-staged passes (in_act_fwd_kernel / in_bwd_reduce_kernel) keep <= 8 x 16 B loads per thread in
+// flight at 2 x 256 threads per SM and drain them before every compute phase; ncu showed dram 37-49 %, sm 34-45 %
+// on the 256^2 launches (profiles/r01_ncu_top_kernels.txt) -- latency bound, ~0.6 of the copy bandwidth. Here the
+// bytes in flight do not depend on registers or occupancy: one producer lane per CTA keeps a ring of 8 KiB
+// cp.async.bulk (1-D TMA) chunks per input tensor in shared memory (3-4 stages x up to 3 tensors, two CTAs per SM =
+// 130-190 KiB in flight per SM against the ~35 KiB that 6.4 TB/s x ~800 ns needs), eight consumer warps read the
+// chunks conflict-free (a thread owns one 8-channel group, so the per-channel constants live in registers) and write
+// results straight to HBM with 16-byte stores. The grid is persistent: every CTA gets the same number of chunks of
+// the flattened (image, pixel) space, so there is no wave quantisation (1216 CTAs on 296 slots before).
+#pragma once
+#include "tg_ptx.cuh"
+
+namespace tg {
+
+constexpr int kStreamConsumers = 256;             // consumer threads (8 warps); + 1 producer warp
+constexpr int kStreamThreads = kStreamConsumers + 32;
+constexpr int kStreamPPT = 2;                     // pixels per consumer thread per chunk
+constexpr int kStreamChunkBytes = kStreamPPT * kStreamConsumers * 16;   // 8 KiB per tensor per stage (upper bound)
+
+struct StreamArgs {
+  const __nv_bfloat16* in0;   // raw (conv output)
+  const __nv_bfloat16* in1;   // gradient route 1 (backward) / unused (forward)
+  const __nv_bfloat16* in2;   // optional second same-resolution gradient route
+  __nv_bfloat16* out;         // forward: y; statistics pass: dn (optional); apply pass: dz
+  const float* mr;            // [N][C][2] mean, rstd
+  const float* gamma;
+  const float* beta;
+  float* red;                 // statistics pass: out (atomics); apply pass: in
+  float* dgamma;
+  float* dbeta;
+  int N, HW, C, c_valid, act;
+  float slope;
+  int stages;
+};
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds16(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+// MODE 0: y = act(S*raw + T)
+// MODE 1: dn = (g1 + g2) * act'(A*raw + B); red[n][c] += (sum dn, rstd * (sum dn*raw - mean * sum dn)); dn stored if out
+// MODE 2: dz = P*dn + Q*raw + R with dn recomputed as in MODE 1 (P, Q, R from red)
+template <int MODE>
+__global__ void __launch_bounds__(kStreamThreads, 2) in_stream_kernel(const StreamArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int NIN = MODE == 0 ? 1 : (a.in2 ? 3 : 2);
+  const int CG = a.C >> 3;
+  const int PL = kStreamConsumers / CG;                 // pixel lanes; threads with pl >= PL idle (C/8 not a divisor)
+  const int CP = kStreamPPT * PL;                       // pixels per chunk
+  const int CPI = (a.HW + CP - 1) / CP;                 // chunks per image
+  const long long TC = (long long)a.N * CPI;
+  const long long k0 = TC * blockIdx.x / gridDim.x, k1 = TC * (blockIdx.x + 1) / gridDim.x;
+  const int S = a.stages;
+  // carve-up: [stages][NIN][chunk] | reduction scratch (MODE 1) | barriers
+  const uint32_t base = smem_u32(smem_raw);
+  const uint32_t chunk_stride = kStreamChunkBytes;
+  const uint32_t ring_bytes = uint32_t(S) * NIN * chunk_stride;
+  float* scratch = reinterpret_cast<float*>(smem_raw + ring_bytes);
+  const uint32_t scratch_bytes = MODE == 1 ? uint32_t(PL) * a.C * 2 * sizeof(float) : 0;
+  const uint32_t bar0 = base + ring_bytes + scratch_bytes;       // full[S], then empty[S]
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar0 + 8 * s, 1);
+      mbar_init(bar0 + 8 * (S + s), kStreamConsumers / 32);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (tid >= kStreamConsumers) {
+    // ------------------------------------------------------------------ producer warp (one lane issues)
+    if (tid == kStreamConsumers) {
+      const __nv_bfloat16* srcs[3] = {a.in0, a.in1, a.in2};
+      int s = 0;
+      uint32_t ph = 1;       // the first pass over the ring finds every stage free
+      for (long long k = k0; k < k1; ++k) {
+        const int n = int(k / CPI), j = int(k % CPI);
+        const int p0 = j * CP;
+        const int np = min(CP, a.HW - p0);
+        const uint32_t bytes = uint32_t(np) * a.C * 2;
+        mbar_wait(bar0 + 8 * (S + s), ph);
+        mbar_arrive_expect_tx(bar0 + 8 * s, bytes * NIN);
+        const size_t off = (size_t(n) * a.HW + p0) * a.C;
+        for (int t = 0; t < NIN; ++t)
+          bulk_load_1d(base + (uint32_t(s) * NIN + t) * chunk_stride, srcs[t] + off, bytes, bar0 + 8 * s);
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumers
+  const int cg = tid % CG, pl = tid / CG;
+  const bool active = pl < PL;
+  const int c0 = cg * 8;
+  if (MODE == 2 && (a.dgamma || a.dbeta) && blockIdx.x == 0) {
+    // affine gradients ride along: dgamma[c] += sum_n red[n][c][1], dbeta[c] += sum_n red[n][c][0]
+    for (int c = tid; c < a.c_valid; c += kStreamConsumers) {
+      float g = 0.f, b = 0.f;
+      for (int k = 0; k < a.N; ++k) {
+        b += a.red[(size_t(k) * a.C + c) * 2];
+        g += a.red[(size_t(k) * a.C + c) * 2 + 1];
+      }
+      if (a.dgamma) atomicAdd(a.dgamma + c, g);
+      if (a.dbeta) atomicAdd(a.dbeta + c, b);
+    }
+  }
+  float A[8], B[8];                 // pre-activation n = A*raw + B  (MODE 0: the output itself before the activation)
+  float P[8], Q[8], R[8];           // MODE 2
+  float s0[8], s1[8];               // MODE 1
+  float mean_[8], rstd_[8];
+  int cur_n = -1;
+  const int act = a.act;
+  const float slope = a.slope;
+  const float inv_hw = 1.f / float(a.HW);
+
+  auto flush = [&]() {
+    // MODE 1: block-level reduction of this image's partial sums, then one atomic per (n, c) and CTA
+    if (MODE != 1) return;
+    if (active) {
+      float* shp = scratch + (size_t(pl) * a.C + c0) * 2;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { shp[2 * j] = s0[j]; shp[2 * j + 1] = s1[j]; }
+    }
+    named_bar_sync(1, kStreamConsumers);
+    for (int c = tid; c < a.C; c += kStreamConsumers) {
+      float d0 = 0.f, d1 = 0.f;
+      for (int k = 0; k < PL; ++k) {
+        d0 += scratch[(size_t(k) * a.C + c) * 2];
+        d1 += scratch[(size_t(k) * a.C + c) * 2 + 1];
+      }
+      const float mean = a.mr[(size_t(cur_n) * a.C + c) * 2], rstd = a.mr[(size_t(cur_n) * a.C + c) * 2 + 1];
+      atomicAdd(a.red + (size_t(cur_n) * a.C + c) * 2, d0);
+      atomicAdd(a.red + (size_t(cur_n) * a.C + c) * 2 + 1, rstd * (d1 - mean * d0));
+    }
+    named_bar_sync(1, kStreamConsumers);
+  };
+
+  int s = 0;
+  uint32_t ph = 0;
+  for (long long k = k0; k < k1; ++k) {
+    const int n = int(k / CPI), j = int(k % CPI);
+    if (n != cur_n) {
+      if (cur_n >= 0) flush();
+      cur_n = n;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const size_t kk = size_t(n) * a.C + c0 + q;
+        const float g = ld_aff(a.gamma, c0 + q, a.c_valid, 1.f);
+        const float b = ld_aff(a.beta, c0 + q, a.c_valid, 0.f);
+        const float mean = active ? a.mr[kk * 2] : 0.f, rstd = active ? a.mr[kk * 2 + 1] : 0.f;
+        mean_[q] = mean;
+        rstd_[q] = rstd;
+        A[q] = g * rstd;
+        B[q] = b - mean * A[q];
+        s0[q] = 0.f;
+        s1[q] = 0.f;
+        if (MODE == 2) {
+          const float am = (active ? a.red[kk * 2] : 0.f) * inv_hw, bm = (active ? a.red[kk * 2 + 1] : 0.f) * inv_hw;
+          P[q] = g * rstd;
+          Q[q] = -g * rstd * rstd * bm;
+          R[q] = -P[q] * am - Q[q] * mean;
+        }
+      }
+    }
+    const int p0 = j * CP;
+    const int np = min(CP, a.HW - p0);
+    mbar_wait(bar0 + 8 * s, ph);
+    if (active) {
+      const uint32_t st = base + uint32_t(s) * NIN * chunk_stride;
+#pragma unroll
+      for (int p = 0; p < kStreamPPT; ++p) {
+        const int lp = p * PL + pl;              // pixel inside the chunk
+        if (lp < np) {
+          const uint32_t so = uint32_t(lp) * a.C * 2 + c0 * 2;
+          float r[8];
+          unpack8(lds16(st + so), r);
+          const size_t lin = (size_t(n) * a.HW + p0 + lp) * a.C + c0;
+          if (MODE == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) r[q] = act_fwd(fmaf(r[q], A[q], B[q]), act, slope);
+            stg16(a.out + lin, pack8(r));
+          } else {
+            float g[8];
+            unpack8(lds16(st + chunk_stride + so), g);
+            if (NIN == 3) {
+              float f[8];
+              unpack8(lds16(st + 2 * chunk_stride + so), f);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) g[q] += f[q];
+            }
+            if (MODE == 1) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                g[q] *= act_grad(fmaf(r[q], A[q], B[q]), act, slope);
+                s0[q] += g[q];
+                s1[q] = fmaf(g[q], r[q], s1[q]);
+              }
+              if (a.out) stg16(a.out + lin, pack8(g));
+            } else {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float dn = g[q] * act_grad(fmaf(r[q], A[q], B[q]), act, slope);
+                g[q] = fmaf(P[q], dn, fmaf(Q[q], r[q], R[q]));
+              }
+              stg16(a.out + lin, pack8(g));
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(bar0 + 8 * (S + s));
+    if (++s == S) { s = 0; ph ^= 1; }
+  }
+  if (cur_n >= 0) flush();
+  (void)mean_; (void)rstd_;
+}
+
+}  // namespace tg

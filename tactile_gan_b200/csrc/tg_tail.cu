@@ -5,7 +5,9 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include "tg_api_internal.h"
+#include "tg_ptx.cuh"
 
 namespace tg {
 
@@ -64,6 +66,10 @@ __device__ __forceinline__ float act_grad(float x, int act, float slope) {
   if (act == 1) return x > 0.f ? 1.f : slope;
   return 1.f;
 }
+
+}  // namespace tg
+#include "tg_stream.cuh"
+namespace tg {
 
 // ------------------------------------------------------------------ layout packs
 // out[n,h,w, c_off + j] = wa[n]*A[n,j,h,w] + wb[n]*B[n,j,h,w]   (fp32 NCHW -> bf16 NHWC), j < cj <= 8.
@@ -1525,6 +1531,45 @@ static inline int grid_for(size_t work, int block, int cap = 148 * 16) {
 #define TG_STREAM(s) reinterpret_cast<cudaStream_t>(s)
 #define TG_RET() return tg_check_launch(__func__)
 
+// Streaming (cp.async.bulk ring) form of the same-resolution passes, tg_stream.cuh. TG_STREAM=0 routes everything
+// back to the register-staged kernels (A/B runs).
+static bool stream_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("TG_STREAM");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+template <int MODE>
+static int launch_stream(tg::StreamArgs a, cudaStream_t s) {
+  using namespace tg;
+  const int nin = MODE == 0 ? 1 : (a.in2 ? 3 : 2);
+  const int CG = a.C >> 3, PL = kStreamConsumers / CG;
+  const size_t scratch = MODE == 1 ? size_t(PL) * a.C * 2 * sizeof(float) : 0;
+  // two CTAs per SM: <= ~110 KiB each
+  int stages = int((108 * 1024 - scratch) / (size_t(nin) * kStreamChunkBytes));
+  if (stages > 8) stages = 8;
+  if (stages < 2) return tg_set_error("in_stream: shared memory budget");
+  a.stages = stages;
+  const size_t smem = size_t(stages) * nin * kStreamChunkBytes + scratch + 16 * stages;
+  static size_t configured[3] = {0, 0, 0};
+  if (smem > configured[MODE]) {
+    if (cudaFuncSetAttribute(in_stream_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) !=
+        cudaSuccess)
+      return tg_set_error("in_stream: cudaFuncSetAttribute");
+    configured[MODE] = smem;
+  }
+  const int CP = kStreamPPT * PL;
+  const long long chunks = (long long)a.N * ((a.HW + CP - 1) / CP);
+  long long grid = 2 * 148;
+  if (grid > chunks) grid = chunks;
+  if (grid < 1) grid = 1;
+  in_stream_kernel<MODE><<<int(grid), kStreamThreads, smem, s>>>(a);
+  return tg_check_launch("in_stream_kernel");
+}
+static bool stream_shape_ok(int C) { return C >= 64 && C <= 2048 && (C & 63) == 0; }
+
 extern "C" {
 
 int tg_pack_nchw(const float* A, const float* B, const float* wa, const float* wb, void* out, int N,
@@ -1621,6 +1666,12 @@ int tg_in_act_fwd(const void* raw, const float* mr, const float* gamma, const fl
   const bool quad = pool || up;
   if (quad && ((H | W) & 1)) return tg_set_error("tg_in_act_fwd: pool/upsample need even H, W");
   if (C > 8192) return tg_set_error("tg_in_act_fwd: C too large");
+  if (!quad && raw && mr && stream_enabled() && stream_shape_ok(C)) {
+    tg::StreamArgs a{};
+    a.in0 = r; a.out = yy; a.mr = mr; a.gamma = gamma; a.beta = beta;
+    a.N = N; a.HW = H * W; a.C = C; a.c_valid = c_valid; a.act = act; a.slope = slope;
+    return launch_stream<0>(a, s);
+  }
   const int units = quad ? (H / 2) * (W / 2) : H * W;
   dim3 grid(strip_count(units, C, N, quad ? 4 : 16), N);
   const int block = strip_block(C);
@@ -1655,6 +1706,13 @@ int tg_in_bwd_reduce(const void* raw, const void* y, const float* mr, const floa
   dim3 grid(strip_count(H * W, C, N, 16), N);
   if (!raw && !dn) return tg_set_error("tg_in_bwd_reduce: a layer without norm needs the dn (= dz) output");
   const bool plain = !g_pool && (g_same || g_up) && (!g_up || g_up_pooled);
+  if (plain && raw && mr && red && stream_enabled() && stream_shape_ok(C)) {
+    tg::StreamArgs sa{};
+    sa.in0 = a.raw; sa.in1 = a.g_same ? a.g_same : a.g_up; sa.in2 = (a.g_same && a.g_up) ? a.g_up : nullptr;
+    sa.out = a.dn; sa.mr = mr; sa.gamma = gamma; sa.beta = beta; sa.red = red;
+    sa.N = N; sa.HW = H * W; sa.C = C; sa.c_valid = c_valid; sa.act = act; sa.slope = slope;
+    return launch_stream<1>(sa, TG_STREAM(stream));
+  }
   if (plain) in_bwd_reduce_kernel<true, 0><<<grid, block, smem, TG_STREAM(stream)>>>(a);
   else in_bwd_reduce_kernel<false, 0><<<grid, block, smem, TG_STREAM(stream)>>>(a);
   TG_RET();
@@ -1678,6 +1736,13 @@ int tg_in_bwd_apply_re(const void* raw, const void* y, const float* mr, const fl
   if (block > 1024) return tg_set_error("tg_in_bwd_apply_re: C too large");
   dim3 grid(strip_count(H * W, C, N, 16), N);
   const bool plain = !g_pool && (g_same || g_up) && (!g_up || g_up_pooled);
+  if (plain && stream_enabled() && stream_shape_ok(C)) {
+    tg::StreamArgs sa{};
+    sa.in0 = a.raw; sa.in1 = a.g_same ? a.g_same : a.g_up; sa.in2 = (a.g_same && a.g_up) ? a.g_up : nullptr;
+    sa.out = a.dz; sa.mr = mr; sa.gamma = gamma; sa.beta = beta; sa.red = a.red; sa.dgamma = dgamma; sa.dbeta = dbeta;
+    sa.N = N; sa.HW = H * W; sa.C = C; sa.c_valid = c_valid; sa.act = act; sa.slope = slope;
+    return launch_stream<2>(sa, TG_STREAM(stream));
+  }
   if (plain) in_bwd_reduce_kernel<true, 1><<<grid, block, 0, TG_STREAM(stream)>>>(a);
   else in_bwd_reduce_kernel<false, 1><<<grid, block, 0, TG_STREAM(stream)>>>(a);
   TG_RET();

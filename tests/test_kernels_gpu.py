@@ -205,6 +205,65 @@ def test_instance_norm_forward_backward_pool_upsample():
         assert rel(dgam_c, dg_ref) < 6e-3 and rel(dbet_c, db_ref) < 6e-3
 
 
+@pytest.mark.parametrize("n,c,h,w,act,two_routes", [(2, 64, 16, 24, 3, False), (3, 72, 31, 17, 3, True),
+                                                    (2, 180, 13, 11, 1, True), (2, 1000, 5, 7, 3, False),
+                                                    (2, 256, 61, 61, 1, False), (5, 512, 2, 2, 3, True),
+                                                    (2, 64, 128, 128, 3, True)])
+def test_instance_norm_streaming_passes(n, c, h, w, act, two_routes):
+    """The cp.async.bulk-ring form of the same-resolution InstanceNorm passes (csrc/tg_stream.cuh): forward, backward
+    statistics (with and without the dn store) and the recomputing apply pass, against torch autograd. Shapes: channel
+    groups that do not divide the CTA (C = 192), odd maps whose pixel count is not a chunk multiple (61^2, 5x7),
+    maps smaller than one chunk (2x2), one and two gradient routes, ReLU and LeakyReLU."""
+    C = _C()
+    from tactile_gan_b200._C import F as f32, ptr
+    g = torch.Generator().manual_seed(7)
+    cp = pad64(c)
+    slope = 0.2
+    x = torch.randn(n, c, h, w, generator=g).to(dev) * 2 + 0.5
+    gamma = (1 + 0.1 * torch.randn(c, generator=g)).to(dev)
+    beta = (0.1 * torch.randn(c, generator=g)).to(dev)
+    raw = nhwc_pad(x)
+    xb = raw[..., :c].permute(0, 3, 1, 2).float().requires_grad_(True)
+    ga, be = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    nrm = F.instance_norm(xb, weight=ga, bias=be, eps=1e-5)
+    y_ref = F.relu(nrm) if act == 3 else F.leaky_relu(nrm, slope)
+    mr = torch.zeros(n, cp, 2, device=dev)
+    C.call("in_stats_direct", ptr(raw), ptr(mr), n, h * w, cp, f32(1e-5))
+    y = torch.full_like(raw, 7.0)
+    C.call("in_act_fwd", ptr(raw), ptr(mr), ptr(gamma), ptr(beta), ptr(y), None, 0, None, n, h, w, cp, c, act,
+           f32(slope))
+    assert rel(y[..., :c].permute(0, 3, 1, 2), y_ref) < 4e-3
+    if cp > c:
+        assert y[..., c:].float().abs().max().item() == 0
+    q = lambda t: t.bfloat16().float()
+    gs = torch.randn(n, c, h, w, generator=g).to(dev)
+    gu = torch.randn(n, c, h, w, generator=g).to(dev)
+    loss = (y_ref * q(gs)).sum() + ((y_ref * q(gu)).sum() if two_routes else 0)
+    dx_ref, dg_ref, db_ref = torch.autograd.grad(loss, [xb, ga, be])
+    gs_p, gu_p = nhwc_pad(gs), nhwc_pad(gu)
+    up_ptr = ptr(gu_p) if two_routes else None
+    dn = torch.zeros_like(raw)
+    red_a, red_b = torch.zeros(n, cp, 2, device=dev), torch.zeros(n, cp, 2, device=dev)
+    C.call("in_bwd_reduce", ptr(raw), ptr(y), ptr(mr), ptr(gamma), ptr(beta), ptr(gs_p), None, 0, up_ptr, 1,
+           ptr(dn), ptr(red_a), n, h, w, cp, c, act, f32(slope))
+    C.call("in_bwd_reduce", ptr(raw), ptr(y), ptr(mr), ptr(gamma), ptr(beta), ptr(gs_p), None, 0, up_ptr, 1,
+           None, ptr(red_b), n, h, w, cp, c, act, f32(slope))
+    torch.cuda.synchronize()
+    assert rel(red_a, red_b) < 1e-5
+    mask = (nrm > 0).float() if act == 3 else torch.where(nrm > 0, 1.0, slope)
+    dn_ref = (q(gs) + (q(gu) if two_routes else 0)) * mask
+    assert rel(dn[..., :c].permute(0, 3, 1, 2), dn_ref) < 6e-3
+    dz = torch.zeros_like(raw)
+    dgam, dbet = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
+    C.call("in_bwd_apply_re", ptr(raw), ptr(y), ptr(mr), ptr(gamma), ptr(beta), ptr(gs_p), None, 0, up_ptr, 1,
+           ptr(red_b), ptr(dz), n, h, w, cp, c, act, f32(slope), ptr(dgam), ptr(dbet))
+    torch.cuda.synchronize()
+    assert C.error_flag() == 0
+    tol = 2e-2 if h * w <= 4 else 1e-2          # 2x2 maps: four samples per statistic
+    assert rel(dz[..., :c].permute(0, 3, 1, 2), dx_ref) < tol
+    assert rel(dgam, dg_ref) < 6e-3 and rel(dbet, db_ref) < 6e-3
+
+
 def test_adam_kernel_matches_torch_adam():
     """tg_adam_step against torch.optim.Adam(betas=(0.9,0.99)) over 3 steps, incl. the bf16 re-pack."""
     from tactile_gan_b200.layers import ConvLayer, ParamStore
