@@ -1569,6 +1569,16 @@ static int launch_stream(tg::StreamArgs a, cudaStream_t s) {
   return tg_check_launch("in_stream_kernel");
 }
 static bool stream_shape_ok(int C) { return C >= 64 && C <= 2048 && (C & 63) == 0; }
+// Which form is faster, measured per shape (profiles/r02_tail_microbench_*.txt): the register-staged passes reach
+// 0.88 of the copy bandwidth on the 268 MB, C = 64 tensors in the write-heavy passes (forward, apply) and start up
+// ~1.5 us faster on tensors under ~20 MB; the bulk-copy ring wins everywhere else (by 1.1-1.5x on 30-230 MB tensors
+// and on every statistics pass).
+static bool stream_wins(int mode, int N, int HW, int C) {
+  const double bytes = 2.0 * N * double(HW) * C;
+  if (mode != 1 && C == 64 && bytes >= 200e6) return false;
+  if (mode != 2 && bytes <= 20e6) return false;
+  return true;
+}
 
 extern "C" {
 
@@ -1666,7 +1676,7 @@ int tg_in_act_fwd(const void* raw, const float* mr, const float* gamma, const fl
   const bool quad = pool || up;
   if (quad && ((H | W) & 1)) return tg_set_error("tg_in_act_fwd: pool/upsample need even H, W");
   if (C > 8192) return tg_set_error("tg_in_act_fwd: C too large");
-  if (!quad && raw && mr && stream_enabled() && stream_shape_ok(C)) {
+  if (!quad && raw && mr && stream_enabled() && stream_shape_ok(C) && stream_wins(0, N, H * W, C)) {
     tg::StreamArgs a{};
     a.in0 = r; a.out = yy; a.mr = mr; a.gamma = gamma; a.beta = beta;
     a.N = N; a.HW = H * W; a.C = C; a.c_valid = c_valid; a.act = act; a.slope = slope;
@@ -1706,7 +1716,7 @@ int tg_in_bwd_reduce(const void* raw, const void* y, const float* mr, const floa
   dim3 grid(strip_count(H * W, C, N, 16), N);
   if (!raw && !dn) return tg_set_error("tg_in_bwd_reduce: a layer without norm needs the dn (= dz) output");
   const bool plain = !g_pool && (g_same || g_up) && (!g_up || g_up_pooled);
-  if (plain && raw && mr && red && stream_enabled() && stream_shape_ok(C)) {
+  if (plain && raw && mr && red && stream_enabled() && stream_shape_ok(C) && stream_wins(1, N, H * W, C)) {
     tg::StreamArgs sa{};
     sa.in0 = a.raw; sa.in1 = a.g_same ? a.g_same : a.g_up; sa.in2 = (a.g_same && a.g_up) ? a.g_up : nullptr;
     sa.out = a.dn; sa.mr = mr; sa.gamma = gamma; sa.beta = beta; sa.red = red;
@@ -1736,7 +1746,7 @@ int tg_in_bwd_apply_re(const void* raw, const void* y, const float* mr, const fl
   if (block > 1024) return tg_set_error("tg_in_bwd_apply_re: C too large");
   dim3 grid(strip_count(H * W, C, N, 16), N);
   const bool plain = !g_pool && (g_same || g_up) && (!g_up || g_up_pooled);
-  if (plain && stream_enabled() && stream_shape_ok(C)) {
+  if (plain && stream_enabled() && stream_shape_ok(C) && stream_wins(2, N, H * W, C)) {
     tg::StreamArgs sa{};
     sa.in0 = a.raw; sa.in1 = a.g_same ? a.g_same : a.g_up; sa.in2 = (a.g_same && a.g_up) ? a.g_up : nullptr;
     sa.out = a.dz; sa.mr = mr; sa.gamma = gamma; sa.beta = beta; sa.red = a.red; sa.dgamma = dgamma; sa.dbeta = dbeta;
