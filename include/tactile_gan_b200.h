@@ -116,6 +116,11 @@ int tg_gp_normsq_img(const float* g, int N, long long per_img, float* nsq, void*
 /* ---- InstanceNorm2d(eps, biased var) (+affine) fused with ReLU / LeakyReLU, optional AvgPool2d(2) /
  *      MaxPool2d(2) copy and nearest Upsample(x2) copy (UNet_plusplus.py:23-24,40-41; BCDUNet.py:110;
  *      PatchDiscriminator.py:16-17) and their backward */
+/* The passes whose inputs all sit at the unit's own resolution have two forms: register-staged loads and a
+ * cp.async.bulk (1-D TMA) shared-memory ring with a persistent grid. policy 0: never the ring, 1 (default): the faster
+ * form per shape as measured (profiles/r02_tail_microbench_*.txt), 2: the ring whenever the shape allows (tests).
+ * Returns the previous policy; a negative argument only queries. Env TG_STREAM=0/1/2 sets the initial value. */
+int tg_in_stream_policy(int policy);
 int tg_in_finalize(const float* partial, float* mr, int N, int T, int C, int count, float eps, void* stream);
 int tg_in_stats_direct(const void* raw, float* mr, int N, int HW, int C, float eps, void* stream);
 int tg_in_act_fwd(const void* raw, const float* mr, const float* gamma, const float* beta, void* y,
@@ -189,6 +194,20 @@ int tg_convlstm_gates(const void* z, int zc, const float* w_ci, const float* w_c
                       const float* c_prev, long long c_prev_stride_n, float* c_out, long long c_out_stride_n,
                       float* h_out, long long h_out_stride_n, void* h_nhwc, int hc, int N, int HW, int C, int act,
                       void* stream);
+
+/* Backward of the same cell (what autograd derives from BCDUNet.py:32-47 when the modules are trained): the gates are
+ * recomputed from the saved z / c_prev / c; dh = dh_ext (fp32 NCHW gradient of the frame's output, may be NULL) +
+ * dh_rec (bf16 NHWC d/dH_prev of the following step, may be NULL); dc_in / dc_out fp32 [N][C][HW] (dc_in NULL = 0,
+ * may alias dc_out); dz bf16 NHWC [N][HW][zc] feeds tg_conv_plan (input gradients w.r.t. X and H_prev) and
+ * tg_wgrad_plan; dW_c* fp32 [C][HW] are accumulated (+=, deterministic).
+ * tg_unpack_nhwc_tiled: bf16 NHWC -> fp32 NCHW with an image stride (the dX time slice), optionally accumulating. */
+int tg_convlstm_gates_bwd(const void* z, int zc, const float* w_ci, const float* w_cf, const float* w_co,
+                          const float* c_prev, long long c_prev_stride_n, const float* c_cur, long long c_cur_stride_n,
+                          const float* dh_ext, long long dh_ext_stride_n, const void* dh_rec, int hc,
+                          const float* dc_in, float* dc_out, void* dz, float* dw_ci, float* dw_cf, float* dw_co,
+                          int N, int HW, int C, int act, void* stream);
+int tg_unpack_nhwc_tiled(const void* in, int Cpad, float* out, long long out_stride_n, int N, int C, int HW,
+                         int accumulate, void* stream);
 
 /* ---- losses: GANLoss (generators/generators.py:80-105), nn.L1Loss (train.py:145), pan_loss
  *      (util.py:41-70), gradient_penalty norm (util.py:92-93) */

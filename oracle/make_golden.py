@@ -211,6 +211,53 @@ def convlstm_case(seed=61):
     return out
 
 
+def convlstm_grad_case(seed=71):
+    """Gradients of the reference's own ConvLSTMCell / ConvLSTM / ConvBLSTM (generators/BCDUNet.py:6-103) under torch
+    autograd on the CPU: loss = sum(out * G) with a seeded G; d loss / d input and d loss / d every parameter. The
+    trainable device modules (tactile_gan_b200/convlstm.py: _SeqFn / _CellFn) are compared against these."""
+    sys.path.insert(0, REF)
+    from generators import BCDUNet as ref
+    out = dict(meta=dict(seed=seed, torch=torch.__version__), cases=OrderedDict())
+    specs = [("cell_tanh", "cell", 24, 16, "tanh", 1), ("lstm_tanh", "lstm", 16, 8, "tanh", 3),
+             ("lstm_relu", "lstm", 8, 8, "relu", 2), ("blstm_tanh", "blstm", 16, 16, "tanh", 3),
+             ("lstm_last", "lstm_last", 8, 16, "tanh", 4)]
+    for name, kind, cin, cout, act, t in specs:
+        torch.manual_seed(seed)
+        frame, b = (16, 24), 2
+        if kind == "cell":
+            m = ref.ConvLSTMCell(cin, cout, (3, 3), (1, 1), act, frame)
+        elif kind in ("lstm", "lstm_last"):
+            m = ref.ConvLSTM(cin, cout, (3, 3), (1, 1), act, frame, return_sequence=kind == "lstm")
+        else:
+            m = ref.ConvBLSTM(cin, cout, (3, 3), (1, 1), act, frame, return_sequence=True)
+        with torch.no_grad():
+            for k, p in m.named_parameters():
+                if k.endswith("conv.weight"):
+                    p.normal_(0, 0.1)
+                elif k.endswith("conv.bias"):
+                    p.normal_(0, 0.2)
+        g = torch.Generator().manual_seed(seed + 1)
+        if kind == "cell":
+            x = torch.randn(b, cin, *frame, generator=g).requires_grad_(True)
+            h0 = (torch.randn(b, cout, *frame, generator=g) * 0.5).requires_grad_(True)
+            c0 = torch.randn(b, cout, *frame, generator=g).requires_grad_(True)
+            h, c = m(x, h0, c0)
+            gh, gc = torch.randn(h.shape, generator=g), torch.randn(c.shape, generator=g)
+            loss = (h * gh).sum() + (c * gc).sum()
+            loss.backward()
+            io = dict(x=x.detach(), h0=h0.detach(), c0=c0.detach(), gh=gh, gc=gc, dx=x.grad, dh0=h0.grad, dc0=c0.grad)
+        else:
+            x = torch.randn(b, t, cin, *frame, generator=g).requires_grad_(True)
+            y = m(x)
+            gy = torch.randn(y.shape, generator=g)
+            (y * gy).sum().backward()
+            io = dict(x=x.detach(), gy=gy, dx=x.grad)
+        out["cases"][name] = dict(kind=kind, cin=cin, cout=cout, act=act, frame=frame,
+                                  sd=OrderedDict((k, v.detach().clone()) for k, v in m.state_dict().items()),
+                                  grads=OrderedDict((k, p.grad.clone()) for k, p in m.named_parameters()), **io)
+    return out
+
+
 def state_dict_keys():
     """Key/shape inventory of all reference networks at nf=64 (the checkpoint-layout contract)."""
     _, create_gen, _, create_disc = reference_modules()
@@ -248,5 +295,6 @@ if __name__ == "__main__":
         print(name, fx["loss"], fx["grad_norm"])
     torch.save(eval_case(), os.path.join(OUT, "eval_pair_fuzzy.pt"))
     torch.save(convlstm_case(), os.path.join(OUT, "convlstm.pt"))
+    torch.save(convlstm_grad_case(), os.path.join(OUT, "convlstm_grad.pt"))
     torch.save(state_dict_keys(), os.path.join(OUT, "state_dict_keys.pt"))
     print("wrote", OUT)

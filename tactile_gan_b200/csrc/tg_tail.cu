@@ -1407,6 +1407,133 @@ convlstm_gates_kernel(const __nv_bfloat16* __restrict__ z, int zc, const float* 
   }
 }
 
+// Backward of one ConvLSTM time step (the adjoint of convlstm_gates_kernel). The gates are recomputed from the saved
+// z (bf16 NHWC), c_prev and c (fp32 NCHW); dh = dh_ext (fp32 NCHW: the gradient of this frame's output, image stride
+// dhe_sn) + dh_rec (bf16 NHWC: d/dH_prev of step t+1, from the gate conv's input gradient); dc_in carries the cell
+// gradient of step t+1 (NULL = 0):
+//   dzo = dh*act(c)*o(1-o)          dc = dc_in + dh*o*act'(c) + dzo*W_co
+//   dzi = dc*g*i(1-i)   dzf = dc*c_prev*f(1-f)   dzg = dc*i*act'(zg)   dc_prev = dc*f + dzi*W_ci + dzf*W_cf
+//   dW_co += sum_n dzo*c   dW_ci += sum_n dzi*c_prev   dW_cf += sum_n dzf*c_prev
+// A block owns 32 pixels x 32 channels and walks the batch itself, so the peephole gradients are plain
+// read-modify-writes (deterministic, no atomics); dz leaves as bf16 NHWC [N][HW][zc] -- the operand of the gate
+// conv's input-gradient and weight-gradient GEMMs.
+__global__ void __launch_bounds__(256)
+convlstm_gates_bwd_kernel(const __nv_bfloat16* __restrict__ z, int zc, const float* __restrict__ w_ci,
+                          const float* __restrict__ w_cf, const float* __restrict__ w_co,
+                          const float* __restrict__ c_prev, long long cp_sn, const float* __restrict__ c_cur,
+                          long long cc_sn, const float* __restrict__ dh_ext, long long dhe_sn,
+                          const __nv_bfloat16* __restrict__ dh_rec, int hc, const float* dc_in, float* dc_out,
+                          __nv_bfloat16* __restrict__ dz, float* __restrict__ dw_ci, float* __restrict__ dw_cf,
+                          float* __restrict__ dw_co, int N, int HW, int C, int act) {
+  __shared__ float zt[4][32][33];
+  __shared__ float ht[32][33];
+  const int cb = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int pl = threadIdx.x & 31, p = p0 + pl;
+  float aci[4] = {0.f, 0.f, 0.f, 0.f}, acf[4] = {0.f, 0.f, 0.f, 0.f}, aco[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int n = 0; n < N; ++n) {
+    for (int v = threadIdx.x; v < 512; v += 256) {
+      const int g = v >> 7, ql = (v >> 2) & 31, k = v & 3;
+      const int q = p0 + ql, c = cb + 8 * k;
+      if (q < HW && c < C) {
+        float f[8];
+        unpack8(ldg16(z + (size_t(n) * HW + q) * zc + g * C + c), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) zt[g][ql][8 * k + j] = f[j];
+      }
+    }
+    if (threadIdx.x < 128) {
+      const int ql = threadIdx.x >> 2, k = threadIdx.x & 3;
+      const int q = p0 + ql, c = cb + 8 * k;
+      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (dh_rec && q < HW && c < C) unpack8(ldg16(dh_rec + (size_t(n) * HW + q) * hc + c), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ht[ql][8 * k + j] = f[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int slot = 0; slot < 4; ++slot) {
+      const int cl = (threadIdx.x >> 5) + 8 * slot;
+      const int c = cb + cl;
+      float dzi = 0.f, dzf = 0.f, dzg = 0.f, dzo = 0.f;
+      if (c < C && p < HW) {
+        const size_t idx = size_t(c) * HW + p;
+        const float cp = c_prev ? c_prev[size_t(n) * cp_sn + idx] : 0.f;
+        const float cn = c_cur[size_t(n) * cc_sn + idx];
+        const float wci = __ldg(w_ci + idx), wcf = __ldg(w_cf + idx), wco = __ldg(w_co + idx);
+        const float gi = sigmoid_f(zt[0][pl][cl] + wci * cp);
+        const float gf = sigmoid_f(zt[1][pl][cl] + wcf * cp);
+        const float zg = zt[2][pl][cl];
+        const float gg = act == 4 ? tanhf(zg) : fmaxf(zg, 0.f);
+        const float dgg = act == 4 ? 1.f - gg * gg : (zg > 0.f ? 1.f : 0.f);
+        const float go = sigmoid_f(zt[3][pl][cl] + wco * cn);
+        const float ac = act == 4 ? tanhf(cn) : fmaxf(cn, 0.f);
+        const float dac = act == 4 ? 1.f - ac * ac : (cn > 0.f ? 1.f : 0.f);
+        const float dh = (dh_ext ? dh_ext[size_t(n) * dhe_sn + idx] : 0.f) + ht[pl][cl];
+        dzo = dh * ac * go * (1.f - go);
+        const float dc = (dc_in ? dc_in[size_t(n) * C * HW + idx] : 0.f) + dh * go * dac + dzo * wco;
+        dzi = dc * gg * gi * (1.f - gi);
+        dzf = dc * cp * gf * (1.f - gf);
+        dzg = dc * gi * dgg;
+        dc_out[size_t(n) * C * HW + idx] = dc * gf + dzi * wci + dzf * wcf;
+        aco[slot] += dzo * cn;
+        aci[slot] += dzi * cp;
+        acf[slot] += dzf * cp;
+      }
+      // the z tile is dead for this (pixel, channel): reuse it for dz
+      zt[0][pl][cl] = dzi; zt[1][pl][cl] = dzf; zt[2][pl][cl] = dzg; zt[3][pl][cl] = dzo;
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < 512; v += 256) {
+      const int g = v >> 7, ql = (v >> 2) & 31, k = v & 3;
+      const int q = p0 + ql, c = cb + 8 * k;
+      if (q < HW && c < C) {
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = zt[g][ql][8 * k + j];
+        stg16(dz + (size_t(n) * HW + q) * zc + g * C + c, pack8(f));
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int slot = 0; slot < 4; ++slot) {
+    const int cl = (threadIdx.x >> 5) + 8 * slot;
+    const int c = cb + cl;
+    if (c < C && p < HW) {
+      const size_t idx = size_t(c) * HW + p;
+      dw_ci[idx] += aci[slot];
+      dw_cf[idx] += acf[slot];
+      dw_co[idx] += aco[slot];
+    }
+  }
+}
+
+// bf16 NHWC [N][HW][Cpad] -> fp32 NCHW (image stride out_sn, first C channels), transposed through shared memory;
+// accumulate != 0 adds into the destination (the input gradient of a frame that feeds two cells)
+__global__ void __launch_bounds__(256)
+unpack_nhwc_tiled_kernel(const __nv_bfloat16* __restrict__ in, int Cpad, float* __restrict__ out, long long out_sn,
+                         int C, int HW, int accumulate) {
+  __shared__ float t[64][65];
+  const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+  for (int v = threadIdx.x; v < 512; v += 256) {
+    const int pl = v >> 3, k = v & 7;
+    const int p = p0 + pl, c = c0 + 8 * k;
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (p < HW && c < Cpad) unpack8(ldg16(in + (size_t(n) * HW + p) * Cpad + c), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[8 * k + j][pl] = f[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4096; i += 256) {
+    const int cl = i >> 6, pl = i & 63;
+    const int c = c0 + cl, p = p0 + pl;
+    if (c < C && p < HW) {
+      float* dst = out + size_t(n) * out_sn + size_t(c) * HW + p;
+      *dst = accumulate ? *dst + t[cl][pl] : t[cl][pl];
+    }
+  }
+}
+
 // Gradient penalty: nsq[n] = sum_{pix, j<cj} (g[n,pix,c_off+j] + 1e-16)^2
 __global__ void gp_normsq_kernel(const __nv_bfloat16* __restrict__ g, int HW, int C, int c_off, int cj,
                                  float* __restrict__ nsq) {
@@ -1533,14 +1660,15 @@ static inline int grid_for(size_t work, int block, int cap = 148 * 16) {
 
 // Streaming (cp.async.bulk ring) form of the same-resolution passes, tg_stream.cuh. TG_STREAM=0 routes everything
 // back to the register-staged kernels (A/B runs).
-static bool stream_enabled() {
-  static int on = -1;
-  if (on < 0) {
+static int g_stream_policy = -1;      // 0 never, 1 per-shape choice, 2 whenever the shape allows
+static int stream_policy() {
+  if (g_stream_policy < 0) {
     const char* e = getenv("TG_STREAM");
-    on = (e && e[0] == '0') ? 0 : 1;
+    g_stream_policy = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
   }
-  return on == 1;
+  return g_stream_policy;
 }
+static bool stream_enabled() { return stream_policy() != 0; }
 template <int MODE>
 static int launch_stream(tg::StreamArgs a, cudaStream_t s) {
   using namespace tg;
@@ -1574,6 +1702,7 @@ static bool stream_shape_ok(int C) { return C >= 64 && C <= 2048 && (C & 63) == 
 // ~1.5 us faster on tensors under ~20 MB; the bulk-copy ring wins everywhere else (by 1.1-1.5x on 30-230 MB tensors
 // and on every statistics pass).
 static bool stream_wins(int mode, int N, int HW, int C) {
+  if (stream_policy() == 2) return true;
   const double bytes = 2.0 * N * double(HW) * C;
   if (mode != 1 && C == 64 && bytes >= 200e6) return false;
   if (mode != 2 && bytes <= 20e6) return false;
@@ -1643,6 +1772,12 @@ int tg_gp_normsq_img(const float* g, int N, long long per_img, float* nsq, void*
   dim3 grid(grid_for(size_t(per_img), 256, 64), N);
   gp_normsq_img_kernel<<<grid, 256, 0, TG_STREAM(stream)>>>(g, size_t(per_img), nsq);
   TG_RET();
+}
+
+int tg_in_stream_policy(int policy) {
+  const int prev = stream_policy();
+  if (policy >= 0 && policy <= 2) g_stream_policy = policy;
+  return prev;
 }
 
 int tg_in_finalize(const float* partial, float* mr, int N, int T, int C, int count, float eps,
@@ -1942,6 +2077,33 @@ int tg_convlstm_gates(const void* z, int zc, const float* w_ci, const float* w_c
   convlstm_gates_kernel<<<grid, 256, 0, TG_STREAM(stream)>>>(
       (const __nv_bfloat16*)z, zc, w_ci, w_cf, w_co, c_prev, c_prev_stride_n, c_out, c_out_stride_n, h_out,
       h_out_stride_n, (__nv_bfloat16*)h_nhwc, hc, HW, C, act);
+  TG_RET();
+}
+
+int tg_convlstm_gates_bwd(const void* z, int zc, const float* w_ci, const float* w_cf, const float* w_co,
+                          const float* c_prev, long long c_prev_stride_n, const float* c_cur, long long c_cur_stride_n,
+                          const float* dh_ext, long long dh_ext_stride_n, const void* dh_rec, int hc,
+                          const float* dc_in, float* dc_out, void* dz, float* dw_ci, float* dw_cf, float* dw_co,
+                          int N, int HW, int C, int act, void* stream) {
+  if (C % 8 || zc < 4 * C || zc % 8) return tg_set_error("tg_convlstm_gates_bwd: C % 8 == 0 and zc >= 4*C required");
+  if (dh_rec && (hc < C || hc % 8)) return tg_set_error("tg_convlstm_gates_bwd: hc must be a multiple of 8 and >= C");
+  if (act != 3 && act != 4) return tg_set_error("tg_convlstm_gates_bwd: activation must be relu (3) or tanh (4)");
+  if (!z || !c_cur || !dc_out || !dz || !dw_ci || !dw_cf || !dw_co)
+    return tg_set_error("tg_convlstm_gates_bwd: null argument");
+  dim3 grid((HW + 31) / 32, (C + 31) / 32);
+  convlstm_gates_bwd_kernel<<<grid, 256, 0, TG_STREAM(stream)>>>(
+      (const __nv_bfloat16*)z, zc, w_ci, w_cf, w_co, c_prev, c_prev_stride_n, c_cur, c_cur_stride_n, dh_ext,
+      dh_ext_stride_n, (const __nv_bfloat16*)dh_rec, hc, dc_in, dc_out, (__nv_bfloat16*)dz, dw_ci, dw_cf, dw_co, N, HW,
+      C, act);
+  TG_RET();
+}
+
+int tg_unpack_nhwc_tiled(const void* in, int Cpad, float* out, long long out_stride_n, int N, int C, int HW,
+                         int accumulate, void* stream) {
+  if (Cpad % 8 || C > Cpad) return tg_set_error("tg_unpack_nhwc_tiled: Cpad must be a multiple of 8 and >= C");
+  dim3 grid((HW + 63) / 64, (C + 63) / 64, N);
+  unpack_nhwc_tiled_kernel<<<grid, 256, 0, TG_STREAM(stream)>>>((const __nv_bfloat16*)in, Cpad, out, out_stride_n, C,
+                                                                HW, accumulate);
   TG_RET();
 }
 

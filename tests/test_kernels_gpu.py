@@ -216,6 +216,14 @@ def test_instance_norm_streaming_passes(n, c, h, w, act, two_routes):
     maps smaller than one chunk (2x2), one and two gradient routes, ReLU and LeakyReLU."""
     C = _C()
     from tactile_gan_b200._C import F as f32, ptr
+    prev = C.lib().tg_in_stream_policy(2)        # the ring form whenever the shape allows (the default picks per shape)
+    try:
+        _streaming_case(C, f32, ptr, n, c, h, w, act, two_routes)
+    finally:
+        C.lib().tg_in_stream_policy(prev)
+
+
+def _streaming_case(C, f32, ptr, n, c, h, w, act, two_routes):
     g = torch.Generator().manual_seed(7)
     cp = pad64(c)
     slope = 0.2
@@ -459,8 +467,8 @@ def test_device_augmentation_matches_oracle(n, h, w, cb):
 
 def _convlstm_module(c):
     from tactile_gan_b200.generators.BCDUNet import ConvBLSTM, ConvLSTM, ConvLSTMCell
-    cls = {"cell": ConvLSTMCell, "lstm": ConvLSTM, "blstm": ConvBLSTM}[c["kind"]]
-    kw = {} if c["kind"] == "cell" else dict(return_sequence=True)
+    cls = {"cell": ConvLSTMCell, "lstm": ConvLSTM, "lstm_last": ConvLSTM, "blstm": ConvBLSTM}[c["kind"]]
+    kw = {} if c["kind"] == "cell" else dict(return_sequence=c["kind"] != "lstm_last")
     m = cls(c["cin"], c["cout"], (3, 3), (1, 1), c["act"], c["frame"], **kw)
     m.load_state_dict(c["sd"])
     return m.cuda()
@@ -472,8 +480,6 @@ def test_convlstm_modules_match_reference_fixture(golden_dir):
     fp32 cell state: rel-l2 <= 1e-2 on H and C after up to 3 recurrent steps."""
     import os
     fx = torch.load(os.path.join(golden_dir, "convlstm.pt"), weights_only=False)
-    with pytest.raises(NotImplementedError):                 # forward-only: refuses to run under autograd
-        _convlstm_module(fx["cases"]["lstm_relu"])(fx["cases"]["lstm_relu"]["x"].cuda())
     with torch.no_grad():
         for name, c in fx["cases"].items():
             m = _convlstm_module(c)
@@ -490,6 +496,42 @@ def test_convlstm_modules_match_reference_fixture(golden_dir):
                 assert torch.equal(m(c["x"].cuda()), out[:, -1])
     with pytest.raises(_C().TgError):
         _convlstm_module(fx["cases"]["lstm_tanh"])(fx["cases"]["lstm_tanh"]["x"])    # CPU tensor: no fallback
+
+
+def test_convlstm_modules_train_against_reference_autograd(golden_dir):
+    """SURVEY 8f row 4 / VERDICT r1 #9: the ConvLSTM modules are trainable. Forward under autograd, then
+    loss = sum(out * G): d loss / d input and every parameter gradient (gate conv weight + bias through the two-source
+    wgrad GEMM, the three peepholes) against what torch autograd gives on the REFERENCE's own classes
+    (tests/golden/convlstm_grad.pt, oracle/make_golden.py:convlstm_grad_case). bf16 operands / bf16 dz, fp32 cell
+    state and gradient carries: rel-l2 <= 2.5 % over up to 4 recurrent steps (cell, sequences with tanh / relu,
+    bidirectional, last-frame-only)."""
+    import os
+    fx = torch.load(os.path.join(golden_dir, "convlstm_grad.pt"), weights_only=False)
+    for name, c in fx["cases"].items():
+        m = _convlstm_module(c)
+        x = c["x"].cuda().requires_grad_(True)
+        if c["kind"] == "cell":
+            h0, c0 = c["h0"].cuda().requires_grad_(True), c["c0"].cuda().requires_grad_(True)
+            h, cc = m(x, h0, c0)
+            ((h * c["gh"].cuda()).sum() + (cc * c["gc"].cuda()).sum()).backward()
+            assert rel(h0.grad, c["dh0"]) < 2.5e-2 and rel(c0.grad, c["dc0"]) < 2.5e-2, name
+        else:
+            y = m(x)
+            assert y.shape == c["gy"].shape, name
+            (y * c["gy"].cuda()).sum().backward()
+        torch.cuda.synchronize()
+        assert _C().error_flag() == 0
+        assert rel(x.grad, c["dx"]) < 2.5e-2, (name, rel(x.grad, c["dx"]))
+        for k, p in m.named_parameters():
+            assert p.grad is not None and rel(p.grad, c["grads"][k]) < 2.5e-2, (name, k, rel(p.grad, c["grads"][k]))
+    # a second backward through a fresh forward gives the same gradients (the arena is zeroed per node)
+    c = fx["cases"]["lstm_tanh"]
+    m = _convlstm_module(c)
+    for _ in range(2):
+        m.zero_grad()
+        x = c["x"].cuda().requires_grad_(True)
+        (m(x) * c["gy"].cuda()).sum().backward()
+    assert rel(m.convLSTMcell.conv.weight.grad, c["grads"]["convLSTMcell.conv.weight"]) < 2.5e-2
 
 
 def test_bcdunet_convlstm_skip_module_full_size():

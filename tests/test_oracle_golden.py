@@ -131,3 +131,27 @@ def test_oracle_convlstm_matches_reference_classes(golden_dir):
             torch.testing.assert_close(fn(c["sd"], c["x"], c["act"]), c["out"], rtol=1e-5, atol=1e-6)
             last = fn(c["sd"], c["x"], c["act"], return_sequence=False)
             assert torch.equal(last, fn(c["sd"], c["x"], c["act"])[:, -1])
+
+
+def test_oracle_convlstm_gradients_match_reference_autograd(golden_dir):
+    """The oracle's ConvLSTM restatement is differentiable torch code: its autograd gradients must equal the ones
+    torch computed on the reference's own classes (tests/golden/convlstm_grad.pt) -- this pins the backward the
+    device modules are tested against."""
+    fx = _load(golden_dir, "convlstm_grad")
+    for name, c in fx["cases"].items():
+        sd = {k: v.clone().requires_grad_(True) for k, v in c["sd"].items()}
+        x = c["x"].clone().requires_grad_(True)
+        if c["kind"] == "cell":
+            h0, c0 = c["h0"].clone().requires_grad_(True), c["c0"].clone().requires_grad_(True)
+            h, cc = orc.convlstm_cell(sd, x, h0, c0, c["act"])
+            ((h * c["gh"]).sum() + (cc * c["gc"]).sum()).backward()
+            assert torch.allclose(h0.grad, c["dh0"], atol=1e-5) and torch.allclose(c0.grad, c["dc0"], atol=1e-5)
+        else:
+            if c["kind"] == "blstm":
+                y = orc.convblstm(sd, x, c["act"])
+            else:
+                y = orc.convlstm(sd, x, c["act"], return_sequence=c["kind"] == "lstm")
+            (y * c["gy"]).sum().backward()
+        assert torch.allclose(x.grad, c["dx"], atol=1e-5), name
+        for k, g in c["grads"].items():
+            assert torch.allclose(sd[k].grad, g, atol=2e-4, rtol=1e-4), (name, k)

@@ -16,8 +16,13 @@ PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if 
     os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6464.9
 
 
+NCU = "--ncu" in sys.argv          # one launch per pass of the first shape only (for `ncu --set full`)
+
+
 def bench(fn, nbytes, reps=12):
-    for i in range(3):
+    if NCU:
+        reps = 1
+    for i in range(0 if NCU else 3):
         fn(i)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -36,7 +41,7 @@ if __name__ == "__main__":
               (64, 63, 63, 128), (64, 61, 61, 256), (64, 59, 59, 512), (4, 256, 256, 64), (4, 2, 2, 512)]
     print("TG_STREAM =", os.environ.get("TG_STREAM", "1"), " peak", PEAK, "GB/s")
     tot_t, tot_b = 0.0, 0.0
-    for n, h, w, c in shapes:
+    for n, h, w, c in (shapes[:1] if NCU else shapes):
         sets = 3 if n * h * w * c * 2 * 3 < 3e9 else 2
         bufs = [[torch.randn(n, h, w, c, device=dev).bfloat16() for _ in range(4)] for _ in range(sets)]
         mr = torch.rand(n, c, 2, device=dev) + 0.5
