@@ -153,12 +153,15 @@ int tg_add(const void* a, const void* b, void* out, long long numel, void* strea
 int tg_act_bwd(const void* g, const void* y, void* out, long long numel, int act, float slope, void* stream);
 
 /* ---- FeatureMapBlock: 1x1 conv + bias (+Tanh) (UNet_plusplus.py:5-16) forward / backward */
+/* w: the module's own fp32 [co][ci] weight (ci <= C = 64 real input channels of the 64-padded NHWC input) */
 int tg_fmap_fwd(const void* x, const float* w, const float* b, float* out, int N, int HW, int C, int co,
-                int use_tanh, void* stream);
-/* dw: fp32 [dw_replicas][co][64] accumulated with atomics (blocks spread over the replicas; the caller sums them) */
+                int use_tanh, int ci, void* stream);
+/* dw: fp32 [dw_replicas][co][64] accumulated with atomics (blocks spread over the replicas);
+ * tg_fmap_wgrad_fold adds their sum to grad [co][ci] and clears them for the next pass */
 int tg_fmap_bwd(const void* x, const float* w, const float* out, const float* g1, const float* g2,
-                void* dx, float* dw, int dw_replicas, float* db, int N, int HW, int C, int co, int use_tanh,
+                void* dx, float* dw, int dw_replicas, float* db, int N, int HW, int C, int co, int use_tanh, int ci,
                 void* stream);
+int tg_fmap_wgrad_fold(float* dw, int dw_replicas, int co, int ci, float* grad, void* stream);
 
 /* ---- version-1 perceptual term, VGGPerceptualLoss (util.py:100-144): input transform (channel repeat,
  *      ImageNet mean / std, bilinear resize align_corners=False) and its transpose, MaxPool2d(2) for layers without
@@ -208,6 +211,9 @@ int tg_convlstm_gates_bwd(const void* z, int zc, const float* w_ci, const float*
                           int N, int HW, int C, int act, void* stream);
 int tg_unpack_nhwc_tiled(const void* in, int Cpad, float* out, long long out_stride_n, int N, int C, int HW,
                          int accumulate, void* stream);
+
+/* gradient-penalty interpolation weights (util.py:79-83): alpha = u, or (u + 1) / 2 for version 2; and 1 - alpha */
+int tg_gp_alpha(const float* u, int version, float* alpha, float* one_minus_alpha, int n, void* stream);
 
 /* ---- losses: GANLoss (generators/generators.py:80-105), nn.L1Loss (train.py:145), pan_loss
  *      (util.py:41-70), gradient_penalty norm (util.py:92-93) */

@@ -922,9 +922,10 @@ __global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ g, const __nv_b
 // out[n,o,h,w] = act(sum_c x[n,h,w,c] * w[o][c] + b[o]); fp32 NCHW out.
 __global__ void fmap_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                                 const float* __restrict__ b, float* __restrict__ out, int N, int HW,
-                                int C, int co, int use_tanh) {
+                                int C, int co, int use_tanh, int ci) {
   __shared__ float sw[4 * 64 + 4];
-  for (int i = threadIdx.x; i < co * C; i += blockDim.x) sw[i] = w[i];
+  // w is the module's own [co][ci] weight (torch layout, ci <= C real input channels); padded channels read 0
+  for (int i = threadIdx.x; i < co * C; i += blockDim.x) sw[i] = (i % C) < ci ? w[(i / C) * ci + i % C] : 0.f;
   if (threadIdx.x < co) sw[4 * 64 + threadIdx.x] = b[threadIdx.x];
   __syncthreads();
   const size_t total = size_t(N) * HW;
@@ -958,10 +959,10 @@ fmap_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w
                 const float* __restrict__ out, const float* __restrict__ g1,
                 const float* __restrict__ g2, __nv_bfloat16* __restrict__ dx,
                 float* __restrict__ dw, float* __restrict__ db, int N, int HW, int C,
-                int co, int use_tanh, int replicas) {
+                int co, int use_tanh, int replicas, int ci) {
   __shared__ float sw[4 * 64];
   __shared__ float sacc[4 * 64 + 4];
-  for (int i = threadIdx.x; i < co * C; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < co * C; i += blockDim.x) sw[i] = (i % C) < ci ? w[(i / C) * ci + i % C] : 0.f;
   for (int i = threadIdx.x; i < 4 * 64 + 4; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
   float lw[4][8];  // this lane accumulates dw for channel group (lane & 7) only
@@ -1658,6 +1659,32 @@ static inline int grid_for(size_t work, int block, int cap = 148 * 16) {
 #define TG_STREAM(s) reinterpret_cast<cudaStream_t>(s)
 #define TG_RET() return tg_check_launch(__func__)
 
+// grad[o][c] += sum_r dw[r][o][c] over the replicas tg_fmap_bwd spread its atomics on; the replicas are cleared for
+// the next backward pass (one launch instead of a fill, a reduction and an add)
+__global__ void fmap_wgrad_fold_kernel(float* __restrict__ dw, int replicas, int co, int ci, float* __restrict__ grad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= co * 64) return;
+  const int o = i >> 6, c = i & 63;
+  float acc = 0.f;
+  for (int r = 0; r < replicas; ++r) {
+    acc += dw[(size_t(r) * co + o) * 64 + c];
+    dw[(size_t(r) * co + o) * 64 + c] = 0.f;
+  }
+  if (c < ci && grad) grad[o * ci + c] += acc;
+}
+
+// util.py:79-83: alpha ~ U[0,1) per sample; version 2 maps it to [0.5, 1). Writes alpha and 1 - alpha (the
+// per-sample weights tg_im2col_pack mixes real_B and fake_B with).
+__global__ void gp_alpha_kernel(const float* __restrict__ u, int version2, float* __restrict__ alpha,
+                                float* __restrict__ one_minus, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a = u[i];
+  if (version2) a = (a + 1.f) / 2.f;
+  alpha[i] = a;
+  one_minus[i] = 1.f - a;
+}
+
 // Streaming (cp.async.bulk ring) form of the same-resolution passes, tg_stream.cuh. TG_STREAM=0 routes everything
 // back to the register-staged kernels (A/B runs).
 static int g_stream_policy = -1;      // 0 never, 1 per-shape choice, 2 whenever the shape allows
@@ -1957,24 +1984,35 @@ int tg_act_bwd(const void* g, const void* y, void* out, long long numel, int act
 }
 
 int tg_fmap_fwd(const void* x, const float* w, const float* b, float* out, int N, int HW, int C, int co,
-                int use_tanh, void* stream) {
-  if (C != 64 || co > 4) return tg_set_error("tg_fmap_fwd: expects C == 64, co <= 4");
+                int use_tanh, int ci, void* stream) {
+  if (C != 64 || co > 4 || ci > C || ci < 1) return tg_set_error("tg_fmap_fwd: expects C == 64, co <= 4, ci <= C");
   fmap_fwd_kernel<<<grid_for(size_t(N) * HW, 256, 148 * 16), 256, 0, TG_STREAM(stream)>>>(
-      (const __nv_bfloat16*)x, w, b, out, N, HW, C, co, use_tanh);
+      (const __nv_bfloat16*)x, w, b, out, N, HW, C, co, use_tanh, ci);
   TG_RET();
 }
 
 int tg_fmap_bwd(const void* x, const float* w, const float* out, const float* g1, const float* g2,
-                void* dx, float* dw, int dw_replicas, float* db, int N, int HW, int C, int co, int use_tanh,
+                void* dx, float* dw, int dw_replicas, float* db, int N, int HW, int C, int co, int use_tanh, int ci,
                 void* stream) {
   if (dw_replicas < 1) return tg_set_error("tg_fmap_bwd: dw_replicas >= 1");
-  if (C != 64 || co > 4) return tg_set_error("tg_fmap_bwd: expects C == 64, co <= 4");
+  if (C != 64 || co > 4 || ci > C || ci < 1) return tg_set_error("tg_fmap_bwd: expects C == 64, co <= 4, ci <= C");
   int strips = (HW + 1023) / 1024;                 // >= 32 pixels per lane per block
   const int cap = (148 * 8 + N - 1) / N;
   if (strips > cap) strips = cap;
   if (strips < 1) strips = 1;
   fmap_bwd_kernel<<<dim3(strips, N), 256, 0, TG_STREAM(stream)>>>(
-      (const __nv_bfloat16*)x, w, out, g1, g2, (__nv_bfloat16*)dx, dw, db, N, HW, C, co, use_tanh, dw_replicas);
+      (const __nv_bfloat16*)x, w, out, g1, g2, (__nv_bfloat16*)dx, dw, db, N, HW, C, co, use_tanh, dw_replicas, ci);
+  TG_RET();
+}
+
+int tg_fmap_wgrad_fold(float* dw, int dw_replicas, int co, int ci, float* grad, void* stream) {
+  if (co > 4 || ci > 64) return tg_set_error("tg_fmap_wgrad_fold: co <= 4, ci <= 64");
+  fmap_wgrad_fold_kernel<<<(co * 64 + 127) / 128, 128, 0, TG_STREAM(stream)>>>(dw, dw_replicas, co, ci, grad);
+  TG_RET();
+}
+
+int tg_gp_alpha(const float* u, int version, float* alpha, float* one_minus_alpha, int n, void* stream) {
+  gp_alpha_kernel<<<(n + 127) / 128, 128, 0, TG_STREAM(stream)>>>(u, version == 2, alpha, one_minus_alpha, n);
   TG_RET();
 }
 

@@ -100,7 +100,7 @@ class ConvUnit:
             self.tpi = _C.conv_query_tiles(n, gh, gw, True)[3] * ph * ph if self.epi_stats else 1
             self.partial = torch.zeros(n, self.tpi, self.c, 2, device=dev) if self.epi_stats else None
             self.mr = torch.zeros(n, self.c, 2, device=dev)
-            self.red = torch.zeros(n, self.c, 2, device=dev)
+            self.red = None          # [n][c][2] backward sums: a slice of the engine's red arena (GraphEngine.finish)
         eng.units.append(self)
 
     def build(self, backward):
@@ -157,7 +157,8 @@ class ConvUnit:
         up_pooled = int(bool(g_up is not None and self.up.grad_pooled))
         g, b = self._aff()
         if self.norm:
-            self.red.zero_()
+            if not eng.red_clean:
+                self.red.zero_()               # stand-alone call; the engines clear the whole arena once per pass
             elems = 2.0 * n * ho * wo * c      # bytes of one bf16 tensor of this unit
             routes = ((1 if g_same is not None else 0) + (0.25 if g_pool is not None else 0) +
                       ((1 if up_pooled else 4) if g_up is not None else 0))
@@ -219,23 +220,21 @@ class HeadUnit:
         self.n, self.hw = n, h * w
         self.out = torch.zeros(n, self.co, h, w, device=eng.device)
         self.dx = bf16(n, h, w, c, device=eng.device)
-        self.wpad = torch.zeros(self.co, 64, device=eng.device)     # fp32 [co][64]
-        self.dwpad = torch.zeros(32, self.co, 64, device=eng.device)   # 32 replicas: see tg_fmap_bwd
+        self.dwpad = torch.zeros(32, self.co, 64, device=eng.device)   # 32 replicas: see tg_fmap_bwd; kept zero between passes
 
     def forward(self):
-        self.wpad[:, :self.ci].copy_(self.weight.detach().view(self.co, self.ci))
-        _C.call("fmap_fwd", ptr(self.src.buf), ptr(self.wpad), ptr(self.bias.detach()), ptr(self.out), self.n,
-                self.hw, 64, self.co, int(self.use_tanh))
+        _C.call("fmap_fwd", ptr(self.src.buf), ptr(self.weight.detach()), ptr(self.bias.detach()), ptr(self.out),
+                self.n, self.hw, 64, self.co, int(self.use_tanh), self.ci)
         return self.out
 
     def backward(self, g1, g2=None, wgrad=True):
         st = self.eng.store
-        self.dwpad.zero_()
-        _C.call("fmap_bwd", ptr(self.src.buf), ptr(self.wpad), ptr(self.out), ptr(g1), ptr(g2), ptr(self.dx),
-                ptr(self.dwpad), self.dwpad.shape[0], ptr(st.grad_of(self.bias)), self.n, self.hw, 64, self.co,
-                int(self.use_tanh))
-        if wgrad:
-            st.grad_of(self.weight).view(self.co, self.ci).add_(self.dwpad.sum(0)[:, :self.ci])
+        _C.call("fmap_bwd", ptr(self.src.buf), ptr(self.weight.detach()), ptr(self.out), ptr(g1), ptr(g2),
+                ptr(self.dx), ptr(self.dwpad), self.dwpad.shape[0], ptr(st.grad_of(self.bias)), self.n, self.hw, 64,
+                self.co, int(self.use_tanh), self.ci)
+        # replicas -> the weight's gradient slot (and cleared for the next pass), one launch
+        _C.call("fmap_wgrad_fold", ptr(self.dwpad), self.dwpad.shape[0], self.co, self.ci,
+                ptr(st.grad_of(self.weight)) if wgrad else None)
         return self.dx
 
 
@@ -255,6 +254,13 @@ class GraphEngine:
             self.store = ParamStore(module, self.device)
         self.units = []
         self.layers = {}
+        self.red_arena = None
+        self.red_clean = False      # True while a pass that cleared the whole red arena is running
+
+    def clear_red(self):
+        """One memset for the backward sums of every unit; ConvUnit.backward then skips its own clear."""
+        self.red_arena.zero_()
+        self.red_clean = True
 
     def conv_layer(self, name, conv, in_split, kind="conv"):
         """One ConvLayer per nn.Conv2d, shared by every engine built on the same module."""
@@ -332,6 +338,13 @@ class GraphEngine:
             self.store.finalize(self.completion_order())
             self.module._tg_store = self.store
         cu = [u for u in self.units if isinstance(u, ConvUnit)]
+        # the backward sums of every InstanceNorm unit live in ONE fp32 arena, cleared by a single memset per pass
+        normed = [u for u in cu if u.norm]
+        self.red_arena = torch.zeros(sum(u.n * u.c * 2 for u in normed) or 1, device=self.device)
+        off = 0
+        for u in normed:
+            u.red = self.red_arena[off:off + u.n * u.c * 2].view(u.n, u.c, 2)
+            off += u.n * u.c * 2
         if self.with_backward:
             mx = max(u.dz.numel() for u in cu)
             mx_up = max([u.up.buf.numel() for u in cu if u.up] + [8])
@@ -413,6 +426,7 @@ class UNetPPEngine(GraphEngine):
     def backward(self, g1, g2=None, after_unit=None):
         """g1 (+ g2): gradients w.r.t. the fp32 NCHW output. Accumulates into the store's grad arena.
         after_unit(unit) is called once a unit's parameter gradients are final (data-parallel overlap)."""
+        self.clear_red()
         dx = self.head.backward(g1, g2)
         for (i, j) in reversed(self.order):
             u0, u1 = self.X[i, j]
@@ -420,6 +434,7 @@ class UNetPPEngine(GraphEngine):
             self._unit_done(u1, after_unit)
             u0.backward()
             self._unit_done(u0, after_unit)
+        self.red_clean = False
         self._join_wgrad()
 
 
@@ -439,10 +454,12 @@ class SequentialGenEngine(GraphEngine):
         return self.head.forward()
 
     def backward(self, g1, g2=None, after_unit=None):
+        self.clear_red()
         dx = self.head.backward(g1, g2)
         for u in reversed(self.units):
             u.backward(g_extra=dx if u is self.last else None)
             self._unit_done(u, after_unit)
+        self.red_clean = False
         self._join_wgrad()
 
     def _double(self, name, block, srcs, pool=0):
@@ -576,6 +593,7 @@ class VGGFeatEngine(GraphEngine):
         if last < 0:
             return grad_image
         started = False
+        self.clear_red()
         for u in reversed(self.units):
             i = tap_of.get(id(u))
             if not started:
@@ -586,6 +604,7 @@ class VGGFeatEngine(GraphEngine):
             # same-resolution route; an unweighted slice output just passes the pooled gradient on
             g_extra = self.g_feat[i] if (i is not None and self.active[i]) else None
             u.backward(g_extra=g_extra, wgrad=False)
+        self.red_clean = False
         self.x_in.run_grad()
         _C.call("vgg_prep_bwd", ptr(self.dx_in), ptr(grad_image), self.n, self.cs, self.h, self.w, self.oh, self.ow, 64,
                 int(self.resize), F(scale))
@@ -678,8 +697,10 @@ class PatchDInstance(GraphEngine):
             _C.call("bias_grad", ptr(u5.dz), ptr(u5.layer.bias_grad), LL(u5.n * u5.ho * u5.wo), u5.c, u5.c_valid)
             for p in u5.wgrad_plans:
                 p.run()
+        self.clear_red()
         for unit in reversed(self.u[:4]):
             unit.backward(wgrad=wgrad)
+        self.red_clean = False
         if input_grad:
             self.x0.run_grad()
         return self.dx0
@@ -702,16 +723,20 @@ class PatchDInstance(GraphEngine):
         so = self.so = {}
         so["seed"] = bf16(*self.x0.buf.shape, device=dev)      # im2col rows of the second-order seed image
         so["g_img"] = None
-        so["nsq"] = torch.zeros(self.n, device=dev)
+        # every accumulator of the second-order sweep in one arena: cleared once, at the start of gp_penalty
+        sizes = [self.n] + [x.n * x.c * 4 for x in self.u[1:4]] + [x.n * x.c * 2 for x in self.u[1:4]]
+        so["zero_arena"] = torch.zeros(sum(sizes), device=dev)
+        cuts = so["zero_arena"].split(sizes)
+        so["nsq"] = cuts[0]
         so["coef"] = torch.zeros(self.n, device=dev)
         so["U"] = [bf16(*x.dz.shape, device=dev) for x in self.u]      # adj(dz_k) (U[4] = adj(dz5))
         so["V"] = [bf16(*x.dz.shape, device=dev) for x in self.u[:4]]  # adj(da_k)
         so["INJ"] = [None] + [bf16(*x.dz.shape, device=dev) for x in self.u[1:4]]
-        so["red2"] = [None] + [torch.zeros(x.n, x.c, 4, device=dev) for x in self.u[1:4]]
+        so["red2"] = [None] + [cuts[1 + k].view(x.n, x.c, 4) for k, x in enumerate(self.u[1:4])]
         so["T5"] = bf16(*u5.dz.shape, device=dev)
         so["E"] = [bf16(*x.dz.shape, device=dev) for x in self.u[:4]]  # adj(a_k) in the downward sweep
         so["Z"] = [bf16(*x.dz.shape, device=dev) for x in self.u[:4]]  # adj(z_k) total
-        so["red_dn"] = [None] + [torch.zeros(x.n, x.c, 2, device=dev) for x in self.u[1:4]]
+        so["red_dn"] = [None] + [cuts[4 + k].view(x.n, x.c, 2) for k, x in enumerate(self.u[1:4])]
         # upward: U_k = conv_k(no bias)(V_{k-1}), V_0 = seed ; wgrad(P = V_{k-1}, Q = dz_k)
         ins = [so["seed"]] + so["V"]
         so["up_conv"] = [L[k].fwd_plans([ins[k]], so["U"][k], use_bias=False) for k in range(5)]
@@ -726,8 +751,10 @@ class PatchDInstance(GraphEngine):
         """d(sum pred)/d(x0): seeds dz5 = sigmoid'(z5) and runs the activation-gradient chain only."""
         u5 = self.u[4]
         _C.call("gp_first_seed", ptr(self.pred), int(self.has_sigmoid), 0, self.n, self.hw5, u5.c, ptr(u5.dz))
+        self.clear_red()
         for unit in reversed(self.u[:4]):
             unit.backward(wgrad=False, keep_dn=True)
+        self.red_clean = False
         self.x0.run_grad()
         return self.dx0
 
@@ -738,7 +765,7 @@ class PatchDInstance(GraphEngine):
         if so["g_img"] is None or so["g_img"].shape[1] != cj:
             so["g_img"] = torch.zeros(n, cj, self.h, self.w, device=self.device)
         g_img = self.input_grad_image(c_off, cj, so["g_img"])
-        so["nsq"].zero_()
+        so["zero_arena"].zero_()        # nsq and the red2 / red_dn sums gp_second_backward accumulates into
         _C.call("gp_normsq_img", ptr(g_img), n, LL(cj * self.h * self.w), ptr(so["nsq"]))
         _C.call("gp_finish", ptr(so["nsq"]), n, F(lambda_gp), F(constant), ptr(loss_slot), ptr(so["coef"]))
         # seed image coef_n * g_n (the + 1e-16 of util.py:92 is far below bf16 resolution), as im2col rows with the
@@ -763,7 +790,6 @@ class PatchDInstance(GraphEngine):
             elif k < 4:
                 x = u[k]
                 g, b = x._aff()
-                so["red2"][k].zero_()
                 _C.call("in_bwd2", ptr(so["U"][k]), ptr(x.raw), ptr(x.dn_keep), ptr(x.mr), g, b, ptr(x.red),
                         ptr(so["red2"][k]), ptr(so["V"][k]), ptr(so["INJ"][k]), x.n, x.ho * x.wo, x.c, x.c_valid,
                         ACT_LRELU, F(0.2))
@@ -784,7 +810,6 @@ class PatchDInstance(GraphEngine):
             if k - 1 >= 1:
                 g, b = x._aff()
                 red = so["red_dn"][k - 1]
-                red.zero_()
                 _C.call("in_bwd_reduce", ptr(x.raw), ptr(x.y.buf), ptr(x.mr), g, b, ptr(e), None, 0, None, 0,
                         None, ptr(red), x.n, x.ho, x.wo, x.c, x.c_valid, ACT_LRELU, F(0.2))
                 aff = x.gamma is not None

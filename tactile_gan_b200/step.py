@@ -88,11 +88,10 @@ class TrainStep:
         """util.py:79-81: alpha ~ U[0,1) on the CUDA generator; version 2 maps it to [0.5, 1)."""
         if alpha is None:
             alpha = torch.rand(self.B, 1, device=self.device)
-        a = alpha.to(self.device).float().view(-1)
-        if self.version == 2:
-            a = (a + 1) / 2
-        self.alpha.copy_(a)
-        self.one_minus_alpha.copy_(1 - a)
+        elif not (alpha.is_cuda and alpha.dtype == torch.float32 and alpha.is_contiguous()):
+            alpha = alpha.to(self.device).float().contiguous()
+        self._alpha_src = alpha       # keep alive: the launch is asynchronous
+        _C.call("gp_alpha", ptr(alpha), self.version, ptr(self.alpha), ptr(self.one_minus_alpha), self.B)
 
     def _gan_loss(self, inst, n0, n1, target_is_real, for_disc, scale, slot, write_dz=True):
         u5 = inst.u[4]
