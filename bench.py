@@ -393,7 +393,12 @@ def run_ours(args):
         ms_e2e = timed(step_host, args.steps)
     sampler.stop()
     if args.layers and rank == 0:
+        # serialised launches (no weight-gradient side stream), so a kernel's duration is its own
+        if side is not None:
+            ts.G.wgrad_stream = None
         layer_table(lambda: step_dev(0), args.layers)
+        if side is not None:
+            ts.G.wgrad_stream = side
 
     if rank == 0:
         hbm, tf_burst, tf_sus, which = peaks()
