@@ -278,6 +278,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=dev)
+        os.environ.setdefault("TG_COMM_PROFILE", "1")     # event pairs around the two waits for gradient collectives
     B, S = args.batch, args.size
     torch.manual_seed(21)
     netG = create_gen(args.gen, 3, 3, 64, True).to(dev)
@@ -364,8 +365,24 @@ def run_ours(args):
             step_host(i)
         ms_e2e = timed(step_host, args.steps)
     _C.COUNTERS["launches"] = 0
+    if train and ts.comm_profile is not None:
+        ts.comm_profile.clear()
     ms = timed(step_dev, args.steps)
     launches = _C.COUNTERS["launches"]
+    comm = None
+    if train and ts.comm_profile is not None:
+        # time the compute stream spent waiting for NCCL (max over ranks): communication the step did not hide
+        tot = {}
+        for tag, a, b in ts.comm_profile:
+            tot[tag] = tot.get(tag, 0.0) + a.elapsed_time(b)
+        t = torch.tensor([tot.get("D", 0.0), tot.get("G", 0.0)], device=dev) / args.steps
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        comm = {"exposed_ms_per_step": {"D_allreduce_wait": t[0].item(), "G_allreduce_wait": t[1].item()},
+                "g_buckets": [(b - a) * 4 for a, b, _ in getattr(ts, "_g_buckets", [])],
+                "d_arena_bytes": ts.DA.store.grad_arena.numel() * 4,
+                "note": "CUDA events on the compute stream around work.wait(); includes waiting for the collective "
+                        "to start behind the kernels it depends on"}
+        ts.comm_profile = None
     losses = ts.loss_dict() if train else {}
     # Per-kernel-family rooflines: the same K steps again with a CUDA-event pair around every implicit-GEMM and
     # InstanceNorm-tail launch. The product path overlaps weight gradients (side stream) with the bandwidth-bound
@@ -425,7 +442,7 @@ def run_ours(args):
                                         "pinned batch -> H2D -> graph-replayed forward -> D2H of the generated images")},
                 "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "images/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                "gpu_launches": launches, "clocks": sampler.summary(), "losses_last_step": losses,
+                "gpu_launches": launches, "clocks": sampler.summary(), "losses_last_step": losses, "comm": comm,
                 "step_tflops": gfl * B * args.steps / (ms / 1e3) / 1e3, "gflop_per_image": gfl}
         if "conv" in agg:
             t, f, c = agg["conv"]

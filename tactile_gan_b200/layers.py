@@ -233,18 +233,28 @@ class TailCall:
         _C.call(self.name, *self.args())
 
 
-def plan_buckets(layout, bucket_elems):
+def plan_buckets(layout, bucket_elems, tail_elems=0):
     """Split an arena layout [(param, offset, size), ...] (completion order) into contiguous buckets of at
     least `bucket_elems` elements: returns [(start, end, last_param), ...]; a bucket may be all-reduced as soon
-    as the gradient of `last_param` is final."""
+    as the gradient of `last_param` is final. tail_elems > 0: the parameters that complete last (at most that many
+    elements) get a bucket of their own -- it is the only collective nothing is left to overlap with, so it is kept
+    small (the bucket before it is launched earlier, while the last units still run)."""
+    layout = [(i, off, size) for i, off, size in layout if size]
+    cut = len(layout)
+    if tail_elems > 0 and len(layout) > 1:
+        acc = 0
+        while cut > 1 and acc + layout[cut - 1][2] <= tail_elems:
+            cut -= 1
+            acc += layout[cut][2]
     buckets, start, last = [], None, None
-    for i, off, size in layout:
-        if size == 0:
-            continue
+    for k, (i, off, size) in enumerate(layout):
+        if k == cut and start is not None:          # close the running bucket in front of the tail bucket
+            buckets.append((start, off, last))
+            start = None
         if start is None:
             start = off
         last = i
-        if off + size - start >= bucket_elems:
+        if k < cut and off + size - start >= bucket_elems:
             buckets.append((start, off + size, last))
             start = None
     if start is not None:

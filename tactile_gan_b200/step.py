@@ -12,6 +12,8 @@ scalars accumulated in one device buffer. Differences from the reference that do
 Data parallel: one process per GPU; the flat fp32 gradient arenas of D and G are all-reduced (sum) with
 NCCL and scaled by 1/world inside the fused Adam kernel.
 """
+import os
+
 import torch
 
 from . import _C
@@ -63,12 +65,14 @@ class TrainStep:
         self.one_minus_alpha = torch.zeros(batch, device=dev)
         self.gan_grad = torch.zeros(batch, self.c_b, height, width, device=dev)
         self.l1_grad = torch.zeros(batch, self.c_b, height, width, device=dev)
-        import os
         if os.environ.get("TG_WGRAD_STREAM", "1") != "0":
             self.G.wgrad_stream = torch.cuda.Stream(device=dev)
         self.real_label = None
         self.label_smoothing = label_smoothing
         self.fake_B = None
+        # TG_COMM_PROFILE=1 (bench.py): CUDA-event pairs around the points where the compute stream waits for a
+        # gradient collective -- the time between them is communication the step could not hide
+        self.comm_profile = [] if (self.world > 1 and os.environ.get("TG_COMM_PROFILE")) else None
 
     # ------------------------------------------------------------------ labels / alpha (host RNG parity)
     def ensure_label(self, generator=None):
@@ -101,19 +105,42 @@ class TrainStep:
                 int(inst.has_sigmoid), F(scale), n0, n1, self.h5 * self.w5, u5.c, ptr(self.losses[slot:slot + 1]),
                 ptr(u5.dz) if write_dz else None)
 
-    def _allreduce(self, store):
-        if self.world > 1:
-            torch.distributed.all_reduce(store.grad_arena, group=self.pg)
+    def _allreduce_async(self, store):
+        """Sum the whole gradient arena over the ranks on the communication stream; returns the work handle (None on
+        one GPU). The compute stream keeps running until _allreduce_wait."""
+        if self.world == 1:
+            return None
+        if not hasattr(self, "_comm_stream"):
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self._comm_stream):
+            self._comm_stream.wait_event(ev)
+            return torch.distributed.all_reduce(store.grad_arena, group=self.pg, async_op=True)
+
+    def _allreduce_wait(self, work, tag):
+        if work is None:
+            return
+        prof = self.comm_profile
+        if prof is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+        work.wait()
+        if prof is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            prof.append((tag, e0, e1))
 
     # ---- generator gradients: bucketed allreduce overlapped with the rest of backward -----------------
     BUCKET_BYTES = 32 << 20
+    TAIL_BUCKET_BYTES = 1 << 20      # the last-completing parameters travel alone: the only exposed collective
 
     def _plan_g_buckets(self):
         """The gradient arena is laid out in backward-completion order (ParamStore.finalize), so bucket k is a
         contiguous range that is final once the unit owning its last parameter has run."""
         from .layers import plan_buckets
         store = self.G.store
-        buckets = plan_buckets(store.arena_layout, self.BUCKET_BYTES // 4)
+        buckets = plan_buckets(store.arena_layout, self.BUCKET_BYTES // 4, self.TAIL_BUCKET_BYTES // 4)
         owner = {}
         for u in self.G.units:
             for p in (getattr(u, "gamma", None), getattr(u, "beta", None), getattr(getattr(u, "layer", None), "weight", None),
@@ -121,7 +148,8 @@ class TrainStep:
                 if p is not None and id(p) in store.index:
                     owner[store.index[id(p)]] = u
         self._g_buckets = [(a, b, owner.get(last)) for a, b, last in buckets]
-        self._comm_stream = torch.cuda.Stream(device=self.device)
+        if not hasattr(self, "_comm_stream"):
+            self._comm_stream = torch.cuda.Stream(device=self.device)
 
     def _g_backward(self):
         G, gs = self.G, self.G.store
@@ -148,8 +176,16 @@ class TrainStep:
         G.backward(self.gan_grad, self.l1_grad, after_unit=after_unit)
         for a, b, _ in pending:          # buckets whose last parameter has no unit (head-only / dead parameters)
             launch(a, b)
+        prof = self.comm_profile
+        if prof is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()                  # backward's own kernels are all queued in front of this marker
         for w in works:
             w.wait()                     # the compute stream waits for the collectives; the host does not block
+        if prof is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            prof.append(("G", e0, e1))
 
     # ------------------------------------------------------------------ the iteration
     def step(self, real_A, real_B, regularize=True, alpha=None, real_B_ready=None):
@@ -183,20 +219,25 @@ class TrainStep:
             S1.gp_first_backward()
             S1.gp_penalty(self.c_a, self.c_b, self.lambda_gp, 1.0, self.losses[1:2])
             S1.gp_second_backward()
-        self._allreduce(ds)
-        ds.adam_step(self.lr, self.beta1, grad_scale=1.0 / self.world)
-        # ---- G step (train.py:138-168), discriminator already updated
+        d_work = self._allreduce_async(ds)
+        # ---- G step (train.py:138-168). What does not depend on the updated discriminator is queued while D's
+        # gradients are in flight: the generator's gradient clear, the im2col rows of the (real_A, fake_B) pair (and of
+        # the real pair for the feature term) and the L1 term
         gs.zero_grad()
         S1.pack_input(real_A, fake)
+        _C.call("l1_loss", ptr(fake), ptr(real_B), LL(fake.numel()), F(self.lambda_a),
+                ptr(self.losses[3:4]), ptr(self.l1_grad))
+        want_feat = self.lambda_per != 0 and self.version == 2
+        if want_feat:
+            S2.pack_input(real_A, real_B)
+        self._allreduce_wait(d_work, "D")
+        ds.adam_step(self.lr, self.beta1, grad_scale=1.0 / self.world)
         S1.forward()
         S1.u[4].dz.zero_()
         self._gan_loss(S1, 0, B, True, False, 1.0, SLOT["G_GAN"])
         S1.backward(wgrad=False, input_grad=True)
         S1.input_grad_image(self.c_a, self.c_b, self.gan_grad)
-        _C.call("l1_loss", ptr(fake), ptr(real_B), LL(fake.numel()), F(self.lambda_a),
-                ptr(self.losses[3:4]), ptr(self.l1_grad))
-        if self.lambda_per != 0 and self.version == 2:
-            S2.pack_input(real_A, real_B)
+        if want_feat:
             S2.forward()
             wsum = sum(self.w_per)
             for fr, ff, w in zip(S2.features(), S1.features(), self.w_per):
