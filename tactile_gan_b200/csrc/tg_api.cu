@@ -19,6 +19,14 @@ int tg_set_error(const char* msg) {
   snprintf(g_err, sizeof(g_err), "%s", msg);
   return -1;
 }
+int tg_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("TG_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on;
+}
 int tg_check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) return 0;
@@ -579,20 +587,27 @@ int tg_wgrad_plan_create(const tg_wgrad_desc* d, tg_plan** out) {
 int tg_plan_run(tg_plan* pl, void* stream) {
   if (!pl) return tg_set_error("tg_plan_run: null plan");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // every GEMM kernel starts with tg::griddep_sync(): launched as programmatic dependents (tg_launch)
+  const dim3 g(pl->grid), b(tg::kNumThreads);
+  cudaError_t e;
   if (pl->kind == 2) {
-    tg::igemm_halo_kernel<<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->halo);
+    e = tg_launch(tg::igemm_halo_kernel, g, b, pl->smem, s, pl->halo);
   } else if (pl->kind == 3) {
-    tg::igemm_rows_kernel<<<pl->grid, tg::kRowsThreads, pl->smem, s>>>(pl->rows);
+    e = tg_launch(tg::igemm_rows_kernel, g, dim3(tg::kRowsThreads), pl->smem, s, pl->rows);
   } else if (pl->kind == 4) {
-    tg::wgrad_taps_kernel<<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->wgt);
+    e = tg_launch(tg::wgrad_taps_kernel, g, b, pl->smem, s, pl->wgt);
   } else if (pl->kind == 0) {
-    if (pl->bn == 256) tg::igemm_conv_kernel<256><<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->conv);
-    else if (pl->bn == 128) tg::igemm_conv_kernel<128><<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->conv);
-    else tg::igemm_conv_kernel<64><<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->conv);
+    if (pl->bn == 256) e = tg_launch(tg::igemm_conv_kernel<256>, g, b, pl->smem, s, pl->conv);
+    else if (pl->bn == 128) e = tg_launch(tg::igemm_conv_kernel<128>, g, b, pl->smem, s, pl->conv);
+    else e = tg_launch(tg::igemm_conv_kernel<64>, g, b, pl->smem, s, pl->conv);
   } else {
-    if (pl->bn == 256) tg::wgrad_kernel<256><<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->wg);
-    else if (pl->bn == 128) tg::wgrad_kernel<128><<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->wg);
-    else tg::wgrad_kernel<64><<<pl->grid, tg::kNumThreads, pl->smem, s>>>(pl->wg);
+    if (pl->bn == 256) e = tg_launch(tg::wgrad_kernel<256>, g, b, pl->smem, s, pl->wg);
+    else if (pl->bn == 128) e = tg_launch(tg::wgrad_kernel<128>, g, b, pl->smem, s, pl->wg);
+    else e = tg_launch(tg::wgrad_kernel<64>, g, b, pl->smem, s, pl->wg);
+  }
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "tg_plan_run: %s", cudaGetErrorString(e));
+    return -1;
   }
   return tg_check_launch("tg_plan_run");
 }

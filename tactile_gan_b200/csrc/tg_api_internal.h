@@ -4,8 +4,35 @@
 #include <cstdint>
 #include <cuda_bf16.h>
 
+#include <cuda_runtime.h>
+
 int tg_set_error(const char* msg);          // records msg, returns -1
 int tg_check_launch(const char* what);      // cudaGetLastError() -> 0 / -1
+int tg_pdl_enabled();                       // env TG_PDL (default on): programmatic dependent launch for tg_launch
+
+// Launch with the programmatic-stream-serialization attribute: the kernel may be scheduled before the previous kernel
+// of the stream has finished and MUST call tg::griddep_sync() before its first global-memory access. Inside a stream
+// capture (the inference forward's CUDA graph) the attribute is left off.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t tg_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                    Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  int on = tg_pdl_enabled();
+  if (on) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) on = 0;
+  }
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = on;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 
 namespace tg {
 

@@ -262,6 +262,7 @@ igemm_conv_kernel(const __grid_constant__ IgemmParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_sync();   // everything above is set-up; global memory is touched from here on
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   const int taps = p.taps;

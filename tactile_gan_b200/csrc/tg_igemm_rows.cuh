@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) igemm_rows_kernel(const __gri
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_sync();   // everything above is set-up; global memory is touched from here on
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   int chunks = 0;

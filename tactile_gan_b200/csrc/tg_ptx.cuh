@@ -22,6 +22,17 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// First thing a kernel launched through tg_launch (tg_api_internal.h) does before it touches global memory: wait for
+// the preceding kernel of the stream to complete and flush (a no-op for an ordinary launch), then let the NEXT kernel
+// of the stream begin its own launch / prologue while this grid runs. The CTAs of a dependent grid that get an SM
+// early (when the last CTAs of a persistent grid are still draining) do their barrier / TMEM / descriptor set-up and
+// then sit in this wait, so launch latency and prologue leave the critical path; data dependencies are untouched.
+__device__ __forceinline__ void griddep_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_stream_kernel(const Stre
     fence_mbar_init();
   }
   __syncthreads();
+  griddep_sync();   // launched as a programmatic dependent (tg_launch): set-up above, global memory below
 
   if (tid >= kStreamConsumers) {
     // ------------------------------------------------------------------ producer warp (one lane issues)

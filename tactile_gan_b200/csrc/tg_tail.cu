@@ -241,6 +241,7 @@ __global__ void in_finalize_kernel(const float* __restrict__ partial, float* __r
                                    int C, float inv_count, float eps) {
   // block = 16 channels x 64 tile lanes (grid (C/16, N)): a (tile, 16-channel) row is one 128-byte line
   __shared__ float sh[64][16][2];
+  griddep_sync();
   const int n = blockIdx.y;
   const int cl = threadIdx.x & 15;
   const int c = blockIdx.x * 16 + cl;
@@ -324,6 +325,7 @@ in_act_fwd_kernel(const __nv_bfloat16* __restrict__ raw, const float* __restrict
                   const float* __restrict__ gamma, const float* __restrict__ beta,
                   __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ pool,
                   __nv_bfloat16* __restrict__ up, int H, int W, int C, int c_valid, int act, float slope) {
+  griddep_sync();
   const int n = blockIdx.y;
   constexpr bool QUAD = POOL != 0 || UP;
   const int H2 = H >> 1, W2 = W >> 1;
@@ -497,6 +499,7 @@ __device__ __forceinline__ void in_bwd_gather(const InBwdArgs& a, int n, int pix
 template <bool PLAIN, int PASS>
 __global__ void __launch_bounds__(256, 2) in_bwd_reduce_kernel(const InBwdArgs a) {
   extern __shared__ float shm[];  // [PL][C][2]
+  griddep_sync();
   const int n = blockIdx.y;
   const int HW = a.H * a.W;
   const StripIdx t = strip_index(a.C, HW);
@@ -1720,7 +1723,8 @@ static int launch_stream(tg::StreamArgs a, cudaStream_t s) {
   long long grid = 2 * 148;
   if (grid > chunks) grid = chunks;
   if (grid < 1) grid = 1;
-  in_stream_kernel<MODE><<<int(grid), kStreamThreads, smem, s>>>(a);
+  if (tg_launch(in_stream_kernel<MODE>, dim3(unsigned(grid)), dim3(kStreamThreads), smem, s, a) != cudaSuccess)
+    return tg_check_launch("in_stream_kernel") ? -1 : tg_set_error("in_stream_kernel: launch failed");
   return tg_check_launch("in_stream_kernel");
 }
 static bool stream_shape_ok(int C) { return C >= 64 && C <= 2048 && (C & 63) == 0; }
@@ -1810,7 +1814,7 @@ int tg_in_stream_policy(int policy) {
 int tg_in_finalize(const float* partial, float* mr, int N, int T, int C, int count, float eps,
                    void* stream) {
   dim3 grid(C / 16, N);
-  in_finalize_kernel<<<grid, 1024, 0, TG_STREAM(stream)>>>(partial, mr, T, C, 1.f / float(count), eps);
+  tg_launch(in_finalize_kernel, grid, dim3(1024), 0, TG_STREAM(stream), partial, (float*)mr, T, C, 1.f / float(count), eps);
   TG_RET();
 }
 
@@ -1848,7 +1852,7 @@ int tg_in_act_fwd(const void* raw, const float* mr, const float* gamma, const fl
   dim3 grid(strip_count(units, C, N, quad ? 4 : 16), N);
   const int block = strip_block(C);
   const int pm = pool ? pool_mode : 0;
-#define LAUNCH(P, U) in_act_fwd_kernel<P, U><<<grid, block, 0, s>>>(r, mr, gamma, beta, yy, pp, uu, H, W, C, c_valid, act, slope)
+#define LAUNCH(P, U) tg_launch(in_act_fwd_kernel<P, U>, grid, dim3(block), 0, s, r, mr, gamma, beta, yy, pp, uu, H, W, C, c_valid, act, slope)
   if (pm == 0 && !up) LAUNCH(0, false);
   else if (pm == 0 && up) LAUNCH(0, true);
   else if (pm == 1 && !up) LAUNCH(1, false);
@@ -1885,8 +1889,8 @@ int tg_in_bwd_reduce(const void* raw, const void* y, const float* mr, const floa
     sa.N = N; sa.HW = H * W; sa.C = C; sa.c_valid = c_valid; sa.act = act; sa.slope = slope;
     return launch_stream<1>(sa, TG_STREAM(stream));
   }
-  if (plain) in_bwd_reduce_kernel<true, 0><<<grid, block, smem, TG_STREAM(stream)>>>(a);
-  else in_bwd_reduce_kernel<false, 0><<<grid, block, smem, TG_STREAM(stream)>>>(a);
+  if (plain) tg_launch(in_bwd_reduce_kernel<true, 0>, grid, dim3(block), smem, TG_STREAM(stream), a);
+  else tg_launch(in_bwd_reduce_kernel<false, 0>, grid, dim3(block), smem, TG_STREAM(stream), a);
   TG_RET();
 }
 
@@ -1915,8 +1919,8 @@ int tg_in_bwd_apply_re(const void* raw, const void* y, const float* mr, const fl
     sa.N = N; sa.HW = H * W; sa.C = C; sa.c_valid = c_valid; sa.act = act; sa.slope = slope;
     return launch_stream<2>(sa, TG_STREAM(stream));
   }
-  if (plain) in_bwd_reduce_kernel<true, 1><<<grid, block, 0, TG_STREAM(stream)>>>(a);
-  else in_bwd_reduce_kernel<false, 1><<<grid, block, 0, TG_STREAM(stream)>>>(a);
+  if (plain) tg_launch(in_bwd_reduce_kernel<true, 1>, grid, dim3(block), 0, TG_STREAM(stream), a);
+  else tg_launch(in_bwd_reduce_kernel<false, 1>, grid, dim3(block), 0, TG_STREAM(stream), a);
   TG_RET();
 }
 

@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(kNumThreads, 2) wgrad_taps_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_sync();   // everything above is set-up; global memory is touched from here on
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   const int tiles_per_img = p.tiles_h * p.tiles_w;

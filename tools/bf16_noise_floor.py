@@ -38,4 +38,42 @@ if __name__ == "__main__":
             y32b = orc.gen_forward(gen, sd, x * (1 + 1e-6))
         print(f"{gen:8s} nf={nf} {size}^2: bf16-storage vs fp32 {rel(yq, y32):.4f} | bf16-storage vs bf16-storage, input "
               f"*(1+1e-6) {rel(yq2, yq):.4f} | fp32 vs fp32, same perturbation {rel(y32b, y32):.2e} | "
-              f"|fake_B| rms {y32.pow(2).mean().sqrt().item():.4f}")
+              f"|fake_B| rms {y32.pow(2).mean().sqrt().item():.4f}", flush=True)
+        # the same experiment on the parameter gradient of sum(out * G), with the ReLU masks / max-pool routes of run A
+        # forced onto run B (what tests/parity_util.py does between the CUDA forward and the oracle): what is left is
+        # the decorrelated bf16 rounding of two runs that differentiate the SAME piecewise-linear map
+        import torch.nn.functional as Fn
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from parity_util import MaskFeed, PoolFeed
+        gout = torch.randn(1, 3, size, size, generator=g) * 0.01
+        names = [k for k, v in sd.items()]
+
+        def grads(x_in, relu, pool):
+            p = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in sd.items())
+            orc.ACT["relu"], orc.POOL["max"] = relu, pool
+            try:
+                y = orc.gen_forward(gen, p, x_in)
+                gr = torch.autograd.grad(y, [p[k] for k in names], gout, allow_unused=True)
+            finally:
+                orc.ACT["relu"], orc.POOL["max"] = Fn.relu, orc.max_pool_2x2
+            return torch.cat([t.flatten() for t in gr if t is not None])
+
+        masks, pools = [], []
+
+        def rec_relu(t):
+            y = Fn.relu(t)
+            masks.append(y.detach() > 0)
+            return y
+
+        def rec_pool(t):
+            o, i = Fn.max_pool2d(t, 2, 2, return_indices=True)
+            pools.append(i)
+            return o
+
+        orc.QUANT["on"] = True
+        ga = grads(x, rec_relu, rec_pool)
+        gb = grads(x * (1 + 1e-6), MaskFeed(masks), PoolFeed(pools))
+        orc.QUANT["on"] = False
+        g32 = grads(x, MaskFeed(masks), PoolFeed(pools))
+        print(f"         flat parameter gradient: bf16-storage run B (input *(1+1e-6), run A's masks) vs run A "
+              f"{rel(gb, ga):.4f} | fp32 with run A's masks vs run A {rel(g32, ga):.4f}", flush=True)
