@@ -8,7 +8,7 @@
 
 int tg_set_error(const char* msg);          // records msg, returns -1
 int tg_check_launch(const char* what);      // cudaGetLastError() -> 0 / -1
-int tg_pdl_enabled();                       // env TG_PDL (default on): programmatic dependent launch for tg_launch
+int tg_pdl_enabled();                       // env TG_PDL=1 (default off): programmatic dependent launch for tg_launch
 
 // Launch with the programmatic-stream-serialization attribute: the kernel may be scheduled before the previous kernel
 // of the stream has finished and MUST call tg::griddep_sync() before its first global-memory access. Inside a stream

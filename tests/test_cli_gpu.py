@@ -178,8 +178,9 @@ def test_reference_loop_with_fused_adam_steps_on_the_summed_gradient():
         sa, sb = net_a.state_dict(), net_b.state_dict()
         d = torch.cat([(sa[k] - sb[k]).flatten() for k in sa if not k.startswith("clstm")])
         # the first Adam step moves every weight by ~lr*sign(grad): a flipped sign of a near-zero gradient costs
-        # 2*lr; the bulk must agree (stepping on a partial gradient moves O(half) of the weights the other way)
-        assert (d.abs() > 0.5 * lr).float().mean().item() < 0.03
-        assert d.abs().mean().item() < 0.05 * lr
+        # 2*lr (measured: 4.4 % of the weights of these nf=8 networks between the two paths); the bulk must agree --
+        # stepping on a partial gradient (the bug) moves O(half) of the weights the other way
+        assert (d.abs() > 0.5 * lr).float().mean().item() < 0.10
+        assert d.abs().mean().item() < 0.2 * lr
     moved = torch.cat([(netD.state_dict()[k] - before_D[k]).flatten() for k in before_D])
     assert moved.abs().mean().item() > 0.5 * lr
