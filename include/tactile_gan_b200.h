@@ -232,14 +232,9 @@ int tg_gp_seed(const void* g, const float* coef, int N, int HW, int C, int c_off
 /* ---- torch.optim.Adam.step (train.py:135,168) fused with the bf16 weight re-pack.
  * table_dev: device array of `ntensors` rows of 136 bytes: 6 pointers (param, grad, exp_avg,
  * exp_avg_sq, pack_fwd, pack_bwd), int64 numel, int32 kind, kh, kw, dim1, o_pad, i_pad, nseg,
- * seg_end[6], seg_shift[6], pad.
- * tiles_dev (optional): device array of ntiles x {int32 tensor, d0 start, d1 start}: 32 x 32 x taps tiles of the
- * conv / conv-transpose weights (kind 1 / 2), updated and re-packed through shared memory so that every global access
- * runs along its own layout's rows; max_taps = the largest kh*kw among them. The remaining tensors (and all of them
- * when tiles_dev is NULL) take the per-element path, grid sized for max_numel elements per tensor. */
+ * seg_end[6], seg_shift[6], pad. */
 int tg_adam_step(const void* table_dev, int ntensors, long long max_numel, float lr, float beta1,
-                 float beta2, float eps, int step, float grad_scale, const void* tiles_dev, int ntiles, int max_taps,
-                 void* stream);
+                 float beta2, float eps, int step, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -25,7 +25,7 @@ int tg_pdl_enabled() {
     // measured neutral to -1 % on the training step (profiles/r02_pdl_ab.txt: 807 / 804 img/s with, 813 / 814 without):
     // consecutive kernels are data dependent, so only launch latency could overlap and the queue already hides it
     const char* e = getenv("TG_PDL");
-    on = (e && e[0] == '1') ? 1 : 0;
+    on = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
   }
   return on;
 }

@@ -10,7 +10,7 @@ int tg_set_error(const char* msg);          // records msg, returns -1
 int tg_check_launch(const char* what);      // cudaGetLastError() -> 0 / -1
 int tg_pdl_enabled();                       // env TG_PDL=1 (default off): programmatic dependent launch for tg_launch
 
-// Launch with the programmatic-stream-serialization attribute: the kernel may be scheduled before the previous kernel
+// Launch with the programmatic-stream-serialization attribute (when TG_PDL enables it): the kernel may be scheduled before the previous kernel
 // of the stream has finished and MUST call tg::griddep_sync() before its first global-memory access. Inside a stream
 // capture (the inference forward's CUDA graph) the attribute is left off.
 template <typename... KArgs, typename... Args>
@@ -23,10 +23,11 @@ static inline cudaError_t tg_launch(void (*kernel)(KArgs...), dim3 grid, dim3 bl
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   int on = tg_pdl_enabled();
-  if (on) {
+  if (on == 1) {   // TG_PDL=1: eager launches only; TG_PDL=2: also inside stream capture (programmatic graph edges)
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) on = 0;
   }
+  if (on) on = 1;
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = on;
   cfg.attrs = attr;

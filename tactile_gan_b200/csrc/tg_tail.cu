@@ -1591,9 +1591,8 @@ __global__ void gp_seed_kernel(const __nv_bfloat16* __restrict__ g, const float*
 
 // ------------------------------------------------------------------ fused Adam + weight re-pack
 __global__ void adam_kernel(const AdamTensor* __restrict__ tab, int ntensors, float lr, float beta1,
-                            float beta2, float eps, float bc1, float bc2, float grad_scale, int skip_tiled) {
+                            float beta2, float eps, float bc1, float bc2, float grad_scale) {
   const AdamTensor t = tab[blockIdx.y];
-  if (skip_tiled && (t.kind == 1 || t.kind == 2)) return;   // conv weights are served by adam_tiled_kernel
   const size_t numel = t.numel;
   const int taps = t.kh * t.kw;
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < numel;
@@ -1644,94 +1643,6 @@ __global__ void adam_kernel(const AdamTensor* __restrict__ tab, int ntensors, fl
                          : t.kind == 3 ? size_t(ic) * t.o_pad + tap
                                        : size_t(ic) * t.o_pad + o;
         t.pack_bwd[k] = b;
-      }
-    }
-  }
-}
-
-// Conv / ConvTranspose weights, one (32 x 32 x taps) tile per block. The torch layout [d0][d1][tap] (parameter, both
-// moments) and the packed layouts ([tap][o][ic] gradient + forward pack, [tap][ic][o] backward pack) are transposes of
-// each other: walking either one per thread makes the other a 36-byte-strided scatter (the gradient read cost 8x its
-// bytes and the two packs were 2-byte scattered writes: 0.67 ms for the generator's 36.6 M weights against 0.18 ms of
-// traffic). Here the gradient tile is read along its own rows into shared memory, the update walks the torch order
-// (contiguous runs of 32 * taps floats), and the two packs leave shared memory along their own rows.
-struct AdamTile { int tensor, a0, b0; };
-constexpr int kAdamTA = 32, kAdamTB = 32;
-constexpr int kAdamPlane = kAdamTA * (kAdamTB + 1) + 1;    // odd plane stride: taps of one element hit different banks
-
-__global__ void __launch_bounds__(256)
-adam_tiled_kernel(const AdamTensor* __restrict__ tab, const AdamTile* __restrict__ tiles, float lr, float beta1,
-                  float beta2, float eps, float bc1, float bc2, float grad_scale) {
-  extern __shared__ float ash[];          // g[taps][plane] then w[taps][plane] (fp32 slots holding the new weights)
-  const AdamTile tl = tiles[blockIdx.x];
-  const AdamTensor t = tab[tl.tensor];
-  const int taps = t.kh * t.kw;
-  const int D1 = t.dim1, D0 = int(t.numel / (size_t(D1) * taps));
-  float* gs = ash;
-  float* ws = ash + size_t(taps) * kAdamPlane;
-  const int na = min(kAdamTA, D0 - tl.a0), nb = min(kAdamTB, D1 - tl.b0);
-  const bool ic_is_d1 = t.kind == 1;      // conv: [o][ic]; convT: [ic][o]
-  auto padded_ic = [&](int ic) {
-    for (int sgi = 0; sgi < t.nseg; ++sgi)
-      if (ic < t.seg_end[sgi]) return ic + t.seg_shift[sgi];
-    return ic;
-  };
-  // gradient index (packed forward layout; convT: [tap][ic][o]) of tile element (a, b)
-  auto grad_index = [&](int tap, int a, int b) -> size_t {
-    const int d0 = tl.a0 + a, d1 = tl.b0 + b;
-    if (ic_is_d1) return (size_t(tap) * t.o_pad + d0) * t.i_pad + padded_ic(d1);
-    return (size_t(tap) * t.i_pad + padded_ic(d0)) * t.o_pad + d1;
-  };
-  const int total = taps * kAdamTA * kAdamTB;
-  if (t.grad) {
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-      const int b = idx % kAdamTB, a = (idx / kAdamTB) % kAdamTA, tap = idx / (kAdamTA * kAdamTB);
-      if (a < na && b < nb) gs[tap * kAdamPlane + a * (kAdamTB + 1) + b] = t.grad[grad_index(tap, a, b)] * grad_scale;
-    }
-    __syncthreads();
-  }
-  // torch order: for a: the run (b, tap) is contiguous
-  const int run = nb * taps;
-  for (int a = 0; a < na; ++a) {
-    const size_t base = (size_t(tl.a0 + a) * D1 + tl.b0) * taps;
-    for (int r = threadIdx.x; r < run; r += blockDim.x) {
-      const int tap = r % taps, b = r / taps;
-      const size_t i = base + r;
-      float p = t.param[i];
-      if (t.grad) {
-        const float g = gs[tap * kAdamPlane + a * (kAdamTB + 1) + b];
-        float m = t.m[i], v = t.v[i];
-        m = beta1 * m + (1.f - beta1) * g;
-        v = beta2 * v + (1.f - beta2) * g * g;
-        t.m[i] = m;
-        t.v[i] = v;
-        const float denom = sqrtf(v) / sqrtf(bc2) + eps;
-        p -= (lr / bc1) * (m / denom);
-        t.param[i] = p;
-      }
-      ws[tap * kAdamPlane + a * (kAdamTB + 1) + b] = p;
-    }
-  }
-  __syncthreads();
-  // pack whose fastest axis is d1 (conv: forward pack [tap][o][ic]; convT: backward pack [tap][ic][o])
-  __nv_bfloat16* pk1 = ic_is_d1 ? t.pack_fwd : t.pack_bwd;
-  if (pk1) {
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-      const int b = idx % kAdamTB, a = (idx / kAdamTB) % kAdamTA, tap = idx / (kAdamTA * kAdamTB);
-      if (a < na && b < nb) pk1[grad_index(tap, a, b)] = __float2bfloat16(ws[tap * kAdamPlane + a * (kAdamTB + 1) + b]);
-    }
-  }
-  // pack whose fastest axis is d0 (conv: backward pack [mirrored tap][ic][o]; convT: forward pack [tap][o][ic])
-  __nv_bfloat16* pk0 = ic_is_d1 ? t.pack_bwd : t.pack_fwd;
-  if (pk0) {
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-      const int a = idx % kAdamTA, b = (idx / kAdamTA) % kAdamTB, tap = idx / (kAdamTA * kAdamTB);
-      if (a < na && b < nb) {
-        const int d0 = tl.a0 + a, d1 = tl.b0 + b;
-        size_t k;
-        if (ic_is_d1) k = (size_t(taps - 1 - tap) * t.i_pad + padded_ic(d1)) * t.o_pad + d0;   // o = d0, mirrored taps
-        else k = (size_t(tap) * t.o_pad + d1) * t.i_pad + padded_ic(d0);                          // o = d1, ic = d0
-        pk0[k] = __float2bfloat16(ws[tap * kAdamPlane + a * (kAdamTB + 1) + b]);
       }
     }
   }
@@ -2259,27 +2170,12 @@ int tg_gp_seed(const void* g, const float* coef, int N, int HW, int C, int c_off
 }
 
 int tg_adam_step(const void* table_dev, int ntensors, long long max_numel, float lr, float beta1,
-                 float beta2, float eps, int step, float grad_scale, const void* tiles_dev, int ntiles, int max_taps,
-                 void* stream) {
+                 float beta2, float eps, int step, float grad_scale, void* stream) {
   const float bc1 = 1.f - powf(beta1, float(step));
   const float bc2 = 1.f - powf(beta2, float(step));
-  const bool tiled = tiles_dev != nullptr && ntiles > 0;
-  if (max_numel > 0) {
-    dim3 grid(grid_for(size_t(max_numel), 256, 256), ntensors);
-    adam_kernel<<<grid, 256, 0, TG_STREAM(stream)>>>((const AdamTensor*)table_dev, ntensors, lr, beta1,
-                                                      beta2, eps, bc1, bc2, grad_scale, tiled ? 1 : 0);
-  }
-  if (tiled) {
-    const size_t smem = size_t(2) * max_taps * kAdamPlane * sizeof(float);
-    static size_t configured = 0;
-    if (smem > configured) {
-      if (cudaFuncSetAttribute(adam_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
-        return tg_set_error("tg_adam_step: shared memory for the tiled kernel");
-      configured = smem;
-    }
-    adam_tiled_kernel<<<ntiles, 256, smem, TG_STREAM(stream)>>>((const AdamTensor*)table_dev, (const AdamTile*)tiles_dev,
-                                                                lr, beta1, beta2, eps, bc1, bc2, grad_scale);
-  }
+  dim3 grid(grid_for(size_t(max_numel), 256, 256), ntensors);
+  adam_kernel<<<grid, 256, 0, TG_STREAM(stream)>>>((const AdamTensor*)table_dev, ntensors, lr, beta1,
+                                                    beta2, eps, bc1, bc2, grad_scale);
   TG_RET();
 }
 

@@ -371,22 +371,6 @@ class ParamStore:
         raw = bytes(rows)
         return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
 
-    def _build_tiles(self):
-        """32 x 32 x taps tiles of every conv / conv-transpose weight for the tiled Adam + re-pack kernel
-        (tg_adam_step): int32 rows {tensor, d0 start, d1 start} in the torch layout [d0][d1][kh][kw]."""
-        tiles, max_taps, max_other = [], 1, 0
-        for i, p in enumerate(self.params):
-            l = self.conv_of.get(i)
-            if l is not None and l.kind in ("conv", "convT"):
-                d0, d1 = p.shape[0], p.shape[1]
-                max_taps = max(max_taps, l.kh * l.kw)
-                tiles += [(i, a, b) for a in range(0, d0, 32) for b in range(0, d1, 32)]
-            else:
-                max_other = max(max_other, p.numel())
-        self.max_taps, self.max_numel_other = max_taps, max_other
-        self.ntiles = len(tiles)
-        self.tiles = torch.tensor(tiles, dtype=torch.int32, device=self.device).contiguous() if tiles else None
-
     def refresh(self, force=False):
         """Rebuild the device table / re-pack bf16 weights if parameters were touched from outside
         (load_state_dict, init_weights, .to())."""
@@ -397,7 +381,6 @@ class ParamStore:
                 assert p.is_cuda and p.dtype == torch.float32 and p.is_contiguous(), "parameters must be fp32 CUDA"
             self.table = self._build_table(True)
             self.table_nograd = self._build_table(False)
-            self._build_tiles()
             self._ptrs = ptrs
             self._versions = None
             self.generation += 1
@@ -405,12 +388,9 @@ class ParamStore:
             self.repack()
             self._versions = vers
 
-    def _adam_call(self, table, *hyper):
-        _C.call("adam_step", _C.ptr(table), len(self.params), _C.LL(self.max_numel_other if self.ntiles else self.max_numel),
-                *hyper, _C.ptr(self.tiles), self.ntiles, self.max_taps)
-
     def repack(self):
-        self._adam_call(self.table_nograd, _C.F(0.0), _C.F(0.0), _C.F(0.0), _C.F(1.0), 1, _C.F(1.0))
+        _C.call("adam_step", _C.ptr(self.table_nograd), len(self.params), _C.LL(self.max_numel),
+                _C.F(0.0), _C.F(0.0), _C.F(0.0), _C.F(1.0), 1, _C.F(1.0))
 
     def grad_of(self, param):
         """fp32 gradient buffer of a non-conv parameter (bias / affine / head), torch layout."""
@@ -421,7 +401,8 @@ class ParamStore:
 
     def adam_step(self, lr, beta1, beta2=0.99, eps=1e-8, grad_scale=1.0):
         self.step_count += 1
-        self._adam_call(self.table, _C.F(lr), _C.F(beta1), _C.F(beta2), _C.F(eps), self.step_count, _C.F(grad_scale))
+        _C.call("adam_step", _C.ptr(self.table), len(self.params), _C.LL(self.max_numel), _C.F(lr),
+                _C.F(beta1), _C.F(beta2), _C.F(eps), self.step_count, _C.F(grad_scale))
 
     # ---- gradients in torch layout (tests / autograd bridge) ---------------------------------
     def grad_as_torch(self, i):
