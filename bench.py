@@ -376,12 +376,18 @@ def run_ours(args):
         for tag, a, b in ts.comm_profile:
             tot[tag] = tot.get(tag, 0.0) + a.elapsed_time(b)
         t = torch.tensor([tot.get("D", 0.0), tot.get("G", 0.0)], device=dev) / args.steps
+        tmin = t.clone()
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        comm = {"exposed_ms_per_step": {"D_allreduce_wait": t[0].item(), "G_allreduce_wait": t[1].item()},
+        torch.distributed.all_reduce(tmin, op=torch.distributed.ReduceOp.MIN)
+        # a collective ends when the LAST rank has joined: the rank that arrives last waits only for the transfer (min
+        # over ranks = communication the step could not hide), every other rank also waits for it (max - min = rank skew:
+        # GPUs on their power caps do not run the ~20 ms between two sync points at the same speed)
+        comm = {"wait_ms_per_step_min_over_ranks": {"D_allreduce": tmin[0].item(), "G_allreduce": tmin[1].item()},
+                "wait_ms_per_step_max_over_ranks": {"D_allreduce": t[0].item(), "G_allreduce": t[1].item()},
                 "g_buckets": [(b - a) * 4 for a, b, _ in getattr(ts, "_g_buckets", [])],
                 "d_arena_bytes": ts.DA.store.grad_arena.numel() * 4,
-                "note": "CUDA events on the compute stream around work.wait(); includes waiting for the collective "
-                        "to start behind the kernels it depends on"}
+                "note": "CUDA events on the compute stream around work.wait(); min over ranks = exposed communication, "
+                        "max - min = skew between ranks"}
         ts.comm_profile = None
     losses = ts.loss_dict() if train else {}
     # Per-kernel-family rooflines: the same K steps again with a CUDA-event pair around every implicit-GEMM and

@@ -17,11 +17,13 @@ run() {  # N batch tag [env...]
 import json
 d = json.load(open("gpurun_out/r02_scale_$tag.json"))
 c = d.get("comm") or {}
-print("$tag: N=%d batch/GPU=%d  %.1f img/s  %.2f ms/step  e2e %.1f  sm %s MHz  exposed comm %s" % (
+print("$tag: N=%d batch/GPU=%d  %.1f img/s  %.2f ms/step  e2e %.1f  sm %s MHz  comm wait min/max over ranks %s / %s" % (
     d["n_gpus"], $b, d["value"], d["ms_per_step"], d["e2e"]["value"], d["clocks"]["sm_mhz"],
-    {k: round(v, 3) for k, v in (c.get("exposed_ms_per_step") or {}).items()}))
+    {k: round(v, 3) for k, v in (c.get("wait_ms_per_step_min_over_ranks") or {}).items()},
+    {k: round(v, 3) for k, v in (c.get("wait_ms_per_step_max_over_ranks") or {}).items()}))
 PY
 }
+if [ "$1" = "n8only" ]; then run 8 32 weak_n8_b; exit 0; fi
 run 1 32 weak_n1
 run 8 32 weak_n8
 run 8 32 weak_n8_nccl8cta NCCL_MAX_CTAS=8
