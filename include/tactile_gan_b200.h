@@ -229,6 +229,16 @@ int tg_gp_normsq(const void* g, int N, int HW, int C, int c_off, int cj, float* 
 int tg_gp_finish(const float* nsq, int N, float lambda, float constant, float* loss, float* coef, void* stream);
 int tg_gp_seed(const void* g, const float* coef, int N, int HW, int C, int c_off, int cj, void* seed, void* stream);
 
+/* ---- data-parallel gradient exchange for small buffers (new; the reference has no multi-GPU path): one-shot
+ * sum over NVLink peer memory. local: this rank's fp32 buffer (numel % 4 == 0), summed in place. peer_bufs_dev /
+ * peer_flags_dev: device arrays of `world` pointers to every rank's symmetric staging buffer (2 * half_stride floats,
+ * half_stride >= numel: two halves used alternately by epoch parity) and flag
+ * pad (ctas * world uint32, zero-initialised) -- memory all ranks of the node can address (torch symmetric memory /
+ * cudaIpc). epoch: 1, 2, 3, ... the same on every rank for the same call. Ranks add in the order 0..world-1, so all
+ * ranks obtain bit-identical sums. */
+int tg_allreduce_oneshot(float* local, const void* peer_bufs_dev, const void* peer_flags_dev, int rank, int world,
+                          long long numel, long long half_stride, unsigned epoch, int ctas, void* stream);
+
 /* ---- torch.optim.Adam.step (train.py:135,168) fused with the bf16 weight re-pack.
  * table_dev: device array of `ntensors` rows of 136 bytes: 6 pointers (param, grad, exp_avg,
  * exp_avg_sq, pack_fwd, pack_bwd), int64 numel, int32 kind, kh, kw, dim1, o_pad, i_pad, nseg,

@@ -23,6 +23,16 @@ from .engine import PatchDInstance, build_generator_engine
 SLOT = {"loss_D": 0, "gp": 1, "G_GAN": 2, "L1": 3, "per": 4}
 
 
+class _EventWork:
+    """work.wait() of a kernel launched on the communication stream: the current stream waits for its event."""
+
+    def __init__(self, event):
+        self.event = event
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.event)
+
+
 class TrainStep:
     def __init__(self, netG, netD, batch, height, width, loss="ls", version=2, lambda_a=1.0, lambda_gp=0.01,
                  lambda_per=1.0, w_per=(0, .1, .3, .6), lr=1e-3, beta1=0.9, label_smoothing=True, gen_kind=None,
@@ -73,6 +83,19 @@ class TrainStep:
         # TG_COMM_PROFILE=1 (bench.py): CUDA-event pairs around the points where the compute stream waits for a
         # gradient collective -- the time between them is communication the step could not hide
         self.comm_profile = [] if (self.world > 1 and os.environ.get("TG_COMM_PROFILE")) else None
+        # D's 6 MB gradient arena (its collective is on the critical path: the G step needs the updated D) and the
+        # generator's small last bucket are summed by a one-shot kernel over NVLink peer memory (p2p.PeerReducer); the
+        # large generator buckets stay on NCCL, which is bandwidth-optimal. TG_P2P=0, or a node where symmetric memory
+        # cannot be set up, keeps NCCL for everything.
+        self.peer = None
+        if self.world > 1 and os.environ.get("TG_P2P", "1") != "0":
+            from .p2p import PeerReducer, PeerUnavailable
+            try:
+                self.peer = PeerReducer(max(self.DA.store.grad_arena.numel(), self.PEER_MAX_BYTES // 4), dev,
+                                        process_group)
+            except PeerUnavailable as e:
+                if torch.distributed.get_rank(process_group) == 0:
+                    print(f"tactile_gan_b200: peer-memory all-reduce unavailable ({e}); using NCCL for every bucket")
 
     # ------------------------------------------------------------------ labels / alpha (host RNG parity)
     def ensure_label(self, generator=None):
@@ -116,7 +139,16 @@ class TrainStep:
         ev.record()
         with torch.cuda.stream(self._comm_stream):
             self._comm_stream.wait_event(ev)
-            return torch.distributed.all_reduce(store.grad_arena, group=self.pg, async_op=True)
+            return self._reduce_on_comm_stream(store.grad_arena)
+
+    def _reduce_on_comm_stream(self, buf):
+        """Called with the communication stream current. Returns something with .wait() (the compute stream waits)."""
+        if self.peer is not None and buf.numel() * 4 <= self.PEER_MAX_BYTES and buf.numel() % 4 == 0:
+            self.peer.allreduce_(buf)
+            done = torch.cuda.Event()
+            done.record()
+            return _EventWork(done)
+        return torch.distributed.all_reduce(buf, group=self.pg, async_op=True)
 
     def _allreduce_wait(self, work, tag):
         if work is None:
@@ -134,6 +166,7 @@ class TrainStep:
     # ---- generator gradients: bucketed allreduce overlapped with the rest of backward -----------------
     BUCKET_BYTES = 32 << 20
     TAIL_BUCKET_BYTES = 1 << 20      # the last-completing parameters travel alone: the only exposed collective
+    PEER_MAX_BYTES = 8 << 20         # buffers up to this size take the one-shot peer-memory all-reduce
 
     def _plan_g_buckets(self):
         """The gradient arena is laid out in backward-completion order (ParamStore.finalize), so bucket k is a
@@ -166,7 +199,7 @@ class TrainStep:
             ev.record()          # on the stream that finalised the bucket (the generator's weight-gradient stream)
             with torch.cuda.stream(self._comm_stream):
                 self._comm_stream.wait_event(ev)
-                works.append(torch.distributed.all_reduce(gs.grad_arena[a:b], group=self.pg, async_op=True))
+                works.append(self._reduce_on_comm_stream(gs.grad_arena[a:b]))
 
         def after_unit(u):
             while pending and pending[0][2] is u:

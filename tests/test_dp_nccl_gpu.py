@@ -49,6 +49,22 @@ def _rank(rank, world, port, out):
     ts.step(a[sl].to(dev), b[sl].to(dev), regularize=True, alpha=alpha[sl])
     torch.cuda.synchronize()
     nb = len(ts._g_buckets)
+    # the one-shot peer-memory all-reduce (p2p.PeerReducer / tg_allreduce_oneshot) against NCCL on the same data: both
+    # staging halves, a full-size and a shorter buffer, bit-identical results on the two ranks
+    peer_ok = ts.peer is not None
+    peer_err, peer_same = 0.0, True
+    if peer_ok:
+        gen = torch.Generator(device=dev).manual_seed(100 + rank)
+        for k, n in enumerate((ts.peer.numel, 4096, ts.peer.numel, 1 << 18)):
+            x = torch.randn(n, device=dev, generator=gen)
+            ref_sum = x.clone()
+            dist.all_reduce(ref_sum)
+            got = ts.peer.allreduce_(x.clone())
+            torch.cuda.synchronize()
+            peer_err = max(peer_err, float((got - ref_sum).abs().max() / ref_sum.abs().max()))
+            other = got.clone()
+            dist.broadcast(other, 0)
+            peer_same = peer_same and bool(torch.equal(other, got))
     got_g = {k: v / world for k, v in ts.G.store.grads_by_name().items()}
     got_d = {k: v / world for k, v in ts.DA.store.grads_by_name().items()}
     if rank == 0:
@@ -62,7 +78,7 @@ def _rank(rank, world, port, out):
         den = sum(float(rg[k].norm() ** 2) for k in rg)
         numd = sum(float((got_d[k] - rd[k]).norm() ** 2) for k in rd)
         dend = sum(float(rd[k].norm() ** 2) for k in rd)
-        out.put((nb, (num / den) ** 0.5, (numd / dend) ** 0.5))
+        out.put((nb, (num / den) ** 0.5, (numd / dend) ** 0.5, peer_ok, peer_err, peer_same))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -78,8 +94,12 @@ def test_two_gpu_bucketed_allreduce_matches_global_batch():
     for p in procs:
         p.join(600)
         assert p.exitcode == 0
-    buckets, err_g, err_d = out.get()
+    buckets, err_g, err_d, peer_ok, peer_err, peer_same = out.get()
+    print(f"\nbuckets {buckets}, G {err_g:.4f}, D {err_d:.4f}, peer-memory all-reduce used: {peer_ok}, "
+          f"vs NCCL {peer_err:.2e}, bit-identical on both ranks: {peer_same}")
     assert buckets >= 2
+    assert peer_ok, "symmetric-memory peer all-reduce could not be set up on this 2-GPU node"
+    assert peer_err < 1e-6 and peer_same
     # bf16 storage + atomics: two launches of the same step differ at this level too
     assert err_g < 5e-2 and err_d < 2e-2
 
