@@ -239,8 +239,10 @@ def layer_table(fn, path, reps=2):
 
 def ncu_traffic():
     """DRAM bytes of one representative launch of the dominant kernel, from the committed `ncu --set full`
-    summary (profiles/r01_ncu_top_kernels.json, written by tools/ncu_summary.py --json)."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_top_kernels.json")
+    summary (profiles/r02_ncu_top_kernels.json, written by tools/ncu_summary.py --json)."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu_top_kernels.json")
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "r01_ncu_top_kernels.json")
     if not os.path.exists(p):
         return None, None
     top = json.load(open(p)).get("roofline_launch")
@@ -251,8 +253,10 @@ def ncu_traffic():
 
 def ncu_tensor_pipe():
     """Time-weighted tensor-pipe utilisation of all conv GEMM launches of the step (BASELINE.json's second metric), from
-    the committed ncu pass profiles/r01_ncu_tensor_pipe.txt (sm__pipe_tensor_cycles_active over every launch)."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_tensor_pipe.txt")
+    the committed ncu pass profiles/r02_ncu_launch_shares.txt (sm__pipe_tensor_cycles_active over every launch)."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu_launch_shares.txt")
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "r01_ncu_tensor_pipe.txt")
     if not os.path.exists(p):
         return None
     for line in open(p):

@@ -524,8 +524,7 @@ def test_convlstm_modules_train_against_reference_autograd(golden_dir):
         torch.cuda.synchronize()
         assert _C().error_flag() == 0
         errs = {k: rel(p.grad, c["grads"][k]) for k, p in m.named_parameters()}
-        print(f"\n{name}: dX {rel(x.grad, c['dx']):.4f}  " + "  ".join(f"{k.split('.')[-2][-4:]}.{k.split('.')[-1]} {v:.4f}"
-                                                                         for k, v in errs.items()))
+        print(f"\n{name}: dX {rel(x.grad, c['dx']):.4f}  " + "  ".join(f"{k.replace('convLSTMcell.', '')} {v:.4f}" for k, v in errs.items()))
         assert rel(x.grad, c["dx"]) < tol, (name, rel(x.grad, c["dx"]))
         for k, v in errs.items():
             assert v < tol, (name, k, v)
