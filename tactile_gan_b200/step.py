@@ -83,12 +83,12 @@ class TrainStep:
         # TG_COMM_PROFILE=1 (bench.py): CUDA-event pairs around the points where the compute stream waits for a
         # gradient collective -- the time between them is communication the step could not hide
         self.comm_profile = [] if (self.world > 1 and os.environ.get("TG_COMM_PROFILE")) else None
-        # D's 6 MB gradient arena (its collective is on the critical path: the G step needs the updated D) and the
-        # generator's small last bucket are summed by a one-shot kernel over NVLink peer memory (p2p.PeerReducer); the
-        # large generator buckets stay on NCCL, which is bandwidth-optimal. TG_P2P=0, or a node where symmetric memory
-        # cannot be set up, keeps NCCL for everything.
+        # TG_P2P=1: D's 6 MB gradient arena and the generator's small last buckets are summed by a one-shot kernel over
+        # NVLink peer memory (p2p.PeerReducer) instead of NCCL. Off by default: measured on 8 B200s NCCL 2.28 reduces
+        # the same 6.35 MB inside the NVSwitch (NVLS) in 65 us, the one-shot kernel reads 7 peers' copies in 106 us and
+        # competes for SMs with the work the step overlaps it with (profiles/r02_p2p_vs_nccl.txt).
         self.peer = None
-        if self.world > 1 and os.environ.get("TG_P2P", "1") != "0":
+        if self.world > 1 and os.environ.get("TG_P2P", "0") == "1":
             from .p2p import PeerReducer, PeerUnavailable
             try:
                 self.peer = PeerReducer(max(self.DA.store.grad_arena.numel(), self.PEER_MAX_BYTES // 4), dev,

@@ -22,7 +22,7 @@ def _rank(rank, world, port, out):
     from tactile_gan_b200.generators.generators import create_gen
     from tactile_gan_b200.step import TrainStep
     from tactile_gan_b200.util import init_weights
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), TG_P2P="1")   # opt-in peer-memory all-reduce
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
