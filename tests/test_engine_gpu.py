@@ -388,3 +388,27 @@ def test_step_from_host_with_prefetch_matches_device_resident_steps():
     for i, (w, gt) in enumerate(zip(want, got)):
         for k in w:
             assert gt[k] == pytest.approx(w[k], rel=1e-3, abs=1e-6), (i, k, gt[k], w[k])
+
+
+def test_inference_graph_is_rebuilt_when_parameter_storage_moves():
+    """forward_graphed captures raw parameter pointers (bias / affine / head weight). When parameter storage is
+    re-allocated (p.data = ..., module.to(), .float()) ParamStore.refresh() bumps its generation and the engine drops
+    the stale graph instead of replaying reads from freed memory."""
+    from tactile_gan_b200.generators.generators import create_gen
+    torch.manual_seed(6)
+    net = create_gen("UNet++", 3, 3, 16, True).cuda()
+    randomize(net, 3)
+    x = torch.rand(2, 3, 64, 64, device="cuda") * 2 - 1
+    with torch.no_grad():
+        y0 = net(x).clone()
+        eng = net._engine(2, 64, 64, False)
+        g0 = eng._graph
+        assert g0 is not None and torch.equal(net(x), y0)           # replayed
+        assert eng._graph is g0
+        for p in net.parameters():                                   # new storage, new values
+            p.data = (p.data * 1.5 + 0.01).clone()
+        y1 = net(x).clone()
+        assert eng._graph is not g0                                   # re-captured against the new pointers
+        fresh = create_gen("UNet++", 3, 3, 16, True).cuda()
+        fresh.load_state_dict(net.state_dict())
+        assert torch.equal(fresh(x), y1) and not torch.equal(y1, y0)
