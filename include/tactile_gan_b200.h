@@ -90,6 +90,11 @@ int tg_plan_run(tg_plan* plan, void* stream);
 void tg_plan_destroy(tg_plan* plan);
 /* device int the kernels set (non-zero) when a pipeline wait times out; host-readable after sync */
 int* tg_error_flag_device_ptr(void);
+/* Programmatic dependent launch of the GEMM / InstanceNorm kernels (each waits with griddepcontrol.wait after its
+ * set-up): 0 off, 1 eager launches, 2 also inside stream capture (programmatic graph edges). Returns the previous value;
+ * a negative argument only queries. Default 0 (env TG_PDL): neutral on the training step, +4..13 % on batch-1 inference,
+ * where the engines switch it on themselves (engine.GraphEngine.forward_graphed). */
+int tg_pdl_policy(int policy);
 int tg_error_flag_read(void); /* synchronising D2H read of that flag (diagnostics / tests only) */
 
 /* ---- layout packs (train.py:101 `.to(device)` + torch.cat at PatchDiscriminator.py:36, and the

@@ -19,8 +19,14 @@ int tg_set_error(const char* msg) {
   snprintf(g_err, sizeof(g_err), "%s", msg);
   return -1;
 }
+static int g_pdl = -1;
+extern "C" int tg_pdl_policy(int policy) {
+  const int prev = tg_pdl_enabled();
+  if (policy >= 0 && policy <= 2) g_pdl = policy;
+  return prev;
+}
 int tg_pdl_enabled() {
-  static int on = -1;
+  int& on = g_pdl;
   if (on < 0) {
     // measured neutral to -1 % on the training step (profiles/r02_pdl_ab.txt: 807 / 804 img/s with, 813 / 814 without):
     // consecutive kernels are data dependent, so only launch latency could overlap and the queue already hides it

@@ -275,6 +275,24 @@ class GraphEngine:
             cache[name] = l
         return cache[name]
 
+    PDL_MAX_PIXELS = 8 * 256 * 256     # inference batches up to this many pixels are launch / prologue bound
+
+    def _pdl(self):
+        """Context: programmatic dependent launch for the launches of a small inference pass (batch 1 at 256^2: 819 ->
+        922 img/s eager, 922 -> 960 through the graph; the training step measured -1 % and keeps it off)."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            on = (not self.with_backward) and self.n * self.h * self.w <= self.PDL_MAX_PIXELS
+            prev = _C.lib().tg_pdl_policy(2) if on else None
+            try:
+                yield
+            finally:
+                if on:
+                    _C.lib().tg_pdl_policy(prev)
+        return ctx()
+
     def forward_graphed(self, x):
         """Inference forward (test.py:202-203) replayed from a CUDA graph: the ~370 launches of a UNet++ forward are
         captured once (static input / output buffers), which is what bounds small batches -- 2.3 ms of launches for
@@ -295,7 +313,7 @@ class GraphEngine:
                 self._forward_launches(self._static_in)
             cur.wait_stream(side)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph), self._pdl():
                 self._graph_out = self._forward_launches(self._static_in)
             self._graph = graph
             self._graph_gen = self.store.generation
@@ -412,7 +430,8 @@ class UNetPPEngine(GraphEngine):
         """x: fp32 NCHW on the engine's device -> fp32 NCHW (tensor owned by the engine)."""
         assert x.shape == (self.n, self.cin, self.h, self.w) and x.dtype == torch.float32 and x.is_contiguous()
         self.store.refresh()
-        return self._forward_launches(x)
+        with self._pdl():
+            return self._forward_launches(x)
 
     def _forward_launches(self, x):
         _C.call("pack_nchw", ptr(x), None, None, None, ptr(self.x_in.buf), self.n, self.h * self.w, self.cin,
@@ -444,7 +463,8 @@ class SequentialGenEngine(GraphEngine):
     def forward(self, x):
         assert x.shape == (self.n, self.cin, self.h, self.w) and x.dtype == torch.float32 and x.is_contiguous()
         self.store.refresh()
-        return self._forward_launches(x)
+        with self._pdl():
+            return self._forward_launches(x)
 
     def _forward_launches(self, x):
         _C.call("pack_nchw", ptr(x), None, None, None, ptr(self.x_in.buf), self.n, self.h * self.w, self.cin,
