@@ -80,6 +80,11 @@ class TrainStep:
         self.real_label = None
         self.label_smoothing = label_smoothing
         self.fake_B = None
+        # Programmatic dependent launch for the step's launches when kernels are short enough that launch latency and
+        # prologues show (measured, profiles/r02_pdl_ab.txt): UNet batch 4 +12.6 %, UNet++ batch 4 +8 %, UNet batch 32
+        # +3 %; UNet++ batch 32 -1 % -> off there. TG_PDL in the environment overrides the choice.
+        small = batch * height * width <= 8 * 256 * 256 or str(kind).lower() == "unet"
+        self.pdl = small if os.environ.get("TG_PDL") is None else None
         # TG_COMM_PROFILE=1 (bench.py): CUDA-event pairs around the points where the compute stream waits for a
         # gradient collective -- the time between them is communication the step could not hide
         self.comm_profile = [] if (self.world > 1 and os.environ.get("TG_COMM_PROFILE")) else None
@@ -224,6 +229,15 @@ class TrainStep:
     def step(self, real_A, real_B, regularize=True, alpha=None, real_B_ready=None):
         """real_A (B,in,H,W) in [-1,1], real_B (B,out,H,W) in [0,1]: fp32, contiguous, on the device.
         Returns the device tensor of loss slots (see SLOT); reading it is the caller's only sync."""
+        if self.pdl:
+            prev = _C.lib().tg_pdl_policy(1)
+            try:
+                return self._step(real_A, real_B, regularize, alpha, real_B_ready)
+            finally:
+                _C.lib().tg_pdl_policy(prev)
+        return self._step(real_A, real_B, regularize, alpha, real_B_ready)
+
+    def _step(self, real_A, real_B, regularize, alpha, real_B_ready):
         B, HW = self.B, self.H * self.W
         G, DA, S1, S2 = self.G, self.DA, self.S1, self.S2
         gs, ds = G.store, DA.store
