@@ -28,8 +28,8 @@ extern "C" int tg_pdl_policy(int policy) {
 int tg_pdl_enabled() {
   int& on = g_pdl;
   if (on < 0) {
-    // measured neutral to -1 % on the training step (profiles/r02_pdl_ab.txt: 807 / 804 img/s with, 813 / 814 without):
-    // consecutive kernels are data dependent, so only launch latency could overlap and the queue already hides it
+    // -1 % on the headline step, +3..13 % on latency-bound configurations (profiles/r02_pdl_ab.txt): off by default here,
+    // switched on per configuration by the Python side (step.TrainStep, engine.GraphEngine) through tg_pdl_policy
     const char* e = getenv("TG_PDL");
     on = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
   }
