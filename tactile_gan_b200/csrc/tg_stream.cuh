@@ -25,6 +25,8 @@ struct StreamArgs {
   const __nv_bfloat16* in0;   // raw (conv output)
   const __nv_bfloat16* in1;   // gradient route 1 (backward) / unused (forward)
   const __nv_bfloat16* in2;   // optional second same-resolution gradient route
+  const __nv_bfloat16* pool;  // optional gradient of the 2x2 average-pooled copy, [N][H/2][W/2][C]: each pixel adds a quarter
+  int W;                      // map width (pool route only: a chunk must lie inside one image row)
   __nv_bfloat16* out;         // forward: y; statistics pass: dn (optional); apply pass: dz
   const float* mr;            // [N][C][2] mean, rstd
   const float* gamma;
@@ -54,7 +56,11 @@ __device__ __forceinline__ uint4 lds16(uint32_t addr) {
 template <int MODE>
 __global__ void __launch_bounds__(kStreamThreads, 2) in_stream_kernel(const StreamArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  const int NIN = MODE == 0 ? 1 : (a.in2 ? 3 : 2);
+  // ring slots of one stage: raw | g1 | g2 | pooled gradient (absent routes take no slot)
+  const int slot_g1 = a.in1 ? 1 : 0;
+  const int slot_g2 = a.in2 ? slot_g1 + 1 : 0;
+  const int slot_pool = a.pool ? (a.in2 ? slot_g2 : slot_g1) + 1 : 0;
+  const int NIN = MODE == 0 ? 1 : 1 + (a.in1 ? 1 : 0) + (a.in2 ? 1 : 0) + (a.pool ? 1 : 0);
   const int CG = a.C >> 3;
   const int PL = kStreamConsumers / CG;                 // pixel lanes; threads with pl >= PL idle (C/8 not a divisor)
   const int CP = kStreamPPT * PL;                       // pixels per chunk
@@ -83,7 +89,6 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_stream_kernel(const Stre
   if (tid >= kStreamConsumers) {
     // ------------------------------------------------------------------ producer warp (one lane issues)
     if (tid == kStreamConsumers) {
-      const __nv_bfloat16* srcs[3] = {a.in0, a.in1, a.in2};
       int s = 0;
       uint32_t ph = 1;       // the first pass over the ring finds every stage free
       for (long long k = k0; k < k1; ++k) {
@@ -92,10 +97,20 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_stream_kernel(const Stre
         const int np = min(CP, a.HW - p0);
         const uint32_t bytes = uint32_t(np) * a.C * 2;
         mbar_wait(bar0 + 8 * (S + s), ph);
-        mbar_arrive_expect_tx(bar0 + 8 * s, bytes * NIN);
         const size_t off = (size_t(n) * a.HW + p0) * a.C;
-        for (int t = 0; t < NIN; ++t)
-          bulk_load_1d(base + (uint32_t(s) * NIN + t) * chunk_stride, srcs[t] + off, bytes, bar0 + 8 * s);
+        const uint32_t st = base + uint32_t(s) * NIN * chunk_stride;
+        const uint32_t pool_bytes = a.pool ? bytes >> 1 : 0;
+        mbar_arrive_expect_tx(bar0 + 8 * s, bytes * (NIN - (a.pool ? 1 : 0)) + pool_bytes);
+        bulk_load_1d(st, a.in0 + off, bytes, bar0 + 8 * s);
+        if (a.in1) bulk_load_1d(st + slot_g1 * chunk_stride, a.in1 + off, bytes, bar0 + 8 * s);
+        if (a.in2) bulk_load_1d(st + slot_g2 * chunk_stride, a.in2 + off, bytes, bar0 + 8 * s);
+        if (a.pool) {
+          // the chunk lies inside image row y (launcher: W % CP == 0): its pooled gradients are np / 2 consecutive
+          // pixels of row y / 2 of the half-resolution tensor
+          const int y = p0 / a.W, x = p0 % a.W;
+          const size_t poff = ((size_t(n) * (a.HW / a.W / 2) + (y >> 1)) * (a.W >> 1) + (x >> 1)) * a.C;
+          bulk_load_1d(st + slot_pool * chunk_stride, a.pool + poff, pool_bytes, bar0 + 8 * s);
+        }
         if (++s == S) { s = 0; ph ^= 1; }
       }
     }
@@ -194,13 +209,19 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_stream_kernel(const Stre
             for (int q = 0; q < 8; ++q) r[q] = act_fwd(fmaf(r[q], A[q], B[q]), act, slope);
             stg16(a.out + lin, pack8(r));
           } else {
-            float g[8];
-            unpack8(lds16(st + chunk_stride + so), g);
-            if (NIN == 3) {
+            float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (slot_g1) unpack8(lds16(st + slot_g1 * chunk_stride + so), g);
+            if (slot_g2) {
               float f[8];
-              unpack8(lds16(st + 2 * chunk_stride + so), f);
+              unpack8(lds16(st + slot_g2 * chunk_stride + so), f);
 #pragma unroll
               for (int q = 0; q < 8; ++q) g[q] += f[q];
+            }
+            if (slot_pool) {
+              float f[8];
+              unpack8(lds16(st + slot_pool * chunk_stride + uint32_t(lp >> 1) * a.C * 2 + c0 * 2), f);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) g[q] = fmaf(0.25f, f[q], g[q]);
             }
             if (MODE == 1) {
 #pragma unroll

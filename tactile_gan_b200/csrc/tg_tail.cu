@@ -1760,7 +1760,7 @@ static bool stream_enabled() { return stream_policy() != 0; }
 template <int MODE>
 static int launch_stream(tg::StreamArgs a, cudaStream_t s) {
   using namespace tg;
-  const int nin = MODE == 0 ? 1 : (a.in2 ? 3 : 2);
+  const int nin = MODE == 0 ? 1 : 1 + (a.in1 ? 1 : 0) + (a.in2 ? 1 : 0) + (a.pool ? 1 : 0);
   const int CG = a.C >> 3, PL = kStreamConsumers / CG;
   const size_t scratch = MODE == 1 ? size_t(PL) * a.C * 2 * sizeof(float) : 0;
   // two CTAs per SM: <= ~110 KiB each
@@ -1786,6 +1786,11 @@ static int launch_stream(tg::StreamArgs a, cudaStream_t s) {
   return tg_check_launch("in_stream_kernel");
 }
 static bool stream_shape_ok(int C) { return C >= 64 && C <= 2048 && (C & 63) == 0; }
+// the average-pool gradient route streams when a chunk (2 * (256 / (C/8)) pixels) lies inside one image row
+static bool stream_pool_ok(int H, int W, int C) {
+  const int CP = tg::kStreamPPT * (tg::kStreamConsumers / (C >> 3));
+  return CP >= 2 && (CP & 1) == 0 && W % CP == 0 && (H & 1) == 0 && (W & 1) == 0;
+}
 // Which form is faster, measured per shape (profiles/r02_tail_microbench_*.txt): the register-staged passes reach
 // 0.88 of the copy bandwidth on the 268 MB, C = 64 tensors in the write-heavy passes (forward, apply) and start up
 // ~1.5 us faster on tensors under ~20 MB; the bulk-copy ring wins everywhere else (by 1.1-1.5x on 30-230 MB tensors
@@ -1940,9 +1945,13 @@ int tg_in_bwd_reduce(const void* raw, const void* y, const float* mr, const floa
   dim3 grid(strip_count(H * W, C, N, 16), N);
   if (!raw && !dn) return tg_set_error("tg_in_bwd_reduce: a layer without norm needs the dn (= dz) output");
   const bool plain = !g_pool && (g_same || g_up) && (!g_up || g_up_pooled);
-  if (plain && raw && mr && red && stream_enabled() && stream_shape_ok(C) && stream_wins(1, N, H * W, C)) {
+  // every route at the unit's own resolution, plus (optionally) the gradient of its 2x2 average-pooled copy
+  const bool streamable = (plain || (g_pool && pool_mode == 1 && (!g_up || g_up_pooled) && stream_pool_ok(H, W, C))) &&
+                          raw && mr && stream_enabled() && stream_shape_ok(C);
+  if (streamable && red && (g_pool || stream_wins(1, N, H * W, C))) {
     tg::StreamArgs sa{};
     sa.in0 = a.raw; sa.in1 = a.g_same ? a.g_same : a.g_up; sa.in2 = (a.g_same && a.g_up) ? a.g_up : nullptr;
+    sa.pool = a.g_pool; sa.W = W;
     sa.out = a.dn; sa.mr = mr; sa.gamma = gamma; sa.beta = beta; sa.red = red;
     sa.N = N; sa.HW = H * W; sa.C = C; sa.c_valid = c_valid; sa.act = act; sa.slope = slope;
     return launch_stream<1>(sa, TG_STREAM(stream));
@@ -1970,9 +1979,12 @@ int tg_in_bwd_apply_re(const void* raw, const void* y, const float* mr, const fl
   if (block > 1024) return tg_set_error("tg_in_bwd_apply_re: C too large");
   dim3 grid(strip_count(H * W, C, N, 16), N);
   const bool plain = !g_pool && (g_same || g_up) && (!g_up || g_up_pooled);
-  if (plain && stream_enabled() && stream_shape_ok(C) && stream_wins(2, N, H * W, C)) {
+  const bool streamable = (plain || (g_pool && pool_mode == 1 && (!g_up || g_up_pooled) && stream_pool_ok(H, W, C))) &&
+                          stream_enabled() && stream_shape_ok(C);
+  if (streamable && (g_pool || stream_wins(2, N, H * W, C))) {
     tg::StreamArgs sa{};
     sa.in0 = a.raw; sa.in1 = a.g_same ? a.g_same : a.g_up; sa.in2 = (a.g_same && a.g_up) ? a.g_up : nullptr;
+    sa.pool = a.g_pool; sa.W = W;
     sa.out = a.dz; sa.mr = mr; sa.gamma = gamma; sa.beta = beta; sa.red = a.red; sa.dgamma = dgamma; sa.dbeta = dbeta;
     sa.N = N; sa.HW = H * W; sa.C = C; sa.c_valid = c_valid; sa.act = act; sa.slope = slope;
     return launch_stream<2>(sa, TG_STREAM(stream));

@@ -205,11 +205,15 @@ def test_instance_norm_forward_backward_pool_upsample():
         assert rel(dgam_c, dg_ref) < 6e-3 and rel(dbet_c, db_ref) < 6e-3
 
 
-@pytest.mark.parametrize("n,c,h,w,act,two_routes", [(2, 64, 16, 24, 3, False), (3, 72, 31, 17, 3, True),
-                                                    (2, 180, 13, 11, 1, True), (2, 1000, 5, 7, 3, False),
-                                                    (2, 256, 61, 61, 1, False), (5, 512, 2, 2, 3, True),
-                                                    (2, 64, 128, 128, 3, True)])
-def test_instance_norm_streaming_passes(n, c, h, w, act, two_routes):
+@pytest.mark.parametrize("n,c,h,w,act,two_routes,pool", [
+    (2, 64, 16, 24, 3, False, False), (3, 72, 31, 17, 3, True, False), (2, 180, 13, 11, 1, True, False),
+    (2, 1000, 5, 7, 3, False, False), (2, 256, 61, 61, 1, False, False), (5, 512, 2, 2, 3, True, False),
+    (2, 64, 128, 128, 3, True, False),
+    # + the gradient of the 2x2 average-pooled copy (UNet++'s x{i}0 second units): streams when a chunk lies inside
+    # one image row, else the gather kernel serves it -- both must give the same answer
+    (2, 64, 16, 64, 3, True, True), (3, 72, 12, 32, 3, False, True), (2, 512, 4, 8, 3, True, True),
+    (2, 64, 16, 24, 3, False, True)])
+def test_instance_norm_streaming_passes(n, c, h, w, act, two_routes, pool):
     """The cp.async.bulk-ring form of the same-resolution InstanceNorm passes (csrc/tg_stream.cuh): forward, backward
     statistics (with and without the dn store) and the recomputing apply pass, against torch autograd. Shapes: channel
     groups that do not divide the CTA (C = 192), odd maps whose pixel count is not a chunk multiple (61^2, 5x7),
@@ -218,12 +222,12 @@ def test_instance_norm_streaming_passes(n, c, h, w, act, two_routes):
     from tactile_gan_b200._C import F as f32, ptr
     prev = C.lib().tg_in_stream_policy(2)        # the ring form whenever the shape allows (the default picks per shape)
     try:
-        _streaming_case(C, f32, ptr, n, c, h, w, act, two_routes)
+        _streaming_case(C, f32, ptr, n, c, h, w, act, two_routes, pool)
     finally:
         C.lib().tg_in_stream_policy(prev)
 
 
-def _streaming_case(C, f32, ptr, n, c, h, w, act, two_routes):
+def _streaming_case(C, f32, ptr, n, c, h, w, act, two_routes, pool):
     g = torch.Generator().manual_seed(7)
     cp = pad64(c)
     slope = 0.2
@@ -246,24 +250,29 @@ def _streaming_case(C, f32, ptr, n, c, h, w, act, two_routes):
     q = lambda t: t.bfloat16().float()
     gs = torch.randn(n, c, h, w, generator=g).to(dev)
     gu = torch.randn(n, c, h, w, generator=g).to(dev)
+    gpl = torch.randn(n, c, h // 2, w // 2, generator=g).to(dev)
     loss = (y_ref * q(gs)).sum() + ((y_ref * q(gu)).sum() if two_routes else 0)
+    if pool:
+        loss = loss + (F.avg_pool2d(y_ref, 2) * q(gpl)).sum()
     dx_ref, dg_ref, db_ref = torch.autograd.grad(loss, [xb, ga, be])
-    gs_p, gu_p = nhwc_pad(gs), nhwc_pad(gu)
+    gs_p, gu_p, gpl_p = nhwc_pad(gs), nhwc_pad(gu), nhwc_pad(gpl)
     up_ptr = ptr(gu_p) if two_routes else None
+    pool_ptr, pm = (ptr(gpl_p), 1) if pool else (None, 0)
     dn = torch.zeros_like(raw)
     red_a, red_b = torch.zeros(n, cp, 2, device=dev), torch.zeros(n, cp, 2, device=dev)
-    C.call("in_bwd_reduce", ptr(raw), ptr(y), ptr(mr), ptr(gamma), ptr(beta), ptr(gs_p), None, 0, up_ptr, 1,
+    C.call("in_bwd_reduce", ptr(raw), ptr(y), ptr(mr), ptr(gamma), ptr(beta), ptr(gs_p), pool_ptr, pm, up_ptr, 1,
            ptr(dn), ptr(red_a), n, h, w, cp, c, act, f32(slope))
-    C.call("in_bwd_reduce", ptr(raw), ptr(y), ptr(mr), ptr(gamma), ptr(beta), ptr(gs_p), None, 0, up_ptr, 1,
+    C.call("in_bwd_reduce", ptr(raw), ptr(y), ptr(mr), ptr(gamma), ptr(beta), ptr(gs_p), pool_ptr, pm, up_ptr, 1,
            None, ptr(red_b), n, h, w, cp, c, act, f32(slope))
     torch.cuda.synchronize()
     assert rel(red_a, red_b) < 1e-5
     mask = (nrm > 0).float() if act == 3 else torch.where(nrm > 0, 1.0, slope)
-    dn_ref = (q(gs) + (q(gu) if two_routes else 0)) * mask
+    dn_ref = (q(gs) + (q(gu) if two_routes else 0) +
+              (0.25 * F.interpolate(q(gpl), scale_factor=2, mode="nearest") if pool else 0)) * mask
     assert rel(dn[..., :c].permute(0, 3, 1, 2), dn_ref) < 6e-3
     dz = torch.zeros_like(raw)
     dgam, dbet = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
-    C.call("in_bwd_apply_re", ptr(raw), ptr(y), ptr(mr), ptr(gamma), ptr(beta), ptr(gs_p), None, 0, up_ptr, 1,
+    C.call("in_bwd_apply_re", ptr(raw), ptr(y), ptr(mr), ptr(gamma), ptr(beta), ptr(gs_p), pool_ptr, pm, up_ptr, 1,
            ptr(red_b), ptr(dz), n, h, w, cp, c, act, f32(slope), ptr(dgam), ptr(dbet))
     torch.cuda.synchronize()
     assert C.error_flag() == 0
