@@ -1590,87 +1590,59 @@ __global__ void gp_seed_kernel(const __nv_bfloat16* __restrict__ g, const float*
 }
 
 // ------------------------------------------------------------------ fused Adam + weight re-pack
-// Elements are walked in torch order (parameter and moments coalesced); the gradient is gathered from the packed
-// layout and the two packs are scattered. Four independent elements per thread and iteration: all sixteen loads are
-// issued before the first update, which is what hides the latency of the strided gradient gather (one element per
-// iteration ran at 1.9 TB/s of its 32 B/param).
-__global__ void __launch_bounds__(256)
-adam_kernel(const AdamTensor* __restrict__ tab, int ntensors, float lr, float beta1,
-            float beta2, float eps, float bc1, float bc2, float grad_scale) {
+__global__ void adam_kernel(const AdamTensor* __restrict__ tab, int ntensors, float lr, float beta1,
+                            float beta2, float eps, float bc1, float bc2, float grad_scale) {
   const AdamTensor t = tab[blockIdx.y];
   const size_t numel = t.numel;
   const int taps = t.kh * t.kw;
-  const size_t stride = size_t(gridDim.x) * blockDim.x;
-  const float inv_sqrt_bc2 = 1.f / sqrtf(bc2), step_size = lr / bc1;
-  constexpr int U = 4;
-  for (size_t i0 = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i0 < numel; i0 += U * stride) {
-    size_t idx[U], gi[U];
-    int o[U], ic[U], tap[U];
-    bool ok[U];
-    float p[U], g[U], m[U], v[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const size_t i = i0 + u * stride;
-      idx[u] = i;
-      ok[u] = i < numel;
-      gi[u] = i;
-      o[u] = ic[u] = tap[u] = 0;
-      if (ok[u] && t.kind != 0) {
-        // torch order: conv [O][I][kh][kw]; convT [I][O][kh][kw]; vectors: kind 0
-        tap[u] = int(i % taps);
-        const size_t r = i / taps;
-        const int d1 = int(r % t.dim1), d0 = int(r / t.dim1);
-        if (t.kind == 2) { ic[u] = d0; o[u] = d1; } else { o[u] = d0; ic[u] = d1; }
-        if (t.kind == 4) ic[u] = tap[u] * t.dim1 + ic[u];   // im2col column of the thin first layer
-        else
-          for (int sgi = 0; sgi < t.nseg; ++sgi)
-            if (ic[u] < t.seg_end[sgi]) { ic[u] += t.seg_shift[sgi]; break; }
-        // gradient lives in the packed forward layout [tap][rows_pad][cols_pad] (kind 3: rows = taps, kind 4: one tap)
-        gi[u] = t.kind == 1   ? (size_t(tap[u]) * t.o_pad + o[u]) * t.i_pad + ic[u]
-                : t.kind == 2 ? (size_t(tap[u]) * t.i_pad + ic[u]) * t.o_pad + o[u]
-                : t.kind == 3 ? size_t(tap[u]) * t.i_pad + ic[u]
-                              : size_t(o[u]) * t.i_pad + ic[u];
-      }
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < numel;
+       i += size_t(gridDim.x) * blockDim.x) {
+    // torch order: conv [O][I][kh][kw]; convT [I][O][kh][kw]; vectors: kind 0
+    size_t gi = i;
+    int o = 0, ic = 0, tap = 0;
+    if (t.kind != 0) {
+      tap = int(i % taps);
+      const size_t r = i / taps;
+      const int d1 = int(r % t.dim1), d0 = int(r / t.dim1);
+      if (t.kind == 2) { ic = d0; o = d1; } else { o = d0; ic = d1; }
+      if (t.kind == 4) ic = tap * t.dim1 + ic;   // im2col column of the thin first layer
+      else
+        for (int sgi = 0; sgi < t.nseg; ++sgi)
+          if (ic < t.seg_end[sgi]) { ic += t.seg_shift[sgi]; break; }
+      // gradient lives in the packed forward layout [tap][rows_pad][cols_pad] (kind 3: rows = taps, kind 4: one tap)
+      gi = t.kind == 1   ? (size_t(tap) * t.o_pad + o) * t.i_pad + ic
+           : t.kind == 2 ? (size_t(tap) * t.i_pad + ic) * t.o_pad + o
+           : t.kind == 3 ? size_t(tap) * t.i_pad + ic
+                         : size_t(o) * t.i_pad + ic;
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      p[u] = ok[u] ? t.param[idx[u]] : 0.f;
-      if (t.grad && ok[u]) {
-        g[u] = t.grad[gi[u]];
-        m[u] = t.m[idx[u]];
-        v[u] = t.v[idx[u]];
-      }
+    float p = t.param[i];
+    if (t.grad) {
+      const float g = t.grad[gi] * grad_scale;
+      float m = t.m[i], v = t.v[i];
+      m = beta1 * m + (1.f - beta1) * g;
+      v = beta2 * v + (1.f - beta2) * g * g;
+      t.m[i] = m;
+      t.v[i] = v;
+      const float denom = sqrtf(v) / sqrtf(bc2) + eps;
+      p -= (lr / bc1) * (m / denom);
+      t.param[i] = p;
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (!ok[u]) continue;
-      if (t.grad) {
-        const float gg = g[u] * grad_scale;
-        const float mm = beta1 * m[u] + (1.f - beta1) * gg;
-        const float vv = beta2 * v[u] + (1.f - beta2) * gg * gg;
-        t.m[idx[u]] = mm;
-        t.v[idx[u]] = vv;
-        const float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
-        p[u] -= step_size * (mm / denom);
-        t.param[idx[u]] = p[u];
+    if (t.kind != 0) {
+      const __nv_bfloat16 b = __float2bfloat16(p);
+      if (t.pack_fwd) {
+        // forward operand: [tap][rows][cols], cols contiguous = reduction channel of the forward op
+        const size_t k = t.kind <= 2   ? (size_t(tap) * t.o_pad + o) * t.i_pad + ic
+                         : t.kind == 3 ? size_t(tap) * t.i_pad + ic
+                                       : size_t(o) * t.i_pad + ic;
+        t.pack_fwd[k] = b;
       }
-      if (t.kind != 0) {
-        const __nv_bfloat16 b = __float2bfloat16(p[u]);
-        if (t.pack_fwd) {
-          // forward operand: [tap][rows][cols], cols contiguous = reduction channel of the forward op
-          const size_t k = t.kind <= 2   ? (size_t(tap[u]) * t.o_pad + o[u]) * t.i_pad + ic[u]
-                           : t.kind == 3 ? size_t(tap[u]) * t.i_pad + ic[u]
-                                         : size_t(o[u]) * t.i_pad + ic[u];
-          t.pack_fwd[k] = b;
-        }
-        if (t.pack_bwd) {
-          // backward-data operand: transposed roles, taps mirrored for Conv2d (flip), same for convT
-          const int btap = t.kind == 1 ? (taps - 1 - tap[u]) : tap[u];
-          const size_t k = t.kind <= 2   ? (size_t(btap) * t.i_pad + ic[u]) * t.o_pad + o[u]
-                           : t.kind == 3 ? size_t(ic[u]) * t.o_pad + tap[u]
-                                         : size_t(ic[u]) * t.o_pad + o[u];
-          t.pack_bwd[k] = b;
-        }
+      if (t.pack_bwd) {
+        // backward-data operand: transposed roles, taps mirrored for Conv2d (flip), same for convT
+        const int btap = t.kind == 1 ? (taps - 1 - tap) : tap;
+        const size_t k = t.kind <= 2   ? (size_t(btap) * t.i_pad + ic) * t.o_pad + o
+                         : t.kind == 3 ? size_t(ic) * t.o_pad + tap
+                                       : size_t(ic) * t.o_pad + o;
+        t.pack_bwd[k] = b;
       }
     }
   }
