@@ -250,6 +250,12 @@ int tg_allreduce_oneshot(float* local, const void* peer_bufs_dev, const void* pe
  * seg_end[6], seg_shift[6], pad. */
 int tg_adam_step(const void* table_dev, int ntensors, long long max_numel, float lr, float beta1,
                  float beta2, float eps, int step, float grad_scale, void* stream);
+/* The same step with its scalars in device memory: hyper_dev = {lr, beta1, beta2, eps, 1 - beta1^step, 1 - beta2^step,
+ * grad_scale}. A CUDA graph that captured this launch can be replayed after the host rewrote the seven floats (the
+ * learning-rate schedule and the step count are the only per-step scalars of the training iteration). */
+int tg_adam_step_dev(const void* table_dev, int ntensors, long long max_numel, const float* hyper_dev, void* stream);
+/* dst[0..n) = values_host[0..n), n <= 16: the values are kernel arguments (read from host memory at call time) */
+int tg_write_floats(float* dst, const float* values_host, int n, void* stream);
 
 #ifdef __cplusplus
 }

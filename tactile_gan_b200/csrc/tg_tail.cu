@@ -1590,8 +1590,15 @@ __global__ void gp_seed_kernel(const __nv_bfloat16* __restrict__ g, const float*
 }
 
 // ------------------------------------------------------------------ fused Adam + weight re-pack
+// hyper != nullptr: {lr, beta1, beta2, eps, 1 - beta1^t, 1 - beta2^t, grad_scale} are read from device memory, so a
+// captured CUDA graph of the whole step can be replayed with a new learning rate / step count (tg_adam_step_dev).
 __global__ void adam_kernel(const AdamTensor* __restrict__ tab, int ntensors, float lr, float beta1,
-                            float beta2, float eps, float bc1, float bc2, float grad_scale) {
+                            float beta2, float eps, float bc1, float bc2, float grad_scale,
+                            const float* __restrict__ hyper) {
+  if (hyper) {
+    lr = hyper[0]; beta1 = hyper[1]; beta2 = hyper[2]; eps = hyper[3]; bc1 = hyper[4]; bc2 = hyper[5];
+    grad_scale = hyper[6];
+  }
   const AdamTensor t = tab[blockIdx.y];
   const size_t numel = t.numel;
   const int taps = t.kh * t.kw;
@@ -1674,6 +1681,13 @@ __global__ void fmap_wgrad_fold_kernel(float* __restrict__ dw, int replicas, int
     dw[(size_t(r) * co + o) * 64 + c] = 0.f;
   }
   if (c < ci && grad) grad[o * ci + c] += acc;
+}
+
+// dst[i] = v.f[i]: up to 16 scalars travel as kernel arguments (copied at launch time), so the host may overwrite its
+// own copy immediately -- unlike an asynchronous memcpy from a reused pinned buffer
+struct Floats16 { float f[16]; };
+__global__ void write_floats_kernel(float* __restrict__ dst, Floats16 v, int n) {
+  if (threadIdx.x < n) dst[threadIdx.x] = v.f[threadIdx.x];
 }
 
 // util.py:79-83: alpha ~ U[0,1) per sample; version 2 maps it to [0.5, 1). Writes alpha and 1 - alpha (the
@@ -2257,7 +2271,23 @@ int tg_adam_step(const void* table_dev, int ntensors, long long max_numel, float
   const float bc2 = 1.f - powf(beta2, float(step));
   dim3 grid(grid_for(size_t(max_numel), 256, 256), ntensors);
   adam_kernel<<<grid, 256, 0, TG_STREAM(stream)>>>((const AdamTensor*)table_dev, ntensors, lr, beta1,
-                                                    beta2, eps, bc1, bc2, grad_scale);
+                                                    beta2, eps, bc1, bc2, grad_scale, nullptr);
+  TG_RET();
+}
+
+int tg_write_floats(float* dst, const float* values_host, int n, void* stream) {
+  if (n < 1 || n > 16 || !dst || !values_host) return tg_set_error("tg_write_floats: 1 <= n <= 16");
+  Floats16 v;
+  for (int i = 0; i < 16; ++i) v.f[i] = i < n ? values_host[i] : 0.f;
+  write_floats_kernel<<<1, 32, 0, TG_STREAM(stream)>>>(dst, v, n);
+  TG_RET();
+}
+
+int tg_adam_step_dev(const void* table_dev, int ntensors, long long max_numel, const float* hyper_dev, void* stream) {
+  if (!hyper_dev) return tg_set_error("tg_adam_step_dev: null hyper-parameter buffer");
+  dim3 grid(grid_for(size_t(max_numel), 256, 256), ntensors);
+  adam_kernel<<<grid, 256, 0, TG_STREAM(stream)>>>((const AdamTensor*)table_dev, ntensors, 0.f, 0.f, 0.f, 1.f, 1.f,
+                                                    1.f, 1.f, hyper_dev);
   TG_RET();
 }
 

@@ -404,6 +404,15 @@ class ParamStore:
         _C.call("adam_step", _C.ptr(self.table), len(self.params), _C.LL(self.max_numel), _C.F(lr),
                 _C.F(beta1), _C.F(beta2), _C.F(eps), self.step_count, _C.F(grad_scale))
 
+    @staticmethod
+    def adam_hyper(lr, beta1, step, beta2=0.99, eps=1e-8, grad_scale=1.0):
+        """The seven floats tg_adam_step_dev reads (computed like tg_adam_step does on the host)."""
+        return [lr, beta1, beta2, eps, 1.0 - beta1 ** step, 1.0 - beta2 ** step, grad_scale]
+
+    def adam_step_dev(self, hyper_dev):
+        """Adam step whose scalars live in device memory (graph-captured steps); the caller advances step_count."""
+        _C.call("adam_step_dev", _C.ptr(self.table), len(self.params), _C.LL(self.max_numel), _C.ptr(hyper_dev))
+
     # ---- gradients in torch layout (tests / autograd bridge) ---------------------------------
     def grad_as_torch(self, i):
         p = self.params[i]

@@ -85,6 +85,15 @@ class TrainStep:
         # +3 %; UNet++ batch 32 -1 % -> off there. TG_PDL in the environment overrides the choice.
         small = batch * height * width <= 8 * 256 * 256 or str(kind).lower() == "unet"
         self.pdl = small if os.environ.get("TG_PDL") is None else None
+        # Small batches are bound by the HOST issuing ~800 launches per step (batch 4 = the reference CLI's default:
+        # 6.4 ms/step of which ~4 ms is launch cost): after two eager iterations the whole step is captured in a CUDA
+        # graph per `regularize` value and replayed. The only per-step scalars -- learning rate and Adam's bias
+        # corrections -- live in device memory (tg_adam_step_dev) and are rewritten before every replay; the GP alpha is
+        # drawn outside the graph into a static buffer. Single process only (NCCL stays eager). TG_STEP_GRAPH=0|1 overrides.
+        env = os.environ.get("TG_STEP_GRAPH")
+        self.use_graph = (batch * height * width <= 8 * 256 * 256) if env is None else env == "1"
+        self.use_graph = self.use_graph and self.world == 1
+        self._graphs, self._eager_done, self._hyper = {}, {}, None
         # TG_COMM_PROFILE=1 (bench.py): CUDA-event pairs around the points where the compute stream waits for a
         # gradient collective -- the time between them is communication the step could not hide
         self.comm_profile = [] if (self.world > 1 and os.environ.get("TG_COMM_PROFILE")) else None
@@ -115,6 +124,7 @@ class TrainStep:
         if label is not None and tuple(label.shape) != (self.B, 1, self.h5, self.w5):
             raise ValueError(f"real-label tensor must be {(self.B, 1, self.h5, self.w5)}, got {tuple(label.shape)}")
         self.real_label = None if label is None else label.to(self.device).float().contiguous()
+        self.reset_graphs()              # a captured step holds the old tensor's address
 
     def draw_alpha(self, alpha=None):
         """util.py:79-81: alpha ~ U[0,1) on the CUDA generator; version 2 maps it to [0.5, 1)."""
@@ -229,6 +239,11 @@ class TrainStep:
     def step(self, real_A, real_B, regularize=True, alpha=None, real_B_ready=None):
         """real_A (B,in,H,W) in [-1,1], real_B (B,out,H,W) in [0,1]: fp32, contiguous, on the device.
         Returns the device tensor of loss slots (see SLOT); reading it is the caller's only sync."""
+        if self.use_graph and not (_C.TIMING["on"] or _C.TIMING["tail"]):
+            return self._step_graphed(real_A, real_B, regularize, alpha, real_B_ready)
+        return self._step_eager(real_A, real_B, regularize, alpha, real_B_ready)
+
+    def _step_eager(self, real_A, real_B, regularize, alpha, real_B_ready):
         if self.pdl:
             prev = _C.lib().tg_pdl_policy(1)
             try:
@@ -237,6 +252,77 @@ class TrainStep:
                 _C.lib().tg_pdl_policy(prev)
         return self._step(real_A, real_B, regularize, alpha, real_B_ready)
 
+    # ---- whole-step CUDA graph (small batches) ----------------------------------------------------------------
+    def reset_graphs(self):
+        """Drop the captured steps (after anything baked into them changed: label tensor, loss weights, ...)."""
+        self._graphs.clear()
+        self._eager_done.clear()
+
+    def _write_hyper(self):
+        """Advance both optimisers' step counts and put this iteration's Adam scalars where the captured launches read
+        them (pinned host -> device on the current stream, ordered before the replay)."""
+        from .layers import ParamStore
+        gs, ds = self.G.store, self.DA.store
+        ds.step_count += 1
+        gs.step_count += 1
+        import ctypes
+        vals = ParamStore.adam_hyper(self.lr, self.beta1, ds.step_count, grad_scale=1.0 / self.world) + [0.0] + \
+            ParamStore.adam_hyper(self.lr, self.beta1, gs.step_count, grad_scale=1.0 / self.world) + [0.0]
+        # sixteen scalars as kernel arguments: no pinned staging buffer the host could overwrite before the copy ran
+        _C.call("write_floats", ptr(self._hyper), (ctypes.c_float * 16)(*vals), 16)
+
+    def _step_graphed(self, real_A, real_B, regularize, alpha, real_B_ready):
+        reg = bool(regularize) and self.lambda_gp != 0
+        if self._eager_done.get(reg, 0) < 2:          # lazy buffers, labels, cuBLAS-free but still: warm every path
+            self._eager_done[reg] = self._eager_done.get(reg, 0) + 1
+            return self._step_eager(real_A, real_B, regularize, alpha, real_B_ready)
+        G, DA = self.G, self.DA
+        cur = torch.cuda.current_stream()
+        if self._hyper is None:
+            self._hyper = torch.zeros(16, device=self.device)     # Adam scalars of D [0:7] and G [8:15]
+            self._gA, self._gB = torch.empty_like(real_A), torch.empty_like(real_B)
+        G.store.refresh()                              # weight re-packs after load_state_dict etc. stay outside the graph
+        DA.store.refresh()
+        self.ensure_label()
+        self._gA.copy_(real_A, non_blocking=True)
+        if real_B_ready is not None:
+            cur.wait_event(real_B_ready)
+        self._gB.copy_(real_B, non_blocking=True)
+        if reg:
+            self.draw_alpha(alpha)                     # static alpha / 1 - alpha buffers, written outside the graph
+        entry = self._graphs.get(reg)
+        if entry is None:
+            entry = self._capture(reg)
+            if entry is None:                          # capture failed: stay eager for good
+                self.use_graph = False
+                return self._step_eager(real_A, real_B, regularize, alpha, real_B_ready)
+            self._graphs[reg] = entry
+        graph, launches = entry
+        self._write_hyper()
+        graph.replay()
+        _C.COUNTERS["launches"] += launches
+        return self.losses
+
+    def _capture(self, reg):
+        launches0 = _C.COUNTERS["launches"]
+        self._in_graph = True
+        # programmatic graph edges wherever the eager step would launch programmatic dependents
+        pdl_on = self.pdl if self.pdl is not None else _C.lib().tg_pdl_policy(-1) != 0
+        prev_pdl = _C.lib().tg_pdl_policy(2 if pdl_on else 0)
+        graph = torch.cuda.CUDAGraph()
+        try:
+            torch.cuda.synchronize(self.device)
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                self._step(self._gA, self._gB, reg, None, None)
+        except Exception as e:  # pragma: no cover - depends on the driver / torch build
+            print(f"tactile_gan_b200: CUDA-graph capture of the training step failed ({type(e).__name__}: {e}); "
+                  f"staying eager")
+            return None
+        finally:
+            self._in_graph = False
+            _C.lib().tg_pdl_policy(prev_pdl)
+        return graph, _C.COUNTERS["launches"] - launches0
+
     def _step(self, real_A, real_B, regularize, alpha, real_B_ready):
         B, HW = self.B, self.H * self.W
         G, DA, S1, S2 = self.G, self.DA, self.S1, self.S2
@@ -244,7 +330,8 @@ class TrainStep:
         self.ensure_label()
         self.losses.zero_()
         regularize = bool(regularize) and self.lambda_gp != 0
-        if regularize:
+        in_graph = getattr(self, "_in_graph", False)
+        if regularize and not in_graph:
             self.draw_alpha(alpha)
         # ---- generator forward (train.py:104)
         fake = G.forward(real_A)
@@ -278,7 +365,10 @@ class TrainStep:
         if want_feat:
             S2.pack_input(real_A, real_B)
         self._allreduce_wait(d_work, "D")
-        ds.adam_step(self.lr, self.beta1, grad_scale=1.0 / self.world)
+        if in_graph:
+            ds.adam_step_dev(self._hyper[0:8])
+        else:
+            ds.adam_step(self.lr, self.beta1, grad_scale=1.0 / self.world)
         S1.forward()
         S1.u[4].dz.zero_()
         self._gan_loss(S1, 0, B, True, False, 1.0, SLOT["G_GAN"])
@@ -301,7 +391,10 @@ class TrainStep:
             self.VF.loss_and_seed(self.VR, self.w_per, self.lambda_per, self.losses[4:5])
             self.VF.backward(self.l1_grad)
         self._g_backward()
-        gs.adam_step(self.lr, self.beta1, grad_scale=1.0 / self.world)
+        if in_graph:
+            gs.adam_step_dev(self._hyper[8:16])
+        else:
+            gs.adam_step(self.lr, self.beta1, grad_scale=1.0 / self.world)
         return self.losses
 
     def step_from_host(self, host_A, host_B, regularize=True, prefetch=None, lag=False, read=True, alpha=None):

@@ -412,3 +412,53 @@ def test_inference_graph_is_rebuilt_when_parameter_storage_moves():
         fresh = create_gen("UNet++", 3, 3, 16, True).cuda()
         fresh.load_state_dict(net.state_dict())
         assert torch.equal(fresh(x), y1) and not torch.equal(y1, y0)
+
+
+def test_small_batch_step_graph_matches_eager():
+    """Batches up to 8 x 256^2 pixels replay the whole iteration from a CUDA graph after two eager steps (the host's
+    ~800 launches per step are what bounds batch 4, the reference CLI's default). Same kernels, same order: the losses of
+    six iterations must match the eager TrainStep's, the Adam scalars (learning rate, bias corrections) must reach the
+    captured launches through device memory -- lr = 0 freezes the weights, the step count keeps advancing -- and a new
+    label tensor drops the captured graphs."""
+    orc, _C = _setup()
+    from tactile_gan_b200.discriminators.discriminators import create_disc
+    from tactile_gan_b200.generators.generators import create_gen
+    from tactile_gan_b200.step import TrainStep
+
+    def build(graph):
+        torch.manual_seed(9)
+        netG = create_gen("UNet++", 3, 3, 16, True)
+        netD = create_disc("patch", 3, 3, 16, True, True)
+        randomize(netG, 1)
+        randomize(netD, 2)
+        ts = TrainStep(netG.cuda(), netD.cuda(), 2, 64, 64, lr=2e-4)
+        ts.use_graph = graph
+        ts.ensure_label(generator=torch.Generator().manual_seed(3))
+        return ts, netG, netD
+
+    g = torch.Generator().manual_seed(5)
+    batches = [tuple(t.cuda() for t in orc.synthetic_batch(g, 2, 64)) for _ in range(6)]
+    alphas = [torch.rand(2, 1, generator=g).cuda() for _ in range(6)]
+    eager, _, _ = build(False)
+    graphed, netG, netD = build(True)
+    assert graphed.use_graph
+    for k, ((a, b), al) in enumerate(zip(batches, alphas)):
+        reg = k != 3                                      # one iteration without the penalty: its own graph / eager path
+        eager.step(a, b, regularize=reg, alpha=al)
+        graphed.step(a, b, regularize=reg, alpha=al)
+        le, lg = eager.loss_dict(), graphed.loss_dict()
+        for name in le:
+            assert lg[name] == pytest.approx(le[name], rel=0.02, abs=2e-3), (k, name, lg[name], le[name])
+    assert _C.error_flag() == 0
+    assert True in graphed._graphs and not eager._graphs          # iterations 3.. of the regularised path were replays
+    assert graphed.G.store.step_count == eager.G.store.step_count == 6
+    wd = torch.cat([(p1 - p2).flatten() for p1, p2 in zip(graphed.netD.parameters(), eager.netD.parameters())])
+    assert wd.abs().mean().item() < 2e-4 * 0.5                     # 6 Adam steps of lr 2e-4 on both sides
+    before = [p.detach().clone() for p in netG.parameters()]
+    graphed.lr = 0.0
+    graphed.step(*batches[0], regularize=True, alpha=alphas[0])
+    torch.cuda.synchronize()
+    assert all(torch.equal(p, q) for p, q in zip(netG.parameters(), before))     # lr reached the replayed Adam launch
+    assert graphed.G.store.step_count == 7
+    graphed.set_label(graphed.real_label.clone())
+    assert not graphed._graphs
