@@ -67,6 +67,12 @@ typedef struct tg_conv_desc {
   int pool_out;           /* 1: `out` is the half-resolution tensor and the epilogue stores the 2x2 SUM of the
                            * (2*out.h x 2*out.w) result -- the input gradient of a conv that read a nearest-
                            * upsampled tensor (nn.Upsample, UNet_plusplus.py:40), folded back without materialising it */
+  float* splitk_ws;       /* optional fp32 workspace (caller-owned, shared by the launches of one stream): convolutions
+                           * with too few output tiles to fill the GPU (the 2x2 .. 8x8 levels of UNet, any tiny batch)
+                           * split their K loop over several CTAs, each writing its partial tile to its own slice, and
+                           * a second kernel sums the slices in a fixed order (deterministic) and applies bias /
+                           * activation. NULL: never split. */
+  long long splitk_ws_bytes;
 } tg_conv_desc;
 
 /* Weight gradient (split-K implicit GEMM over pixels, fp32 accumulation into dw with red.add):

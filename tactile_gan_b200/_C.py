@@ -38,7 +38,8 @@ class ConvDesc(Structure):
                 ("stride", c_int), ("tap_dy", c_int8 * TG_MAX_TAPS), ("tap_dx", c_int8 * TG_MAX_TAPS),
                 ("tap_w", c_int8 * TG_MAX_TAPS), ("bias", c_void_p), ("bias_len", c_int),
                 ("stats_partial", c_void_p), ("stats_tiles_total", c_int), ("stats_tile_off", c_int),
-                ("act", c_int), ("slope", c_float), ("pool_out", c_int)]
+                ("act", c_int), ("slope", c_float), ("pool_out", c_int), ("splitk_ws", c_void_p),
+                ("splitk_ws_bytes", c_longlong)]
 
 
 class WgradDesc(Structure):
@@ -135,6 +136,19 @@ def conv_query_tiles(n, ho, wo, want_stats):
     return tuple(out)  # th, tw, tn, tiles_per_img
 
 
+SPLITK_WS_BYTES = 256 << 20
+_splitk_ws = {}
+
+
+def splitk_workspace(device):
+    """One fp32 workspace per device for the split-K convolutions (tg_conv_desc.splitk_ws): the conv launches of a
+    step are ordered on one stream, so they can share it."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _splitk_ws:
+        _splitk_ws[key] = torch.empty(SPLITK_WS_BYTES // 4, dtype=torch.float32, device=torch.device("cuda", key))
+    return _splitk_ws[key]
+
+
 def conv_plan(srcs, out, taps, stride=1, bias=None, stats_partial=None, act=ACT_NONE, slope=0.2,
               stats_tiles_total=0, stats_tile_off=0, cout_real=None, flops=None, pool_out=False):
     """srcs: list of dict(act=tensor NHWC, wgt=packed bf16 [taps][rows][k], k_off=0, row_off=0)
@@ -167,6 +181,10 @@ def conv_plan(srcs, out, taps, stride=1, bias=None, stats_partial=None, act=ACT_
     d.act = act
     d.slope = slope
     d.pool_out = int(pool_out)
+    if os.environ.get("TG_SPLITK", "1") != "0":
+        ws = splitk_workspace(out.device)
+        d.splitk_ws, d.splitk_ws_bytes = ws.data_ptr(), ws.numel() * 4
+        keep.append(ws)
     h = c_void_p()
     check(lib().tg_conv_plan_create(byref(d), byref(h)), "tg_conv_plan_create")
     # algorithmic FLOPs of this launch: real (unpadded) channels, every output pixel, every tap

@@ -156,6 +156,8 @@ struct tg_plan {
   int bn;
   int grid;
   size_t smem;
+  int fin_grid;              // > 0: split-K conv, splitk_finalize_kernel follows the GEMM
+  tg::SplitFinParams fin;
   tg::IgemmParams conv;
   tg::WgradParams wg;
   tg::HaloParams halo;
@@ -410,7 +412,37 @@ int tg_conv_plan_create(const tg_conv_desc* d, tg_plan** out) {
   }
   if (make_act_map(&p.out, d->out, 0, cout, tw / up, th / up, tn, 1)) { delete pl; return -1; }
   const int total = p.tiles_img * p.tiles_h * p.tiles_w * p.n_tiles;
-  pl->grid = total < sm_count() ? total : sm_count();
+  // Split-K: on maps of up to 8x8 pixels (UNet's deepest levels) a launch has a handful of tiles, each with a serial K
+  // loop of up to 16 taps x 16 chunks, on a handful of CTAs while the rest of the GPU idles. Spread the K iterations
+  // of every tile over `splits` CTAs (>= 4 iterations each). The split count depends on the layer only, never on the
+  // batch, so a sample's result does not depend on which batch it was computed in (bit-exactly: chunked inference).
+  p.splits = 1;
+  pl->fin_grid = 0;
+  {
+    static const bool off = getenv("TG_SPLITK") != nullptr && getenv("TG_SPLITK")[0] == '0';
+    int k_iters = 0;
+    for (int s = 0; s < d->num_src; ++s) k_iters += d->taps * (d->src[s].act.c / 64);
+    const long long slice = (long long)p.N * p.Ho * p.Wo * cout;
+    if (!off && d->splitk_ws && !d->stats_partial && !d->pool_out && p.Ho * p.Wo <= 64 && k_iters >= 8) {
+      int splits = k_iters / 4 < 16 ? k_iters / 4 : 16;
+      if ((long long)splits * slice * 4 > d->splitk_ws_bytes) splits = 1;   // enormous batch of tiny maps: enough tiles anyway
+      if (splits >= 2) {
+        p.splits = splits;
+        p.ws = d->splitk_ws;
+        p.ws_slice = slice;
+        tg::SplitFinParams& f = pl->fin;
+        f.ws = d->splitk_ws; f.ws_slice = slice; f.splits = splits;
+        f.out = static_cast<__nv_bfloat16*>(d->out.ptr);
+        f.sn = d->out.sn; f.sh = d->out.sh; f.sw = d->out.sw;
+        f.N = p.N; f.Ho = p.Ho; f.Wo = p.Wo; f.cout = cout;
+        f.bias = d->bias; f.bias_len = d->bias_len; f.act = d->act; f.slope = d->slope;
+        const long long work = (long long)p.N * p.Ho * p.Wo * (cout / 8);
+        pl->fin_grid = int(work / 256 + 1 < 148 * 8 ? work / 256 + 1 : 148 * 8);
+      }
+    }
+  }
+  const int items = total * p.splits;
+  pl->grid = items < sm_count() ? items : sm_count();
   cudaError_t e;
   if (bn == 256) {
     pl->smem = tg::IgemmCfg<256>::kSmemTotal;
@@ -613,6 +645,8 @@ int tg_plan_run(tg_plan* pl, void* stream) {
     else if (pl->bn == 128) e = tg_launch(tg::wgrad_kernel<128>, g, b, pl->smem, s, pl->wg);
     else e = tg_launch(tg::wgrad_kernel<64>, g, b, pl->smem, s, pl->wg);
   }
+  if (e == cudaSuccess && pl->kind == 0 && pl->fin_grid > 0)
+    e = tg_launch(tg::splitk_finalize_kernel, dim3(pl->fin_grid), dim3(256), 0, s, pl->fin);
   if (e != cudaSuccess) {
     snprintf(g_err, sizeof(g_err), "tg_plan_run: %s", cudaGetErrorString(e));
     return -1;

@@ -55,7 +55,60 @@ struct alignas(64) IgemmParams {
   int cout;               // padded Cout (row pitch of stats)
   int pool_out;           // epilogue stores the 2x2 sum (tile is 16x8, `out` map is the half-resolution tensor)
   int* err_flag;
+  // split-K: item = (tile, split); split s runs k-iterations [k_iters*s/splits, k_iters*(s+1)/splits) and writes its fp32
+  // partial tile to ws + s*ws_slice (pixel-major [N*Ho*Wo][cout]); splitk_finalize_kernel sums the slices in order
+  int splits;
+  float* ws;
+  long long ws_slice;
 };
+
+// Second half of a split-K convolution: out = act(sum_s ws[s] + bias) as bf16 NHWC through the output view's strides.
+struct SplitFinParams {
+  const float* ws;
+  long long ws_slice;
+  int splits;
+  __nv_bfloat16* out;
+  long long sn, sh, sw;   // element strides of the output view
+  int N, Ho, Wo, cout;
+  const float* bias;
+  int bias_len, act;
+  float slope;
+};
+
+__global__ void __launch_bounds__(256) splitk_finalize_kernel(const SplitFinParams p) {
+  griddep_sync();
+  const int groups = p.cout >> 3;
+  const long long total = (long long)p.N * p.Ho * p.Wo * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = int(i % groups);
+    const long long pix = i / groups;
+    const int wo = int(pix % p.Wo), ho = int((pix / p.Wo) % p.Ho), n = int(pix / ((long long)p.Wo * p.Ho));
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float* src = p.ws + pix * p.cout + g * 8;
+    for (int s = 0; s < p.splits; ++s) {
+      const float4 a = *reinterpret_cast<const float4*>(src + s * p.ws_slice);
+      const float4 b = *reinterpret_cast<const float4*>(src + s * p.ws_slice + 4);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+      acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x0 = acc[2 * j], x1 = acc[2 * j + 1];
+      const int c = g * 8 + 2 * j;
+      if (p.bias) {
+        if (c < p.bias_len) x0 += p.bias[c];
+        if (c + 1 < p.bias_len) x1 += p.bias[c + 1];
+      }
+      if (p.act == ACT_LRELU) { x0 = x0 > 0.f ? x0 : x0 * p.slope; x1 = x1 > 0.f ? x1 : x1 * p.slope; }
+      else if (p.act == ACT_RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+      else if (p.act == ACT_SIGMOID) { x0 = 1.f / (1.f + __expf(-x0)); x1 = 1.f / (1.f + __expf(-x1)); }
+      else if (p.act == ACT_TANH) { x0 = tanhf(x0); x1 = tanhf(x1); }
+      w[j] = pack_bf16x2(x0, x1);
+    }
+    *reinterpret_cast<uint4*>(p.out + n * p.sn + ho * p.sh + wo * p.sw + g * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
 
 template <int BN>
 struct IgemmCfg {
@@ -270,14 +323,18 @@ igemm_conv_kernel(const __grid_constant__ IgemmParams p) {
   for (int s = 0; s < p.num_src; ++s) k_iters += taps * p.src[s].c_chunks;
   const int tiles_per_img = p.tiles_h * p.tiles_w;
   const int m_tiles = p.tiles_img * tiles_per_img;
-  const int total_tiles = m_tiles * p.n_tiles;
+  const int splits = p.splits > 1 ? p.splits : 1;
+  const int total_tiles = m_tiles * p.n_tiles * splits;     // work items: (tile, split of the K loop)
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+        const int tile = item / splits, sp = item % splits;
+        const int k_lo = k_iters * sp / splits, k_hi = k_iters * (sp + 1) / splits;
+        int kcount = 0;
         const int n_tile = tile % p.n_tiles;
         const int m_tile = tile / p.n_tiles;
         const int img = m_tile / tiles_per_img;
@@ -291,7 +348,8 @@ igemm_conv_kernel(const __grid_constant__ IgemmParams p) {
             const int hi0 = ho0 * p.stride + p.tap_dy[tap];
             const int wi0 = wo0 * p.stride + p.tap_dx[tap];
             const int wtap = p.tap_w[tap];
-            for (int cc = 0; cc < src.c_chunks; ++cc) {
+            for (int cc = 0; cc < src.c_chunks; ++cc, ++kcount) {
+              if (kcount < k_lo || kcount >= k_hi) continue;
               mbar_wait_guard(empty_bar(stage), phase ^ 1, p.err_flag, 1);
               const uint32_t a_dst = stage_base + stage * Cfg::kStageBytes;
               const uint32_t b_dst = a_dst + kABytes;
@@ -312,11 +370,13 @@ igemm_conv_kernel(const __grid_constant__ IgemmParams p) {
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+        const int sp = item % splits;
+        const int n_k = k_iters * (sp + 1) / splits - k_iters * sp / splits;
         mbar_wait_guard(tempty_bar(as), aphase ^ 1, p.err_flag, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(as * BN);
-        for (int ki = 0; ki < k_iters; ++ki) {
+        for (int ki = 0; ki < n_k; ++ki) {
           mbar_wait_guard(full_bar(stage), phase, p.err_flag, 3);
           tc_fence_after();
           const uint32_t a_addr = stage_base + stage * Cfg::kStageBytes;
@@ -352,7 +412,8 @@ igemm_conv_kernel(const __grid_constant__ IgemmParams p) {
     const float e_slope = p.slope;
     const float* e_bias = p.bias;
     float* e_stats = p.stats_partial;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+      const int tile = item / splits, sp = item % splits;
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
       const int img = m_tile / tiles_per_img;
@@ -360,6 +421,41 @@ igemm_conv_kernel(const __grid_constant__ IgemmParams p) {
       const int ho0 = (t_in / p.tiles_w) * p.th;
       const int wo0 = (t_in % p.tiles_w) * p.tw;
       const int n0 = img * p.tn;
+      if (splits > 1) {
+        // split-K: this item's fp32 partial tile goes to its own workspace slice (plain stores, no atomics: the
+        // finalize kernel adds the slices in a fixed order); tile row -> (image, y, x) in the box order n, h, w
+        const int iw = row % p.tw, ih = (row / p.tw) % p.th, in = row / (p.tw * p.th);
+        const bool inside = n0 + in < p.N && ho0 + ih < p.Ho && wo0 + iw < p.Wo;
+        float* dst = p.ws + (long long)sp * p.ws_slice +
+                     ((long long)((n0 + in) * p.Ho + ho0 + ih) * p.Wo + wo0 + iw) * p.cout + n_tile * BN;
+        mbar_wait_guard(tfull_bar(as), aphase, p.err_flag, 4);
+        tc_fence_after();
+#pragma unroll 1
+        for (int chunk = 0; chunk < BN / 64; ++chunk) {
+          const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN + chunk * 64);
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32(taddr, v0);
+          tmem_ld_32x32(taddr + 32, v1);
+          tmem_ld_wait();
+          if (chunk == BN / 64 - 1) {
+            tc_fence_before();
+            mbar_arrive(tempty_bar(as));
+          }
+          if (inside) {
+            float4* d4 = reinterpret_cast<float4*>(dst + chunk * 64);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              d4[j] = make_float4(__uint_as_float(v0[4 * j]), __uint_as_float(v0[4 * j + 1]),
+                                  __uint_as_float(v0[4 * j + 2]), __uint_as_float(v0[4 * j + 3]));
+              d4[8 + j] = make_float4(__uint_as_float(v1[4 * j]), __uint_as_float(v1[4 * j + 1]),
+                                      __uint_as_float(v1[4 * j + 2]), __uint_as_float(v1[4 * j + 3]));
+            }
+          }
+        }
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+        continue;
+      }
       // which of this warp-group's 32 statistic rows lie inside the image (tiles may overhang)
       uint32_t valid_mask = 0xffffffffu;
       if (e_stats && (ho0 + p.th > p.Ho || wo0 + p.tw > p.Wo)) {

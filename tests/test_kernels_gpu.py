@@ -71,12 +71,37 @@ CONV_CASES = [
     dict(n=1, cins=[24, 8], cout=24, h=4, w=128, k=3, stride=1, pad=1, bias=True, act=3),     # one strip, ragged channels
     dict(n=8, cins=[64, 64], cout=64, h=128, w=128, k=3, stride=1, pad=1, stats=True),        # several items per CTA
     dict(n=8, cins=[64], cout=128, h=128, w=128, k=3, stride=1, pad=1, stats=True),           # resident, 512 items
+    # maps of <= 8x8 output pixels: split-K (each tile's K loop spread over several CTAs + splitk_finalize_kernel)
+    dict(n=4, cins=[256], cout=512, h=8, w=8, k=3, stride=1, pad=1),                          # 36 k-iterations -> 9 splits
+    dict(n=3, cins=[512], cout=512, h=4, w=4, k=3, stride=1, pad=1, bias=True, act=3),        # 72 -> 16 splits, bias + ReLU
+    dict(n=5, cins=[512], cout=512, h=4, w=4, k=4, stride=2, pad=1),                          # UNet conv7: 2x2 output
+    dict(n=2, cins=[128, 192], cout=256, h=8, w=8, k=3, stride=1, pad=1, bias=True, act=1),   # two segments, ragged split
+    dict(n=33, cins=[256], cout=256, h=2, w=2, k=3, stride=1, pad=1),                         # tiles spanning images
 ]
 
 
 @pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: f"{c['cins']}to{c['cout']}_{c['h']}_k{c['k']}s{c['stride']}")
 def test_conv_forward(case):
     run_conv(**case)
+
+
+def test_split_k_result_does_not_depend_on_the_batch():
+    """The split count is a function of the layer, not of the batch: a sample convolved alone equals, bit for bit, the
+    same sample convolved inside a larger batch (what chunked inference and sample-independence tests rely on)."""
+    C = _C()
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(7, 256, 8, 8, generator=g).to(dev)
+    wt = (torch.randn(512, 256, 3, 3, generator=g) * 0.05).to(dev)
+    wp = wt.permute(2, 3, 0, 1).reshape(9, 512, 256).bfloat16().contiguous()
+    outs = []
+    for sl in (slice(0, 7), slice(2, 3), slice(4, 7)):
+        xs = nhwc_pad(x[sl])
+        out = torch.zeros(xs.shape[0], 8, 8, 512, dtype=torch.bfloat16, device=dev)
+        C.conv_plan([dict(act=xs, wgt=wp)], out, conv_taps(3, 3, 1)).run()
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.equal(outs[0][2:3], outs[1]) and torch.equal(outs[0][4:7], outs[2])
+    assert C.error_flag() == 0
 
 
 @pytest.mark.parametrize("cin,cout,h,w", [(64, 128, 32, 48), (64, 64, 16, 16), (128, 256, 32, 32), (192, 512, 16, 32),
