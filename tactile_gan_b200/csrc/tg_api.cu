@@ -414,8 +414,10 @@ int tg_conv_plan_create(const tg_conv_desc* d, tg_plan** out) {
   const int total = p.tiles_img * p.tiles_h * p.tiles_w * p.n_tiles;
   // Split-K: on maps of up to 8x8 pixels (UNet's deepest levels) a launch has a handful of tiles, each with a serial K
   // loop of up to 16 taps x 16 chunks, on a handful of CTAs while the rest of the GPU idles. Spread the K iterations
-  // of every tile over `splits` CTAs (>= 4 iterations each). The split count depends on the layer only, never on the
-  // batch, so a sample's result does not depend on which batch it was computed in (bit-exactly: chunked inference).
+  // of every tile over `splits` CTAs (>= 4 iterations each) when the launch has at most a quarter of the SMs' worth of
+  // tiles (measured: UNet batch 4 +6.8 %; at batch 32 the 8x8 level already has 32 tiles and the extra finalize pass
+  // costs more than the split returns). The split COUNT depends on the layer only, so two batches on the same side of
+  // that threshold give a sample bit-identical results (chunked inference against one engine).
   p.splits = 1;
   pl->fin_grid = 0;
   {
@@ -423,7 +425,8 @@ int tg_conv_plan_create(const tg_conv_desc* d, tg_plan** out) {
     int k_iters = 0;
     for (int s = 0; s < d->num_src; ++s) k_iters += d->taps * (d->src[s].act.c / 64);
     const long long slice = (long long)p.N * p.Ho * p.Wo * cout;
-    if (!off && d->splitk_ws && !d->stats_partial && !d->pool_out && p.Ho * p.Wo <= 64 && k_iters >= 8) {
+    if (!off && d->splitk_ws && !d->stats_partial && !d->pool_out && p.Ho * p.Wo <= 64 && k_iters >= 8 &&
+        total * 4 <= sm_count()) {
       int splits = k_iters / 4 < 16 ? k_iters / 4 : 16;
       if ((long long)splits * slice * 4 > d->splitk_ws_bytes) splits = 1;   // enormous batch of tiny maps: enough tiles anyway
       if (splits >= 2) {
