@@ -416,8 +416,8 @@ int tg_conv_plan_create(const tg_conv_desc* d, tg_plan** out) {
   // loop of up to 16 taps x 16 chunks, on a handful of CTAs while the rest of the GPU idles. Spread the K iterations
   // of every tile over `splits` CTAs (>= 4 iterations each) when the launch has at most a quarter of the SMs' worth of
   // tiles (measured: UNet batch 4 +6.8 %; at batch 32 the 8x8 level already has 32 tiles and the extra finalize pass
-  // costs more than the split returns). The split COUNT depends on the layer only, so two batches on the same side of
-  // that threshold give a sample bit-identical results (chunked inference against one engine).
+  // costs more than the split returns). For small batches the split COUNT is capped by the layer (min(16, k/4)), not by
+  // the batch, so chunked inference reproduces the single-engine result bit for bit.
   p.splits = 1;
   pl->fin_grid = 0;
   {
@@ -425,9 +425,12 @@ int tg_conv_plan_create(const tg_conv_desc* d, tg_plan** out) {
     int k_iters = 0;
     for (int s = 0; s < d->num_src; ++s) k_iters += d->taps * (d->src[s].act.c / 64);
     const long long slice = (long long)p.N * p.Ho * p.Wo * cout;
-    if (!off && d->splitk_ws && !d->stats_partial && !d->pool_out && p.Ho * p.Wo <= 64 && k_iters >= 8 &&
+    if (!off && d->splitk_ws && !d->stats_partial && !d->pool_out && p.Ho * p.Wo <= 64 && k_iters >= 16 &&
         total * 4 <= sm_count()) {
+      // all (tile, split) items in ONE wave; fewer than four splits do not pay for the finalize pass
       int splits = k_iters / 4 < 16 ? k_iters / 4 : 16;
+      if (splits > sm_count() / total) splits = sm_count() / total;
+      if (splits < 4) splits = 1;
       if ((long long)splits * slice * 4 > d->splitk_ws_bytes) splits = 1;   // enormous batch of tiny maps: enough tiles anyway
       if (splits >= 2) {
         p.splits = splits;
