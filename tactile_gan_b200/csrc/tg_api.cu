@@ -425,11 +425,8 @@ int tg_conv_plan_create(const tg_conv_desc* d, tg_plan** out) {
     int k_iters = 0;
     for (int s = 0; s < d->num_src; ++s) k_iters += d->taps * (d->src[s].act.c / 64);
     const long long slice = (long long)p.N * p.Ho * p.Wo * cout;
-    // with InstanceNorm statistics (maps of >= 128 pixels per image: tn == 1) the finalize pass also writes the tile
-    // partials; those layers split up to 32x32 maps (a batch-1 forward has 8 / 2 tiles on its two deepest levels)
-    const int max_px = d->stats_partial ? 1024 : 64;
-    if (!off && d->splitk_ws && !d->pool_out && p.Ho * p.Wo <= max_px && k_iters >= 16 && total * 4 <= sm_count() &&
-        (!d->stats_partial || (tn == 1 && !d->bias && d->act == 0))) {
+    if (!off && d->splitk_ws && !d->stats_partial && !d->pool_out && p.Ho * p.Wo <= 64 && k_iters >= 16 &&
+        total * 4 <= sm_count()) {
       // all (tile, split) items in ONE wave; fewer than four splits do not pay for the finalize pass
       int splits = k_iters / 4 < 16 ? k_iters / 4 : 16;
       if (splits > sm_count() / total) splits = sm_count() / total;
@@ -445,12 +442,8 @@ int tg_conv_plan_create(const tg_conv_desc* d, tg_plan** out) {
         f.sn = d->out.sn; f.sh = d->out.sh; f.sw = d->out.sw;
         f.N = p.N; f.Ho = p.Ho; f.Wo = p.Wo; f.cout = cout;
         f.bias = d->bias; f.bias_len = d->bias_len; f.act = d->act; f.slope = d->slope;
-        f.stats_partial = d->stats_partial;
-        f.stats_tiles_total = p.stats_tiles_total; f.stats_tile_off = p.stats_tile_off;
-        f.th = th; f.tw = tw; f.tiles_w = p.tiles_w; f.tiles_per_img = p.tiles_h * p.tiles_w;
         const long long work = (long long)p.N * p.Ho * p.Wo * (cout / 8);
-        pl->fin_grid = d->stats_partial ? p.N * p.tiles_h * p.tiles_w
-                                        : int(work / 256 + 1 < 148 * 8 ? work / 256 + 1 : 148 * 8);
+        pl->fin_grid = int(work / 256 + 1 < 148 * 8 ? work / 256 + 1 : 148 * 8);
       }
     }
   }
@@ -658,12 +651,8 @@ int tg_plan_run(tg_plan* pl, void* stream) {
     else if (pl->bn == 128) e = tg_launch(tg::wgrad_kernel<128>, g, b, pl->smem, s, pl->wg);
     else e = tg_launch(tg::wgrad_kernel<64>, g, b, pl->smem, s, pl->wg);
   }
-  if (e == cudaSuccess && pl->kind == 0 && pl->fin_grid > 0) {
-    if (pl->fin.stats_partial)
-      e = tg_launch(tg::splitk_finalize_stats_kernel, dim3(pl->fin_grid, pl->fin.cout / 64), dim3(256), 0, s, pl->fin);
-    else
-      e = tg_launch(tg::splitk_finalize_kernel, dim3(pl->fin_grid), dim3(256), 0, s, pl->fin);
-  }
+  if (e == cudaSuccess && pl->kind == 0 && pl->fin_grid > 0)
+    e = tg_launch(tg::splitk_finalize_kernel, dim3(pl->fin_grid), dim3(256), 0, s, pl->fin);
   if (e != cudaSuccess) {
     snprintf(g_err, sizeof(g_err), "tg_plan_run: %s", cudaGetErrorString(e));
     return -1;

@@ -73,56 +73,7 @@ struct SplitFinParams {
   const float* bias;
   int bias_len, act;
   float slope;
-  // InstanceNorm follows: per-tile (sum, sum of squares) partials like the GEMM epilogue writes them
-  float* stats_partial;
-  int stats_tiles_total, stats_tile_off, th, tw, tiles_w, tiles_per_img;
 };
-
-// The same with the InstanceNorm statistics of the layer: one block per (image, GEMM tile, 64-channel chunk) so that the
-// partials land in the slots -- and are summed over the same pixels -- the unsplit epilogue would have used. A thread
-// owns 8 channels of the pixels lane, lane+32, ...; sums are taken over the bf16 values actually stored.
-__global__ void __launch_bounds__(256) splitk_finalize_stats_kernel(const SplitFinParams p) {
-  __shared__ float red[32][64][2];
-  griddep_sync();
-  const int m_tile = blockIdx.x, c_base = blockIdx.y * 64;
-  const int n = m_tile / p.tiles_per_img, t_in = m_tile % p.tiles_per_img;
-  const int ho0 = (t_in / p.tiles_w) * p.th, wo0 = (t_in % p.tiles_w) * p.tw;
-  const int g = threadIdx.x & 7, pl = threadIdx.x >> 3;
-  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int r = pl; r < p.th * p.tw; r += 32) {
-    const int ho = ho0 + r / p.tw, wo = wo0 + r % p.tw;
-    if (ho >= p.Ho || wo >= p.Wo) continue;
-    const long long pix = ((long long)n * p.Ho + ho) * p.Wo + wo;
-    const float* src = p.ws + pix * p.cout + c_base + g * 8;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int sp = 0; sp < p.splits; ++sp) {
-      const float4 a = *reinterpret_cast<const float4*>(src + sp * p.ws_slice);
-      const float4 b = *reinterpret_cast<const float4*>(src + sp * p.ws_slice + 4);
-      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-      acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
-    }
-    uint32_t w[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const __nv_bfloat162 v = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
-      w[j] = *reinterpret_cast<const uint32_t*>(&v);
-      const float x0 = __low2float(v), x1 = __high2float(v);
-      s[2 * j] += x0; s[2 * j + 1] += x1;
-      q[2 * j] += x0 * x0; q[2 * j + 1] += x1 * x1;
-    }
-    *reinterpret_cast<uint4*>(p.out + n * p.sn + ho * p.sh + wo * p.sw + c_base + g * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { red[pl][g * 8 + j][0] = s[j]; red[pl][g * 8 + j][1] = q[j]; }
-  __syncthreads();
-  if (threadIdx.x < 128) {
-    const int c = threadIdx.x >> 1, st = threadIdx.x & 1;
-    float tot = 0.f;
-    for (int k = 0; k < 32; ++k) tot += red[k][c][st];
-    const size_t tile_lin = size_t(n) * p.stats_tiles_total + p.stats_tile_off + t_in;
-    p.stats_partial[(tile_lin * p.cout + c_base) * 2 + threadIdx.x] = tot;
-  }
-}
 
 __global__ void __launch_bounds__(256) splitk_finalize_kernel(const SplitFinParams p) {
   griddep_sync();

@@ -77,10 +77,6 @@ CONV_CASES = [
     dict(n=5, cins=[512], cout=512, h=4, w=4, k=4, stride=2, pad=1),                          # UNet conv7: 2x2 output
     dict(n=2, cins=[128, 192], cout=256, h=8, w=8, k=3, stride=1, pad=1, bias=True, act=1),   # two segments, ragged split
     dict(n=33, cins=[256], cout=256, h=2, w=2, k=3, stride=1, pad=1),                         # tiles spanning images
-    # split-K with the InstanceNorm partials written by the finalize pass (small batches of 16x16 / 32x32 maps)
-    dict(n=1, cins=[256], cout=512, h=32, w=32, k=3, stride=1, pad=1, stats=True),
-    dict(n=2, cins=[256, 256], cout=1024, h=16, w=16, k=3, stride=1, pad=1, stats=True),
-    dict(n=1, cins=[192], cout=256, h=24, w=20, k=3, stride=1, pad=1, stats=True),            # overhanging tiles
 ]
 
 
