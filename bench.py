@@ -2,12 +2,15 @@
 """Benchmark of the tactile-gan G+D training step (BASELINE.json metric: train images/sec, UNet++ 256^2).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
-    python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle port, host cores)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (the unmodified reference modules
+                                                             # from baseline/_ref on the host cores)
 
 One "step" = one full G+D iteration (reference train.py:99-168) on a per-GPU batch of 32 synthetic
 256x256 pairs (configs[1]); N > 1 = one rank per GPU, NCCL gradient allreduce, weak scaling.
 `value` is timed with inputs resident in HBM; `e2e` goes through TrainStep.step_from_host (pinned host
-batch -> H2D -> step -> D2H of the loss scalars). `roofline*` are measured live in the same process with CUDA
+batch -> H2D -> step -> D2H of the loss scalars). `cudnn_baseline` (N=1) runs the same reference modules on the same
+GPU under eager PyTorch + cuDNN; `comm` (N>1) reports the time the compute stream waited for gradient collectives.
+`roofline*` are measured live in the same process with CUDA
 events around every implicit-GEMM launch (tensor roofline) and every InstanceNorm tail launch (HBM roofline) of
 K further steps run with serialised launches; `traffic` is the DRAM byte count of one representative launch
 from the committed ncu capture.

@@ -2,7 +2,8 @@
 generators/BCDUNet.py). The reference constructs ConvLSTM / ConvBLSTM skip modules but never calls them
 in forward (BCDUNet.py:154-181): inside BCDUNet they are parameter holders (30 state_dict keys,
 Xavier-initialised peepholes). Called on their own they run the device engine of
-tactile_gan_b200/convlstm.py (two-source implicit GEMM + fused gate kernel, forward only, no eager fallback).
+tactile_gan_b200/convlstm.py (two-source implicit GEMM + fused gate kernel, forward and -- under autograd -- backward;
+no eager fallback).
 BCDUNet.forward() runs engine.BCDUNetEngine."""
 import numpy as np
 import torch
