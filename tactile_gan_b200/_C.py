@@ -11,7 +11,7 @@ from ctypes import (POINTER, Structure, byref, c_char_p, c_float, c_int, c_int8,
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtactile_gan_b200.so")
+LIB_PATH = os.environ.get("TG_LIB_PATH") or os.path.join(_HERE, "libtactile_gan_b200.so")   # TG_LIB_PATH: A/B builds
 
 TG_MAX_SRC = 6
 TG_MAX_TAPS = 16

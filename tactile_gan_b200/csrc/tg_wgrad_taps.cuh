@@ -23,7 +23,10 @@ constexpr int kWtTH = 16, kWtTW = 8;
 constexpr int kWtXBytes = (kWtTH + 2) * kWtTW * 128;   // 18 KiB
 constexpr int kWtYBytes = kWtTH * (kWtTW + 2) * 128;   // 20 KiB
 constexpr int kWtStageBytes = kWtXBytes + kWtYBytes;   // 38 KiB, both parts 1 KiB aligned
-constexpr int kWtStages = 5;
+#ifndef TG_WT_STAGES
+#define TG_WT_STAGES 5
+#endif
+constexpr int kWtStages = TG_WT_STAGES;
 constexpr int kWtSmem = 1024 + kWtStages * kWtStageBytes + 256;
 
 struct alignas(64) WgradTapsParams {
