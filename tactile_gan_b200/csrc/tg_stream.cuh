@@ -1,12 +1,12 @@
-// Streaming form of the InstanceNorm passes whose gradient routes all sit at the unit's own resolution (the common
-// case: 26 of UNet++'s 30 units backward, every forward without pooled / upsampled copies, the discriminator's
-// units): normalise+activation forward, backward statistics, backward apply.
+// Streaming form of the InstanceNorm passes whose gradient routes sit at the unit's own resolution, optionally plus the
+// gradient of the unit's 2x2 average-pooled copy (all 30 of UNet++'s units backward, every forward without pooled /
+// upsampled copies, the discriminator's units): normalise+activation forward, backward statistics, backward apply.
 //
 // Why: the register-staged passes (in_act_fwd_kernel / in_bwd_reduce_kernel) keep <= 8 x 16 B loads per thread in
 // flight at 2 x 256 threads per SM and drain them before every compute phase; ncu showed dram 37-49 %, sm 34-45 %
 // on the 256^2 launches (profiles/r01_ncu_top_kernels.txt) -- latency bound, ~0.6 of the copy bandwidth. Here the
 // bytes in flight do not depend on registers or occupancy: one producer lane per CTA keeps a ring of 8 KiB
-// cp.async.bulk (1-D TMA) chunks per input tensor in shared memory (3-4 stages x up to 3 tensors, two CTAs per SM =
+// cp.async.bulk (1-D TMA) chunks per input tensor in shared memory (2-8 stages x up to 4 tensors, two CTAs per SM =
 // 130-190 KiB in flight per SM against the ~35 KiB that 6.4 TB/s x ~800 ns needs), eight consumer warps read the
 // chunks conflict-free (a thread owns one 8-channel group, so the per-channel constants live in registers) and write
 // results straight to HBM with 16-byte stores. The grid is persistent: every CTA gets the same number of chunks of
