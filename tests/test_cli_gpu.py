@@ -45,6 +45,20 @@ def test_train_and_test_cli(tmp_path, monkeypatch):
     assert np.isfinite(out).all() and np.abs(out).max() <= 1.0
     ev = (tmp_path / "Outputs" / "run1" / "eval.txt").read_text().splitlines()     # reference format, test.py:175-181
     assert ev[0].startswith("Pixel Accuracy => min:") and ev[1].startswith("Dice Coeff") and ev[2].startswith("Jaccard")
+    # two_step_test.py: the two trained generators chained, gen2(gen1(x)) (reference two_step_test.py:21-23)
+    from tactile_gan_b200 import two_step_test as tg_two
+    tg_two.main(["--s1_dir", "run1", "--s2_dir", "run2", "--data", "data", "--synthetic", "2", "--batch", "2"])
+    two = tmp_path / "Outputs" / "run1+run2_data"
+    out2 = np.load(two / "out" / "2.npy")
+    assert out2.shape == out.shape and np.isfinite(out2).all() and (two / "eval.txt").exists()
+    dev = torch.device("cuda:0")
+    g1 = tg_test.load_model(str(mdir / "final_model.pth"), tg_test.load_opt(str(mdir / "params.txt")), dev)
+    m2 = tmp_path / "models" / "run2"
+    g2 = tg_test.load_model(str(m2 / "final_model.pth"), tg_test.load_opt(str(m2 / "params.txt")), dev)
+    from tactile_gan_b200.train import SyntheticPairs
+    xa = torch.stack([SyntheticPairs(2, 64)[i][0] for i in range(2)]).to(dev)
+    with torch.no_grad():
+        assert np.array_equal(g2(g1(xa))[1].cpu().numpy(), out2)
 
 
 def test_train_cli_on_image_folder_with_device_augmentation(tmp_path, monkeypatch):
