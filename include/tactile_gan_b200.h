@@ -132,6 +132,15 @@ int tg_gp_normsq_img(const float* g, int N, long long per_img, float* nsq, void*
  * form per shape as measured (profiles/r02_tail_microbench_*.txt), 2: the ring whenever the shape allows (tests).
  * Returns the previous policy; a negative argument only queries. Env TG_STREAM=0/1/2 sets the initial value. */
 int tg_in_stream_policy(int policy);
+/* Slim form of the ring's backward passes (4 KiB chunks, one CTA per SM, <= TG_SLIM_KB = 32 KiB of shared memory):
+ * it fits on an SM beside a persistent weight-gradient GEMM CTA, so the engine switches it on (1) for the backward
+ * passes it issues while a weight gradient runs on the side stream and off (0) otherwise. Returns the previous
+ * value; any other argument only queries. */
+int tg_in_stream_slim(int on);
+/* Serpentine order: bit 0 / 1 / 2 makes the forward / statistics / apply pass walk its tensor from the end, so that it
+ * starts on the part its predecessor (which walked the other way) left in L2. Results do not depend on it. Returns
+ * the previous mask; an argument outside 0..7 only queries. Env TG_SERP sets the initial value (default 3). */
+int tg_in_stream_serpentine(int mask);
 int tg_in_finalize(const float* partial, float* mr, int N, int T, int C, int count, float eps, void* stream);
 int tg_in_stats_direct(const void* raw, float* mr, int N, int HW, int C, float eps, void* stream);
 int tg_in_act_fwd(const void* raw, const float* mr, const float* gamma, const float* beta, void* y,

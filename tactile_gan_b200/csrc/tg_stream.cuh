@@ -18,8 +18,9 @@ namespace tg {
 
 constexpr int kStreamConsumers = 256;             // consumer threads (8 warps); + 1 producer warp
 constexpr int kStreamThreads = kStreamConsumers + 32;
-constexpr int kStreamPPT = 2;                     // pixels per consumer thread per chunk
+constexpr int kStreamPPT = 2;                     // pixels per consumer thread per chunk (1 in the slim form)
 constexpr int kStreamChunkBytes = kStreamPPT * kStreamConsumers * 16;   // 8 KiB per tensor per stage (upper bound)
+__host__ __device__ constexpr int stream_chunk_bytes(int ppt) { return ppt * kStreamConsumers * 16; }
 
 struct StreamArgs {
   const __nv_bfloat16* in0;   // raw (conv output)
@@ -37,6 +38,11 @@ struct StreamArgs {
   int N, HW, C, c_valid, act;
   float slope;
   int stages;
+  int rev;                    // walk the chunks from the tensor's end: a pass that follows a kernel which walked them
+                              // upwards starts on what that kernel left in L2 (tg_in_stream_serpentine)
+  int slim;                   // small-footprint form that shares an SM with a persistent weight-gradient CTA
+                              // (tg_in_stream_slim): 4 KiB chunks, one CTA per SM, statistics folded through
+                              // warp shuffles + shared-memory atomics instead of the [PL][C][2] scratch
 };
 
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -53,7 +59,7 @@ __device__ __forceinline__ uint4 lds16(uint32_t addr) {
 // MODE 0: y = act(S*raw + T)
 // MODE 1: dn = (g1 + g2) * act'(A*raw + B); red[n][c] += (sum dn, rstd * (sum dn*raw - mean * sum dn)); dn stored if out
 // MODE 2: dz = P*dn + Q*raw + R with dn recomputed as in MODE 1 (P, Q, R from red)
-template <int MODE>
+template <int MODE, int PPT>
 __global__ void __launch_bounds__(kStreamThreads, 2) in_stream_kernel(const StreamArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   // ring slots of one stage: raw | g1 | g2 | pooled gradient (absent routes take no slot)
@@ -63,17 +69,17 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_stream_kernel(const Stre
   const int NIN = MODE == 0 ? 1 : 1 + (a.in1 ? 1 : 0) + (a.in2 ? 1 : 0) + (a.pool ? 1 : 0);
   const int CG = a.C >> 3;
   const int PL = kStreamConsumers / CG;                 // pixel lanes; threads with pl >= PL idle (C/8 not a divisor)
-  const int CP = kStreamPPT * PL;                       // pixels per chunk
+  const int CP = PPT * PL;                              // pixels per chunk
   const int CPI = (a.HW + CP - 1) / CP;                 // chunks per image
   const long long TC = (long long)a.N * CPI;
   const long long k0 = TC * blockIdx.x / gridDim.x, k1 = TC * (blockIdx.x + 1) / gridDim.x;
   const int S = a.stages;
   // carve-up: [stages][NIN][chunk] | reduction scratch (MODE 1) | barriers
   const uint32_t base = smem_u32(smem_raw);
-  const uint32_t chunk_stride = kStreamChunkBytes;
+  const uint32_t chunk_stride = uint32_t(stream_chunk_bytes(PPT));
   const uint32_t ring_bytes = uint32_t(S) * NIN * chunk_stride;
   float* scratch = reinterpret_cast<float*>(smem_raw + ring_bytes);
-  const uint32_t scratch_bytes = MODE == 1 ? uint32_t(PL) * a.C * 2 * sizeof(float) : 0;
+  const uint32_t scratch_bytes = MODE == 1 ? uint32_t(a.slim ? 1 : PL) * a.C * 2 * sizeof(float) : 0;
   const uint32_t bar0 = base + ring_bytes + scratch_bytes;       // full[S], then empty[S]
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -92,7 +98,8 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_stream_kernel(const Stre
       int s = 0;
       uint32_t ph = 1;       // the first pass over the ring finds every stage free
       for (long long k = k0; k < k1; ++k) {
-        const int n = int(k / CPI), j = int(k % CPI);
+        const long long kk = a.rev ? TC - 1 - k : k;
+        const int n = int(kk / CPI), j = int(kk % CPI);
         const int p0 = j * CP;
         const int np = min(CP, a.HW - p0);
         const uint32_t bytes = uint32_t(np) * a.C * 2;
@@ -133,6 +140,10 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_stream_kernel(const Stre
       if (a.dbeta) atomicAdd(a.dbeta + c, b);
     }
   }
+  if (MODE == 1 && a.slim) {
+    for (int c = tid; c < 2 * a.C; c += kStreamConsumers) scratch[c] = 0.f;
+    named_bar_sync(1, kStreamConsumers);
+  }
   float A[8], B[8];                 // pre-activation n = A*raw + B  (MODE 0: the output itself before the activation)
   float P[8], Q[8], R[8];           // MODE 2
   float s0[8], s1[8];               // MODE 1
@@ -145,6 +156,35 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_stream_kernel(const Stre
   auto flush = [&]() {
     // MODE 1: block-level reduction of this image's partial sums, then one atomic per (n, c) and CTA
     if (MODE != 1) return;
+    if (a.slim) {
+      // lanes of a warp that own the same channel group sit CG apart (CG = 8 or 16); other widths go straight
+      // to the shared-memory accumulators (8 warps -> at most 8-way contention per address)
+      const bool fold = CG == 8 || CG == 16;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v0 = s0[j], v1 = s1[j];
+        if (fold)
+          for (int off = 16; off >= CG; off >>= 1) {
+            v0 += __shfl_xor_sync(0xffffffffu, v0, off);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, off);
+          }
+        if (active && (!fold || (tid & 31) < CG)) {
+          atomicAdd(scratch + (c0 + j) * 2, v0);
+          atomicAdd(scratch + (c0 + j) * 2 + 1, v1);
+        }
+      }
+      named_bar_sync(1, kStreamConsumers);
+      for (int c = tid; c < a.C; c += kStreamConsumers) {
+        const float d0 = scratch[c * 2], d1 = scratch[c * 2 + 1];
+        scratch[c * 2] = 0.f;
+        scratch[c * 2 + 1] = 0.f;
+        const float mean = a.mr[(size_t(cur_n) * a.C + c) * 2], rstd = a.mr[(size_t(cur_n) * a.C + c) * 2 + 1];
+        atomicAdd(a.red + (size_t(cur_n) * a.C + c) * 2, d0);
+        atomicAdd(a.red + (size_t(cur_n) * a.C + c) * 2 + 1, rstd * (d1 - mean * d0));
+      }
+      named_bar_sync(1, kStreamConsumers);
+      return;
+    }
     if (active) {
       float* shp = scratch + (size_t(pl) * a.C + c0) * 2;
 #pragma unroll
@@ -167,7 +207,8 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_stream_kernel(const Stre
   int s = 0;
   uint32_t ph = 0;
   for (long long k = k0; k < k1; ++k) {
-    const int n = int(k / CPI), j = int(k % CPI);
+    const long long kk = a.rev ? TC - 1 - k : k;
+    const int n = int(kk / CPI), j = int(kk % CPI);
     if (n != cur_n) {
       if (cur_n >= 0) flush();
       cur_n = n;
@@ -197,7 +238,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_stream_kernel(const Stre
     if (active) {
       const uint32_t st = base + uint32_t(s) * NIN * chunk_stride;
 #pragma unroll
-      for (int p = 0; p < kStreamPPT; ++p) {
+      for (int p = 0; p < PPT; ++p) {
         const int lp = p * PL + pl;              // pixel inside the chunk
         if (lp < np) {
           const uint32_t so = uint32_t(lp) * a.C * 2 + c0 * 2;

@@ -304,7 +304,7 @@ __global__ void in_stats_direct_kernel(const __nv_bfloat16* __restrict__ raw, fl
 struct StripIdx {
   int cg, pl, PL, c0, p0, p1;
 };
-__device__ __forceinline__ StripIdx strip_index(int C, int units) {
+__device__ __forceinline__ StripIdx strip_index(int C, int units, int rev = 0) {
   StripIdx s;
   const int CG = C >> 3;
   s.PL = blockDim.x / CG;
@@ -312,7 +312,7 @@ __device__ __forceinline__ StripIdx strip_index(int C, int units) {
   s.pl = threadIdx.x / CG;
   s.c0 = s.cg * 8;
   const int strip = (units + gridDim.x - 1) / gridDim.x;
-  s.p0 = blockIdx.x * strip;
+  s.p0 = (rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * strip;   // rev: serpentine order, see serp_mask()
   s.p1 = min(units, s.p0 + strip);
   return s;
 }
@@ -324,12 +324,13 @@ __global__ void __launch_bounds__(256)
 in_act_fwd_kernel(const __nv_bfloat16* __restrict__ raw, const float* __restrict__ mr,
                   const float* __restrict__ gamma, const float* __restrict__ beta,
                   __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ pool,
-                  __nv_bfloat16* __restrict__ up, int H, int W, int C, int c_valid, int act, float slope) {
+                  __nv_bfloat16* __restrict__ up, int H, int W, int C, int c_valid, int act, float slope,
+                  int rev) {
   griddep_sync();
-  const int n = blockIdx.y;
+  const int n = rev ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
   constexpr bool QUAD = POOL != 0 || UP;
   const int H2 = H >> 1, W2 = W >> 1;
-  const StripIdx t = strip_index(C, QUAD ? H2 * W2 : H * W);
+  const StripIdx t = strip_index(C, QUAD ? H2 * W2 : H * W, rev);
   if (t.pl >= t.PL) return;
   float S[8], T[8];
 #pragma unroll
@@ -430,6 +431,7 @@ struct InBwdArgs {
   __nv_bfloat16* dz;
   float* dgamma;
   float* dbeta;
+  int rev;                    // serpentine block order (serp_mask())
 };
 
 // Per-pixel work of the backward reduce for the general case (pooled / upsampled gradient routes).
@@ -500,9 +502,9 @@ template <bool PLAIN, int PASS>
 __global__ void __launch_bounds__(256, 2) in_bwd_reduce_kernel(const InBwdArgs a) {
   extern __shared__ float shm[];  // [PL][C][2]
   griddep_sync();
-  const int n = blockIdx.y;
+  const int n = a.rev ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
   const int HW = a.H * a.W;
-  const StripIdx t = strip_index(a.C, HW);
+  const StripIdx t = strip_index(a.C, HW, a.rev);
   const int c0 = t.c0;
   if (PASS == 1 && (a.dgamma || a.dbeta) && blockIdx.x == 0 && blockIdx.y == 0) {
     // affine gradients ride along (one block): dgamma[c] += sum_n red[n][c][1], dbeta[c] += sum_n red[n][c][0]
@@ -1771,38 +1773,83 @@ static int stream_policy() {
   return g_stream_policy;
 }
 static bool stream_enabled() { return stream_policy() != 0; }
-template <int MODE>
-static int launch_stream(tg::StreamArgs a, cudaStream_t s) {
+// Serpentine order (TG_SERP / tg_in_stream_serpentine, bit m = pass m walks its chunks from the tensor's end): the
+// GEMMs walk images upwards, so the last tens of MB they wrote are what the 126 MB L2 still holds when the pass that
+// consumes them starts; the apply pass then walks the other way than the statistics pass, for the same reason.
+static int g_serp = -1;
+static int serp_mask() {
+  if (g_serp < 0) {
+    const char* e = getenv("TG_SERP");
+    g_serp = (e && e[0] >= '0' && e[0] <= '7') ? e[0] - '0' : 3;
+  }
+  return g_serp;
+}
+// Slim form (tg_in_stream_slim): the engine switches it on for the backward passes it issues while a weight-gradient
+// GEMM runs on the side stream. A persistent wgrad CTA (191-194 KiB of shared memory, 25 K registers) leaves ~33 KiB
+// and 40 K registers on its SM: one 288-thread CTA of this kernel with a ring of 4 KiB chunks fits beside it, so the
+// bandwidth-bound pass and the tensor-bound GEMM share the SM instead of taking turns (the 108 KiB ring cannot).
+static int g_slim = 0;
+static int slim_budget() {
+  static int kb = -1;
+  if (kb < 0) {
+    const char* e = getenv("TG_SLIM_KB");
+    kb = e ? atoi(e) : 32;
+    if (kb < 16 || kb > 108) kb = 32;
+  }
+  return kb * 1024;
+}
+template <int MODE, int PPT>
+static int launch_stream_ppt(tg::StreamArgs a, cudaStream_t s, bool slim) {
   using namespace tg;
   const int nin = MODE == 0 ? 1 : 1 + (a.in1 ? 1 : 0) + (a.in2 ? 1 : 0) + (a.pool ? 1 : 0);
   const int CG = a.C >> 3, PL = kStreamConsumers / CG;
-  const size_t scratch = MODE == 1 ? size_t(PL) * a.C * 2 * sizeof(float) : 0;
-  // two CTAs per SM: <= ~110 KiB each
-  int stages = int((108 * 1024 - scratch) / (size_t(nin) * kStreamChunkBytes));
+  const size_t chunk = size_t(stream_chunk_bytes(PPT));
+  const size_t scratch = MODE == 1 ? size_t(slim ? 1 : PL) * a.C * 2 * sizeof(float) : 0;
+  // two CTAs per SM: <= ~110 KiB each; slim: what a persistent GEMM CTA leaves
+  const size_t budget = slim ? size_t(slim_budget()) : size_t(108 * 1024);
+  if (scratch + 256 >= budget) return tg_set_error("in_stream: shared memory budget");
+  int stages = int((budget - scratch - 256) / (size_t(nin) * chunk));
   if (stages > 8) stages = 8;
   if (stages < 2) return tg_set_error("in_stream: shared memory budget");
   a.stages = stages;
-  const size_t smem = size_t(stages) * nin * kStreamChunkBytes + scratch + 16 * stages;
-  static size_t configured[3] = {0, 0, 0};
-  if (smem > configured[MODE]) {
-    if (cudaFuncSetAttribute(in_stream_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) !=
+  a.slim = slim ? 1 : 0;
+  a.rev = (serp_mask() >> MODE) & 1;
+  const size_t smem = size_t(stages) * nin * chunk + scratch + 16 * stages;
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(in_stream_kernel<MODE, PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) !=
         cudaSuccess)
       return tg_set_error("in_stream: cudaFuncSetAttribute");
-    configured[MODE] = smem;
+    configured = smem;
   }
-  const int CP = kStreamPPT * PL;
+  const int CP = PPT * PL;
   const long long chunks = (long long)a.N * ((a.HW + CP - 1) / CP);
-  long long grid = 2 * 148;
+  long long grid = slim ? 148 : 2 * 148;
   if (grid > chunks) grid = chunks;
   if (grid < 1) grid = 1;
-  if (tg_launch(in_stream_kernel<MODE>, dim3(unsigned(grid)), dim3(kStreamThreads), smem, s, a) != cudaSuccess)
+  if (tg_launch(in_stream_kernel<MODE, PPT>, dim3(unsigned(grid)), dim3(kStreamThreads), smem, s, a) != cudaSuccess)
     return tg_check_launch("in_stream_kernel") ? -1 : tg_set_error("in_stream_kernel: launch failed");
   return tg_check_launch("in_stream_kernel");
 }
+static bool stream_pool_ok(int H, int W, int C, int ppt);   // defined below
+// slim only where it fits and the chunk geometry allows (backward passes; the pooled route needs even chunks)
+static bool slim_applies(int mode, const tg::StreamArgs& a) {
+  if (!g_slim || mode == 0) return false;
+  const int nin = 1 + (a.in1 ? 1 : 0) + (a.in2 ? 1 : 0) + (a.pool ? 1 : 0);
+  const size_t scratch = mode == 1 ? size_t(a.C) * 2 * sizeof(float) : 0;
+  if (scratch + 256 + 2 * size_t(nin) * tg::stream_chunk_bytes(1) > size_t(slim_budget())) return false;
+  if (a.pool && !stream_pool_ok(a.HW / a.W, a.W, a.C, 1)) return false;
+  return true;
+}
+template <int MODE>
+static int launch_stream(tg::StreamArgs a, cudaStream_t s) {
+  if (slim_applies(MODE, a)) return launch_stream_ppt<MODE, 1>(a, s, true);
+  return launch_stream_ppt<MODE, tg::kStreamPPT>(a, s, false);
+}
 static bool stream_shape_ok(int C) { return C >= 64 && C <= 2048 && (C & 63) == 0; }
 // the average-pool gradient route streams when a chunk (2 * (256 / (C/8)) pixels) lies inside one image row
-static bool stream_pool_ok(int H, int W, int C) {
-  const int CP = tg::kStreamPPT * (tg::kStreamConsumers / (C >> 3));
+static bool stream_pool_ok(int H, int W, int C, int ppt = tg::kStreamPPT) {
+  const int CP = ppt * (tg::kStreamConsumers / (C >> 3));
   return CP >= 2 && (CP & 1) == 0 && W % CP == 0 && (H & 1) == 0 && (W & 1) == 0;
 }
 // Which form is faster, measured per shape (profiles/r02_tail_microbench_*.txt): the register-staged passes reach
@@ -1811,6 +1858,7 @@ static bool stream_pool_ok(int H, int W, int C) {
 // and on every statistics pass).
 static bool stream_wins(int mode, int N, int HW, int C) {
   if (stream_policy() == 2) return true;
+  if (g_slim && mode != 0) return true;   // beside a weight-gradient GEMM only the slim ring fits
   const double bytes = 2.0 * N * double(HW) * C;
   if (mode != 1 && C == 64 && bytes >= 200e6) return false;
   if (mode != 2 && bytes <= 20e6) return false;
@@ -1888,6 +1936,18 @@ int tg_in_stream_policy(int policy) {
   return prev;
 }
 
+int tg_in_stream_slim(int on) {
+  const int prev = g_slim;
+  if (on == 0 || on == 1) g_slim = on;
+  return prev;
+}
+
+int tg_in_stream_serpentine(int mask) {
+  const int prev = serp_mask();
+  if (mask >= 0 && mask <= 7) g_serp = mask;
+  return prev;
+}
+
 int tg_in_finalize(const float* partial, float* mr, int N, int T, int C, int count, float eps,
                    void* stream) {
   dim3 grid(C / 16, N);
@@ -1929,7 +1989,8 @@ int tg_in_act_fwd(const void* raw, const float* mr, const float* gamma, const fl
   dim3 grid(strip_count(units, C, N, quad ? 4 : 16), N);
   const int block = strip_block(C);
   const int pm = pool ? pool_mode : 0;
-#define LAUNCH(P, U) tg_launch(in_act_fwd_kernel<P, U>, grid, dim3(block), 0, s, r, mr, gamma, beta, yy, pp, uu, H, W, C, c_valid, act, slope)
+  const int rev = serp_mask() & 1;
+#define LAUNCH(P, U) tg_launch(in_act_fwd_kernel<P, U>, grid, dim3(block), 0, s, r, mr, gamma, beta, yy, pp, uu, H, W, C, c_valid, act, slope, rev)
   if (pm == 0 && !up) LAUNCH(0, false);
   else if (pm == 0 && up) LAUNCH(0, true);
   else if (pm == 1 && !up) LAUNCH(1, false);
@@ -1945,6 +2006,7 @@ int tg_in_bwd_reduce(const void* raw, const void* y, const float* mr, const floa
                      const void* g_up, int g_up_pooled, void* dn, float* red, int N, int H, int W, int C,
                      int c_valid, int act, float slope, void* stream) {
   InBwdArgs a;
+  a.rev = (serp_mask() >> 1) & 1;
   a.up_pooled = g_up_pooled;
   a.dz = nullptr; a.dgamma = nullptr; a.dbeta = nullptr;
   a.raw = (const __nv_bfloat16*)raw; a.y = (const __nv_bfloat16*)y; a.mr = mr; a.gamma = gamma;
@@ -1983,6 +2045,7 @@ int tg_in_bwd_apply_re(const void* raw, const void* y, const float* mr, const fl
                        float* dgamma, float* dbeta, void* stream) {
   if (!raw || !mr || !red || !dz) return tg_set_error("tg_in_bwd_apply_re: null argument");
   InBwdArgs a;
+  a.rev = (serp_mask() >> 2) & 1;
   a.raw = (const __nv_bfloat16*)raw; a.y = (const __nv_bfloat16*)y; a.mr = mr; a.gamma = gamma;
   a.beta = beta; a.g_same = (const __nv_bfloat16*)g_same; a.g_pool = (const __nv_bfloat16*)g_pool;
   a.g_up = (const __nv_bfloat16*)g_up; a.dn = nullptr; a.red = const_cast<float*>(red);

@@ -44,7 +44,10 @@ struct WgradCfg {
   static constexpr int kABytes = 2 * kWgBoxBytes;
   static constexpr int kBBytes = (BN / 64) * kWgBoxBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+#ifndef TG_WG256_STAGES
+#define TG_WG256_STAGES 4
+#endif
+  static constexpr int kStages = BN == 256 ? TG_WG256_STAGES : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kSmemTotal = 1024 + kStages * kStageBytes + 256;
 };

@@ -8,6 +8,8 @@ Graph vocabulary
              2x-upsampled copies of the output written by the same normalise pass
   HeadUnit   FeatureMapBlock: 1x1 conv + bias (+tanh) -> fp32 NCHW
 """
+import os
+
 import torch
 
 from . import _C
@@ -155,6 +157,10 @@ class ConvUnit:
         g_pool = self.pool.run_grad() if (self.pool and self.pool.consumers) else None
         g_up = self.up.run_grad() if (self.up and self.up.consumers) else None
         up_pooled = int(bool(g_up is not None and self.up.grad_pooled))
+        # the previous unit's weight gradient goes to the side stream AFTER this unit's input-gradient GEMMs were
+        # queued: both become ready at the same moment, the GPU takes them in submission order, so the weight gradient
+        # runs while the passes below do -- and those take the slim form that fits beside its CTAs
+        slim = eng._flush_wgrad(2.0 * n * ho * wo * c * 5 if self.norm else 0.0)
         g, b = self._aff()
         if self.norm:
             if not eng.red_clean:
@@ -166,6 +172,7 @@ class ConvUnit:
             stored = g_pool is not None and self.pool_mode == 2
             keep = (keep_dn and self.norm) or stored
             routes += 4 if stored else 0
+            prev_slim = _C.lib().tg_in_stream_slim(1) if slim else None
             # pass 1: statistics of dn = g * act'(n) (dn itself is stored only for the GP double backward);
             # pass 2: the same loads again, dn recomputed, dz written -- 5 tensor-sizes instead of 6
             _C.call("in_bwd_reduce", ptr(self.raw), ptr(self.y.buf), ptr(self.mr), g, b, ptr(g_same), ptr(g_pool),
@@ -181,6 +188,8 @@ class ConvUnit:
                 _C.call("in_bwd_apply_re", ptr(self.raw), ptr(self.y.buf), ptr(self.mr), g, b, ptr(g_same),
                         ptr(g_pool), self.pool_mode, ptr(g_up), up_pooled, ptr(self.red), ptr(self.dz), n, ho, wo, c,
                         self.c_valid, self.act, F(self.slope), dg, db, nbytes=elems * (2 + routes))
+            if slim:
+                _C.lib().tg_in_stream_slim(prev_slim)
         else:
             _C.call("in_bwd_reduce", None, ptr(self.y.buf), None, None, None, ptr(g_same), ptr(g_pool),
                     self.pool_mode, ptr(g_up), up_pooled, ptr(self.dz), None, n, ho, wo, c, self.c_valid, self.act,
@@ -191,13 +200,15 @@ class ConvUnit:
                 self._weight_grads()
             else:
                 # the weight gradient only needs dz (final now) and the unit's inputs: it leaves the dependency
-                # chain of backward and runs on a side stream, where it overlaps the bandwidth-bound passes of the
-                # following units (a persistent GEMM CTA leaves room for one or two normalise / apply blocks per SM)
+                # chain of backward and runs on a side stream, beside the bandwidth-bound passes of the next unit
                 ev = torch.cuda.Event()
                 ev.record()
-                with torch.cuda.stream(ws):
-                    ws.wait_event(ev)
-                    self._weight_grads()
+                if eng.defer_wgrad:
+                    eng._pending_wgrad = [self, ev, None, False]
+                else:
+                    with torch.cuda.stream(ws):
+                        ws.wait_event(ev)
+                        self._weight_grads()
 
     def _weight_grads(self):
         if self.layer.bias is not None:
@@ -256,6 +267,12 @@ class GraphEngine:
         self.layers = {}
         self.red_arena = None
         self.red_clean = False      # True while a pass that cleared the whole red arena is running
+        # side-stream weight gradients (TrainStep sets wgrad_stream): queued one unit late, behind the next unit's
+        # input-gradient GEMMs, and the InstanceNorm passes beside them take the slim form (tg_in_stream_slim)
+        self._pending_wgrad = None
+        self.defer_wgrad = os.environ.get("TG_WGRAD_DEFER", "1") != "0"
+        self.slim_tail = os.environ.get("TG_SLIM", "1") != "0"
+        self.slim_min_ratio = float(os.environ.get("TG_SLIM_MIN_RATIO", "0.3"))
 
     def clear_red(self):
         """One memset for the backward sums of every unit; ConvUnit.backward then skips its own clear."""
@@ -321,8 +338,31 @@ class GraphEngine:
         self._graph.replay()
         return self._graph_out
 
+    def _flush_wgrad(self, tail_bytes=0.0):
+        """Queue the deferred weight gradient (ConvUnit.backward) on the side stream. Returns True when the caller's
+        InstanceNorm passes (`tail_bytes` of traffic) should take the slim form, i.e. when that GEMM is long enough
+        to cover a useful part of them (TG_SLIM_MIN_RATIO, default 0.3, of their time at 4.5 TB/s)."""
+        pend, self._pending_wgrad = self._pending_wgrad, None
+        if pend is None:
+            return False
+        unit, ev, after_unit, done = pend
+        ws = self.wgrad_stream
+        with torch.cuda.stream(ws):
+            ws.wait_event(ev)
+            unit._weight_grads()
+            if done and after_unit is not None:
+                after_unit(unit)
+        if not self.slim_tail or tail_bytes <= 0:
+            return False
+        w_est = sum(p.flops for p in unit.wgrad_plans) / 1.0e15
+        return w_est >= self.slim_min_ratio * tail_bytes / 4.5e12
+
     def _unit_done(self, unit, after_unit):
         """after_unit(unit) runs in the stream that finalises the unit's parameter gradients."""
+        pend = self._pending_wgrad
+        if pend is not None and pend[0] is unit:
+            pend[2], pend[3] = after_unit, True      # runs behind the deferred weight gradient (_flush_wgrad)
+            return
         if after_unit is None:
             return
         ws = getattr(self, "wgrad_stream", None)
@@ -334,6 +374,7 @@ class GraphEngine:
 
     def _join_wgrad(self):
         ws = getattr(self, "wgrad_stream", None)
+        self._flush_wgrad()
         if ws is not None:
             torch.cuda.current_stream().wait_stream(ws)
 

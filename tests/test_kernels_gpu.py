@@ -238,18 +238,25 @@ def test_instance_norm_forward_backward_pool_upsample():
     # one image row, else the gather kernel serves it -- both must give the same answer
     (2, 64, 16, 64, 3, True, True), (3, 72, 12, 32, 3, False, True), (2, 512, 4, 8, 3, True, True),
     (2, 64, 16, 24, 3, False, True)])
-def test_instance_norm_streaming_passes(n, c, h, w, act, two_routes, pool):
-    """The cp.async.bulk-ring form of the same-resolution InstanceNorm passes (csrc/tg_stream.cuh): forward, backward
+@pytest.mark.parametrize("slim,serp", [(0, 3), (1, 4), (1, 3), (0, 0), (0, 7)])
+def test_instance_norm_streaming_passes(n, c, h, w, act, two_routes, pool, slim, serp):
+    """slim: the 4 KiB-chunk, one-CTA-per-SM form that shares an SM with a weight-gradient GEMM (tg_in_stream_slim);
+    serp: which passes walk their tensor from the end (tg_in_stream_serpentine) -- neither may change a result.
+    The cp.async.bulk-ring form of the same-resolution InstanceNorm passes (csrc/tg_stream.cuh): forward, backward
     statistics (with and without the dn store) and the recomputing apply pass, against torch autograd. Shapes: channel
     groups that do not divide the CTA (C = 192), odd maps whose pixel count is not a chunk multiple (61^2, 5x7),
     maps smaller than one chunk (2x2), one and two gradient routes, ReLU and LeakyReLU."""
     C = _C()
     from tactile_gan_b200._C import F as f32, ptr
     prev = C.lib().tg_in_stream_policy(2)        # the ring form whenever the shape allows (the default picks per shape)
+    prev_slim = C.lib().tg_in_stream_slim(slim)
+    prev_serp = C.lib().tg_in_stream_serpentine(serp)
     try:
         _streaming_case(C, f32, ptr, n, c, h, w, act, two_routes, pool)
     finally:
         C.lib().tg_in_stream_policy(prev)
+        C.lib().tg_in_stream_slim(prev_slim)
+        C.lib().tg_in_stream_serpentine(prev_serp)
 
 
 def _streaming_case(C, f32, ptr, n, c, h, w, act, two_routes, pool):

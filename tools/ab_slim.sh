@@ -1,0 +1,33 @@
+#!/bin/bash
+# A/B of the round-2 scheduling changes on one box: serpentine order, deferred weight gradient, slim InstanceNorm
+# backward beside the weight-gradient GEMM. Usage (GPU box): bash tools/ab_slim.sh
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+O=gpurun_out/ab_slim.txt
+: > $O
+timeout 300 python -m pytest tests/test_kernels_gpu.py -x -q -k "streaming" 2>&1 | tail -3 >> $O
+echo "== slim_probe (default lib, 32 KiB)" >> $O
+timeout 120 python tools/slim_probe.py >> $O 2>&1
+echo "== slim_probe (wgrad 4/3 stages, 72 KiB)" >> $O
+TG_LIB_PATH=$PWD/ab/libtg_wt4.so TG_SLIM_KB=72 timeout 120 python tools/slim_probe.py >> $O 2>&1
+run() {
+  name=$1; shift
+  env "$@" timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --no-cudnn > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err
+  python - "$name" >> $O <<'PY'
+import json, sys
+name = sys.argv[1]
+try:
+    d = json.loads(open(f"gpurun_out/ab_{name}.json").read().strip().splitlines()[-1])
+    print(f"{name:28s} value {d['value']:7.1f}  e2e {d['e2e']['value']:7.1f}  ms {d['ms_per_step']:6.2f}  tail {d['roofline_tail']['frac']:.3f}  conv {d['roofline']['frac']:.3f}  wgrad {d['roofline_wgrad']['frac']:.3f}  mhz {d['clocks']['sm_mhz']}")
+except Exception as e:
+    print(name, "FAILED", e, open(f"gpurun_out/ab_{name}.err").read()[-600:])
+PY
+}
+run base        TG_SLIM=0 TG_WGRAD_DEFER=0 TG_SERP=0
+run serp3       TG_SLIM=0 TG_WGRAD_DEFER=0 TG_SERP=3
+run defer       TG_SLIM=0 TG_WGRAD_DEFER=1 TG_SERP=0
+run defer_slim  TG_SLIM=1 TG_WGRAD_DEFER=1 TG_SERP=0
+run all         TG_SLIM=1 TG_WGRAD_DEFER=1 TG_SERP=3
+run all_wt4     TG_SLIM=1 TG_WGRAD_DEFER=1 TG_SERP=3 TG_LIB_PATH=$PWD/ab/libtg_wt4.so TG_SLIM_KB=72
+run base2       TG_SLIM=0 TG_WGRAD_DEFER=0 TG_SERP=0
+cat $O
