@@ -57,16 +57,75 @@ __device__ __forceinline__ uint4 lds16(uint32_t addr) {
 }
 
 // MODE 0: y = act(S*raw + T)
-// MODE 1: dn = (g1 + g2) * act'(A*raw + B); red[n][c] += (sum dn, rstd * (sum dn*raw - mean * sum dn)); dn stored if out
+// MODE 1: dn = (g1 + g2 + pool/4) * act'(A*raw + B); red[n][c] += (sum dn, rstd * (sum dn*raw - mean * sum dn)); dn stored if out
 // MODE 2: dz = P*dn + Q*raw + R with dn recomputed as in MODE 1 (P, Q, R from red)
-template <int MODE, int PPT>
+// G2 / POOL: a second same-resolution gradient route / the gradient of the 2x2 average-pooled copy are present
+// (compile-time, like the activation's branch-free form: the first version of this kernel decided both per element
+// and spent ~245 SASS instructions per 8-channel group -- issue bound at 0.78 of the copy bandwidth; profiles/
+// r02_stream_sass.txt has the before / after counts).
+//
+// One pixel group (8 channels of one pixel) of a chunk, fully inlined; OK = the group lies inside the chunk's valid part.
+template <int MODE, bool G2, bool POOL>
+struct StreamMath {
+  float A[8], B[8];                 // pre-activation n = A*raw + B  (MODE 0: the output itself before the activation)
+  float P[8], Q[8], R[8];           // MODE 2
+  float s0[8], s1[8];               // MODE 1
+  float neg;                        // act'(n <= 0): 0 ReLU, slope LeakyReLU, 1 none
+
+  __device__ __forceinline__ void group(const uint4& vr, const uint4& v1, const uint4& v2, const uint4& vp,
+                                        __nv_bfloat16* out, bool store) {
+    float r[8];
+    unpack8(vr, r);
+    if (MODE == 0) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float n = fmaf(r[q], A[q], B[q]);
+        r[q] = fmaf(neg, fminf(n, 0.f), fmaxf(n, 0.f));
+      }
+      stg16(out, pack8(r));
+      return;
+    }
+    float g[8];
+    unpack8(v1, g);
+    if (G2) {
+      float f[8];
+      unpack8(v2, f);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) g[q] += f[q];
+    }
+    if (POOL) {
+      float f[8];
+      unpack8(vp, f);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) g[q] = fmaf(0.25f, f[q], g[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float m = fmaf(r[q], A[q], B[q]) > 0.f ? 1.f : neg;
+      g[q] *= m;
+    }
+    if (MODE == 1) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        s0[q] += g[q];
+        s1[q] = fmaf(g[q], r[q], s1[q]);
+      }
+      if (store) stg16(out, pack8(g));
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) g[q] = fmaf(P[q], g[q], fmaf(Q[q], r[q], R[q]));
+      stg16(out, pack8(g));
+    }
+  }
+};
+
+template <int MODE, int PPT, bool G2, bool POOL>
 __global__ void __launch_bounds__(kStreamThreads, 2) in_stream_kernel(const StreamArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   // ring slots of one stage: raw | g1 | g2 | pooled gradient (absent routes take no slot)
-  const int slot_g1 = a.in1 ? 1 : 0;
-  const int slot_g2 = a.in2 ? slot_g1 + 1 : 0;
-  const int slot_pool = a.pool ? (a.in2 ? slot_g2 : slot_g1) + 1 : 0;
-  const int NIN = MODE == 0 ? 1 : 1 + (a.in1 ? 1 : 0) + (a.in2 ? 1 : 0) + (a.pool ? 1 : 0);
+  constexpr int slot_g2 = 2;
+  constexpr int slot_pool = G2 ? 3 : 2;
+  constexpr int NIN = MODE == 0 ? 1 : 2 + (G2 ? 1 : 0) + (POOL ? 1 : 0);
   const int CG = a.C >> 3;
   const int PL = kStreamConsumers / CG;                 // pixel lanes; threads with pl >= PL idle (C/8 not a divisor)
   const int CP = PPT * PL;                              // pixels per chunk
@@ -76,7 +135,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_stream_kernel(const Stre
   const int S = a.stages;
   // carve-up: [stages][NIN][chunk] | reduction scratch (MODE 1) | barriers
   const uint32_t base = smem_u32(smem_raw);
-  const uint32_t chunk_stride = uint32_t(stream_chunk_bytes(PPT));
+  constexpr uint32_t chunk_stride = uint32_t(stream_chunk_bytes(PPT));
   const uint32_t ring_bytes = uint32_t(S) * NIN * chunk_stride;
   float* scratch = reinterpret_cast<float*>(smem_raw + ring_bytes);
   const uint32_t scratch_bytes = MODE == 1 ? uint32_t(a.slim ? 1 : PL) * a.C * 2 * sizeof(float) : 0;
@@ -106,12 +165,12 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_stream_kernel(const Stre
         mbar_wait(bar0 + 8 * (S + s), ph);
         const size_t off = (size_t(n) * a.HW + p0) * a.C;
         const uint32_t st = base + uint32_t(s) * NIN * chunk_stride;
-        const uint32_t pool_bytes = a.pool ? bytes >> 1 : 0;
-        mbar_arrive_expect_tx(bar0 + 8 * s, bytes * (NIN - (a.pool ? 1 : 0)) + pool_bytes);
+        const uint32_t pool_bytes = POOL ? bytes >> 1 : 0;
+        mbar_arrive_expect_tx(bar0 + 8 * s, bytes * (NIN - (POOL ? 1 : 0)) + pool_bytes);
         bulk_load_1d(st, a.in0 + off, bytes, bar0 + 8 * s);
-        if (a.in1) bulk_load_1d(st + slot_g1 * chunk_stride, a.in1 + off, bytes, bar0 + 8 * s);
-        if (a.in2) bulk_load_1d(st + slot_g2 * chunk_stride, a.in2 + off, bytes, bar0 + 8 * s);
-        if (a.pool) {
+        if (MODE != 0) bulk_load_1d(st + chunk_stride, a.in1 + off, bytes, bar0 + 8 * s);
+        if (G2) bulk_load_1d(st + slot_g2 * chunk_stride, a.in2 + off, bytes, bar0 + 8 * s);
+        if (POOL) {
           // the chunk lies inside image row y (launcher: W % CP == 0): its pooled gradients are np / 2 consecutive
           // pixels of row y / 2 of the half-resolution tensor
           const int y = p0 / a.W, x = p0 % a.W;
@@ -144,14 +203,21 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_stream_kernel(const Stre
     for (int c = tid; c < 2 * a.C; c += kStreamConsumers) scratch[c] = 0.f;
     named_bar_sync(1, kStreamConsumers);
   }
-  float A[8], B[8];                 // pre-activation n = A*raw + B  (MODE 0: the output itself before the activation)
-  float P[8], Q[8], R[8];           // MODE 2
-  float s0[8], s1[8];               // MODE 1
-  float mean_[8], rstd_[8];
+  StreamMath<MODE, G2, POOL> m;
+  m.neg = a.act == 3 ? 0.f : (a.act == 1 ? a.slope : 1.f);
   int cur_n = -1;
-  const int act = a.act;
-  const float slope = a.slope;
   const float inv_hw = 1.f / float(a.HW);
+  // per-thread constants of the chunk geometry: byte offset of pixel group p inside a ring slot (and inside the
+  // half-size pooled slot), element offset inside the chunk's slice of the output tensor
+  uint32_t so[PPT], po[PPT], eo[PPT];
+#pragma unroll
+  for (int p = 0; p < PPT; ++p) {
+    const int lp = p * PL + pl;
+    so[p] = uint32_t(lp) * a.C * 2 + c0 * 2;
+    po[p] = uint32_t(lp >> 1) * a.C * 2 + c0 * 2;
+    eo[p] = uint32_t(lp) * a.C + c0;
+  }
+  const bool store_dn = MODE != 1 || a.out != nullptr;
 
   auto flush = [&]() {
     // MODE 1: block-level reduction of this image's partial sums, then one atomic per (n, c) and CTA
@@ -162,7 +228,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_stream_kernel(const Stre
       const bool fold = CG == 8 || CG == 16;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float v0 = s0[j], v1 = s1[j];
+        float v0 = m.s0[j], v1 = m.s1[j];
         if (fold)
           for (int off = 16; off >= CG; off >>= 1) {
             v0 += __shfl_xor_sync(0xffffffffu, v0, off);
@@ -188,7 +254,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_stream_kernel(const Stre
     if (active) {
       float* shp = scratch + (size_t(pl) * a.C + c0) * 2;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { shp[2 * j] = s0[j]; shp[2 * j + 1] = s1[j]; }
+      for (int j = 0; j < 8; ++j) { shp[2 * j] = m.s0[j]; shp[2 * j + 1] = m.s1[j]; }
     }
     named_bar_sync(1, kStreamConsumers);
     for (int c = tid; c < a.C; c += kStreamConsumers) {
@@ -214,21 +280,19 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_stream_kernel(const Stre
       cur_n = n;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const size_t kk = size_t(n) * a.C + c0 + q;
+        const size_t kq = size_t(n) * a.C + c0 + q;
         const float g = ld_aff(a.gamma, c0 + q, a.c_valid, 1.f);
         const float b = ld_aff(a.beta, c0 + q, a.c_valid, 0.f);
-        const float mean = active ? a.mr[kk * 2] : 0.f, rstd = active ? a.mr[kk * 2 + 1] : 0.f;
-        mean_[q] = mean;
-        rstd_[q] = rstd;
-        A[q] = g * rstd;
-        B[q] = b - mean * A[q];
-        s0[q] = 0.f;
-        s1[q] = 0.f;
+        const float mean = active ? a.mr[kq * 2] : 0.f, rstd = active ? a.mr[kq * 2 + 1] : 0.f;
+        m.A[q] = g * rstd;
+        m.B[q] = b - mean * m.A[q];
+        m.s0[q] = 0.f;
+        m.s1[q] = 0.f;
         if (MODE == 2) {
-          const float am = (active ? a.red[kk * 2] : 0.f) * inv_hw, bm = (active ? a.red[kk * 2 + 1] : 0.f) * inv_hw;
-          P[q] = g * rstd;
-          Q[q] = -g * rstd * rstd * bm;
-          R[q] = -P[q] * am - Q[q] * mean;
+          const float am = (active ? a.red[kq * 2] : 0.f) * inv_hw, bm = (active ? a.red[kq * 2 + 1] : 0.f) * inv_hw;
+          m.P[q] = g * rstd;
+          m.Q[q] = -g * rstd * rstd * bm;
+          m.R[q] = -m.P[q] * am - m.Q[q] * mean;
         }
       }
     }
@@ -237,51 +301,24 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_stream_kernel(const Stre
     mbar_wait(bar0 + 8 * s, ph);
     if (active) {
       const uint32_t st = base + uint32_t(s) * NIN * chunk_stride;
+      __nv_bfloat16* outc = a.out ? a.out + (size_t(n) * a.HW + p0) * a.C : nullptr;
+      // every load of the chunk first (the groups are independent), then the math
+      uint4 vr[PPT], v1[PPT], v2[PPT], vp[PPT];
 #pragma unroll
       for (int p = 0; p < PPT; ++p) {
-        const int lp = p * PL + pl;              // pixel inside the chunk
-        if (lp < np) {
-          const uint32_t so = uint32_t(lp) * a.C * 2 + c0 * 2;
-          float r[8];
-          unpack8(lds16(st + so), r);
-          const size_t lin = (size_t(n) * a.HW + p0 + lp) * a.C + c0;
-          if (MODE == 0) {
+        vr[p] = lds16(st + so[p]);
+        if (MODE != 0) v1[p] = lds16(st + chunk_stride + so[p]);
+        if (G2) v2[p] = lds16(st + slot_g2 * chunk_stride + so[p]);
+        if (POOL) vp[p] = lds16(st + slot_pool * chunk_stride + po[p]);
+      }
+      if (np == CP) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) r[q] = act_fwd(fmaf(r[q], A[q], B[q]), act, slope);
-            stg16(a.out + lin, pack8(r));
-          } else {
-            float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (slot_g1) unpack8(lds16(st + slot_g1 * chunk_stride + so), g);
-            if (slot_g2) {
-              float f[8];
-              unpack8(lds16(st + slot_g2 * chunk_stride + so), f);
+        for (int p = 0; p < PPT; ++p) m.group(vr[p], v1[p], v2[p], vp[p], outc + eo[p], store_dn);
+      } else {
+        // last chunk of an image whose pixel count is not a chunk multiple: groups past the end hold stale bytes
 #pragma unroll
-              for (int q = 0; q < 8; ++q) g[q] += f[q];
-            }
-            if (slot_pool) {
-              float f[8];
-              unpack8(lds16(st + slot_pool * chunk_stride + uint32_t(lp >> 1) * a.C * 2 + c0 * 2), f);
-#pragma unroll
-              for (int q = 0; q < 8; ++q) g[q] = fmaf(0.25f, f[q], g[q]);
-            }
-            if (MODE == 1) {
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                g[q] *= act_grad(fmaf(r[q], A[q], B[q]), act, slope);
-                s0[q] += g[q];
-                s1[q] = fmaf(g[q], r[q], s1[q]);
-              }
-              if (a.out) stg16(a.out + lin, pack8(g));
-            } else {
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float dn = g[q] * act_grad(fmaf(r[q], A[q], B[q]), act, slope);
-                g[q] = fmaf(P[q], dn, fmaf(Q[q], r[q], R[q]));
-              }
-              stg16(a.out + lin, pack8(g));
-            }
-          }
-        }
+        for (int p = 0; p < PPT; ++p)
+          if (p * PL + pl < np) m.group(vr[p], v1[p], v2[p], vp[p], outc + eo[p], store_dn);
       }
     }
     __syncwarp();
@@ -289,7 +326,6 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_stream_kernel(const Stre
     if (++s == S) { s = 0; ph ^= 1; }
   }
   if (cur_n >= 0) flush();
-  (void)mean_; (void)rstd_;
 }
 
 }  // namespace tg

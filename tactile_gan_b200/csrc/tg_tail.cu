@@ -14,11 +14,12 @@ namespace tg {
 static_assert(sizeof(AdamTensor) == 136, "AdamTensor layout is part of the C-ABI (tg_adam_step)");
 
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+  // bf16 -> fp32 is the upper half of the word: one shift / one mask per element
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    f[2 * i] = __low2float(h[i]);
-    f[2 * i + 1] = __high2float(h[i]);
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
   }
 }
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
@@ -56,15 +57,14 @@ __device__ __forceinline__ float ld_aff(const float* p, int c, int c_valid, floa
   return (p && c < c_valid) ? __ldg(p + c) : dflt;
 }
 
+// Branch-free: neg = act'(x <= 0) (0 ReLU, slope LeakyReLU, 1 none) is loop invariant, so the per-element work is
+// two min/max + one fma (forward) or one compare-select (gradient) instead of a switch on `act`.
+__device__ __forceinline__ float act_neg(int act, float slope) { return act == 3 ? 0.f : (act == 1 ? slope : 1.f); }
 __device__ __forceinline__ float act_fwd(float x, int act, float slope) {
-  if (act == 3) return fmaxf(x, 0.f);
-  if (act == 1) return x > 0.f ? x : x * slope;
-  return x;
+  return fmaf(act_neg(act, slope), fminf(x, 0.f), fmaxf(x, 0.f));
 }
 __device__ __forceinline__ float act_grad(float x, int act, float slope) {
-  if (act == 3) return x > 0.f ? 1.f : 0.f;
-  if (act == 1) return x > 0.f ? 1.f : slope;
-  return 1.f;
+  return x > 0.f ? 1.f : act_neg(act, slope);
 }
 
 }  // namespace tg
@@ -1798,10 +1798,10 @@ static int slim_budget() {
   }
   return kb * 1024;
 }
-template <int MODE, int PPT>
-static int launch_stream_ppt(tg::StreamArgs a, cudaStream_t s, bool slim) {
+template <int MODE, int PPT, bool G2, bool POOL>
+static int launch_stream_cfg(tg::StreamArgs a, cudaStream_t s, bool slim) {
   using namespace tg;
-  const int nin = MODE == 0 ? 1 : 1 + (a.in1 ? 1 : 0) + (a.in2 ? 1 : 0) + (a.pool ? 1 : 0);
+  constexpr int nin = MODE == 0 ? 1 : 2 + (G2 ? 1 : 0) + (POOL ? 1 : 0);
   const int CG = a.C >> 3, PL = kStreamConsumers / CG;
   const size_t chunk = size_t(stream_chunk_bytes(PPT));
   const size_t scratch = MODE == 1 ? size_t(slim ? 1 : PL) * a.C * 2 * sizeof(float) : 0;
@@ -1815,11 +1815,14 @@ static int launch_stream_ppt(tg::StreamArgs a, cudaStream_t s, bool slim) {
   a.slim = slim ? 1 : 0;
   a.rev = (serp_mask() >> MODE) & 1;
   const size_t smem = size_t(stages) * nin * chunk + scratch + 16 * stages;
+  auto kern = in_stream_kernel<MODE, PPT, G2, POOL>;
   static size_t configured = 0;
   if (smem > configured) {
-    if (cudaFuncSetAttribute(in_stream_kernel<MODE, PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
       return tg_set_error("in_stream: cudaFuncSetAttribute");
+    // the same (maximum) shared-memory carve-out as the GEMM kernels: a CTA can only join an SM whose L1 / shared
+    // split already matches, and the slim form is meant to run beside a resident GEMM CTA
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, int(cudaSharedmemCarveoutMaxShared));
     configured = smem;
   }
   const int CP = PPT * PL;
@@ -1827,9 +1830,21 @@ static int launch_stream_ppt(tg::StreamArgs a, cudaStream_t s, bool slim) {
   long long grid = slim ? 148 : 2 * 148;
   if (grid > chunks) grid = chunks;
   if (grid < 1) grid = 1;
-  if (tg_launch(in_stream_kernel<MODE, PPT>, dim3(unsigned(grid)), dim3(kStreamThreads), smem, s, a) != cudaSuccess)
+  if (tg_launch(kern, dim3(unsigned(grid)), dim3(kStreamThreads), smem, s, a) != cudaSuccess)
     return tg_check_launch("in_stream_kernel") ? -1 : tg_set_error("in_stream_kernel: launch failed");
   return tg_check_launch("in_stream_kernel");
+}
+template <int MODE, int PPT>
+static int launch_stream_ppt(tg::StreamArgs a, cudaStream_t s, bool slim) {
+  if constexpr (MODE == 0) {
+    return launch_stream_cfg<MODE, PPT, false, false>(a, s, slim);
+  } else {
+    if (!a.in1) return tg_set_error("in_stream: the backward passes need a same-resolution gradient route");
+    if (a.in2 && a.pool) return launch_stream_cfg<MODE, PPT, true, true>(a, s, slim);
+    if (a.in2) return launch_stream_cfg<MODE, PPT, true, false>(a, s, slim);
+    if (a.pool) return launch_stream_cfg<MODE, PPT, false, true>(a, s, slim);
+    return launch_stream_cfg<MODE, PPT, false, false>(a, s, slim);
+  }
 }
 static bool stream_pool_ok(int H, int W, int C, int ppt);   // defined below
 // slim only where it fits and the chunk geometry allows (backward passes; the pooled route needs even chunks)
@@ -1843,7 +1858,9 @@ static bool slim_applies(int mode, const tg::StreamArgs& a) {
 }
 template <int MODE>
 static int launch_stream(tg::StreamArgs a, cudaStream_t s) {
-  if (slim_applies(MODE, a)) return launch_stream_ppt<MODE, 1>(a, s, true);
+  if constexpr (MODE != 0) {
+    if (slim_applies(MODE, a)) return launch_stream_ppt<MODE, 1>(a, s, true);
+  }
   return launch_stream_ppt<MODE, tg::kStreamPPT>(a, s, false);
 }
 static bool stream_shape_ok(int C) { return C >= 64 && C <= 2048 && (C & 63) == 0; }
@@ -2022,7 +2039,8 @@ int tg_in_bwd_reduce(const void* raw, const void* y, const float* mr, const floa
   if (!raw && !dn) return tg_set_error("tg_in_bwd_reduce: a layer without norm needs the dn (= dz) output");
   const bool plain = !g_pool && (g_same || g_up) && (!g_up || g_up_pooled);
   // every route at the unit's own resolution, plus (optionally) the gradient of its 2x2 average-pooled copy
-  const bool streamable = (plain || (g_pool && pool_mode == 1 && (!g_up || g_up_pooled) && stream_pool_ok(H, W, C))) &&
+  const bool streamable = (plain || (g_pool && pool_mode == 1 && (g_same || g_up) && (!g_up || g_up_pooled) &&
+                                     stream_pool_ok(H, W, C))) &&
                           raw && mr && stream_enabled() && stream_shape_ok(C);
   if (streamable && red && (g_pool || stream_wins(1, N, H * W, C))) {
     tg::StreamArgs sa{};
@@ -2056,7 +2074,8 @@ int tg_in_bwd_apply_re(const void* raw, const void* y, const float* mr, const fl
   if (block > 1024) return tg_set_error("tg_in_bwd_apply_re: C too large");
   dim3 grid(strip_count(H * W, C, N, 16), N);
   const bool plain = !g_pool && (g_same || g_up) && (!g_up || g_up_pooled);
-  const bool streamable = (plain || (g_pool && pool_mode == 1 && (!g_up || g_up_pooled) && stream_pool_ok(H, W, C))) &&
+  const bool streamable = (plain || (g_pool && pool_mode == 1 && (g_same || g_up) && (!g_up || g_up_pooled) &&
+                                     stream_pool_ok(H, W, C))) &&
                           stream_enabled() && stream_shape_ok(C);
   if (streamable && (g_pool || stream_wins(2, N, H * W, C))) {
     tg::StreamArgs sa{};

@@ -5,7 +5,13 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 O=gpurun_out/ab_slim.txt
 : > $O
-timeout 300 python -m pytest tests/test_kernels_gpu.py -x -q -k "streaming" 2>&1 | tail -3 >> $O
+timeout 600 python -m pytest tests/test_kernels_gpu.py -x -q 2>&1 | tail -3 >> $O
+echo "== tail_bench default policy" >> $O
+timeout 120 python tools/tail_bench.py >> $O 2>&1
+echo "== tail_bench ring everywhere (TG_STREAM=2)" >> $O
+TG_STREAM=2 timeout 120 python tools/tail_bench.py >> $O 2>&1
+echo "== tail_bench slim alone" >> $O
+timeout 120 python tools/tail_bench.py --slim >> $O 2>&1
 echo "== slim_probe (default lib, 32 KiB)" >> $O
 timeout 120 python tools/slim_probe.py >> $O 2>&1
 echo "== slim_probe (wgrad 4/3 stages, 72 KiB)" >> $O
@@ -24,10 +30,8 @@ except Exception as e:
 PY
 }
 run base        TG_SLIM=0 TG_WGRAD_DEFER=0 TG_SERP=0
-run serp3       TG_SLIM=0 TG_WGRAD_DEFER=0 TG_SERP=3
-run defer       TG_SLIM=0 TG_WGRAD_DEFER=1 TG_SERP=0
-run defer_slim  TG_SLIM=1 TG_WGRAD_DEFER=1 TG_SERP=0
-run all         TG_SLIM=1 TG_WGRAD_DEFER=1 TG_SERP=3
-run all_wt4     TG_SLIM=1 TG_WGRAD_DEFER=1 TG_SERP=3 TG_LIB_PATH=$PWD/ab/libtg_wt4.so TG_SLIM_KB=72
+run ring_all    TG_SLIM=0 TG_WGRAD_DEFER=0 TG_SERP=0 TG_STREAM=2
+run defer_slim  TG_SLIM=1 TG_WGRAD_DEFER=1 TG_SERP=0 TG_SLIM_MIN_RATIO=1.0
+run wt4_slim    TG_SLIM=1 TG_WGRAD_DEFER=1 TG_SERP=0 TG_SLIM_MIN_RATIO=1.0 TG_LIB_PATH=$PWD/ab/libtg_wt4.so TG_SLIM_KB=72
 run base2       TG_SLIM=0 TG_WGRAD_DEFER=0 TG_SERP=0
 cat $O
