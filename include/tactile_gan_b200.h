@@ -139,7 +139,7 @@ int tg_in_stream_policy(int policy);
 int tg_in_stream_slim(int on);
 /* Serpentine order: bit 0 / 1 / 2 makes the forward / statistics / apply pass walk its tensor from the end, so that it
  * starts on the part its predecessor (which walked the other way) left in L2. Results do not depend on it. Returns
- * the previous mask; an argument outside 0..7 only queries. Env TG_SERP sets the initial value (default 3). */
+ * the previous mask; an argument outside 0..7 only queries. Env TG_SERP sets the initial value (default 0: measured neutral). */
 int tg_in_stream_serpentine(int mask);
 int tg_in_finalize(const float* partial, float* mr, int N, int T, int C, int count, float eps, void* stream);
 int tg_in_stats_direct(const void* raw, float* mr, int N, int HW, int C, float eps, void* stream);

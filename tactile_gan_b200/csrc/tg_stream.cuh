@@ -68,7 +68,7 @@ __device__ __forceinline__ uint4 lds16(uint32_t addr) {
 template <int MODE, bool G2, bool POOL>
 struct StreamMath {
   float A[8], B[8];                 // pre-activation n = A*raw + B  (MODE 0: the output itself before the activation)
-  float P[8], Q[8], R[8];           // MODE 2
+  float P[8], Pn[8], Q[8], R[8];    // MODE 2 (Pn = P * neg)
   float s0[8], s1[8];               // MODE 1
   float neg;                        // act'(n <= 0): 0 ReLU, slope LeakyReLU, 1 none
 
@@ -99,21 +99,21 @@ struct StreamMath {
 #pragma unroll
       for (int q = 0; q < 8; ++q) g[q] = fmaf(0.25f, f[q], g[q]);
     }
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float m = fmaf(r[q], A[q], B[q]) > 0.f ? 1.f : neg;
-      g[q] *= m;
-    }
     if (MODE == 1) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
+        g[q] *= fmaf(r[q], A[q], B[q]) > 0.f ? 1.f : neg;
         s0[q] += g[q];
         s1[q] = fmaf(g[q], r[q], s1[q]);
       }
       if (store) stg16(out, pack8(g));
     } else {
+      // dz = P*act'(n)*g + Q*raw + R: the activation's slope is folded into P (Pn = P*neg), one select per element
 #pragma unroll
-      for (int q = 0; q < 8; ++q) g[q] = fmaf(P[q], g[q], fmaf(Q[q], r[q], R[q]));
+      for (int q = 0; q < 8; ++q) {
+        const float pm = fmaf(r[q], A[q], B[q]) > 0.f ? P[q] : Pn[q];
+        g[q] = fmaf(pm, g[q], fmaf(Q[q], r[q], R[q]));
+      }
       stg16(out, pack8(g));
     }
   }
@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_stream_kernel(const Stre
           m.P[q] = g * rstd;
           m.Q[q] = -g * rstd * rstd * bm;
           m.R[q] = -m.P[q] * am - m.Q[q] * mean;
+          m.Pn[q] = m.P[q] * m.neg;
         }
       }
     }

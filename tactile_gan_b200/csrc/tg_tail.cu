@@ -1780,7 +1780,7 @@ static int g_serp = -1;
 static int serp_mask() {
   if (g_serp < 0) {
     const char* e = getenv("TG_SERP");
-    g_serp = (e && e[0] >= '0' && e[0] <= '7') ? e[0] - '0' : 3;
+    g_serp = (e && e[0] >= '0' && e[0] <= '7') ? e[0] - '0' : 0;   // measured neutral in the step: off
   }
   return g_serp;
 }
@@ -1869,16 +1869,16 @@ static bool stream_pool_ok(int H, int W, int C, int ppt = tg::kStreamPPT) {
   const int CP = ppt * (tg::kStreamConsumers / (C >> 3));
   return CP >= 2 && (CP & 1) == 0 && W % CP == 0 && (H & 1) == 0 && (W & 1) == 0;
 }
-// Which form is faster, measured per shape (profiles/r02_tail_microbench_*.txt): the register-staged passes reach
-// 0.88 of the copy bandwidth on the 268 MB, C = 64 tensors in the write-heavy passes (forward, apply) and start up
-// ~1.5 us faster on tensors under ~20 MB; the bulk-copy ring wins everywhere else (by 1.1-1.5x on 30-230 MB tensors
-// and on every statistics pass).
+// Which form is faster, measured per shape (profiles/r02_tail_microbench_*.txt, tools/tail_bench.py): since the
+// ring's per-element work became branch-free it wins every backward pass (statistics 0.97 vs 0.72 of the copy
+// bandwidth on the 268 MB tensors, apply 0.85 vs 0.72); the register-staged forward keeps the 268 MB, C = 64 tensors
+// (0.88 vs 0.77: a read + write stream from 1184 short-lived CTAs) and the tensors under ~20 MB, where it starts up
+// ~1.5 us faster.
 static bool stream_wins(int mode, int N, int HW, int C) {
   if (stream_policy() == 2) return true;
-  if (g_slim && mode != 0) return true;   // beside a weight-gradient GEMM only the slim ring fits
   const double bytes = 2.0 * N * double(HW) * C;
-  if (mode != 1 && C == 64 && bytes >= 200e6) return false;
-  if (mode != 2 && bytes <= 20e6) return false;
+  if (mode == 0 && C == 64 && bytes >= 200e6) return false;
+  if (mode == 0 && bytes <= 20e6) return false;
   return true;
 }
 
