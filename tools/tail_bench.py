@@ -40,9 +40,11 @@ if __name__ == "__main__":
     dev = "cuda"
     shapes = [(32, 256, 256, 64), (32, 128, 128, 128), (32, 64, 64, 256), (32, 32, 32, 512), (32, 16, 16, 1024),
               (64, 63, 63, 128), (64, 61, 61, 256), (64, 59, 59, 512), (4, 256, 256, 64), (4, 2, 2, 512)]
-    print("TG_STREAM =", os.environ.get("TG_STREAM", "1"), " slim" if SLIM else "", " peak", PEAK, "GB/s")
+    KNOB = int(sys.argv[sys.argv.index("--knob") + 1]) if "--knob" in sys.argv else 0
+    print("TG_STREAM =", os.environ.get("TG_STREAM", "1"), " slim" if SLIM else "", " knob", KNOB, " peak", PEAK, "GB/s")
     if SLIM:
         _C.lib().tg_in_stream_slim(1)
+    _C.lib().tg_debug_knob(KNOB)
     tot_t, tot_b = 0.0, 0.0
     for n, h, w, c in (shapes[:1] if NCU else shapes):
         sets = 3 if n * h * w * c * 2 * 3 < 3e9 else 2
@@ -73,14 +75,25 @@ if __name__ == "__main__":
             _C.call("in_bwd_apply_re", ptr(b[0]), ptr(b[1]), ptr(mr), ptr(gamma), ptr(beta), ptr(b[2]), None, 0, None, 0,
                     ptr(red), ptr(b[3]), n, h, w, c, c, 3, F(0.0), ptr(dg), ptr(db))
 
+        upb = [torch.empty(n, 2 * h, 2 * w, c, device=dev, dtype=torch.bfloat16) for _ in range(2)] \
+            if (n == 32 and h in (128, 64, 32)) else None
+
+        def fwd_up(i):
+            b = bufs[i % sets]
+            _C.call("in_act_fwd", ptr(b[0]), ptr(mr), ptr(gamma), ptr(beta), ptr(b[1]), None, 0, ptr(upb[i % 2]), n, h, w,
+                    c, c, 3, F(0.0))
+
         row = [f"{n:3d}x{h:3d}x{w:3d}x{c:4d} ({size / 1e6:6.1f} MB)"]
-        for name, fn, k in (("fwd", fwd, 2), ("reduce", reduce1, 2), ("reduce2", reduce2, 3), ("apply", apply1, 3)):
+        passes = [("fwd", fwd, 2), ("reduce", reduce1, 2), ("reduce2", reduce2, 3), ("apply", apply1, 3)]
+        if upb is not None:
+            passes.append(("fwd+up", fwd_up, 6))
+        for name, fn, k in passes:
             us, gbs = bench(fn, k * size)
             row.append(f"{name} {us:7.1f}us {gbs:6.0f} GB/s ({gbs / PEAK:.2f})")
             if n >= 32:
                 tot_t += us
                 tot_b += k * size
         print("  ".join(row), flush=True)
-        del bufs
+        del bufs, upb
         torch.cuda.empty_cache()
     print(f"aggregate (step shapes): {tot_b / tot_t / 1e3:.0f} GB/s = {tot_b / tot_t / 1e3 / PEAK:.3f} of peak")
