@@ -141,10 +141,6 @@ int tg_in_stream_slim(int on);
  * starts on the part its predecessor (which walked the other way) left in L2. Results do not depend on it. Returns
  * the previous mask; an argument outside 0..7 only queries. Env TG_SERP sets the initial value (default 0: measured neutral). */
 int tg_in_stream_serpentine(int mask);
-/* Experiment bits for A/B runs (env TG_KNOB; 0 = product behaviour): 1 ring loads with an L2 evict-first policy,
- * 2 streaming (.cs) stores in the ring passes, 4 streaming stores for the 4x upsampled copy. Returns the previous
- * value; a negative argument only queries. */
-int tg_debug_knob(int bits);
 int tg_in_finalize(const float* partial, float* mr, int N, int T, int C, int count, float eps, void* stream);
 int tg_in_stats_direct(const void* raw, float* mr, int N, int HW, int C, float eps, void* stream);
 int tg_in_act_fwd(const void* raw, const float* mr, const float* gamma, const float* beta, void* y,

@@ -40,8 +40,6 @@ struct StreamArgs {
   int stages;
   int rev;                    // walk the chunks from the tensor's end: a pass that follows a kernel which walked them
                               // upwards starts on what that kernel left in L2 (tg_in_stream_serpentine)
-  int knob;                   // experiment bits (tg_debug_knob): 1 = bulk loads with an L2 evict-first policy,
-                              // 2 = streaming (.cs) result stores
   int slim;                   // small-footprint form that shares an SM with a persistent weight-gradient CTA
                               // (tg_in_stream_slim): 4 KiB chunks, one CTA per SM, statistics folded through
                               // warp shuffles + shared-memory atomics instead of the [PL][C][2] scratch
@@ -52,18 +50,6 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void bulk_load_1d_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
-                                                  uint64_t policy) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar), "l"(policy)
-               : "memory");
-}
-__device__ __forceinline__ uint64_t l2_evict_first_policy() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ void stg16_cs(void* p, const uint4& v) { __stcs(reinterpret_cast<uint4*>(p), v); }
 __device__ __forceinline__ uint4 lds16(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -85,11 +71,6 @@ struct StreamMath {
   float P[8], Pn[8], Q[8], R[8];    // MODE 2 (Pn = P * neg)
   float s0[8], s1[8];               // MODE 1
   float neg;                        // act'(n <= 0): 0 ReLU, slope LeakyReLU, 1 none
-  bool cs;                          // streaming stores (experiment, tg_debug_knob bit 1)
-  __device__ __forceinline__ void st(void* p, const uint4& v) const {
-    if (cs) stg16_cs(p, v);
-    else stg16(p, v);
-  }
 
   __device__ __forceinline__ void group(const uint4& vr, const uint4& v1, const uint4& v2, const uint4& vp,
                                         __nv_bfloat16* out, bool store) {
@@ -101,7 +82,7 @@ struct StreamMath {
         const float n = fmaf(r[q], A[q], B[q]);
         r[q] = fmaf(neg, fminf(n, 0.f), fmaxf(n, 0.f));
       }
-      st(out, pack8(r));
+      stg16(out, pack8(r));
       return;
     }
     float g[8];
@@ -125,7 +106,7 @@ struct StreamMath {
         s0[q] += g[q];
         s1[q] = fmaf(g[q], r[q], s1[q]);
       }
-      if (store) st(out, pack8(g));
+      if (store) stg16(out, pack8(g));
     } else {
       // dz = P*act'(n)*g + Q*raw + R: the activation's slope is folded into P (Pn = P*neg), one select per element
 #pragma unroll
@@ -133,7 +114,7 @@ struct StreamMath {
         const float pm = fmaf(r[q], A[q], B[q]) > 0.f ? P[q] : Pn[q];
         g[q] = fmaf(pm, g[q], fmaf(Q[q], r[q], R[q]));
       }
-      st(out, pack8(g));
+      stg16(out, pack8(g));
     }
   }
 };
@@ -175,12 +156,6 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_stream_kernel(const Stre
     if (tid == kStreamConsumers) {
       int s = 0;
       uint32_t ph = 1;       // the first pass over the ring finds every stage free
-      const bool hint = a.knob & 1;
-      const uint64_t pol = l2_evict_first_policy();
-      auto load = [&](uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-        if (hint) bulk_load_1d_hint(dst, src, bytes, bar, pol);
-        else bulk_load_1d(dst, src, bytes, bar);
-      };
       for (long long k = k0; k < k1; ++k) {
         const long long kk = a.rev ? TC - 1 - k : k;
         const int n = int(kk / CPI), j = int(kk % CPI);
@@ -192,15 +167,15 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_stream_kernel(const Stre
         const uint32_t st = base + uint32_t(s) * NIN * chunk_stride;
         const uint32_t pool_bytes = POOL ? bytes >> 1 : 0;
         mbar_arrive_expect_tx(bar0 + 8 * s, bytes * (NIN - (POOL ? 1 : 0)) + pool_bytes);
-        load(st, a.in0 + off, bytes, bar0 + 8 * s);
-        if (MODE != 0) load(st + chunk_stride, a.in1 + off, bytes, bar0 + 8 * s);
-        if (G2) load(st + slot_g2 * chunk_stride, a.in2 + off, bytes, bar0 + 8 * s);
+        bulk_load_1d(st, a.in0 + off, bytes, bar0 + 8 * s);
+        if (MODE != 0) bulk_load_1d(st + chunk_stride, a.in1 + off, bytes, bar0 + 8 * s);
+        if (G2) bulk_load_1d(st + slot_g2 * chunk_stride, a.in2 + off, bytes, bar0 + 8 * s);
         if (POOL) {
           // the chunk lies inside image row y (launcher: W % CP == 0): its pooled gradients are np / 2 consecutive
           // pixels of row y / 2 of the half-resolution tensor
           const int y = p0 / a.W, x = p0 % a.W;
           const size_t poff = ((size_t(n) * (a.HW / a.W / 2) + (y >> 1)) * (a.W >> 1) + (x >> 1)) * a.C;
-          load(st + slot_pool * chunk_stride, a.pool + poff, pool_bytes, bar0 + 8 * s);
+          bulk_load_1d(st + slot_pool * chunk_stride, a.pool + poff, pool_bytes, bar0 + 8 * s);
         }
         if (++s == S) { s = 0; ph ^= 1; }
       }
@@ -230,7 +205,6 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_stream_kernel(const Stre
   }
   StreamMath<MODE, G2, POOL> m;
   m.neg = a.act == 3 ? 0.f : (a.act == 1 ? a.slope : 1.f);
-  m.cs = (a.knob & 2) != 0;
   int cur_n = -1;
   const float inv_hw = 1.f / float(a.HW);
   // per-thread constants of the chunk geometry: byte offset of pixel group p inside a ring slot (and inside the

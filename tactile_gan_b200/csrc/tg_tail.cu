@@ -327,8 +327,6 @@ in_act_fwd_kernel(const __nv_bfloat16* __restrict__ raw, const float* __restrict
                   __nv_bfloat16* __restrict__ up, int H, int W, int C, int c_valid, int act, float slope,
                   int rev) {
   griddep_sync();
-  const bool up_cs = (rev & 4) != 0;    // experiment (tg_debug_knob bit 2): streaming stores for the 4x copy
-  rev &= 1;
   const int n = rev ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
   constexpr bool QUAD = POOL != 0 || UP;
   const int H2 = H >> 1, W2 = W >> 1;
@@ -394,17 +392,10 @@ in_act_fwd_kernel(const __nv_bfloat16* __restrict__ raw, const float* __restrict
         }
         if (UP) {
           const size_t ubase = (size_t(n) * 2 * H + 2 * yy) * (2 * W) + 2 * xx;
-          if (up_cs) {
-            stg16_cs(up + ubase * C + t.c0, pv);
-            stg16_cs(up + (ubase + 1) * C + t.c0, pv);
-            stg16_cs(up + (ubase + 2 * W) * C + t.c0, pv);
-            stg16_cs(up + (ubase + 2 * W + 1) * C + t.c0, pv);
-          } else {
-            stg16(up + ubase * C + t.c0, pv);
-            stg16(up + (ubase + 1) * C + t.c0, pv);
-            stg16(up + (ubase + 2 * W) * C + t.c0, pv);
-            stg16(up + (ubase + 2 * W + 1) * C + t.c0, pv);
-          }
+          stg16(up + ubase * C + t.c0, pv);
+          stg16(up + (ubase + 1) * C + t.c0, pv);
+          stg16(up + (ubase + 2 * W) * C + t.c0, pv);
+          stg16(up + (ubase + 2 * W + 1) * C + t.c0, pv);
         }
       }
       if (POOL) {
@@ -1798,14 +1789,7 @@ static int serp_mask() {
 // and 40 K registers on its SM: one 288-thread CTA of this kernel with a ring of 4 KiB chunks fits beside it, so the
 // bandwidth-bound pass and the tensor-bound GEMM share the SM instead of taking turns (the 108 KiB ring cannot).
 static int g_slim = 0;
-static int g_knob = -1;     // experiment bits, tg_debug_knob / TG_KNOB
-static int knob() {
-  if (g_knob < 0) {
-    const char* e = getenv("TG_KNOB");
-    g_knob = e ? atoi(e) : 0;
-  }
-  return g_knob;
-}
+
 static int slim_budget() {
   static int kb = -1;
   if (kb < 0) {
@@ -1831,7 +1815,6 @@ static int launch_stream_cfg(tg::StreamArgs a, cudaStream_t s, bool slim) {
   a.stages = stages;
   a.slim = slim ? 1 : 0;
   a.rev = (serp_mask() >> MODE) & 1;
-  a.knob = knob();
   const size_t smem = size_t(stages) * nin * chunk + scratch + 16 * stages;
   auto kern = in_stream_kernel<MODE, PPT, G2, POOL>;
   static size_t configured = 0;
@@ -1977,12 +1960,6 @@ int tg_in_stream_slim(int on) {
   return prev;
 }
 
-int tg_debug_knob(int bits) {
-  const int prev = knob();
-  if (bits >= 0) g_knob = bits;
-  return prev;
-}
-
 int tg_in_stream_serpentine(int mask) {
   const int prev = serp_mask();
   if (mask >= 0 && mask <= 7) g_serp = mask;
@@ -2030,7 +2007,7 @@ int tg_in_act_fwd(const void* raw, const float* mr, const float* gamma, const fl
   dim3 grid(strip_count(units, C, N, quad ? 4 : 16), N);
   const int block = strip_block(C);
   const int pm = pool ? pool_mode : 0;
-  const int rev = (serp_mask() & 1) | (knob() & 4);
+  const int rev = serp_mask() & 1;
 #define LAUNCH(P, U) tg_launch(in_act_fwd_kernel<P, U>, grid, dim3(block), 0, s, r, mr, gamma, beta, yy, pp, uu, H, W, C, c_valid, act, slope, rev)
   if (pm == 0 && !up) LAUNCH(0, false);
   else if (pm == 0 && up) LAUNCH(0, true);

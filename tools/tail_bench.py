@@ -40,11 +40,9 @@ if __name__ == "__main__":
     dev = "cuda"
     shapes = [(32, 256, 256, 64), (32, 128, 128, 128), (32, 64, 64, 256), (32, 32, 32, 512), (32, 16, 16, 1024),
               (64, 63, 63, 128), (64, 61, 61, 256), (64, 59, 59, 512), (4, 256, 256, 64), (4, 2, 2, 512)]
-    KNOB = int(sys.argv[sys.argv.index("--knob") + 1]) if "--knob" in sys.argv else 0
-    print("TG_STREAM =", os.environ.get("TG_STREAM", "1"), " slim" if SLIM else "", " knob", KNOB, " peak", PEAK, "GB/s")
+    print("TG_STREAM =", os.environ.get("TG_STREAM", "1"), " slim" if SLIM else "", " peak", PEAK, "GB/s")
     if SLIM:
         _C.lib().tg_in_stream_slim(1)
-    _C.lib().tg_debug_knob(KNOB)
     tot_t, tot_b = 0.0, 0.0
     for n, h, w, c in (shapes[:1] if NCU else shapes):
         sets = 3 if n * h * w * c * 2 * 3 < 3e9 else 2
