@@ -925,6 +925,67 @@ __global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ g, const __nv_b
 
 // ------------------------------------------------------------------ 1x1 feature-map head (64 -> co<=4)
 // out[n,o,h,w] = act(sum_c x[n,h,w,c] * w[o][c] + b[o]); fp32 NCHW out.
+// C == 64, HW % 4 == 0: eight lanes share a pixel (one 16-byte load each = the pixel's whole 128-byte line), four
+// pixels per lane group and iteration; partial dot products are folded over the eight lanes with shuffles and lane o
+// of the group stores output plane o as one float4. (The per-thread-pixel form below reads a different line per
+// lane and load: 8x the L1 wavefronts for the same bytes.)
+__global__ void __launch_bounds__(256)
+fmap_fwd64_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                  float* __restrict__ out, int N, int HW, int co, int use_tanh, int ci) {
+  __shared__ float sw[4 * 64 + 4];
+  for (int i = threadIdx.x; i < 4 * 64; i += blockDim.x)
+    sw[i] = (i / 64 < co && (i % 64) < ci) ? w[(i / 64) * ci + i % 64] : 0.f;
+  if (threadIdx.x < 4) sw[4 * 64 + threadIdx.x] = threadIdx.x < co ? b[threadIdx.x] : 0.f;
+  __syncthreads();
+  const int grp = threadIdx.x & 7;
+  float wreg[4][8];
+#pragma unroll
+  for (int o = 0; o < 4; ++o)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wreg[o][j] = sw[o * 64 + grp * 8 + j];
+  const float bias = sw[4 * 64 + (grp & 3)];
+  const size_t quads = size_t(N) * HW / 4;
+  // the loop bound is per warp (four lane groups): the shuffles below need all 32 lanes
+  for (size_t qb = blockIdx.x * size_t(32) + (threadIdx.x >> 5) * 4; qb < quads; qb += size_t(gridDim.x) * 32) {
+    const size_t q = qb + ((threadIdx.x >> 3) & 3);
+    const bool valid = q < quads;
+    const size_t i0 = (valid ? q : quads - 1) * 4;
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = ldg16(x + (i0 + k) * 64 + grp * 8);
+    float acc[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float f[8];
+      unpack8(v[k], f);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a = fmaf(f[j], wreg[o][j], a);
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        acc[k][o] = a;
+      }
+    }
+    if (valid && grp < co) {
+      float r[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float t = acc[k][0];
+        if (grp == 1) t = acc[k][1];
+        if (grp == 2) t = acc[k][2];
+        if (grp == 3) t = acc[k][3];
+        t += bias;
+        r[k] = use_tanh ? tanhf(t) : t;
+      }
+      const size_t n = i0 / HW, pix = i0 % HW;
+      *reinterpret_cast<float4*>(out + (n * co + grp) * HW + pix) = make_float4(r[0], r[1], r[2], r[3]);
+    }
+  }
+}
+
 __global__ void fmap_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                                 const float* __restrict__ b, float* __restrict__ out, int N, int HW,
                                 int C, int co, int use_tanh, int ci) {
@@ -1871,14 +1932,15 @@ static bool stream_pool_ok(int H, int W, int C, int ppt = tg::kStreamPPT) {
   return CP >= 2 && (CP & 1) == 0 && W % CP == 0 && (H & 1) == 0 && (W & 1) == 0;
 }
 // Which form is faster, measured per shape (profiles/r02_tail_microbench_*.txt, tools/tail_bench.py): since the
-// ring's per-element work became branch-free it wins every backward pass (statistics 0.97 vs 0.72 of the copy
-// bandwidth on the 268 MB tensors, apply 0.85 vs 0.72); the register-staged forward keeps the 268 MB, C = 64 tensors
-// (0.88 vs 0.77: a read + write stream from 1184 short-lived CTAs) and the tensors under ~20 MB, where it starts up
-// ~1.5 us faster.
+// ring's per-element work became branch-free it wins every backward pass (statistics 0.95-0.97 vs 0.72 of the copy
+// bandwidth on the 268 MB tensors, apply 0.85 vs 0.72-0.88). The forward pass -- one read and one write stream --
+// stays register-staged on the wide maps with few channels (C <= 128 and >= 100 MB: 94.5 vs 107 us at 268 MB, 52.5
+// vs 56 us at 134 MB; 1184 short-lived CTAs walk the tensor as one moving window, 296 persistent ones as 296
+// separate streams) and under ~20 MB, where it starts up ~1.5 us faster.
 static bool stream_wins(int mode, int N, int HW, int C) {
   if (stream_policy() == 2) return true;
   const double bytes = 2.0 * N * double(HW) * C;
-  if (mode == 0 && C == 64 && bytes >= 200e6) return false;
+  if (mode == 0 && C <= 128 && bytes >= 100e6) return false;
   if (mode == 0 && bytes <= 20e6) return false;
   return true;
 }
@@ -2157,8 +2219,12 @@ int tg_act_bwd(const void* g, const void* y, void* out, long long numel, int act
 int tg_fmap_fwd(const void* x, const float* w, const float* b, float* out, int N, int HW, int C, int co,
                 int use_tanh, int ci, void* stream) {
   if (C != 64 || co > 4 || ci > C || ci < 1) return tg_set_error("tg_fmap_fwd: expects C == 64, co <= 4, ci <= C");
-  fmap_fwd_kernel<<<grid_for(size_t(N) * HW, 256, 148 * 16), 256, 0, TG_STREAM(stream)>>>(
-      (const __nv_bfloat16*)x, w, b, out, N, HW, C, co, use_tanh, ci);
+  if ((HW & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+    fmap_fwd64_kernel<<<grid_for(size_t(N) * HW / 4, 32, 148 * 8), 256, 0, TG_STREAM(stream)>>>(
+        (const __nv_bfloat16*)x, w, b, out, N, HW, co, use_tanh, ci);
+  else
+    fmap_fwd_kernel<<<grid_for(size_t(N) * HW, 256, 148 * 16), 256, 0, TG_STREAM(stream)>>>(
+        (const __nv_bfloat16*)x, w, b, out, N, HW, C, co, use_tanh, ci);
   TG_RET();
 }
 

@@ -313,6 +313,27 @@ def _streaming_case(C, f32, ptr, n, c, h, w, act, two_routes, pool):
     assert rel(dgam, dg_ref) < 6e-3 and rel(dbet, db_ref) < 6e-3
 
 
+@pytest.mark.parametrize("n,h,w,ci,co,tanh", [(2, 16, 24, 64, 3, True), (3, 8, 12, 16, 3, True), (2, 7, 9, 64, 1, False),
+                                              (1, 32, 32, 4, 4, True), (5, 6, 6, 64, 2, False)])
+def test_feature_map_block_forward(n, h, w, ci, co, tanh):
+    """FeatureMapBlock head (1x1 conv + bias + tanh, UNet_plusplus.py:86 / BCDUNet.py:181) on a 64-channel padded
+    input -> fp32 NCHW: the eight-lanes-per-pixel kernel (H*W divisible by 4) and the per-pixel fallback (7x9)."""
+    C = _C()
+    from tactile_gan_b200._C import ptr
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(n, ci, h, w, generator=g).to(dev)
+    wt = (0.2 * torch.randn(co, ci, generator=g)).to(dev)
+    bs = (0.1 * torch.randn(co, generator=g)).to(dev)
+    xp = nhwc_pad(x)
+    assert xp.shape[3] == 64
+    out = torch.full((n, co, h, w), 9.0, device=dev)
+    C.call("fmap_fwd", ptr(xp), ptr(wt), ptr(bs), ptr(out), n, h * w, 64, co, int(tanh), ci)
+    torch.cuda.synchronize()
+    ref = F.conv2d(xp[..., :ci].permute(0, 3, 1, 2).float(), wt.view(co, ci, 1, 1), bs)
+    ref = torch.tanh(ref) if tanh else ref
+    assert rel(out, ref) < 1e-5
+
+
 def test_adam_kernel_matches_torch_adam():
     """tg_adam_step against torch.optim.Adam(betas=(0.9,0.99)) over 3 steps, incl. the bf16 re-pack."""
     from tactile_gan_b200.layers import ConvLayer, ParamStore
