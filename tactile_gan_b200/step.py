@@ -85,13 +85,16 @@ class TrainStep:
         # +3 %; UNet++ batch 32 -1 % -> off there. TG_PDL in the environment overrides the choice.
         small = batch * height * width <= 8 * 256 * 256 or str(kind).lower() == "unet"
         self.pdl = small if os.environ.get("TG_PDL") is None else None
+        # After two eager iterations the whole step is captured in a CUDA graph per `regularize` value and replayed.
         # Small batches are bound by the HOST issuing ~800 launches per step (batch 4 = the reference CLI's default:
-        # 6.4 ms/step of which ~4 ms is launch cost): after two eager iterations the whole step is captured in a CUDA
-        # graph per `regularize` value and replayed. The only per-step scalars -- learning rate and Adam's bias
-        # corrections -- live in device memory (tg_adam_step_dev) and are rewritten before every replay; the GP alpha is
-        # drawn outside the graph into a static buffer. Single process only (NCCL stays eager). TG_STEP_GRAPH=0|1 overrides.
+        # 6.4 ms/step of which ~4 ms is launch cost); at batch 32 the host keeps ahead, but the ~450 graph nodes start
+        # ~1.5 us sooner each than stream launches do: 39.6 -> 38.9 ms/step, +1.7 % (ABAB on one box,
+        # profiles/r02_step_graph_ab.txt) -- so every single-process step is replayed from the graph. The only
+        # per-step scalars -- learning rate and Adam's bias corrections -- live in device memory (tg_adam_step_dev) and
+        # are rewritten before every replay; the GP alpha is drawn outside the graph into a static buffer. Single
+        # process only (NCCL stays eager). TG_STEP_GRAPH=0|1 overrides.
         env = os.environ.get("TG_STEP_GRAPH")
-        self.use_graph = (batch * height * width <= 8 * 256 * 256) if env is None else env == "1"
+        self.use_graph = True if env is None else env == "1"
         self.use_graph = self.use_graph and self.world == 1
         self._graphs, self._eager_done, self._hyper = {}, {}, None
         # TG_COMM_PROFILE=1 (bench.py): CUDA-event pairs around the points where the compute stream waits for a
