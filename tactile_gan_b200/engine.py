@@ -157,9 +157,9 @@ class ConvUnit:
         g_pool = self.pool.run_grad() if (self.pool and self.pool.consumers) else None
         g_up = self.up.run_grad() if (self.up and self.up.consumers) else None
         up_pooled = int(bool(g_up is not None and self.up.grad_pooled))
-        # the previous unit's weight gradient goes to the side stream AFTER this unit's input-gradient GEMMs were
-        # queued: both become ready at the same moment, the GPU takes them in submission order, so the weight gradient
-        # runs while the passes below do -- and those take the slim form that fits beside its CTAs
+        # opt-in (TG_WGRAD_DEFER=1 / TG_SLIM=1; a no-op otherwise): the previous unit's weight gradient goes
+        # to the side stream AFTER this unit's input-gradient GEMMs were queued, so that it is the GEMM running while the
+        # passes below do -- and those take the slim form that fits on an SM beside its CTAs
         slim = eng._flush_wgrad(2.0 * n * ho * wo * c * 5 if self.norm else 0.0)
         g, b = self._aff()
         if self.norm:
@@ -267,10 +267,10 @@ class GraphEngine:
         self.layers = {}
         self.red_arena = None
         self.red_clean = False      # True while a pass that cleared the whole red arena is running
-        # side-stream weight gradients (TrainStep sets wgrad_stream): queued one unit late, behind the next unit's
-        # input-gradient GEMMs, and the InstanceNorm passes beside them take the slim form (tg_in_stream_slim)
+        # side-stream weight gradients (TrainStep sets wgrad_stream) can be queued one unit late, behind the next unit's
+        # input-gradient GEMMs, with the InstanceNorm passes beside them in the slim form (tg_in_stream_slim): measured
+        # on the headline step at 821 vs 826 / 810 img/s and 825.0 vs 825.5 (ABAB) -- inside box noise -- so both are opt-in
         self._pending_wgrad = None
-        # (measured on the headline step: 821 vs 826 / 810 img/s without -- inside box noise -- so both stay opt-in)
         self.defer_wgrad = os.environ.get("TG_WGRAD_DEFER", "0") != "0"
         self.slim_tail = os.environ.get("TG_SLIM", "0") != "0"
         self.slim_min_ratio = float(os.environ.get("TG_SLIM_MIN_RATIO", "1.0"))
@@ -342,7 +342,7 @@ class GraphEngine:
     def _flush_wgrad(self, tail_bytes=0.0):
         """Queue the deferred weight gradient (ConvUnit.backward) on the side stream. Returns True when the caller's
         InstanceNorm passes (`tail_bytes` of traffic) should take the slim form, i.e. when that GEMM is long enough
-        to cover a useful part of them (TG_SLIM_MIN_RATIO, default 0.3, of their time at 4.5 TB/s)."""
+        to cover them (TG_SLIM_MIN_RATIO, default 1.0, of their time at 4.5 TB/s)."""
         pend, self._pending_wgrad = self._pending_wgrad, None
         if pend is None:
             return False
