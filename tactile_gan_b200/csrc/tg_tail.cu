@@ -791,13 +791,12 @@ __global__ void in_bwd2_reduce_kernel(const __nv_bfloat16* __restrict__ u,
       mean[j] = mr[(size_t(n) * C + c0 + j) * 2];
       rstd[j] = mr[(size_t(n) * C + c0 + j) * 2 + 1];
     }
-    // four pixels per iteration: all twelve 16-byte loads are issued before the first use (one pixel per iteration
-    // left three loads in flight per thread -- latency bound at ~0.5 of the copy bandwidth)
-    auto acc = [&](const uint4& vu, const uint4& vr, const uint4& vd) {
+    for (int pix = p0 + pl; pix < p1; pix += PL) {
+      const size_t lin = (size_t(n) * HW + pix) * C + c0;
       float fu[8], fr[8], fd[8];
-      unpack8(vu, fu);
-      unpack8(vr, fr);
-      unpack8(vd, fd);
+      unpack8(ldg16(u + lin), fu);
+      unpack8(ldg16(raw + lin), fr);
+      unpack8(ldg16(dn + lin), fd);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float xh = (fr[j] - mean[j]) * rstd[j];
@@ -805,23 +804,6 @@ __global__ void in_bwd2_reduce_kernel(const __nv_bfloat16* __restrict__ u,
         s1[j] += fu[j] * xh;
         s2[j] += fu[j] * fd[j];
       }
-    };
-    int pix = p0 + pl;
-    for (; pix + 3 * PL < p1; pix += 4 * PL) {
-      uint4 vu[4], vr[4], vd[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const size_t lin = (size_t(n) * HW + pix + k * PL) * C + c0;
-        vu[k] = ldg16(u + lin);
-        vr[k] = ldg16(raw + lin);
-        vd[k] = ldg16(dn + lin);
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) acc(vu[k], vr[k], vd[k]);
-    }
-    for (; pix < p1; pix += PL) {
-      const size_t lin = (size_t(n) * HW + pix) * C + c0;
-      acc(ldg16(u + lin), ldg16(raw + lin), ldg16(dn + lin));
     }
     float* shp = shm + (size_t(pl) * C + c0) * 3;
 #pragma unroll
@@ -837,7 +819,7 @@ __global__ void in_bwd2_reduce_kernel(const __nv_bfloat16* __restrict__ u,
 
 // Pass 2: writes adj_da = adj(dn) * act'(n) (upward) and adj_z (downward injection); accumulates
 // adj(gamma) partial sums into red2[..][3].
-__global__ void __launch_bounds__(256, 2) in_bwd2_apply_kernel(const __nv_bfloat16* __restrict__ u,
+__global__ void in_bwd2_apply_kernel(const __nv_bfloat16* __restrict__ u,
                                      const __nv_bfloat16* __restrict__ raw,
                                      const __nv_bfloat16* __restrict__ dn,
                                      const float* __restrict__ mr, const float* __restrict__ gamma,
@@ -870,11 +852,12 @@ __global__ void __launch_bounds__(256, 2) in_bwd2_apply_kernel(const __nv_bfloat
       c2[j] = red2[k * 4 + 1] * inv;
       e[j] = gm[j] * red2[k * 4 + 2] * inv;   // mean(u * dxh)
     }
-    auto emit = [&](size_t lin, const uint4& vu, const uint4& vr, const uint4& vd) {
+    for (int pix = p0 + pl; pix < p1; pix += PL) {
+      const size_t lin = (size_t(n) * HW + pix) * C + c0;
       float fu[8], fr[8], fd[8], oa[8], oz[8];
-      unpack8(vu, fu);
-      unpack8(vr, fr);
-      unpack8(vd, fd);
+      unpack8(ldg16(u + lin), fu);
+      unpack8(ldg16(raw + lin), fr);
+      unpack8(ldg16(dn + lin), fd);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float xh = (fr[j] - mean[j]) * rstd[j];
@@ -888,19 +871,6 @@ __global__ void __launch_bounds__(256, 2) in_bwd2_apply_kernel(const __nv_bfloat
       }
       stg16(adj_da + lin, pack8(oa));
       stg16(adj_z + lin, pack8(oz));
-    };
-    // two pixels per iteration, the six loads first (see in_bwd2_reduce_kernel)
-    int pix = p0 + pl;
-    for (; pix + PL < p1; pix += 2 * PL) {
-      const size_t l0 = (size_t(n) * HW + pix) * C + c0, l1 = l0 + size_t(PL) * C;
-      const uint4 u0 = ldg16(u + l0), r0 = ldg16(raw + l0), d0 = ldg16(dn + l0);
-      const uint4 u1 = ldg16(u + l1), r1 = ldg16(raw + l1), d1 = ldg16(dn + l1);
-      emit(l0, u0, r0, d0);
-      emit(l1, u1, r1, d1);
-    }
-    for (; pix < p1; pix += PL) {
-      const size_t lin = (size_t(n) * HW + pix) * C + c0;
-      emit(lin, ldg16(u + lin), ldg16(raw + lin), ldg16(dn + lin));
     }
     float* shp = shm + size_t(pl) * C + c0;
 #pragma unroll
@@ -2211,8 +2181,8 @@ int tg_in_bwd2(const void* u, const void* raw, const void* dn, const float* mr, 
                const float* beta, const float* red1, float* red2, void* adj_da, void* adj_z, int N,
                int HW, int C, int c_valid, int act, float slope, void* stream) {
   const int CG = C / 8;
-  const int block = 256;
-  if (CG > block) return tg_set_error("tg_in_bwd2: C <= 2048 (one 8-channel group per thread of a 256-thread block)");
+  const int block = CG >= 256 ? CG : 256;
+  if (block > 1024) return tg_set_error("tg_in_bwd2: C too large");
   const int PL = block / CG;
   int strips = (HW + PL * 8 - 1) / (PL * 8);
   const int cap = (148 * 8 + N - 1) / N;
