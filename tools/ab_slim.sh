@@ -1,6 +1,10 @@
 #!/bin/bash
 # A/B of the round-2 scheduling changes on one box: serpentine order, deferred weight gradient, slim InstanceNorm
 # backward beside the weight-gradient GEMM. Usage (GPU box): bash tools/ab_slim.sh
+# The "wt4" variants need a second build of the library with shallower weight-gradient pipelines (more shared memory
+# left for the slim ring), made here before the call:
+#   mkdir -p ab && (cd tactile_gan_b200/csrc && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 \
+#     -Xcompiler -fPIC -shared -DTG_WT_STAGES=4 -DTG_WG256_STAGES=3 -o ../../ab/libtg_wt4.so tg_api.cu tg_tail.cu)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 O=gpurun_out/ab_slim.txt
