@@ -137,15 +137,19 @@ def conv_query_tiles(n, ho, wo, want_stats):
 
 
 SPLITK_WS_BYTES = 256 << 20
+SPLITK_SLOT = 0          # plans created while this is k > 0 use the k-th extra workspace (launch chains on side streams)
 _splitk_ws = {}
 
 
-def splitk_workspace(device):
+def splitk_workspace(device, slot=0):
     """One fp32 workspace per device for the split-K convolutions (tg_conv_desc.splitk_ws): the conv launches of a
-    step are ordered on one stream, so they can share it."""
-    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    step are ordered on one stream, so they can share it. Engines that run chains of units on side streams
+    (UNetPPEngine's small inference batches) give every stream its own, smaller one (`slot` > 0)."""
+    dev = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    key = (dev, slot)
     if key not in _splitk_ws:
-        _splitk_ws[key] = torch.empty(SPLITK_WS_BYTES // 4, dtype=torch.float32, device=torch.device("cuda", key))
+        nbytes = SPLITK_WS_BYTES if slot == 0 else SPLITK_WS_BYTES // 8
+        _splitk_ws[key] = torch.empty(nbytes // 4, dtype=torch.float32, device=torch.device("cuda", dev))
     return _splitk_ws[key]
 
 
@@ -182,7 +186,7 @@ def conv_plan(srcs, out, taps, stride=1, bias=None, stats_partial=None, act=ACT_
     d.slope = slope
     d.pool_out = int(pool_out)
     if os.environ.get("TG_SPLITK", "1") != "0":
-        ws = splitk_workspace(out.device)
+        ws = splitk_workspace(out.device, SPLITK_SLOT)
         d.splitk_ws, d.splitk_ws_bytes = ws.data_ptr(), ws.numel() * 4
         keep.append(ws)
     h = c_void_p()

@@ -107,10 +107,14 @@ class ConvUnit:
 
     def build(self, backward):
         srcs = [t.buf for t in self.srcs]
-        if self.norm:
-            self.fwd_plans = self.layer.fwd_plans(srcs, self.raw, stats_partial=self.partial)
-        else:
-            self.fwd_plans = self.layer.fwd_plans(srcs, self.y.buf, act=self.act, slope=self.slope)
+        _C.SPLITK_SLOT = getattr(self, "ws_slot", 0)     # units launched on a side stream: that stream's workspace
+        try:
+            if self.norm:
+                self.fwd_plans = self.layer.fwd_plans(srcs, self.raw, stats_partial=self.partial)
+            else:
+                self.fwd_plans = self.layer.fwd_plans(srcs, self.y.buf, act=self.act, slope=self.slope)
+        finally:
+            _C.SPLITK_SLOT = 0
         if backward:
             eng = self.eng
             self.wgrad_plans = self.layer.wgrad_plans(srcs, self.dz)
@@ -294,6 +298,7 @@ class GraphEngine:
         return cache[name]
 
     PDL_MAX_PIXELS = 8 * 256 * 256     # inference batches up to this many pixels are launch / prologue bound
+    MS_MAX_PIXELS = 4 * 256 * 256      # ... and up to this many leave SMs idle: UNet++ walks its chains on three streams
 
     def _pdl(self):
         """Context: programmatic dependent launch for the launches of a small inference pass (batch 1 at 256^2: 819 ->
@@ -464,6 +469,22 @@ class UNetPPEngine(GraphEngine):
             u1 = ConvUnit(self, f"x{i}{j}b", l1, [u0.y], True, g1, b1, relu, pool=pool, up=up)
             X[i, j] = (u0, u1)
         self.X = X
+        # Small inference batches leave most SMs idle in the deep levels (one to eight tiles per launch at batch 1):
+        # the nested grid is walked as its five anti-diagonal chains X(d,0) -> X(d-1,1) -> ... -> X(0,d) on three
+        # streams (chain d on stream d % 3), each node waiting for the events of its same-row sources; the critical
+        # path is 9 of the 15 nodes. TG_INFER_STREAMS=0 keeps the single launch sequence.
+        self.multi_stream = ((not backward) and n * h * w <= self.MS_MAX_PIXELS and
+                             os.environ.get("TG_INFER_STREAMS", "1") != "0")
+        if self.multi_stream:
+            level = {}
+            for (i, j) in order:        # longest path to the node: sources come first in `order`
+                deps = [(i, k) for k in range(j)] + ([(i + 1, j - 1)] if j else ([(i - 1, 0)] if i else []))
+                level[i, j] = 1 + max([level[d] for d in deps], default=-1)
+            self.level_order = sorted(order, key=lambda ij: (level[ij], ij[0]))
+            self._side = None
+            for (i, j) in order:
+                for u in X[i, j]:
+                    u.ws_slot = (i + j) % 3
         self.head = HeadUnit(self, "downfeature", module.downfeature.conv.weight, module.downfeature.conv.bias,
                              X[0, 4][1].y, module.downfeature.activation)
         self.finish()
@@ -478,10 +499,36 @@ class UNetPPEngine(GraphEngine):
     def _forward_launches(self, x):
         _C.call("pack_nchw", ptr(x), None, None, None, ptr(self.x_in.buf), self.n, self.h * self.w, self.cin,
                 self.x_in.buf.shape[3], 0)
-        for (i, j) in self.order:
-            u0, u1 = self.X[i, j]
-            u0.forward()
-            u1.forward()
+        if not self.multi_stream:
+            for (i, j) in self.order:
+                u0, u1 = self.X[i, j]
+                u0.forward()
+                u1.forward()
+            return self.head.forward()
+        cur = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+        streams = [cur] + self._side
+        start = torch.cuda.Event()
+        start.record(cur)
+        for s in self._side:
+            s.wait_event(start)
+        done = {}
+        for (i, j) in self.level_order:
+            st = streams[(i + j) % 3]
+            with torch.cuda.stream(st):
+                # X(i+1, j-1) is the previous node of this chain (same stream); the same-row sources X(i, k < j) and,
+                # for the first node of a chain, X(i-1, 0) were produced by other chains
+                for d in [(i, k) for k in range(j)] + ([(i - 1, 0)] if (j == 0 and i) else []):
+                    if (d[0] + d[1]) % 3 != (i + j) % 3:
+                        st.wait_event(done[d])
+                u0, u1 = self.X[i, j]
+                u0.forward()
+                u1.forward()
+                done[i, j] = torch.cuda.Event()
+                done[i, j].record(st)
+        for s in self._side:
+            cur.wait_stream(s)
         return self.head.forward()
 
     def backward(self, g1, g2=None, after_unit=None):

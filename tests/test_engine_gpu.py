@@ -414,6 +414,31 @@ def test_inference_graph_is_rebuilt_when_parameter_storage_moves():
         assert torch.equal(fresh(x), y1) and not torch.equal(y1, y0)
 
 
+@pytest.mark.parametrize("n,size", [(1, 64), (2, 128)])
+def test_multi_stream_inference_equals_single_stream(monkeypatch, n, size):
+    """Small UNet++ inference batches walk the nested grid as five anti-diagonal chains on three streams (events between
+    chains): launches eagerly and through the CUDA graph must reproduce the single-sequence forward bit for bit. At
+    128^2 the 8x8 level runs split-K convolutions, whose workspace is per stream."""
+    from tactile_gan_b200.engine import UNetPPEngine
+    from tactile_gan_b200.generators.generators import create_gen
+    torch.manual_seed(8)
+    net = create_gen("UNet++", 3, 3, 16, True).cuda()
+    randomize(net, 5)
+    x = torch.rand(n, 3, size, size, device="cuda") * 2 - 1
+    monkeypatch.setenv("TG_INFER_STREAMS", "0")
+    single = UNetPPEngine(net, n, size, size, backward=False)
+    monkeypatch.setenv("TG_INFER_STREAMS", "1")
+    multi = UNetPPEngine(net, n, size, size, backward=False)
+    assert not single.multi_stream and multi.multi_stream
+    with torch.no_grad():
+        ref = single.forward(x).clone()
+        for _ in range(3):
+            assert torch.equal(multi.forward(x), ref)
+        for _ in range(3):
+            assert torch.equal(multi.forward_graphed(x), ref)
+    torch.cuda.synchronize()
+
+
 def test_small_batch_step_graph_matches_eager():
     """Batches up to 8 x 256^2 pixels replay the whole iteration from a CUDA graph after two eager steps (the host's
     ~800 launches per step are what bounds batch 4, the reference CLI's default). Same kernels, same order: the losses of
