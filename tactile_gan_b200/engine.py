@@ -432,6 +432,24 @@ def _affine(norm):
     return (norm.weight, norm.bias) if getattr(norm, "weight", None) is not None else (None, None)
 
 
+def unetpp_chain_schedule(depth=5, n_streams=3):
+    """Launch plan of the nested UNet++ grid on `n_streams` streams (pure host logic, tested on the CPU).
+    X(i,j) reads its row X(i, k<j) and X(i+1, j-1) (X(i,0) reads X(i-1,0)): the anti-diagonals X(d,0) -> X(d-1,1) ->
+    ... -> X(0,d) are serial chains, chain d one step behind chain d-1. Chain d runs on stream d % n_streams; nodes are
+    queued by longest-path level, so every stream sees its nodes in dependency order, and a node only waits (events)
+    for sources produced on OTHER streams. Returns (order, stream_of, waits, deps, level)."""
+    nodes = [(i, 0) for i in range(depth)] + [(i, j) for j in range(1, depth) for i in range(depth - j)]
+    deps = {(i, j): [(i, k) for k in range(j)] + ([(i + 1, j - 1)] if j else ([(i - 1, 0)] if i else []))
+            for (i, j) in nodes}
+    level = {}
+    for nd in nodes:                     # `nodes` lists every source before its consumers
+        level[nd] = 1 + max([level[d] for d in deps[nd]], default=-1)
+    order = sorted(nodes, key=lambda ij: (level[ij], ij[0]))
+    stream_of = {nd: (nd[0] + nd[1]) % n_streams for nd in nodes}
+    waits = {nd: [d for d in deps[nd] if stream_of[d] != stream_of[nd]] for nd in nodes}
+    return order, stream_of, waits, deps, level
+
+
 class UNetPPEngine(GraphEngine):
     """UNet++ (reference generators/UNet_plusplus.py:37-86): nested grid X(i,j) of ConvBlocks.
     torch.cat and nn.Upsample never materialise a concat: each operand is a separate K-loop source;
@@ -476,15 +494,11 @@ class UNetPPEngine(GraphEngine):
         self.multi_stream = ((not backward) and n * h * w <= self.MS_MAX_PIXELS and
                              os.environ.get("TG_INFER_STREAMS", "1") != "0")
         if self.multi_stream:
-            level = {}
-            for (i, j) in order:        # longest path to the node: sources come first in `order`
-                deps = [(i, k) for k in range(j)] + ([(i + 1, j - 1)] if j else ([(i - 1, 0)] if i else []))
-                level[i, j] = 1 + max([level[d] for d in deps], default=-1)
-            self.level_order = sorted(order, key=lambda ij: (level[ij], ij[0]))
+            self.level_order, self.stream_of, self.waits, _, _ = unetpp_chain_schedule(5, 3)
             self._side = None
-            for (i, j) in order:
-                for u in X[i, j]:
-                    u.ws_slot = (i + j) % 3
+            for nd in order:
+                for u in X[nd]:
+                    u.ws_slot = self.stream_of[nd]
         self.head = HeadUnit(self, "downfeature", module.downfeature.conv.weight, module.downfeature.conv.bias,
                              X[0, 4][1].y, module.downfeature.activation)
         self.finish()
@@ -514,19 +528,16 @@ class UNetPPEngine(GraphEngine):
         for s in self._side:
             s.wait_event(start)
         done = {}
-        for (i, j) in self.level_order:
-            st = streams[(i + j) % 3]
+        for nd in self.level_order:
+            st = streams[self.stream_of[nd]]
             with torch.cuda.stream(st):
-                # X(i+1, j-1) is the previous node of this chain (same stream); the same-row sources X(i, k < j) and,
-                # for the first node of a chain, X(i-1, 0) were produced by other chains
-                for d in [(i, k) for k in range(j)] + ([(i - 1, 0)] if (j == 0 and i) else []):
-                    if (d[0] + d[1]) % 3 != (i + j) % 3:
-                        st.wait_event(done[d])
-                u0, u1 = self.X[i, j]
+                for d in self.waits[nd]:           # sources produced on another stream (unetpp_chain_schedule)
+                    st.wait_event(done[d])
+                u0, u1 = self.X[nd]
                 u0.forward()
                 u1.forward()
-                done[i, j] = torch.cuda.Event()
-                done[i, j].record(st)
+                done[nd] = torch.cuda.Event()
+                done[nd].record(st)
         for s in self._side:
             cur.wait_stream(s)
         return self.head.forward()
