@@ -61,6 +61,22 @@ def test_tile_choice(lib):
         assert tpi == (max(generic, halo) if stats else generic)
 
 
+def test_policy_setters_return_the_previous_value(lib):
+    """tg_in_stream_policy / tg_in_stream_slim / tg_in_stream_serpentine / tg_pdl_policy are host-side switches: they
+    return the value they replace, ignore out-of-range arguments (query only) and need no GPU."""
+    for fn, values, query in ((lib.tg_in_stream_policy, (0, 2, 1), -1), (lib.tg_in_stream_slim, (1, 0), -1),
+                              (lib.tg_in_stream_serpentine, (5, 7, 0), 9), (lib.tg_pdl_policy, (1, 2, 0), -1)):
+        first = fn(query)
+        assert fn(query) == first                      # a query changes nothing
+        prev = first
+        for v in values:
+            assert fn(v) == prev
+            assert fn(query) == v
+            prev = v
+        fn(first)
+        assert fn(query) == first
+
+
 def test_phase_taps_cover_transposed_conv():
     """Every (output pixel, tap) pair of a stride-2 transposed conv appears in exactly one phase."""
     from tactile_gan_b200.layers import phase_taps
